@@ -1,0 +1,694 @@
+// pw_engine.cu — host orchestration of the filter -> group_by -> agg operator:
+//   frame upload (Arrow buffers -> HBM), query lowering (PwQuery -> ScanPlan + result plan), strategy
+//   selection from key samples (the analogue of can_run_partitioned / estimate_unique_count,
+//   polars-mem-engine/src/executors/group_by_streaming.rs:114-244), kernel launches, finalisation and
+//   Arrow result construction.  One process per GPU; every call runs on the calling thread's stream.
+#include <cub/device/device_radix_sort.cuh>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "pw_engine.h"
+
+namespace pw {
+
+// ------------------------------------------------------------------------------------------------------
+// thread context / errors / device memory
+// ------------------------------------------------------------------------------------------------------
+static thread_local ThreadCtx g_ctx;
+ThreadCtx& ctx() { return g_ctx; }
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_ctx.last_error = buf;
+  return code;
+}
+
+static std::mutex g_pool_mu;
+static bool g_pool_done[64] = {false};
+
+int ensure_device() {
+  ThreadCtx& c = ctx();
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(PW_ERR_CUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (c.device >= n) return fail(PW_ERR_CUDA, "device %d out of range (%d devices)", c.device, n);
+  PW_CUDA(cudaSetDevice(c.device));
+  if (!c.pool_ready) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (c.device < 64 && !g_pool_done[c.device]) {
+      cudaMemPool_t pool;
+      PW_CUDA(cudaDeviceGetDefaultMemPool(&pool, c.device));
+      uint64_t thr = UINT64_MAX;  // keep freed blocks cached: allocation stays off the hot path
+      PW_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+      g_pool_done[c.device] = true;
+    }
+    PW_CUDA(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, c.device));
+    c.pool_ready = true;
+  }
+  if (!c.ev_ready) {
+    for (auto& e2 : c.ev) PW_CUDA(cudaEventCreate(&e2));
+    c.ev_ready = true;
+  }
+  return 0;
+}
+
+int dev_alloc(void** p, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  PW_CUDA(cudaMallocAsync(p, bytes, ctx().stream));
+  return 0;
+}
+void dev_free(void* p) {
+  if (p) cudaFreeAsync(p, ctx().stream);
+}
+
+static inline int dtype_bytes(int dt) {
+  switch (dt) {
+    case DT_I8: case DT_U8: return 1;
+    case DT_I16: case DT_U16: return 2;
+    case DT_I32: case DT_U32: case DT_F32: return 4;
+    case DT_VIEW: return 16;
+    default: return 8;
+  }
+}
+static inline int dtype_class(int dt) {
+  switch (dt) {
+    case DT_U8: case DT_U16: case DT_U32: case DT_U64: return CLS_U64;
+    case DT_F32: case DT_F64: return CLS_F64;
+    default: return CLS_I64;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// query lowering
+// ------------------------------------------------------------------------------------------------------
+namespace {
+struct Lowerer {
+  const PwQuery* q;
+  const PwFrame* f;
+  Lowered* L;
+  int slot_of_col[256];
+
+  int slot_for(int col) {
+    if (slot_of_col[col] >= 0) return slot_of_col[col];
+    const FrameColumn& c = f->cols[col];
+    ScanPlan& P = L->plan;
+    const int need = c.dtype == DT_VIEW ? 2 : 1;
+    if (P.n_slots + need > MAX_SLOTS) return -1;
+    const int s = P.n_slots;
+    P.slots[s].values = c.values;
+    P.slots[s].validity = c.null_count ? c.validity : nullptr;
+    P.slots[s].dtype = c.dtype;
+    P.slots[s].bit_offset = c.bit_offset;
+    if (need == 2) {
+      P.slots[s + 1] = P.slots[s];
+      P.slots[s + 1].dtype = DT_VIEW_HI;
+      P.slots[s + 1].validity = nullptr;
+    }
+    P.n_slots += need;
+    slot_of_col[col] = s;
+    return s;
+  }
+  int vexpr_plain(int col) {
+    ScanPlan& P = L->plan;
+    const int s = slot_for(col);
+    if (s < 0) return -1;
+    for (int e = 0; e < P.n_vexpr; ++e)
+      if (P.vexprs[e].n_factors == 0 && P.vexprs[e].slot == s) return e;
+    if (P.n_vexpr >= MAX_VEXPR) return -1;
+    VExpr& ve = P.vexprs[P.n_vexpr];
+    ve.n_factors = 0; ve.slot = s; ve.cls = dtype_class(f->cols[col].dtype);
+    return P.n_vexpr++;
+  }
+  int vexpr_product(const PwAgg& a) {
+    ScanPlan& P = L->plan;
+    VExpr ve{};
+    ve.n_factors = a.n_factors; ve.slot = 0; ve.cls = CLS_F64;
+    for (int i = 0; i < a.n_factors; ++i) {
+      const int s = slot_for(a.factors[i].column);
+      if (s < 0) return -1;
+      ve.f[i].a = a.factors[i].a; ve.f[i].b = a.factors[i].b; ve.f[i].slot = s;
+    }
+    for (int e = 0; e < P.n_vexpr; ++e) {
+      const VExpr& o = P.vexprs[e];
+      if (o.n_factors != ve.n_factors) continue;
+      bool same = true;
+      for (int i = 0; i < ve.n_factors; ++i)
+        same = same && o.f[i].a == ve.f[i].a && o.f[i].b == ve.f[i].b && o.f[i].slot == ve.f[i].slot;
+      if (same) return e;
+    }
+    if (P.n_vexpr >= MAX_VEXPR) return -1;
+    P.vexprs[P.n_vexpr] = ve;
+    return P.n_vexpr++;
+  }
+  int acc(int op, int src, int vexpr) {
+    ScanPlan& P = L->plan;
+    for (int a = 0; a < P.n_acc; ++a)
+      if (P.accs[a].op == op && P.accs[a].src == src && P.accs[a].vexpr == vexpr) return a;
+    if (P.n_acc >= MAX_ACC) return -1;
+    P.accs[P.n_acc].op = op; P.accs[P.n_acc].src = src; P.accs[P.n_acc].vexpr = vexpr;
+    return P.n_acc++;
+  }
+};
+
+}  // namespace
+
+int lower_query(const PwQuery* q, const PwFrame* f, Lowered* L) {
+  if (!q || !f) return fail(PW_ERR_INVALID, "null query or frame");
+  if (q->abi_version != PW_ABI_VERSION) return fail(PW_ERR_INVALID, "PwQuery.abi_version %u != %u", q->abi_version, PW_ABI_VERSION);
+  if (f->cols.size() > 256) return fail(PW_ERR_UNSUPPORTED, "more than 256 columns");
+  const int ncols = (int)f->cols.size();
+  Lowerer lw{q, f, L, {}};
+  for (int i = 0; i < 256; ++i) lw.slot_of_col[i] = -1;
+  ScanPlan& P = L->plan;
+  memset(&P, 0, sizeof P);
+  P.n_rows = f->n_rows;
+  P.row_begin = 0; P.row_stride = 1;
+  P.row_offset = q->row_offset;
+  auto col_ok = [&](int c) { return c >= 0 && c < ncols; };
+
+  // ---- predicates (a1/a2)
+  if (q->n_predicates > MAX_PREDS) return fail(PW_ERR_UNSUPPORTED, "more than %d predicate conjuncts", MAX_PREDS);
+  for (int i = 0; i < q->n_predicates; ++i) {
+    const PwPredicate& p = q->predicates[i];
+    if (!col_ok(p.column)) return fail(PW_ERR_INVALID, "predicate column %d out of range", p.column);
+    const FrameColumn& c = f->cols[p.column];
+    if (c.dtype == DT_VIEW || c.dtype == DT_BOOL) return fail(PW_ERR_UNSUPPORTED, "predicate on column '%s' of format %s", c.name.c_str(), c.format.c_str());
+    const int s = lw.slot_for(p.column);
+    if (s < 0) return fail(PW_ERR_UNSUPPORTED, "query touches more than %d column slots", MAX_SLOTS);
+    Pred& d = P.preds[P.n_preds++];
+    d.slot = s; d.op = p.op; d.cls = dtype_class(c.dtype);
+    if (d.cls == CLS_F64) {
+      double v = p.scalar_is_float ? p.scalar.f : (double)p.scalar.i;
+      memcpy(&d.scalar, &v, 8);
+    } else {
+      if (p.scalar_is_float) return fail(PW_ERR_UNSUPPORTED, "float scalar compared with integer column '%s'", c.name.c_str());
+      d.scalar = p.scalar.u;
+    }
+  }
+
+  // ---- dynamic options
+  const PwDynamic* dyn = q->dynamic;
+  int dyn_slot = -1;
+  if (dyn) {
+    if (!col_ok(dyn->index_column)) return fail(PW_ERR_INVALID, "index column out of range");
+    const FrameColumn& c = f->cols[dyn->index_column];
+    if (dtype_class(c.dtype) != CLS_I64 || c.dtype == DT_VIEW) return fail(PW_ERR_INVALID, "group_by_dynamic index column '%s' must be a signed integer / temporal column", c.name.c_str());
+    if (c.null_count) return fail(PW_ERR_INVALID, "null values in `group_by_dynamic` index column are not supported");
+    if (dyn->every <= 0) return fail(PW_ERR_INVALID, "'every' argument must be positive");
+    if (dyn->period <= 0) return fail(PW_ERR_INVALID, "'period' argument must be positive");
+    dyn_slot = lw.slot_for(dyn->index_column);
+    if (dyn_slot < 0) return fail(PW_ERR_UNSUPPORTED, "too many column slots");
+    const bool overlapping = dyn->closed == PW_CLOSED_BOTH ? dyn->period >= dyn->every : dyn->period > dyn->every;  // dynamic.rs:312-315
+    L->tumbling = !overlapping;
+    P.dyn.enabled = 1; P.dyn.slot = dyn_slot; P.dyn.closed = dyn->closed;
+    P.dyn.every = dyn->every; P.dyn.period = dyn->period;
+    // window starts lie on the grid offset + k*every: truncate(t0, every) + offset (window.rs:115-170)
+    P.dyn.origin = dyn->offset;
+    P.check_sorted = q->n_keys == 0;
+  }
+
+  // ---- keys (a3/a4/a8)
+  if (q->n_keys > MAX_KEYS) return fail(PW_ERR_UNSUPPORTED, "more than %d key columns (multi-column row encoding is SURVEY 8f rank 1)", MAX_KEYS);
+  int n_words = 0;
+  bool any_nullable = false;
+  for (int i = 0; i < q->n_keys; ++i) {
+    const int kcol = q->key_columns[i];
+    if (!col_ok(kcol)) return fail(PW_ERR_INVALID, "key column %d out of range", kcol);
+    const FrameColumn& c = f->cols[kcol];
+    if (c.dtype == DT_BOOL) return fail(PW_ERR_UNSUPPORTED, "boolean key column '%s'", c.name.c_str());
+    const int s = lw.slot_for(kcol);
+    if (s < 0) return fail(PW_ERR_UNSUPPORTED, "too many column slots");
+    KeyCol& k = P.keys[P.n_keys++];
+    k.slot = s; k.dtype = c.dtype; k.n_words = c.dtype == DT_VIEW ? 2 : 1; k.nullable = c.null_count != 0;
+    any_nullable = any_nullable || k.nullable;
+    n_words += k.n_words;
+  }
+  if (dyn) n_words += 1;
+  const bool single_plain_key = q->n_keys == 1 && !dyn && P.keys[0].n_words == 1;
+  if (any_nullable && !single_plain_key) { P.has_null_word = 1; L->null_word = n_words; n_words += 1; }
+  else L->null_word = -1;
+  L->single_key_null = (any_nullable && single_plain_key) ? 1 : 0;
+  if (n_words == 0) n_words = 1;  // global aggregation: one constant key word
+  if (n_words > MAX_KW) return fail(PW_ERR_UNSUPPORTED, "key wider than %d 64-bit words", MAX_KW);
+  P.n_kw = n_words;
+
+  // ---- output plan: keys first
+  int word = 0;
+  for (int i = 0; i < q->n_keys; ++i) {
+    const FrameColumn& c = f->cols[q->key_columns[i]];
+    OutCol o;
+    o.name = c.name; o.format = c.format; o.nullable = c.null_count != 0;
+    o.emit.kind = c.dtype == DT_VIEW ? EMIT_KEY_VIEW : EMIT_KEY_INT;
+    o.emit.out_dtype = c.dtype; o.out_dtype = c.dtype;
+    o.emit.word = word;
+    o.emit.null_word = P.keys[i].nullable ? L->null_word : -1;
+    o.emit.nullbit = i;
+    o.emit.single_key_null = (P.keys[i].nullable && L->null_word < 0) ? 1 : 0;
+    L->outs.push_back(o);
+    word += P.keys[i].n_words;
+  }
+  const int dyn_word = word;
+  if (dyn) {
+    const FrameColumn& c = f->cols[dyn->index_column];
+    auto bound_col = [&](const char* name, int kind) {
+      OutCol o; o.name = name; o.format = c.format; o.nullable = false;
+      o.emit.kind = kind; o.emit.out_dtype = c.dtype; o.out_dtype = c.dtype; o.emit.word = dyn_word;
+      o.emit.every = dyn->every; o.emit.period = dyn->period; o.emit.origin = dyn->offset;
+      o.emit.null_word = -1;
+      L->outs.push_back(o);
+    };
+    if (dyn->include_boundaries) { bound_col("_lower_boundary", EMIT_DYN_LOWER); bound_col("_upper_boundary", EMIT_DYN_UPPER); }
+    if (dyn->label == PW_LABEL_LEFT) bound_col(c.name.c_str(), EMIT_DYN_LOWER);
+    else if (dyn->label == PW_LABEL_RIGHT) bound_col(c.name.c_str(), EMIT_DYN_UPPER);
+    else {
+      const int a = lw.acc(OP_MIN_I64, SRC_INDEX_T, 0);
+      OutCol o; o.name = c.name; o.format = c.format; o.nullable = false;
+      o.emit.kind = EMIT_ACC_I64; o.emit.acc = a; o.emit.out_dtype = c.dtype; o.out_dtype = c.dtype; o.emit.null_word = -1;
+      L->outs.push_back(o);
+    }
+  }
+
+  // ---- aggregations (a6/a10)
+  for (int i = 0; i < q->n_aggs; ++i) {
+    const PwAgg& a = q->aggs[i];
+    OutCol o;
+    o.name = a.name ? a.name : "";
+    o.emit.null_word = -1;
+    o.emit.row_offset = q->row_offset;
+    if (a.kind == PW_LEN) {
+      const int acc = lw.acc(OP_ADD_I64, SRC_ONE, 0);
+      if (acc < 0) return fail(PW_ERR_UNSUPPORTED, "too many accumulators");
+      o.format = "I"; o.out_dtype = DT_U32; o.emit.kind = EMIT_COUNT; o.emit.acc = acc; o.emit.out_dtype = DT_U32;
+      L->outs.push_back(o);
+      continue;
+    }
+    int ve, in_dtype = DT_F64;
+    std::string in_format = "g";
+    if (a.n_factors > 0) {
+      if (a.n_factors > PW_MAX_FACTORS) return fail(PW_ERR_INVALID, "too many factors");
+      for (int k = 0; k < a.n_factors; ++k) {
+        if (!col_ok(a.factors[k].column)) return fail(PW_ERR_INVALID, "factor column out of range");
+        const int dt = f->cols[a.factors[k].column].dtype;
+        if (dt == DT_VIEW || dt == DT_BOOL) return fail(PW_ERR_UNSUPPORTED, "arithmetic on a non-numeric column");
+      }
+      ve = lw.vexpr_product(a);
+    } else {
+      if (!col_ok(a.column)) return fail(PW_ERR_INVALID, "aggregation column %d out of range", a.column);
+      const FrameColumn& c = f->cols[a.column];
+      if (c.dtype == DT_VIEW || c.dtype == DT_BOOL) {
+        if (a.kind == PW_COUNT) { /* fine: only validity is read */ }
+        else return fail(PW_ERR_UNSUPPORTED, "aggregation over column '%s' of format %s (strings/booleans are SURVEY 8f)", c.name.c_str(), c.format.c_str());
+      }
+      in_dtype = c.dtype; in_format = c.format;
+      ve = lw.vexpr_plain(a.column);
+    }
+    if (ve < 0) return fail(PW_ERR_UNSUPPORTED, "query needs more than %d column slots / %d value expressions", MAX_SLOTS, MAX_VEXPR);
+    const int cls = P.vexprs[ve].cls;
+    const bool is_float = cls == CLS_F64;
+    const bool temporal = in_format.size() > 1 && in_format[0] == 't';
+    int a0 = -1, a1 = -1, a2 = -1;
+    switch (a.kind) {
+      case PW_SUM:
+        if (temporal && in_format[1] != 'D') return fail(PW_ERR_UNSUPPORTED, "`sum` operation not supported for dtype %s", in_format.c_str());
+        if (is_float) {
+          a0 = lw.acc(OP_ADD_F64, SRC_F64, ve);
+          o.emit.kind = EMIT_SUM_F64; o.out_dtype = in_dtype == DT_F32 ? DT_F32 : DT_F64; o.format = in_dtype == DT_F32 ? "f" : "g";
+        } else {
+          a0 = lw.acc(OP_ADD_I64, SRC_BITS, ve);
+          o.emit.kind = EMIT_SUM_INT;
+          // i8/i16/u8/u16 -> Int64, others keep their dtype (sum.rs:40-47)
+          if (in_dtype == DT_I8 || in_dtype == DT_I16 || in_dtype == DT_U8 || in_dtype == DT_U16) { o.out_dtype = DT_I64; o.format = "l"; }
+          else { o.out_dtype = in_dtype; o.format = in_format; }
+        }
+        o.nullable = false;
+        break;
+      case PW_MEAN:
+        a0 = lw.acc(OP_ADD_F64, SRC_F64, ve);
+        a1 = lw.acc(OP_ADD_I64, SRC_VALID, ve);
+        o.emit.kind = EMIT_MEAN; o.nullable = true;
+        if (in_dtype == DT_F32 && !temporal) { o.emit.mean_out = MEAN_F32; o.out_dtype = DT_F32; o.format = "f"; }
+        else if (in_format == "tdD") { o.emit.mean_out = MEAN_DATE_US; o.out_dtype = DT_I64; o.format = "tsu:"; }
+        else if (temporal) { o.emit.mean_out = MEAN_I64; o.out_dtype = DT_I64; o.format = in_format; }
+        else { o.emit.mean_out = MEAN_F64; o.out_dtype = DT_F64; o.format = "g"; }
+        break;
+      case PW_MIN: case PW_MAX: {
+        const bool is_min = a.kind == PW_MIN;
+        a1 = lw.acc(OP_ADD_I64, SRC_VALID, ve);
+        if (is_float) {
+          a0 = lw.acc(is_min ? OP_MIN_I64 : OP_MAX_I64, SRC_F64_ORD, ve);
+          a2 = lw.acc(OP_ADD_I64, SRC_NOT_NAN, ve);
+          o.emit.kind = EMIT_MINMAX_F64;
+        } else {
+          a0 = cls == CLS_U64 ? lw.acc(is_min ? OP_MIN_U64 : OP_MAX_U64, SRC_BITS, ve)
+                              : lw.acc(is_min ? OP_MIN_I64 : OP_MAX_I64, SRC_BITS, ve);
+          o.emit.kind = EMIT_MINMAX_INT;
+        }
+        o.out_dtype = in_dtype; o.format = in_format; o.nullable = true;
+        break; }
+      case PW_COUNT:
+        a0 = lw.acc(OP_ADD_I64, SRC_VALID, ve);
+        o.emit.kind = EMIT_COUNT; o.out_dtype = DT_U32; o.format = "I";
+        break;
+      case PW_FIRST: case PW_LAST:
+        if (a.n_factors > 0) return fail(PW_ERR_UNSUPPORTED, "first/last of a computed expression");
+        a0 = lw.acc(a.kind == PW_FIRST ? OP_MIN_U64 : OP_MAX_U64, SRC_ROWIDX, ve);
+        o.emit.kind = EMIT_FIRSTLAST; o.out_dtype = in_dtype; o.format = in_format; o.nullable = true;
+        o.emit.src = P.slots[P.vexprs[ve].slot];
+        break;
+      default: return fail(PW_ERR_INVALID, "unknown aggregation kind %d", a.kind);
+    }
+    if (a0 < 0 || (a.kind == PW_MEAN && a1 < 0)) return fail(PW_ERR_UNSUPPORTED, "query needs more than %d accumulator words", MAX_ACC);
+    o.emit.acc = a0; o.emit.acc_cnt = a1; o.emit.acc_nn = a2; o.emit.out_dtype = o.out_dtype; o.emit.src_cls = cls;
+    L->outs.push_back(o);
+  }
+
+  // ---- ordering
+  if (dyn) {
+    // key slices ascending (nulls first) then windows ascending: group_by_rolling.rs:17-58 + dynamic.rs:317-362
+    SortSpec w{}; w.src = SORT_WORD_I64; w.word = dyn_word; L->sort.push_back(w);  // least significant
+    int wd = dyn_word;
+    for (int i = q->n_keys - 1; i >= 0; --i) {
+      wd -= P.keys[i].n_words;
+      SortSpec s{}; s.word = wd; s.nullbit = i; s.single_key_null = 0;
+      const int dt = P.keys[i].dtype;
+      const int nullable = P.keys[i].nullable;
+      auto push = [&](int src) { SortSpec t = s; t.src = src; if (!nullable) t.nullbit = 63; L->sort.push_back(t); };
+      if (dt == DT_VIEW) { push(SORT_VIEW_LO); push(SORT_VIEW_HI); }
+      else if (dtype_class(dt) == CLS_F64) push(SORT_WORD_F64);
+      else if (dtype_class(dt) == CLS_U64) push(SORT_WORD_U64);
+      else push(SORT_WORD_I64);
+      if (nullable) push(SORT_NULLBIT);
+    }
+  } else if (q->maintain_order) {
+    const int a = lw.acc(OP_MIN_U64, SRC_ROW, 0);
+    if (a < 0) return fail(PW_ERR_UNSUPPORTED, "too many accumulators");
+    SortSpec s{}; s.src = SORT_ACC_U64; s.acc = a; L->sort.push_back(s);
+  }
+  if (P.n_acc == 0) lw.acc(OP_ADD_I64, SRC_ONE, 0);  // a table needs at least one word per group
+
+  // vector loads need 16-byte aligned column bases
+  P.vec_ok = 1;
+  for (int s = 0; s < P.n_slots; ++s)
+    if (((uintptr_t)P.slots[s].values & 15u) != 0) P.vec_ok = 0;
+  L->n_nc = P.n_slots;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// launches
+// ------------------------------------------------------------------------------------------------------
+
+static int launch_scan(ScanPlan P, int sm, cudaStream_t st) {
+  // the kernel is compiled for a few (slots, key words) classes; round the key width up (extra words are 0)
+  if (P.n_kw == 3) P.n_kw = 4;
+  if (P.n_kw == 5) P.n_kw = 6;
+  if (P.n_slots <= 4) return launch_scan_nc4(P, sm, st);
+  return launch_scan_nc12(P, sm, st);
+}
+static int padded_kw(int n_kw) { return n_kw == 3 ? 4 : (n_kw == 5 ? 6 : n_kw); }
+
+static int hot_slots_for(const ScanPlan& P, int requested) {
+  if (requested > 0) {
+    int s = 16;
+    while (s < requested) s <<= 1;
+    return s;
+  }
+  const size_t per = (size_t)padded_kw(P.n_kw) * 8 + (size_t)P.n_acc * 8 + 4;
+  int s = 4096;
+  while (s > 256 && (size_t)s * per > 96 * 1024) s >>= 1;  // two CTAs per SM
+  return s;
+}
+
+struct Control {  // device control block (zeroed per run)
+  int32_t overflow;
+  int32_t not_sorted;
+  unsigned long long spilled;
+  unsigned long long counter;
+  unsigned long long null_counts[64];
+};
+
+static int alloc_table(Table* T, int n_kw, int n_acc, uint64_t cap, Control* dctl) {
+  const uint64_t n = cap + 2;
+  void* p = nullptr;
+  PW_TRY(dev_alloc(&p, n * 8 * (uint64_t)n_kw)); T->keys = (uint64_t*)p;
+  PW_TRY(dev_alloc(&p, n * 4)); T->state = (uint32_t*)p;
+  PW_TRY(dev_alloc(&p, n * 8 * (uint64_t)n_acc)); T->accs = (uint64_t*)p;
+  T->cap = cap;
+  T->overflow = &dctl->overflow;
+  T->spilled = &dctl->spilled;
+  return 0;
+}
+void free_table(Table& T) {
+  dev_free(T.keys); dev_free(T.state); dev_free(T.accs);
+  T.keys = nullptr; T.state = nullptr; T.accs = nullptr;
+}
+static int init_table(const Table& T, const ScanPlan& P, cudaStream_t st) {
+  AccOps ops{};
+  ops.n = P.n_acc;
+  for (int a = 0; a < P.n_acc; ++a) ops.op[a] = P.accs[a].op;
+  const uint64_t n = T.cap + 2;
+  int grid = (int)std::min<uint64_t>((n + 255) / 256, 148 * 8);
+  table_init_kernel<<<grid, 256, 0, st>>>(T, padded_kw(P.n_kw), ops);
+  PW_CUDA(cudaGetLastError());
+  ctx().timings.kernel_launches++;
+  return 0;
+}
+
+// distinct keys among `n_sample` rows starting at row_begin with the given stride (pilot launch)
+static int sample_distinct(const Lowered& L, int64_t row_begin, int64_t stride, int64_t n_sample, Control* dctl,
+                           Control* hctl, uint64_t* distinct) {
+  ThreadCtx& c = ctx();
+  ScanPlan P = L.plan;
+  P.n_rows = n_sample; P.row_begin = row_begin; P.row_stride = stride;
+  P.vec_ok = (L.plan.vec_ok && stride == 1 && (row_begin % 2) == 0) ? 1 : 0;
+  P.hot_slots = 0; P.check_sorted = 0; P.n_preds = 0;
+  // only group identity matters: one len accumulator
+  P.n_acc = 1; P.accs[0].op = OP_ADD_I64; P.accs[0].src = SRC_ONE; P.accs[0].vexpr = 0; P.n_vexpr = 0;
+  Table T{};
+  PW_TRY(alloc_table(&T, padded_kw(P.n_kw), 1, (uint64_t)n_sample * 2 + 64, dctl));
+  PW_TRY(init_table(T, P, c.stream));
+  P.table = T; P.not_sorted = &dctl->not_sorted;
+  PW_CUDA(cudaMemsetAsync(dctl, 0, sizeof(Control), c.stream));
+  PW_TRY(launch_scan(P, c.sm_count, c.stream));
+  uint32_t* dummy = nullptr;
+  void* p = nullptr;
+  PW_TRY(dev_alloc(&p, (T.cap + 2) * 4)); dummy = (uint32_t*)p;
+  int grid = (int)std::min<uint64_t>((T.cap + 2 + 255) / 256, 148 * 8);
+  compact_kernel<<<grid, 256, 0, c.stream>>>(T, padded_kw(P.n_kw), dummy, &dctl->counter);
+  PW_CUDA(cudaGetLastError());
+  c.timings.kernel_launches++;
+  PW_CUDA(cudaMemcpyAsync(hctl, dctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream));
+  PW_CUDA(cudaStreamSynchronize(c.stream));
+  *distinct = hctl->counter;
+  dev_free(dummy);
+  free_table(T);
+  if (hctl->overflow == 2) return fail(PW_ERR_UNSUPPORTED, "string key longer than 12 bytes (long views need the data buffers: SURVEY 8f rank 1)");
+  return 0;
+}
+
+// d distinct values seen in a uniform sample of n rows -> number of groups, assuming equally likely
+// groups: d = G (1 - exp(-n/G)).  (The reference extrapolates from a sqrt(N) sample the same way,
+// group_by_streaming.rs:114-153.)
+static double solve_groups(double d, double n) {
+  if (d >= 0.995 * n) return 1e18;
+  double lo = d, hi = 1e15;
+  for (int i = 0; i < 200; ++i) {
+    double mid = sqrt(lo * hi);
+    double seen = mid * (1.0 - exp(-n / mid));
+    if (seen < d) lo = mid; else hi = mid;
+    if (hi / lo < 1.0001) break;
+  }
+  return hi;
+}
+
+int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out, uint32_t** slot_list_out, uint64_t* n_groups_out) {
+  ThreadCtx& c = ctx();
+  ScanPlan& P = L.plan;
+  const int64_t N = f->n_rows;
+  PwTimings& tm = c.timings;
+  tm.n_rows = N;
+
+  Control* dctl = nullptr;
+  { void* p = nullptr; PW_TRY(dev_alloc(&p, sizeof(Control))); dctl = (Control*)p; }
+  Control hctl{};
+
+  // ---- strategy + table size -------------------------------------------------------------------
+  PW_CUDA(cudaEventRecord(c.ev[1], c.stream));
+  const int default_hot = hot_slots_for(P, q->hot_table_slots);
+  uint64_t cap = 0;
+  bool use_hot = true;
+  const int64_t SMALL = 1 << 18;
+  if (q->initial_table_slots > 0) cap = (uint64_t)q->initial_table_slots;
+  if (N <= SMALL) {
+    if (!cap) cap = (uint64_t)std::max<int64_t>(2 * N, 64);
+  } else if (!cap || !(q->flags & (PW_FLAG_FORCE_HOT_TABLE | PW_FLAG_FORCE_GLOBAL_TABLE))) {
+    // (1) strided sample over the whole input -> table size
+    const int64_t n_s = SMALL;
+    uint64_t d = 0;
+    PW_TRY(sample_distinct(L, 0, N / n_s, n_s, dctl, &hctl, &d));
+    double g = solve_groups((double)d, (double)n_s);
+    if (P.n_preds == 0 || true) g = std::min(g, (double)N);
+    if (!cap) cap = (uint64_t)std::max(1024.0, std::min(2.0 * (double)N + 64.0, 2.5 * g + 1024.0));
+    // (2) a contiguous block from the middle -> do consecutive rows share few groups? (hot table pays)
+    const int64_t n_b = 1 << 16;
+    int64_t mid = ((N / 2) / ROWS_PER_STEP) * ROWS_PER_STEP;
+    if (mid + n_b > N) mid = 0;
+    uint64_t dl = 0;
+    PW_TRY(sample_distinct(L, mid, 1, n_b, dctl, &hctl, &dl));
+    use_hot = dl <= (uint64_t)(default_hot / 2);
+  }
+  if (q->flags & PW_FLAG_FORCE_HOT_TABLE) use_hot = true;
+  if (q->flags & PW_FLAG_FORCE_GLOBAL_TABLE) use_hot = false;
+  if (cap > 0xFFFFFFF0ull) return fail(PW_ERR_UNSUPPORTED, "table larger than 2^32 slots");
+  PW_CUDA(cudaEventRecord(c.ev[2], c.stream));
+
+  // ---- scan (with growth retries) ------------------------------------------------------------------
+  Table T{};
+  tm.retries = 0;
+  for (;;) {
+    PW_TRY(alloc_table(&T, padded_kw(P.n_kw), P.n_acc, cap, dctl));
+    PW_TRY(init_table(T, P, c.stream));
+    PW_CUDA(cudaMemsetAsync(dctl, 0, sizeof(Control), c.stream));
+    P.table = T;
+    P.not_sorted = &dctl->not_sorted;
+    P.hot_slots = use_hot ? default_hot : 0;
+    PW_CUDA(cudaEventRecord(c.ev[8], c.stream));
+    if (N > 0) PW_TRY(launch_scan(P, c.sm_count, c.stream));
+    PW_CUDA(cudaEventRecord(c.ev[9], c.stream));
+    PW_CUDA(cudaMemcpyAsync(&hctl, dctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream));
+    PW_CUDA(cudaStreamSynchronize(c.stream));
+    if (hctl.overflow == 2) { free_table(T); dev_free(dctl); return fail(PW_ERR_UNSUPPORTED, "string key longer than 12 bytes (long views need the data buffers: SURVEY 8f rank 1)"); }
+    if (hctl.overflow == 1) {
+      free_table(T);
+      if (cap >= (uint64_t)2 * (uint64_t)N + 64) { dev_free(dctl); return fail(PW_ERR_INTERNAL, "hash table overflow at maximum size"); }
+      cap = std::min<uint64_t>(cap * 4, (uint64_t)2 * (uint64_t)N + 64);
+      tm.retries++;
+      continue;
+    }
+    break;
+  }
+  if (hctl.not_sorted) {
+    free_table(T); dev_free(dctl);
+    return fail(PW_ERR_NOT_SORTED, "argument in operation 'group_by_dynamic' is not sorted, please sort the 'expr/series/column' first");
+  }
+  tm.strategy = use_hot ? 1 : 2;
+  tm.spilled_rows = (int64_t)hctl.spilled;
+  tm.table_slots = (int64_t)cap;
+  PW_CUDA(cudaEventRecord(c.ev[3], c.stream));
+
+  // ---- compact + order --------------------------------------------------------------------------------
+  uint32_t* slots = nullptr;
+  { void* p = nullptr; PW_TRY(dev_alloc(&p, (cap + 2) * 4)); slots = (uint32_t*)p; }
+  PW_CUDA(cudaMemsetAsync(&dctl->counter, 0, sizeof(unsigned long long), c.stream));
+  {
+    int grid = (int)std::min<uint64_t>((cap + 2 + 255) / 256, 148 * 8);
+    compact_kernel<<<grid, 256, 0, c.stream>>>(T, padded_kw(P.n_kw), slots, &dctl->counter);
+    PW_CUDA(cudaGetLastError());
+    tm.kernel_launches++;
+  }
+  PW_CUDA(cudaMemcpyAsync(&hctl, dctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream));
+  PW_CUDA(cudaStreamSynchronize(c.stream));
+  const uint64_t G = hctl.counter;
+  tm.n_groups = (int64_t)G;
+
+  if (G > 1 && !L.sort.empty()) {
+    uint64_t *k_in = nullptr, *k_out = nullptr;
+    uint32_t *v_out = nullptr;
+    void* p = nullptr;
+    PW_TRY(dev_alloc(&p, G * 8)); k_in = (uint64_t*)p;
+    PW_TRY(dev_alloc(&p, G * 8)); k_out = (uint64_t*)p;
+    PW_TRY(dev_alloc(&p, G * 4)); v_out = (uint32_t*)p;
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, slots, v_out, (int64_t)G, 0, 64, c.stream);
+    void* tmp = nullptr;
+    PW_TRY(dev_alloc(&tmp, tmp_bytes));
+    const int grid = (int)((G + 255) / 256);
+    for (const SortSpec& sp : L.sort) {  // LSD: least significant word first, every pass stable
+      sort_key_kernel<<<grid, 256, 0, c.stream>>>(T, padded_kw(P.n_kw), L.null_word, sp, slots, G, k_in);
+      PW_CUDA(cudaGetLastError());
+      PW_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, slots, v_out, (int64_t)G, 0, 64, c.stream));
+      std::swap(slots, v_out);
+      tm.kernel_launches += 2;
+    }
+    dev_free(tmp); dev_free(k_in); dev_free(k_out); dev_free(v_out);
+  }
+  dev_free(dctl);
+  *table_out = T;
+  *slot_list_out = slots;
+  *n_groups_out = G;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// result emission: one kernel per output column, then D2H into malloc'd Arrow buffers
+// ------------------------------------------------------------------------------------------------------
+int emit_results(const Lowered& L, const Table& T, const uint32_t* slot_list, uint64_t G,
+                 struct ArrowArray* out_cols, struct ArrowSchema* out_schemas, size_t* n_out) {
+  ThreadCtx& c = ctx();
+  const size_t ncol = L.outs.size();
+  if (*n_out < ncol) return fail(PW_ERR_INVALID, "output capacity %zu < %zu result columns", *n_out, ncol);
+  if (ncol > 64) return fail(PW_ERR_UNSUPPORTED, "more than 64 result columns");
+  unsigned long long* d_nulls = nullptr;
+  { void* p = nullptr; PW_TRY(dev_alloc(&p, 64 * 8)); d_nulls = (unsigned long long*)p; }
+  PW_CUDA(cudaMemsetAsync(d_nulls, 0, 64 * 8, c.stream));
+  std::vector<void*> d_vals(ncol, nullptr), d_valid(ncol, nullptr);
+  std::vector<size_t> val_bytes(ncol), valid_bytes(ncol);
+  const int grid = (int)std::max<uint64_t>(1, (G + 255) / 256);
+  const int kw = padded_kw(L.plan.n_kw);
+  for (size_t i = 0; i < ncol; ++i) {
+    const OutCol& o = L.outs[i];
+    val_bytes[i] = (size_t)G * dtype_bytes(o.out_dtype);
+    valid_bytes[i] = ((G + 31) / 32) * 4;
+    PW_TRY(dev_alloc(&d_vals[i], val_bytes[i]));
+    PW_TRY(dev_alloc(&d_valid[i], valid_bytes[i]));
+    EmitDesc d = o.emit;
+    d.out_values = d_vals[i];
+    d.out_validity = (uint32_t*)d_valid[i];
+    d.null_count = d_nulls + i;
+    if (G) {
+      emit_kernel<<<grid, 256, 0, c.stream>>>(T, kw, d, slot_list, G);
+      PW_CUDA(cudaGetLastError());
+      c.timings.kernel_launches++;
+    }
+  }
+  PW_CUDA(cudaEventRecord(c.ev[4], c.stream));
+  unsigned long long h_nulls[64] = {0};
+  PW_CUDA(cudaMemcpyAsync(h_nulls, d_nulls, 64 * 8, cudaMemcpyDeviceToHost, c.stream));
+  std::vector<void*> h_vals(ncol, nullptr), h_valid(ncol, nullptr);
+  for (size_t i = 0; i < ncol; ++i) {
+    h_vals[i] = malloc(val_bytes[i] + 64);
+    h_valid[i] = malloc(valid_bytes[i] + 64);
+    if (!h_vals[i] || !h_valid[i]) return fail(PW_ERR_INTERNAL, "out of host memory");
+    if (G) {
+      PW_CUDA(cudaMemcpyAsync(h_vals[i], d_vals[i], val_bytes[i], cudaMemcpyDeviceToHost, c.stream));
+      PW_CUDA(cudaMemcpyAsync(h_valid[i], d_valid[i], valid_bytes[i], cudaMemcpyDeviceToHost, c.stream));
+    }
+  }
+  PW_CUDA(cudaEventRecord(c.ev[5], c.stream));
+  PW_CUDA(cudaStreamSynchronize(c.stream));
+  for (size_t i = 0; i < ncol; ++i) {
+    const OutCol& o = L.outs[i];
+    PW_TRY(make_host_array((int64_t)G, (int64_t)h_nulls[i], h_valid[i], h_vals[i], o.out_dtype == DT_VIEW ? 1 : 0, &out_cols[i]));
+    PW_TRY(make_schema(o.format.c_str(), o.name.c_str(), true, &out_schemas[i]));
+    dev_free(d_vals[i]); dev_free(d_valid[i]);
+  }
+  dev_free(d_nulls);
+  *n_out = ncol;
+  return 0;
+}
+
+}  // namespace pw

@@ -1,0 +1,101 @@
+// pw_engine.h — host-side structures of libpolarway_b200 (internal; the public ABI is include/polarway_b200.h)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/polarway_b200.h"
+#include "pw_finalize.cuh"
+#include "pw_plan.h"
+
+namespace pw {
+
+struct ThreadCtx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+  PwTimings timings{};
+  cudaEvent_t ev[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ev_ready = false;
+  int sm_count = 0;
+  bool pool_ready = false;
+};
+ThreadCtx& ctx();
+int fail(int code, const char* fmt, ...);
+
+#define PW_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) return ::pw::fail(PW_ERR_CUDA, "%s failed: %s (%s:%d)", #call,          \
+                                             cudaGetErrorString(_e), __FILE__, __LINE__);          \
+  } while (0)
+#define PW_TRY(expr)            \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != 0) return _rc;   \
+  } while (0)
+
+struct FrameColumn {
+  std::string format, name;
+  int32_t dtype = DT_I64;       // physical DType
+  int64_t null_count = 0;
+  const void* values = nullptr; // device
+  const uint8_t* validity = nullptr;
+  int32_t bit_offset = 0;
+  void* owned_values = nullptr; // freed with the frame
+  void* owned_validity = nullptr;
+};
+
+}  // namespace pw
+
+struct PwFrame {
+  int device = 0;
+  int64_t n_rows = 0;
+  std::vector<pw::FrameColumn> cols;
+};
+
+namespace pw {
+
+// one result column: how to emit it + its Arrow schema
+struct OutCol {
+  std::string name, format;
+  EmitDesc emit{};
+  int32_t out_dtype = DT_I64;  // buffer dtype (DT_VIEW for string keys)
+  bool nullable = false;
+};
+
+struct Lowered {
+  ScanPlan plan{};
+  std::vector<OutCol> outs;
+  std::vector<SortSpec> sort;  // least-significant first
+  int null_word = -1;
+  int single_key_null = 0;
+  int n_nc = 0;                // raw slots in use
+  bool tumbling = true;
+};
+
+int launch_scan_nc4(const ScanPlan& P, int sm, cudaStream_t st);
+int launch_scan_nc12(const ScanPlan& P, int sm, cudaStream_t st);
+int ensure_device();
+int dev_alloc(void** p, size_t bytes);
+void dev_free(void* p);
+
+int lower_query(const PwQuery* q, const PwFrame* f, Lowered* out);
+int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out, uint32_t** slot_list_out, uint64_t* n_groups_out);
+int emit_results(const Lowered& L, const Table& T, const uint32_t* slot_list, uint64_t n_groups,
+                 struct ArrowArray* out_cols, struct ArrowSchema* out_schemas, size_t* n_out);
+void free_table(Table& T);
+
+// segmented (sorted-run) dynamic path, pw_segmented.cu
+int run_dynamic_segmented(const PwQuery* q, const PwFrame* f, struct ArrowArray* out_cols, struct ArrowSchema* out_schemas,
+                          size_t* n_out, bool* handled);
+
+// Arrow helpers (pw_arrow.cpp)
+int parse_format(const char* fmt, int32_t* dtype);
+int make_host_array(int64_t length, int64_t null_count, void* validity, void* values, size_t n_extra_buffers,
+                    struct ArrowArray* out);
+int make_schema(const char* format, const char* name, bool nullable, struct ArrowSchema* out);
+
+}  // namespace pw

@@ -1,0 +1,126 @@
+// pw_plan.h — device-side query plan shared by the host engine and the kernels.
+//
+// The host lowers a PwQuery (include/polarway_b200.h) over a resident frame into a ScanPlan:
+//   raw slots  -> the distinct columns the kernels must read (each 8-byte-or-narrower column is one slot,
+//                 a 16-byte string view column takes two slots: even rows / odd rows of a row pair)
+//   predicates -> conjunction of `slot <op> scalar`, null => false           
+//   key words  -> canonical 64-bit words per row (+ optional null-mask word) (a3/a4/a8)
+//   vexprs     -> value expressions (plain column or product of affine factors)
+//   accs       -> 64-bit accumulator words per group with an associative op   (a6/a10)
+// Everything is runtime data so one compiled kernel serves every query of a given shape class
+// (template parameters: number of raw slots, number of key words, hot table on/off).
+#pragma once
+#include <stdint.h>
+
+namespace pw {
+
+enum DType : int32_t {
+  DT_I8 = 0, DT_I16, DT_I32, DT_I64, DT_U8, DT_U16, DT_U32, DT_U64, DT_F32, DT_F64,
+  DT_VIEW,     // 16-byte Utf8View/BinaryView (inline strings only)
+  DT_VIEW_HI,  // second raw slot of a view column (odd row of the pair)
+  DT_BOOL
+};
+enum ValClass : int32_t { CLS_I64 = 0, CLS_U64 = 1, CLS_F64 = 2 };
+
+// accumulator ops: every one is a native 64-bit atomic on sm_100a (global) and an associative,
+// commutative merge, which is what makes partial aggregates exchangeable.
+enum AccOp : int32_t { OP_ADD_F64 = 0, OP_ADD_I64, OP_MIN_I64, OP_MAX_I64, OP_MIN_U64, OP_MAX_U64 };
+// what a row contributes to an accumulator
+enum AccSrc : int32_t {
+  SRC_BITS = 0,   // raw 64-bit value (int sum / int min / int max); skipped when null
+  SRC_F64,        // value as f64 (f64 sum, mean numerator); skipped when null
+  SRC_F64_ORD,    // order-preserving int64 image of the f64 value (float min/max); null and NaN skipped
+  SRC_VALID,      // 1 when the value is non-null (count, mean denominator, min/max validity)
+  SRC_NOT_NAN,    // 1 when non-null and not NaN (float min/max: all-NaN group -> NaN)
+  SRC_ONE,        // 1 per row (len)
+  SRC_ROWIDX,     // (global_row << 1) | valid   (first = MIN, last = MAX; nulls included)
+  SRC_ROW,        // global row index (group first occurrence for maintain_order / key gather)
+  SRC_INDEX_T     // the dynamic index value itself (label = datapoint -> MIN_I64)
+};
+
+constexpr int MAX_SLOTS = 12;  // raw column slots
+constexpr int MAX_PREDS = 4;
+constexpr int MAX_KEYS = 4;    // key columns
+constexpr int MAX_KW = 6;      // key words (4 cols x up to 2 words is capped by the templates below)
+constexpr int MAX_VEXPR = 8;
+constexpr int MAX_FACTORS = 4;
+constexpr int MAX_ACC = 24;
+
+struct RawSlot {
+  const void* values;       // device pointer, element 0 = row 0 of the frame
+  const uint8_t* validity;  // LSB-first bitmap or nullptr
+  int32_t dtype;            // DType
+  int32_t bit_offset;       // validity bit offset of row 0
+};
+
+struct Pred {
+  int32_t slot, op, cls, pad;
+  uint64_t scalar;  // bit pattern in `cls`
+};
+
+struct KeyCol {
+  int32_t slot;     // first raw slot
+  int32_t n_words;  // 1, or 2 for views
+  int32_t dtype;
+  int32_t nullable; // contributes a bit to the null-mask word
+};
+
+struct Factor { double a, b; int32_t slot, pad; };
+struct VExpr {
+  int32_t n_factors;  // 0 => plain column `slot`
+  int32_t slot;
+  int32_t cls;        // class of the result (plain: class of the column; product: F64)
+  int32_t pad;
+  Factor f[MAX_FACTORS];
+};
+
+struct Acc { int32_t op, src, vexpr, pad; };
+
+struct Dyn {
+  int32_t enabled, slot, closed, pad;
+  int64_t every, period, origin;  // window k = [origin + k*every, origin + k*every + period)
+};
+
+// HBM open-addressing table (also the partial-aggregate state exchanged between GPUs)
+struct Table {
+  uint64_t* keys;    // [n_kw][cap + 2] SoA; word 0 doubles as the occupancy marker when n_kw == 1
+  uint32_t* state;   // [cap + 2]: 0 empty, 1 busy, 2 ready   (n_kw > 1)
+  uint64_t* accs;    // [n_acc][cap + 2] SoA
+  uint64_t cap;      // probe range; slots cap and cap+1 are the escape slots for sentinel-valued keys
+  int32_t* overflow; // set to 1 when a probe sequence exhausts the table (host retries bigger)
+  unsigned long long* spilled; // rows that bypassed the hot table
+};
+
+struct ScanPlan {
+  int64_t n_rows;          // logical rows scanned by this launch
+  int64_t row_begin;       // physical row of logical row 0
+  int64_t row_stride;      // physical = row_begin + logical * row_stride (1 except for the key-sample pilot)
+  int64_t row_offset;      // global index of physical row 0 (multi-GPU shards)
+  int32_t n_slots, n_preds, n_keys, n_kw, n_vexpr, n_acc;
+  int32_t has_null_word;   // last key word = null mask
+  int32_t vec_ok;          // every slot pointer 16-byte aligned -> 128-bit loads
+  int32_t hot_slots;       // shared-memory hot table capacity (power of two) or 0
+  int32_t check_sorted;    // dynamic without keys: flag descending index
+  RawSlot slots[MAX_SLOTS];
+  Pred preds[MAX_PREDS];
+  KeyCol keys[MAX_KEYS];
+  VExpr vexprs[MAX_VEXPR];
+  Acc accs[MAX_ACC];
+  Dyn dyn;
+  Table table;
+  int32_t* not_sorted;     // device flag
+};
+
+constexpr uint64_t KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;  // n_kw == 1 occupancy sentinel
+constexpr uint64_t KEY_NULL = 0xFFFFFFFFFFFFFFFEull;   // n_kw == 1 image of a null key
+
+__host__ __device__ inline uint64_t acc_init(int32_t op) {
+  switch (op) {
+    case OP_MIN_I64: return 0x7FFFFFFFFFFFFFFFull;
+    case OP_MAX_I64: return 0x8000000000000000ull;
+    case OP_MIN_U64: return 0xFFFFFFFFFFFFFFFFull;
+    default: return 0ull;  // ADD_*, MAX_U64
+  }
+}
+
+}  // namespace pw

@@ -1,0 +1,427 @@
+"""ctypes binding of libpolarway_b200.so (include/polarway_b200.h) + the glue that turns a
+``plan.GroupByPlan`` over a pyarrow Table into one C-ABI call.
+
+This is the Python stand-in for the Rust operator binding described in INTEGRATION.md: columns
+cross as Arrow C Data Interface structs (``pyarrow.Array._export_to_c``), the query as a ``PwQuery``.
+There is no CPU fallback: if the shared library or a CUDA device is missing every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import datetime as _dt
+import os
+from typing import Optional
+
+import pyarrow as pa
+
+from . import plan as P
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpolarway_b200.so")
+
+PW_MAX_FACTORS = 4
+FLAG_FORCE_HOT = 1 << 0
+FLAG_FORCE_GLOBAL = 1 << 1
+FLAG_FORCE_SEGMENTED = 1 << 2
+FLAG_NO_SEGMENTED = 1 << 3
+
+
+class PolarwayError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+
+
+class _Scalar(C.Union):
+    _fields_ = [("i", C.c_int64), ("u", C.c_uint64), ("f", C.c_double)]
+
+
+class PwPredicate(C.Structure):
+    _fields_ = [("column", C.c_int32), ("op", C.c_int32), ("scalar_is_float", C.c_int32), ("reserved", C.c_int32),
+                ("scalar", _Scalar)]
+
+
+class PwFactor(C.Structure):
+    _fields_ = [("a", C.c_double), ("b", C.c_double), ("column", C.c_int32), ("reserved", C.c_int32)]
+
+
+class PwAgg(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("column", C.c_int32), ("n_factors", C.c_int32), ("reserved", C.c_int32),
+                ("factors", PwFactor * PW_MAX_FACTORS), ("name", C.c_char_p)]
+
+
+class PwDynamic(C.Structure):
+    _fields_ = [("index_column", C.c_int32), ("closed", C.c_int32), ("label", C.c_int32), ("include_boundaries", C.c_int32),
+                ("every", C.c_int64), ("period", C.c_int64), ("offset", C.c_int64)]
+
+
+class PwQuery(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("maintain_order", C.c_int32), ("n_predicates", C.c_int32),
+                ("n_keys", C.c_int32), ("n_aggs", C.c_int32), ("hot_table_slots", C.c_int32),
+                ("predicates", C.POINTER(PwPredicate)), ("key_columns", C.POINTER(C.c_int32)),
+                ("aggs", C.POINTER(PwAgg)), ("dynamic", C.POINTER(PwDynamic)), ("flags", C.c_uint64),
+                ("row_offset", C.c_int64), ("initial_table_slots", C.c_int64)]
+
+
+class PwTimings(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("estimate_ms", C.c_float), ("scan_ms", C.c_float), ("finalize_ms", C.c_float),
+                ("d2h_ms", C.c_float), ("total_device_ms", C.c_float), ("n_rows", C.c_int64), ("n_groups", C.c_int64),
+                ("table_slots", C.c_int64), ("strategy", C.c_int32), ("retries", C.c_int32),
+                ("kernel_launches", C.c_int64), ("spilled_rows", C.c_int64), ("scan_kernel_ms", C.c_float),
+                ("reserved", C.c_float)]
+
+
+class ArrowSchema(C.Structure):
+    pass
+
+
+class ArrowArray(C.Structure):
+    pass
+
+
+ArrowSchema._fields_ = [("format", C.c_char_p), ("name", C.c_char_p), ("metadata", C.c_char_p), ("flags", C.c_int64),
+                        ("n_children", C.c_int64), ("children", C.POINTER(C.POINTER(ArrowSchema))),
+                        ("dictionary", C.POINTER(ArrowSchema)), ("release", C.c_void_p), ("private_data", C.c_void_p)]
+ArrowArray._fields_ = [("length", C.c_int64), ("null_count", C.c_int64), ("offset", C.c_int64), ("n_buffers", C.c_int64),
+                       ("n_children", C.c_int64), ("buffers", C.POINTER(C.c_void_p)),
+                       ("children", C.POINTER(C.POINTER(ArrowArray))), ("dictionary", C.POINTER(ArrowArray)),
+                       ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+_lib = None
+
+
+def lib():
+    """Loads the CUDA library; raises if it has not been built (there is no other engine)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PolarwayError(-3, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                                    "polaroid_b200 has no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.pw_b200_last_error.restype = C.c_char_p
+        L.pw_b200_abi_version.restype = C.c_uint32
+        L.pw_b200_frame_num_rows.restype = C.c_int64
+        L.pw_b200_frame_num_rows.argtypes = [C.c_void_p]
+        L.pw_b200_frame_free.argtypes = [C.c_void_p]
+        L.pw_b200_set_stream.argtypes = [C.c_void_p]
+        L.pw_b200_frame_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.pw_b200_frame_from_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.pw_b200_frame_groupby.argtypes = [C.POINTER(PwQuery), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]
+        L.pw_b200_filter_groupby_agg.argtypes = [C.POINTER(PwQuery), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                                 C.c_void_p, C.POINTER(C.c_size_t)]
+        L.pw_b200_last_timings.argtypes = [C.POINTER(PwTimings)]
+        L.pw_b200_filter.argtypes = [C.POINTER(PwPredicate), C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.pw_b200_frame_filter_select.argtypes = [C.POINTER(PwPredicate), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                  C.POINTER(C.c_int64)]
+        L.pw_b200_frame_group_tuples.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pw_b200_frame_groupby_partial.argtypes = [C.POINTER(PwQuery), C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+        L.pw_b200_partial_row_bytes.restype = C.c_int64
+        L.pw_b200_partial_row_bytes.argtypes = [C.c_void_p]
+        L.pw_b200_partial_device_rows.restype = C.c_void_p
+        L.pw_b200_partial_device_rows.argtypes = [C.c_void_p]
+        L.pw_b200_partial_offsets.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.pw_b200_partial_free.argtypes = [C.c_void_p]
+        L.pw_b200_merge_partials.argtypes = [C.POINTER(PwQuery), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                             C.POINTER(C.c_size_t)]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise PolarwayError(rc, lib().pw_b200_last_error().decode("utf-8", "replace"))
+
+
+def last_timings() -> dict:
+    t = PwTimings()
+    lib().pw_b200_last_timings(C.byref(t))
+    return {k: getattr(t, k) for k, _ in PwTimings._fields_}
+
+
+# ---- Arrow export / import ---------------------------------------------------------------------------
+def _to_abi_array(col) -> pa.Array:
+    """One contiguous array in a format the C ABI reads: strings become Utf8View (what Polars itself
+    exports, polars-ffi/src/version_0.rs:64)."""
+    if isinstance(col, pa.ChunkedArray):
+        col = col.combine_chunks() if col.num_chunks != 1 else col.chunk(0)
+    t = col.type
+    if pa.types.is_string(t) or pa.types.is_large_string(t):
+        col = col.cast(pa.string_view())
+    elif pa.types.is_binary(t) or pa.types.is_large_binary(t):
+        col = col.cast(pa.binary_view())
+    return col
+
+
+class _Exported:
+    """Keeps the exported ArrowArray/ArrowSchema structs (and their pyarrow owners) alive for a call."""
+
+    def __init__(self, arrays):
+        n = len(arrays)
+        self.arrays = arrays
+        self.c_arrays = (ArrowArray * n)()
+        self.c_schemas = (ArrowSchema * n)()
+        for i, a in enumerate(arrays):
+            a._export_to_c(C.addressof(self.c_arrays[i]), C.addressof(self.c_schemas[i]))
+        self.arr_ptrs = (C.c_void_p * n)(*[C.addressof(self.c_arrays[i]) for i in range(n)])
+        self.sch_ptrs = (C.c_void_p * n)(*[C.addressof(self.c_schemas[i]) for i in range(n)])
+        self.n = n
+
+    def set_names(self, names):
+        self._names = [n.encode() for n in names]
+        for i, b in enumerate(self._names):
+            self.c_schemas[i].name = b
+
+    def release(self):
+        for i in range(self.n):
+            for st in (self.c_arrays[i], self.c_schemas[i]):
+                if st.release:
+                    C.CFUNCTYPE(None, C.c_void_p)(st.release)(C.addressof(st))
+
+
+def _import_columns(out_arrays, out_schemas, n) -> tuple:
+    names, cols = [], []
+    for i in range(n):
+        name = out_schemas[i].name.decode() if out_schemas[i].name else ""
+        arr = pa.Array._import_from_c(C.addressof(out_arrays[i]), C.addressof(out_schemas[i]))
+        names.append(name)
+        cols.append(arr)
+    return names, cols
+
+
+def _restore_types(names, cols, table: pa.Table, key_names) -> list:
+    """Result string keys come back as Utf8View; hand them back in the caller's string type."""
+    out = []
+    for n, c in zip(names, cols):
+        if n in key_names and n in table.column_names:
+            t = table.schema.field(n).type
+            if c.type != t and (pa.types.is_string(t) or pa.types.is_large_string(t) or pa.types.is_binary(t) or pa.types.is_large_binary(t)):
+                c = c.cast(t)
+        out.append(c)
+    return out
+
+
+# ---- plan -> PwQuery -----------------------------------------------------------------------------------
+def _physical_scalar(value, typ: pa.DataType):
+    if isinstance(value, _dt.datetime):
+        if pa.types.is_timestamp(typ):
+            return pa.scalar(value, type=pa.timestamp(typ.unit)).cast(pa.int64()).as_py()
+        if pa.types.is_date32(typ):
+            return pa.scalar(value.date(), type=pa.date32()).cast(pa.int32()).as_py()
+    if isinstance(value, _dt.date):
+        if pa.types.is_date32(typ):
+            return pa.scalar(value, type=pa.date32()).cast(pa.int32()).as_py()
+        if pa.types.is_timestamp(typ):
+            return pa.scalar(_dt.datetime(value.year, value.month, value.day), type=pa.timestamp(typ.unit)).cast(pa.int64()).as_py()
+    if isinstance(value, _dt.timedelta):
+        return pa.scalar(value, type=typ).cast(pa.int64()).as_py()
+    return value
+
+
+def _index_unit_ns(typ: pa.DataType) -> int:
+    if pa.types.is_timestamp(typ):
+        return {"ns": 1, "us": 1_000, "ms": 1_000_000, "s": 1_000_000_000}[typ.unit]
+    if pa.types.is_date32(typ):
+        return 86_400_000_000_000
+    return 1
+
+
+class _BuiltQuery:
+    """Owns every ctypes buffer a PwQuery points to."""
+
+    def __init__(self, schema: pa.Schema, plan: P.GroupByPlan, flags: int = 0, hot_table_slots: int = 0,
+                 initial_table_slots: int = 0, row_offset: int = 0):
+        names = schema.names
+        idx = {n: i for i, n in enumerate(names)}
+
+        def col(name):
+            if name not in idx:
+                raise KeyError(f"column {name!r} not found")
+            return idx[name]
+
+        self.preds = (PwPredicate * max(1, len(plan.predicates)))()
+        for i, p in enumerate(plan.predicates):
+            typ = schema.field(p.col).type
+            v = _physical_scalar(p.value, typ)
+            self.preds[i].column = col(p.col)
+            self.preds[i].op = P.CMP_OPS[p.op]
+            if pa.types.is_floating(typ):
+                self.preds[i].scalar_is_float = 1
+                self.preds[i].scalar.f = float(v)
+            elif isinstance(v, float):
+                if v != int(v):
+                    raise NotImplementedError("non-integral float scalar compared with an integer column")
+                self.preds[i].scalar.i = int(v)
+            elif pa.types.is_unsigned_integer(typ):
+                self.preds[i].scalar.u = int(v)
+            else:
+                self.preds[i].scalar.i = int(v)
+        self.keys = (C.c_int32 * max(1, len(plan.keys)))(*[col(k) for k in plan.keys])
+        self.aggs = (PwAgg * max(1, len(plan.aggs)))()
+        self._names = []
+        for i, a in enumerate(plan.aggs):
+            self.aggs[i].kind = P.AGG_KINDS[a.kind]
+            nm = a.name.encode()
+            self._names.append(nm)
+            self.aggs[i].name = nm
+            if a.expr is None:
+                self.aggs[i].column = -1
+            elif a.expr.factors is None:
+                self.aggs[i].column = col(a.expr.col)
+            else:
+                if len(a.expr.factors) > PW_MAX_FACTORS:
+                    raise NotImplementedError("more than 4 factors in a product expression")
+                self.aggs[i].column = -1
+                self.aggs[i].n_factors = len(a.expr.factors)
+                for j, f in enumerate(a.expr.factors):
+                    self.aggs[i].factors[j].a = f.a
+                    self.aggs[i].factors[j].b = f.b
+                    self.aggs[i].factors[j].column = col(f.col)
+        self.dyn = None
+        if plan.dynamic is not None:
+            d = plan.dynamic
+            typ = schema.field(d.index_column).type
+            every, period, offset = d.every, d.period, d.offset
+            if getattr(plan, "_durations_in_ns", True) and not pa.types.is_integer(typ):
+                u = _index_unit_ns(typ)
+                for x in (every, period, offset):
+                    if x % u:
+                        raise ValueError("duration is not a multiple of the index column's time unit")
+                every, period, offset = every // u, period // u, offset // u
+            self.dyn = PwDynamic(col(d.index_column), P.CLOSED[d.closed], P.LABEL[d.label], int(d.include_boundaries),
+                                 every, period, offset)
+        q = PwQuery()
+        q.abi_version = 1
+        q.maintain_order = int(plan.maintain_order)
+        q.n_predicates = len(plan.predicates)
+        q.n_keys = len(plan.keys)
+        q.n_aggs = len(plan.aggs)
+        q.hot_table_slots = hot_table_slots
+        q.predicates = C.cast(self.preds, C.POINTER(PwPredicate))
+        q.key_columns = C.cast(self.keys, C.POINTER(C.c_int32))
+        q.aggs = C.cast(self.aggs, C.POINTER(PwAgg))
+        q.dynamic = C.pointer(self.dyn) if self.dyn is not None else None
+        q.flags = flags
+        q.row_offset = row_offset
+        q.initial_table_slots = initial_table_slots
+        self.q = q
+
+
+# ---- resident frames -----------------------------------------------------------------------------------
+class DeviceFrame:
+    """Columns resident in HBM (``pw_b200_frame_upload``)."""
+
+    def __init__(self, table: pa.Table):
+        L = lib()
+        self.table_schema = table.schema
+        arrays = [_to_abi_array(table.column(i)) for i in range(table.num_columns)]
+        ex = _Exported(arrays)
+        ex.set_names(table.column_names)
+        h = C.c_void_p()
+        try:
+            _check(L.pw_b200_frame_upload(ex.arr_ptrs, ex.sch_ptrs, ex.n, C.byref(h)))
+        finally:
+            ex.release()
+        self.handle = h
+        self.abi_schema = pa.schema([pa.field(n, a.type) for n, a in zip(table.column_names, arrays)])
+        self.num_rows = table.num_rows
+
+    def free(self):
+        if self.handle:
+            lib().pw_b200_frame_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def group_by(self, plan: P.GroupByPlan, **opts) -> pa.Table:
+        L = lib()
+        bq = _BuiltQuery(self.table_schema, plan, **opts)
+        cap = len(plan.keys) + len(plan.aggs) + 4
+        out_arrays = (ArrowArray * cap)()
+        out_schemas = (ArrowSchema * cap)()
+        n_out = C.c_size_t(cap)
+        _check(L.pw_b200_frame_groupby(C.byref(bq.q), self.handle, out_arrays, out_schemas, C.byref(n_out)))
+        names, cols = _import_columns(out_arrays, out_schemas, n_out.value)
+        cols = _restore_string_types(names, cols, self.table_schema, plan.keys)
+        return pa.Table.from_arrays(cols, names=names)
+
+
+def _restore_string_types(names, cols, schema: pa.Schema, key_names) -> list:
+    out = []
+    for n, c in zip(names, cols):
+        if n in key_names and n in schema.names:
+            t = schema.field(n).type
+            if c.type != t and (pa.types.is_string(t) or pa.types.is_large_string(t) or pa.types.is_binary(t)
+                                or pa.types.is_large_binary(t)):
+                c = c.cast(t)
+        out.append(c)
+    return out
+
+
+# ---- the calls the LazyFrame mirror makes ----------------------------------------------------------------
+_DEFAULT_OPTS: dict = {}
+
+
+def set_default_options(**opts):
+    """Strategy overrides for tests (the analogue of POLARS_FORCE_PARTITION etc.)."""
+    _DEFAULT_OPTS.clear()
+    _DEFAULT_OPTS.update(opts)
+
+
+def run_group_by(table: pa.Table, plan: P.GroupByPlan, **opts) -> pa.Table:
+    """Host buffers in, host result out: one ``pw_b200_filter_groupby_agg`` call."""
+    L = lib()
+    o = dict(_DEFAULT_OPTS)
+    o.update(opts)
+    # only ship the columns the query touches
+    used = []
+    for n in ([p.col for p in plan.predicates] + list(plan.keys)
+              + ([plan.dynamic.index_column] if plan.dynamic else [])
+              + [c for a in plan.aggs if a.expr is not None for c in a.expr.columns()]):
+        if n not in used:
+            used.append(n)
+    if not used:
+        used = table.column_names[:1]
+    sub = table.select(used)
+    arrays = [_to_abi_array(sub.column(i)) for i in range(sub.num_columns)]
+    ex = _Exported(arrays)
+    ex.set_names(sub.column_names)
+    bq = _BuiltQuery(sub.schema, plan, **o)
+    cap = len(plan.keys) + len(plan.aggs) + 4
+    out_arrays = (ArrowArray * cap)()
+    out_schemas = (ArrowSchema * cap)()
+    n_out = C.c_size_t(cap)
+    try:
+        _check(L.pw_b200_filter_groupby_agg(C.byref(bq.q), ex.arr_ptrs, ex.sch_ptrs, ex.n, out_arrays, out_schemas,
+                                            C.byref(n_out)))
+    finally:
+        ex.release()
+    names, cols = _import_columns(out_arrays, out_schemas, n_out.value)
+    cols = _restore_string_types(names, cols, sub.schema, plan.keys)
+    return pa.Table.from_arrays(cols, names=names)
+
+
+def run_filter(table: pa.Table, preds) -> pa.Table:
+    """FilterExec alone: ``pw_b200_filter``."""
+    L = lib()
+    if not preds:
+        return table
+    arrays = [_to_abi_array(table.column(i)) for i in range(table.num_columns)]
+    ex = _Exported(arrays)
+    ex.set_names(table.column_names)
+    plan = P.GroupByPlan(predicates=list(preds))
+    bq = _BuiltQuery(table.schema, plan)
+    n = table.num_columns
+    out_arrays = (ArrowArray * n)()
+    out_schemas = (ArrowSchema * n)()
+    try:
+        _check(L.pw_b200_filter(bq.preds, len(preds), ex.arr_ptrs, ex.sch_ptrs, n, out_arrays, out_schemas))
+    finally:
+        ex.release()
+    names, cols = _import_columns(out_arrays, out_schemas, n)
+    cols = _restore_string_types(names, cols, table.schema, table.column_names)
+    return pa.Table.from_arrays(cols, names=names)
