@@ -281,6 +281,7 @@ def main():
                          "whole_step_frac": (algo_bytes / (ms * 1e-3) / 1e9) / peak},
             "cpu_baseline": cpu,
             "phases_ms": {k: tm[k] for k in ("estimate_ms", "scan_ms", "scan_kernel_ms", "finalize_ms", "d2h_ms", "total_device_ms")},
+            "spilled_rows": tm["spilled_rows"], "table_slots": tm["table_slots"], "n_groups": tm["n_groups"],
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -275,25 +275,28 @@ int lower_query(const PwQuery* q, const PwFrame* f, Lowered* L) {
     if (dyn->label == PW_LABEL_LEFT) bound_col(c.name.c_str(), EMIT_DYN_LOWER);
     else if (dyn->label == PW_LABEL_RIGHT) bound_col(c.name.c_str(), EMIT_DYN_UPPER);
     else {
-      const int a = lw.acc(OP_MIN_I64, SRC_INDEX_T, 0);
       OutCol o; o.name = c.name; o.format = c.format; o.nullable = false;
-      o.emit.kind = EMIT_ACC_I64; o.emit.acc = a; o.emit.out_dtype = c.dtype; o.out_dtype = c.dtype; o.emit.null_word = -1;
+      o.emit.kind = EMIT_ACC_I64; o.emit.acc = -1 /* patched below */; o.emit.out_dtype = c.dtype; o.out_dtype = c.dtype; o.emit.null_word = -1;
       L->outs.push_back(o);
     }
   }
 
-  // ---- aggregations (a6/a10)
+  // ---- aggregations (a6/a10): first collect, per value expression, which aggregate words are needed
+  struct AggTmp { OutCol o; int ve; int kind; bool ve_nullable; bool is_float; int cls; };
+  std::vector<AggTmp> tmp;
+  int gflags = 0;
   for (int i = 0; i < q->n_aggs; ++i) {
     const PwAgg& a = q->aggs[i];
-    OutCol o;
+    AggTmp t{};
+    OutCol& o = t.o;
     o.name = a.name ? a.name : "";
     o.emit.null_word = -1;
     o.emit.row_offset = q->row_offset;
+    t.kind = a.kind; t.ve = -1;
     if (a.kind == PW_LEN) {
-      const int acc = lw.acc(OP_ADD_I64, SRC_ONE, 0);
-      if (acc < 0) return fail(PW_ERR_UNSUPPORTED, "too many accumulators");
-      o.format = "I"; o.out_dtype = DT_U32; o.emit.kind = EMIT_COUNT; o.emit.acc = acc; o.emit.out_dtype = DT_U32;
-      L->outs.push_back(o);
+      gflags |= GF_LEN;
+      o.format = "I"; o.out_dtype = DT_U32; o.emit.kind = EMIT_COUNT; o.emit.out_dtype = DT_U32;
+      tmp.push_back(t);
       continue;
     }
     int ve, in_dtype = DT_F64;
@@ -309,96 +312,143 @@ int lower_query(const PwQuery* q, const PwFrame* f, Lowered* L) {
     } else {
       if (!col_ok(a.column)) return fail(PW_ERR_INVALID, "aggregation column %d out of range", a.column);
       const FrameColumn& c = f->cols[a.column];
-      if (c.dtype == DT_VIEW || c.dtype == DT_BOOL) {
-        if (a.kind == PW_COUNT) { /* fine: only validity is read */ }
-        else return fail(PW_ERR_UNSUPPORTED, "aggregation over column '%s' of format %s (strings/booleans are SURVEY 8f)", c.name.c_str(), c.format.c_str());
-      }
+      if ((c.dtype == DT_VIEW || c.dtype == DT_BOOL) && a.kind != PW_COUNT)
+        return fail(PW_ERR_UNSUPPORTED, "aggregation over column '%s' of format %s (strings/booleans are SURVEY 8f)", c.name.c_str(), c.format.c_str());
       in_dtype = c.dtype; in_format = c.format;
       ve = lw.vexpr_plain(a.column);
     }
     if (ve < 0) return fail(PW_ERR_UNSUPPORTED, "query needs more than %d column slots / %d value expressions", MAX_SLOTS, MAX_VEXPR);
-    const int cls = P.vexprs[ve].cls;
+    VExpr& V = P.vexprs[ve];
+    const int cls = V.cls;
     const bool is_float = cls == CLS_F64;
     const bool temporal = in_format.size() > 1 && in_format[0] == 't';
-    int a0 = -1, a1 = -1, a2 = -1;
+    // non-null count of this value: an expression without nulls shares the single per-group row counter
+    bool ve_nullable = false;
+    if (V.n_factors == 0) ve_nullable = P.slots[V.slot].validity != nullptr;
+    else for (int k = 0; k < V.n_factors; ++k) ve_nullable = ve_nullable || P.slots[V.f[k].slot].validity != nullptr;
+    auto need_count = [&]() { if (ve_nullable) V.flags |= VF_COUNT; else gflags |= GF_LEN; };
+    t.ve = ve; t.ve_nullable = ve_nullable; t.is_float = is_float; t.cls = cls;
     switch (a.kind) {
       case PW_SUM:
         if (temporal && in_format[1] != 'D') return fail(PW_ERR_UNSUPPORTED, "`sum` operation not supported for dtype %s", in_format.c_str());
         if (is_float) {
-          a0 = lw.acc(OP_ADD_F64, SRC_F64, ve);
+          V.flags |= VF_SUM_F;
           o.emit.kind = EMIT_SUM_F64; o.out_dtype = in_dtype == DT_F32 ? DT_F32 : DT_F64; o.format = in_dtype == DT_F32 ? "f" : "g";
         } else {
-          a0 = lw.acc(OP_ADD_I64, SRC_BITS, ve);
+          V.flags |= VF_SUM_I;
           o.emit.kind = EMIT_SUM_INT;
           // i8/i16/u8/u16 -> Int64, others keep their dtype (sum.rs:40-47)
           if (in_dtype == DT_I8 || in_dtype == DT_I16 || in_dtype == DT_U8 || in_dtype == DT_U16) { o.out_dtype = DT_I64; o.format = "l"; }
           else { o.out_dtype = in_dtype; o.format = in_format; }
         }
-        o.nullable = false;
         break;
       case PW_MEAN:
-        a0 = lw.acc(OP_ADD_F64, SRC_F64, ve);
-        a1 = lw.acc(OP_ADD_I64, SRC_VALID, ve);
+        V.flags |= VF_SUM_F; need_count();
         o.emit.kind = EMIT_MEAN; o.nullable = true;
         if (in_dtype == DT_F32 && !temporal) { o.emit.mean_out = MEAN_F32; o.out_dtype = DT_F32; o.format = "f"; }
         else if (in_format == "tdD") { o.emit.mean_out = MEAN_DATE_US; o.out_dtype = DT_I64; o.format = "tsu:"; }
         else if (temporal) { o.emit.mean_out = MEAN_I64; o.out_dtype = DT_I64; o.format = in_format; }
         else { o.emit.mean_out = MEAN_F64; o.out_dtype = DT_F64; o.format = "g"; }
         break;
-      case PW_MIN: case PW_MAX: {
-        const bool is_min = a.kind == PW_MIN;
-        a1 = lw.acc(OP_ADD_I64, SRC_VALID, ve);
-        if (is_float) {
-          a0 = lw.acc(is_min ? OP_MIN_I64 : OP_MAX_I64, SRC_F64_ORD, ve);
-          a2 = lw.acc(OP_ADD_I64, SRC_NOT_NAN, ve);
-          o.emit.kind = EMIT_MINMAX_F64;
-        } else {
-          a0 = cls == CLS_U64 ? lw.acc(is_min ? OP_MIN_U64 : OP_MAX_U64, SRC_BITS, ve)
-                              : lw.acc(is_min ? OP_MIN_I64 : OP_MAX_I64, SRC_BITS, ve);
-          o.emit.kind = EMIT_MINMAX_INT;
-        }
+      case PW_MIN: case PW_MAX:
+        V.flags |= (a.kind == PW_MIN ? VF_MIN : VF_MAX); need_count();
+        o.emit.kind = is_float ? EMIT_MINMAX_F64 : EMIT_MINMAX_INT;
         o.out_dtype = in_dtype; o.format = in_format; o.nullable = true;
-        break; }
+        break;
       case PW_COUNT:
-        a0 = lw.acc(OP_ADD_I64, SRC_VALID, ve);
+        need_count();
         o.emit.kind = EMIT_COUNT; o.out_dtype = DT_U32; o.format = "I";
         break;
       case PW_FIRST: case PW_LAST:
         if (a.n_factors > 0) return fail(PW_ERR_UNSUPPORTED, "first/last of a computed expression");
-        a0 = lw.acc(a.kind == PW_FIRST ? OP_MIN_U64 : OP_MAX_U64, SRC_ROWIDX, ve);
+        V.flags |= (a.kind == PW_FIRST ? VF_FIRST : VF_LAST);
         o.emit.kind = EMIT_FIRSTLAST; o.out_dtype = in_dtype; o.format = in_format; o.nullable = true;
-        o.emit.src = P.slots[P.vexprs[ve].slot];
+        o.emit.src = P.slots[V.slot];
         break;
       default: return fail(PW_ERR_INVALID, "unknown aggregation kind %d", a.kind);
     }
-    if (a0 < 0 || (a.kind == PW_MEAN && a1 < 0)) return fail(PW_ERR_UNSUPPORTED, "query needs more than %d accumulator words", MAX_ACC);
-    o.emit.acc = a0; o.emit.acc_cnt = a1; o.emit.acc_nn = a2; o.emit.out_dtype = o.out_dtype; o.emit.src_cls = cls;
+    o.emit.out_dtype = o.out_dtype; o.emit.src_cls = cls;
+    tmp.push_back(t);
+  }
+  const bool want_row = !dyn && q->maintain_order;
+  const bool want_tmin = dyn && dyn->label == PW_LABEL_DATAPOINT;
+  if (want_row) gflags |= GF_ROW;
+  if (want_tmin) gflags |= GF_TMIN;
+
+  // ---- accumulator words: consecutive per value expression in VFlag order, then LEN, ROW, TMIN
+  auto push_acc = [&](int op, int src, int ve) { P.accs[P.n_acc].op = op; P.accs[P.n_acc].src = src; P.accs[P.n_acc].vexpr = ve; return P.n_acc++; };
+  {
+    int words = 0;
+    for (int e = 0; e < P.n_vexpr; ++e) words += __builtin_popcount(P.vexprs[e].flags);
+    words += __builtin_popcount(gflags);
+    if (words > MAX_ACC) return fail(PW_ERR_UNSUPPORTED, "query needs more than %d accumulator words", MAX_ACC);
+  }
+  for (int e = 0; e < P.n_vexpr; ++e) {
+    VExpr& V = P.vexprs[e];
+    V.acc_base = P.n_acc;
+    const bool u = V.cls == CLS_U64, fl = V.cls == CLS_F64;
+    if (V.flags & VF_SUM_I) push_acc(OP_ADD_I64, SRC_BITS, e);
+    if (V.flags & VF_SUM_F) push_acc(OP_ADD_F64, SRC_F64, e);
+    if (V.flags & VF_COUNT) push_acc(OP_ADD_I64, SRC_VALID, e);
+    if (V.flags & VF_MIN) push_acc(u ? OP_MIN_U64 : OP_MIN_I64, fl ? SRC_F64_ORD : SRC_BITS, e);
+    if (V.flags & VF_MAX) push_acc(u ? OP_MAX_U64 : OP_MAX_I64, fl ? SRC_F64_ORD : SRC_BITS, e);
+    if (V.flags & VF_FIRST) push_acc(OP_MIN_U64, SRC_ROWIDX, e);
+    if (V.flags & VF_LAST) push_acc(OP_MAX_U64, SRC_ROWIDX, e);
+  }
+  if (P.n_acc == 0 && gflags == 0) gflags |= GF_LEN;  // a table needs at least one word per group
+  P.gflags = gflags;
+  P.acc_gbase = P.n_acc;
+  int acc_len = -1, acc_row = -1, acc_tmin = -1;
+  if (gflags & GF_LEN) acc_len = push_acc(OP_ADD_I64, SRC_ONE, 0);
+  if (gflags & GF_ROW) acc_row = push_acc(OP_MIN_U64, SRC_ROW, 0);
+  if (gflags & GF_TMIN) acc_tmin = push_acc(OP_MIN_I64, SRC_INDEX_T, 0);
+  auto acc_of = [&](int e, int flag) {
+    const VExpr& V = P.vexprs[e];
+    int a = V.acc_base;
+    for (int b2 = 1; b2 < flag; b2 <<= 1) if (V.flags & b2) ++a;
+    return a;
+  };
+  for (AggTmp& t : tmp) {
+    OutCol& o = t.o;
+    auto cnt = [&]() { return t.ve_nullable ? acc_of(t.ve, VF_COUNT) : acc_len; };
+    switch (t.kind) {
+      case PW_LEN: o.emit.acc = acc_len; break;
+      case PW_SUM: o.emit.acc = acc_of(t.ve, t.is_float ? VF_SUM_F : VF_SUM_I); break;
+      case PW_MEAN: o.emit.acc = acc_of(t.ve, VF_SUM_F); o.emit.acc_cnt = cnt(); break;
+      case PW_MIN: case PW_MAX:
+        o.emit.acc = acc_of(t.ve, t.kind == PW_MIN ? VF_MIN : VF_MAX); o.emit.acc_cnt = cnt();
+        o.emit.every = (int64_t)acc_init(P.accs[o.emit.acc].op);  // "no non-NaN value seen" marker for floats
+        break;
+      case PW_COUNT: o.emit.acc = cnt(); break;
+      default: o.emit.acc = acc_of(t.ve, t.kind == PW_FIRST ? VF_FIRST : VF_LAST); break;
+    }
     L->outs.push_back(o);
+  }
+  if (want_tmin) {
+    // label = datapoint: the index value of the first row of the window = its minimum (sorted input)
+    for (OutCol& o : L->outs) if (o.emit.kind == EMIT_ACC_I64) o.emit.acc = acc_tmin;
   }
 
   // ---- ordering
   if (dyn) {
     // key slices ascending (nulls first) then windows ascending: group_by_rolling.rs:17-58 + dynamic.rs:317-362
-    SortSpec w{}; w.src = SORT_WORD_I64; w.word = dyn_word; L->sort.push_back(w);  // least significant
+    SortSpec w{}; w.src = SORT_WORD_I64; w.word = dyn_word; w.nullbit = 63; L->sort.push_back(w);  // least significant
     int wd = dyn_word;
     for (int i = q->n_keys - 1; i >= 0; --i) {
       wd -= P.keys[i].n_words;
-      SortSpec s{}; s.word = wd; s.nullbit = i; s.single_key_null = 0;
+      SortSpec sp{}; sp.word = wd; sp.nullbit = i; sp.single_key_null = 0;
       const int dt = P.keys[i].dtype;
       const int nullable = P.keys[i].nullable;
-      auto push = [&](int src) { SortSpec t = s; t.src = src; if (!nullable) t.nullbit = 63; L->sort.push_back(t); };
+      auto push = [&](int src) { SortSpec t2 = sp; t2.src = src; if (!nullable) t2.nullbit = 63; L->sort.push_back(t2); };
       if (dt == DT_VIEW) { push(SORT_VIEW_LO); push(SORT_VIEW_HI); }
       else if (dtype_class(dt) == CLS_F64) push(SORT_WORD_F64);
       else if (dtype_class(dt) == CLS_U64) push(SORT_WORD_U64);
       else push(SORT_WORD_I64);
       if (nullable) push(SORT_NULLBIT);
     }
-  } else if (q->maintain_order) {
-    const int a = lw.acc(OP_MIN_U64, SRC_ROW, 0);
-    if (a < 0) return fail(PW_ERR_UNSUPPORTED, "too many accumulators");
-    SortSpec s{}; s.src = SORT_ACC_U64; s.acc = a; L->sort.push_back(s);
+  } else if (want_row) {
+    SortSpec sp{}; sp.src = SORT_ACC_U64; sp.acc = acc_row; L->sort.push_back(sp);
   }
-  if (P.n_acc == 0) lw.acc(OP_ADD_I64, SRC_ONE, 0);  // a table needs at least one word per group
 
   // vector loads need 16-byte aligned column bases
   P.vec_ok = 1;
@@ -412,26 +462,104 @@ int lower_query(const PwQuery* q, const PwFrame* f, Lowered* L) {
 // launches
 // ------------------------------------------------------------------------------------------------------
 
+// the narrow kernel class holds <= 4 raw slots and <= 2 value expressions in registers
+static bool narrow_class(const ScanPlan& P) { return P.n_slots <= 4 && P.n_vexpr <= NVof<4>::value; }
 static int launch_scan(ScanPlan P, int sm, cudaStream_t st) {
   // the kernel is compiled for a few (slots, key words) classes; round the key width up (extra words are 0)
   if (P.n_kw == 3) P.n_kw = 4;
   if (P.n_kw == 5) P.n_kw = 6;
-  if (P.n_slots <= 4) return launch_scan_nc4(P, sm, st);
+  const bool narrow = narrow_class(P);
+  // query-shape specialised kernel (NVRTC); falls back to the ahead-of-time kernel of the same class
+  const int kwc = P.n_kw <= 1 ? 1 : (P.n_kw <= 2 ? 2 : (P.n_kw <= 4 ? 4 : 6));
+  const int rc = launch_scan_jit(P, narrow ? 4 : 12, kwc, P.hot_slots > 0, narrow ? ScanCfg<4>::THREADS : ScanCfg<12>::THREADS, sm, st);
+  if (rc <= 0) { if (rc == 0) ctx().timings.reserved = 1.0f; return rc; }
+  if (narrow) return launch_scan_nc4(P, sm, st);
   return launch_scan_nc12(P, sm, st);
 }
 static int padded_kw(int n_kw) { return n_kw == 3 ? 4 : (n_kw == 5 ? 6 : n_kw); }
 
-static int hot_slots_for(const ScanPlan& P, int requested) {
-  if (requested > 0) {
-    int s = 16;
-    while (s < requested) s <<= 1;
-    return s;
+// Shared-memory hot table geometry for `groups_hint` live groups (see pw_scan.cuh).  Returns false when no
+// useful table fits.
+static bool plan_hot(ScanPlan& P, int64_t groups_hint, int requested_gcap) {
+  HotGeom& g = P.hot;
+  memset(&g, 0, sizeof g);
+  const int kw = padded_kw(P.n_kw);
+  const int warps = (narrow_class(P) ? ScanCfg<4>::THREADS : ScanCfg<12>::THREADS) / 32;
+  int n_priv64 = 0, n_priv32 = 0, n_mm = 0;
+  auto is_add = [&](int a) { return P.accs[a].op == OP_ADD_F64 || P.accs[a].op == OP_ADD_I64; };
+  auto is_count = [&](int a) { return P.accs[a].op == OP_ADD_I64 && (P.accs[a].src == SRC_ONE || P.accs[a].src == SRC_VALID); };
+  for (int a = 0; a < P.n_acc; ++a) { if (is_count(a)) n_priv32++; else if (is_add(a)) n_priv64++; else n_mm++; }
+  // dense ids: a little head-room over the live-group estimate; the key index has >= 2x as many slots
+  int gcap = requested_gcap > 0 ? requested_gcap : (int)std::min<int64_t>(4096, std::max<int64_t>(8, groups_hint + groups_hint / 8 + 4));
+  for (;; gcap = gcap * 3 / 4) {
+    if (gcap < 4) return false;
+    int S = 8;
+    while (S < 2 * gcap) S <<= 1;  // tag buckets of 4 at <= 50 % load: a full bucket is rare
+    const size_t shared = (size_t)S * 4 + (size_t)gcap * 8 * kw + 32;
+    auto per_warp = [&](int R, int mmp) { return (((size_t)gcap * R * ((size_t)(n_priv64 + mmp) * 8 + (size_t)n_priv32 * 4 + 1)) + 15) & ~(size_t)15; };
+    auto total = [&](int R, int mmp) { return shared + (size_t)(n_mm - mmp) * gcap * 8 + per_warp(R, mmp) * warps; };
+    // prefer two CTAs per SM; accept one when the table needs the room
+    const size_t budget2 = 110 * 1024, budget1 = 224 * 1024;
+    int mmp = n_mm;
+    size_t budget = budget2;
+    if (total(1, n_mm) > budget2) {
+      if (total(1, 0) <= budget2) mmp = 0;
+      else if (total(1, n_mm) <= budget1) budget = budget1;
+      else if (total(1, 0) <= budget1) { mmp = 0; budget = budget1; }
+      else continue;  // fewer ids
+    }
+    int R = 32;
+    while (R > 1 && total(R, mmp) > budget) R >>= 1;
+    if (requested_gcap > 0 && requested_gcap <= 64) R = std::min(R, 2);  // test hook: exercise the claim path
+    g.idx_slots = S; g.gcap = gcap; g.replicas = R; g.n_mm = n_mm - mmp;
+    size_t off = (size_t)S * 4;
+    off = (off + 15) & ~(size_t)15; g.keys_off = (int32_t)off; off += (size_t)gcap * 8 * kw;
+    g.mm_off = (int32_t)off; off += (size_t)g.n_mm * gcap * 8;
+    g.count_off = (int32_t)off; off += 16;
+    g.warp_off = (int32_t)off;
+    size_t woff = 0;
+    int mm_idx = 0;
+    for (int pass = 0; pass < 2; ++pass) {  // 8-byte words first, then 4-byte counters
+      for (int a = 0; a < P.n_acc; ++a) {
+        if (pass == 0) {
+          if (is_count(a)) continue;
+          if (!is_add(a) && mmp == 0) { g.acc_kind[a] = HOT_SHARED_MM; g.acc_off[a] = mm_idx++; continue; }
+          g.acc_kind[a] = HOT_PRIV64; g.acc_off[a] = (int32_t)woff; woff += (size_t)gcap * R * 8;
+        } else if (is_count(a)) {
+          g.acc_kind[a] = HOT_PRIV32; g.acc_off[a] = (int32_t)woff; woff += (size_t)gcap * R * 4;
+        }
+      }
+    }
+    g.claim_off = (int32_t)woff; woff += (size_t)gcap * R;
+    woff = (woff + 15) & ~(size_t)15;
+    g.warp_bytes = (int32_t)woff;
+    g.total_bytes = (int32_t)(off + woff * warps);
+    return true;
   }
-  const size_t per = (size_t)padded_kw(P.n_kw) * 8 + (size_t)P.n_acc * 8 + 4;
-  int s = 4096;
-  while (s > 256 && (size_t)s * per > 96 * 1024) s >>= 1;  // two CTAs per SM
-  return s;
 }
+
+}  // namespace pw
+// Diagnostics: NVRTC-compiles the specialised scan kernel for a C2-shaped plan (int64 key, f64 value,
+// sum/mean/min/max).  Needs no GPU; used by build() as the "does the JIT path build" check.
+extern "C" __attribute__((visibility("default"))) int pw_b200_jit_selftest(char* log, size_t log_len) {
+  using namespace pw;
+  ScanPlan P;
+  memset(&P, 0, sizeof P);
+  P.n_rows = 1 << 20; P.row_stride = 1; P.n_slots = 2; P.vec_ok = 1;
+  P.slots[0].dtype = DT_I64; P.slots[1].dtype = DT_F64;
+  P.n_keys = 1; P.keys[0].slot = 0; P.keys[0].n_words = 1; P.keys[0].dtype = DT_I64; P.n_kw = 1;
+  P.n_vexpr = 1; P.vexprs[0].slot = 1; P.vexprs[0].cls = CLS_F64; P.vexprs[0].flags = VF_SUM_F | VF_MIN | VF_MAX; P.vexprs[0].acc_base = 0;
+  P.accs[0].op = OP_ADD_F64; P.accs[0].src = SRC_F64; P.accs[1].op = OP_MIN_I64; P.accs[1].src = SRC_F64_ORD;
+  P.accs[2].op = OP_MAX_I64; P.accs[2].src = SRC_F64_ORD; P.accs[3].op = OP_ADD_I64; P.accs[3].src = SRC_ONE;
+  P.n_acc = 4; P.gflags = GF_LEN; P.acc_gbase = 3;
+  if (!plan_hot(P, 1000, 0)) return -1;
+  P.hot_slots = P.hot.idx_slots;
+  std::string err;
+  const int rc = jit_selftest_compile(P, 4, 1, true, ScanCfg<4>::THREADS, &err);
+  if (log && log_len) { strncpy(log, err.c_str(), log_len - 1); log[log_len - 1] = 0; }
+  return rc;
+}
+namespace pw {
 
 struct Control {  // device control block (zeroed per run)
   int32_t overflow;
@@ -478,6 +606,7 @@ static int sample_distinct(const Lowered& L, int64_t row_begin, int64_t stride, 
   P.hot_slots = 0; P.check_sorted = 0; P.n_preds = 0;
   // only group identity matters: one len accumulator
   P.n_acc = 1; P.accs[0].op = OP_ADD_I64; P.accs[0].src = SRC_ONE; P.accs[0].vexpr = 0; P.n_vexpr = 0;
+  P.gflags = GF_LEN; P.acc_gbase = 0;
   Table T{};
   PW_TRY(alloc_table(&T, padded_kw(P.n_kw), 1, (uint64_t)n_sample * 2 + 64, dctl));
   PW_TRY(init_table(T, P, c.stream));
@@ -528,9 +657,9 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
 
   // ---- strategy + table size -------------------------------------------------------------------
   PW_CUDA(cudaEventRecord(c.ev[1], c.stream));
-  const int default_hot = hot_slots_for(P, q->hot_table_slots);
   uint64_t cap = 0;
   bool use_hot = true;
+  int64_t live_groups = 0;  // distinct keys among consecutive rows (sizes the hot table)
   const int64_t SMALL = 1 << 18;
   if (q->initial_table_slots > 0) cap = (uint64_t)q->initial_table_slots;
   if (N <= SMALL) {
@@ -549,11 +678,18 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     if (mid + n_b > N) mid = 0;
     uint64_t dl = 0;
     PW_TRY(sample_distinct(L, mid, 1, n_b, dctl, &hctl, &dl));
-    use_hot = dl <= (uint64_t)(default_hot / 2);
+    live_groups = (int64_t)dl;
+    use_hot = dl <= 2048;
   }
   if (q->flags & PW_FLAG_FORCE_HOT_TABLE) use_hot = true;
   if (q->flags & PW_FLAG_FORCE_GLOBAL_TABLE) use_hot = false;
+  if (live_groups == 0) live_groups = std::min<int64_t>(std::max<int64_t>(N, 4), 1024);
+  if (use_hot && !plan_hot(P, live_groups, q->hot_table_slots)) use_hot = false;
   if (cap > 0xFFFFFFF0ull) return fail(PW_ERR_UNSUPPORTED, "table larger than 2^32 slots");
+  if (getenv("PW_DEBUG"))
+    fprintf(stderr, "[pw] rows=%lld kw=%d slots=%d accs=%d cap=%llu hot=%d live=%lld gcap=%d S=%d R=%d n_mm=%d smem=%d\n", (long long)N, P.n_kw,
+            P.n_slots, P.n_acc, (unsigned long long)cap, (int)use_hot, (long long)live_groups, P.hot.gcap, P.hot.idx_slots, P.hot.replicas,
+            P.hot.n_mm, P.hot.total_bytes);
   PW_CUDA(cudaEventRecord(c.ev[2], c.stream));
 
   // ---- scan (with growth retries) ------------------------------------------------------------------
@@ -565,7 +701,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     PW_CUDA(cudaMemsetAsync(dctl, 0, sizeof(Control), c.stream));
     P.table = T;
     P.not_sorted = &dctl->not_sorted;
-    P.hot_slots = use_hot ? default_hot : 0;
+    P.hot_slots = use_hot ? P.hot.idx_slots : 0;
     PW_CUDA(cudaEventRecord(c.ev[8], c.stream));
     if (N > 0) PW_TRY(launch_scan(P, c.sm_count, c.stream));
     PW_CUDA(cudaEventRecord(c.ev[9], c.stream));

@@ -182,8 +182,10 @@ static __global__ void emit_kernel(Table T, int n_kw, EmitDesc d, const uint32_t
         break;
       case EMIT_MINMAX_F64: {
         valid = T.accs[(uint64_t)d.acc_cnt * stride + slot] != 0;
-        const bool any_num = T.accs[(uint64_t)d.acc_nn * stride + slot] != 0;
-        uint64_t b = any_num ? ordered_to_f64_bits((int64_t)T.accs[(uint64_t)d.acc * stride + slot]) : 0x7FF8000000000000ull;
+        // the ordered image of a real value never equals the init sentinel (INT64_MAX/MIN map to NaN payloads)
+        const uint64_t raw = T.accs[(uint64_t)d.acc * stride + slot];
+        const bool any_num = raw != (uint64_t)d.every;  // d.every carries acc_init(op) for this emit kind
+        uint64_t b = any_num ? ordered_to_f64_bits((int64_t)raw) : 0x7FF8000000000000ull;
         store_typed(d.out_values, i, d.out_dtype, valid ? b : 0);
         break; }
       case EMIT_COUNT:

@@ -1,0 +1,287 @@
+// pw_jit.cu — query-shape specialisation of the scan kernel with NVRTC.
+//
+// The ahead-of-time kernels interpret the query plan at run time (RtCtl).  The first time a query SHAPE
+// (dtypes, key layout, aggregate flags, hot-table geometry — no pointers, no row counts) is seen, this
+// module generates a `JitCtl` policy whose accessors are constexpr, compiles `scan_body<JitCtl,...>` from
+// the very same pw_scan.cuh for sm_100a, and caches the CUfunction for the life of the process.  NVRTC and
+// the driver API are dlopen'ed lazily so the library still loads on a machine without a GPU; when either is
+// missing the engine keeps using the AOT kernels (still on the GPU — there is no CPU path).
+#include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "pw_engine.h"
+#include "pw_scan.cuh"
+
+namespace pw {
+namespace {
+
+// ---- minimal NVRTC / driver API surface (resolved with dlsym) -------------------------------------------
+typedef struct _nvrtcProgram* nvrtcProgram;
+typedef int nvrtcResult;
+typedef int CUresult;
+typedef struct CUmod_st* CUmodule;
+typedef struct CUfunc_st* CUfunction;
+typedef struct CUstream_st* CUstream;
+
+struct Api {
+  bool ok = false;
+  std::string why;
+  nvrtcResult (*nvrtcCreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*);
+  nvrtcResult (*nvrtcCompileProgram)(nvrtcProgram, int, const char* const*);
+  nvrtcResult (*nvrtcGetProgramLogSize)(nvrtcProgram, size_t*);
+  nvrtcResult (*nvrtcGetProgramLog)(nvrtcProgram, char*);
+  nvrtcResult (*nvrtcGetCUBINSize)(nvrtcProgram, size_t*);
+  nvrtcResult (*nvrtcGetCUBIN)(nvrtcProgram, char*);
+  nvrtcResult (*nvrtcDestroyProgram)(nvrtcProgram*);
+  CUresult (*cuModuleLoadData)(CUmodule*, const void*);
+  CUresult (*cuModuleGetFunction)(CUfunction*, CUmodule, const char*);
+  CUresult (*cuFuncSetAttribute)(CUfunction, int, int);
+  CUresult (*cuOccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t);
+  CUresult (*cuLaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**);
+};
+
+Api& api() {
+  static Api a;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* rtc = nullptr;
+    for (const char* n : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"})
+      if ((rtc = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!rtc) { a.why = "libnvrtc not found"; return; }
+    void* drv = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!drv) { a.why = "libcuda.so.1 not found"; return; }
+#define PW_SYM(lib, name)                                                        \
+  *(void**)(&a.name) = dlsym(lib, #name);                                        \
+  if (!a.name) { a.why = std::string("missing symbol ") + #name; return; }
+    PW_SYM(rtc, nvrtcCreateProgram) PW_SYM(rtc, nvrtcCompileProgram) PW_SYM(rtc, nvrtcGetProgramLogSize)
+    PW_SYM(rtc, nvrtcGetProgramLog) PW_SYM(rtc, nvrtcGetCUBINSize) PW_SYM(rtc, nvrtcGetCUBIN) PW_SYM(rtc, nvrtcDestroyProgram)
+    PW_SYM(drv, cuModuleLoadData) PW_SYM(drv, cuModuleGetFunction) PW_SYM(drv, cuFuncSetAttribute)
+    PW_SYM(drv, cuOccupancyMaxActiveBlocksPerMultiprocessor) PW_SYM(drv, cuLaunchKernel)
+#undef PW_SYM
+    a.ok = true;
+  });
+  return a;
+}
+
+std::string csrc_dir() {
+  if (const char* e = getenv("PW_CSRC_DIR")) return e;
+  Dl_info info;
+  if (dladdr((void*)&csrc_dir, &info) && info.dli_fname) {
+    std::string p = info.dli_fname;  // .../polaroid_b200/lib/libpolarway_b200.so
+    size_t k = p.rfind('/');
+    if (k != std::string::npos) p = p.substr(0, k);
+    k = p.rfind('/');
+    if (k != std::string::npos) return p.substr(0, k) + "/csrc";
+  }
+  return "polaroid_b200/csrc";
+}
+
+// ---- JitCtl generation -------------------------------------------------------------------------------------
+struct Gen {
+  std::ostringstream o;
+  void scalar(const char* type, const char* name, long long v) {
+    o << "  static __device__ __forceinline__ constexpr " << type << " " << name << "(const ScanPlan&) { return " << v << "; }\n";
+  }
+  template <class F>
+  void table1(const char* type, const char* name, int n, F f) {
+    o << "  static __device__ __forceinline__ constexpr " << type << " " << name << "(const ScanPlan&, int i) { return ";
+    for (int i = 0; i < n; ++i) o << "i == " << i << " ? " << f(i) << " : ";
+    o << "0; }\n";
+  }
+};
+
+std::string hexdouble(double d) {
+  char buf[64];
+  snprintf(buf, sizeof buf, "%a", d);
+  return buf;
+}
+
+std::string jit_ctl(const ScanPlan& P) {
+  Gen g;
+  g.o << "struct JitCtl {\n";
+  g.scalar("int", "n_slots", P.n_slots);
+  g.table1("int", "slot_dtype", P.n_slots, [&](int i) { return P.slots[i].dtype; });
+  g.table1("bool", "slot_nullable", P.n_slots, [&](int i) { return P.slots[i].validity != nullptr ? 1 : 0; });
+  g.scalar("int", "n_preds", P.n_preds);
+  g.table1("int", "pred_slot", P.n_preds, [&](int i) { return P.preds[i].slot; });
+  g.table1("int", "pred_op", P.n_preds, [&](int i) { return P.preds[i].op; });
+  g.table1("int", "pred_cls", P.n_preds, [&](int i) { return P.preds[i].cls; });
+  g.scalar("int", "n_keys", P.n_keys);
+  g.table1("int", "key_slot", P.n_keys, [&](int i) { return P.keys[i].slot; });
+  g.table1("int", "key_dtype", P.n_keys, [&](int i) { return P.keys[i].dtype; });
+  g.table1("int", "key_words", P.n_keys, [&](int i) { return P.keys[i].n_words; });
+  g.scalar("bool", "has_null_word", P.has_null_word);
+  g.scalar("bool", "dyn_enabled", P.dyn.enabled);
+  g.scalar("int", "dyn_slot", P.dyn.slot);
+  g.scalar("int", "dyn_closed", P.dyn.closed);
+  g.scalar("int", "n_vexpr", P.n_vexpr);
+  g.table1("int", "ve_nf", P.n_vexpr, [&](int i) { return P.vexprs[i].n_factors; });
+  g.table1("int", "ve_slot", P.n_vexpr, [&](int i) { return P.vexprs[i].slot; });
+  g.table1("int", "ve_cls", P.n_vexpr, [&](int i) { return P.vexprs[i].cls; });
+  g.table1("int", "ve_flags", P.n_vexpr, [&](int i) { return P.vexprs[i].flags; });
+  g.table1("int", "ve_acc", P.n_vexpr, [&](int i) { return P.vexprs[i].acc_base; });
+  auto table2 = [&](const char* type, const char* name, auto f) {
+    g.o << "  static __device__ __forceinline__ constexpr " << type << " " << name << "(const ScanPlan&, int e, int f) { return ";
+    for (int e = 0; e < P.n_vexpr; ++e)
+      for (int k = 0; k < P.vexprs[e].n_factors; ++k) g.o << "(e == " << e << " && f == " << k << ") ? " << f(e, k) << " : ";
+    g.o << "0; }\n";
+  };
+  table2("int", "fac_slot", [&](int e, int k) { return std::to_string(P.vexprs[e].f[k].slot); });
+  table2("double", "fac_a", [&](int e, int k) { return hexdouble(P.vexprs[e].f[k].a); });
+  table2("double", "fac_b", [&](int e, int k) { return hexdouble(P.vexprs[e].f[k].b); });
+  g.scalar("int", "gflags", P.gflags);
+  g.scalar("int", "acc_gbase", P.acc_gbase);
+  g.scalar("int", "n_acc", P.n_acc);
+  g.table1("int", "acc_op", P.n_acc, [&](int i) { return P.accs[i].op; });
+  g.scalar("bool", "vec_ok", P.vec_ok);
+  g.scalar("bool", "check_sorted", P.check_sorted);
+  g.scalar("int", "h_slots", P.hot.idx_slots);
+  g.scalar("int", "h_gcap", P.hot.gcap);
+  g.scalar("int", "h_rep", P.hot.replicas > 0 ? P.hot.replicas : 1);
+  g.scalar("int", "h_keys_off", P.hot.keys_off);
+  g.scalar("int", "h_mm_off", P.hot.mm_off);
+  g.scalar("int", "h_count_off", P.hot.count_off);
+  g.scalar("int", "h_warp_off", P.hot.warp_off);
+  g.scalar("int", "h_warp_bytes", P.hot.warp_bytes);
+  g.scalar("int", "h_claim_off", P.hot.claim_off);
+  g.table1("int", "h_kind", P.n_acc, [&](int i) { return P.hot.acc_kind[i]; });
+  g.table1("int", "h_off", P.n_acc, [&](int i) { return P.hot.acc_off[i]; });
+  g.o << "};\n";
+  return g.o.str();
+}
+
+struct Compiled { CUfunction fn = nullptr; bool failed = false; };
+std::mutex g_mu;
+std::map<std::string, Compiled> g_cache;
+
+Compiled compile(const std::string& key, const std::string& ctl, int nc, int kw, bool hot, int threads) {
+  Api& a = api();
+  Compiled c;
+  std::ostringstream src;
+  src << "#include \"pw_scan.cuh\"\nnamespace pw {\n" << ctl << "}\n"
+      << "extern \"C\" __global__ void __launch_bounds__(" << threads << ", 1) pw_scan_jit(const __grid_constant__ pw::ScanPlan P) {\n"
+      << "  pw::scan_body<pw::JitCtl, " << nc << ", " << kw << ", " << (hot ? "true" : "false") << ">(P);\n}\n";
+  const std::string text = src.str();
+  nvrtcProgram prog = nullptr;
+  if (a.nvrtcCreateProgram(&prog, text.c_str(), "pw_scan_jit.cu", 0, nullptr, nullptr) != 0) { c.failed = true; return c; }
+  const std::string inc = "--include-path=" + csrc_dir();
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", inc.c_str(), "-lineinfo", "--device-as-default-execution-space"};
+  const nvrtcResult rc = a.nvrtcCompileProgram(prog, 5, opts);
+  if (rc != 0 || getenv("PW_DEBUG")) {
+    size_t n = 0;
+    a.nvrtcGetProgramLogSize(prog, &n);
+    if (n > 1) {
+      std::vector<char> log(n + 1);
+      a.nvrtcGetProgramLog(prog, log.data());
+      if (rc != 0 || n > 2) fprintf(stderr, "[pw jit] nvrtc rc=%d\n%s\n", rc, log.data());
+    }
+    if (getenv("PW_DEBUG") && rc == 0) fprintf(stderr, "[pw jit] compiled shape (nc=%d kw=%d hot=%d):\n%s", nc, kw, (int)hot, ctl.c_str());
+  }
+  if (rc != 0) { a.nvrtcDestroyProgram(&prog); c.failed = true; return c; }
+  size_t sz = 0;
+  a.nvrtcGetCUBINSize(prog, &sz);
+  std::vector<char> cubin(sz);
+  a.nvrtcGetCUBIN(prog, cubin.data());
+  a.nvrtcDestroyProgram(&prog);
+  if (const char* dump = getenv("PW_JIT_DUMP")) {
+    FILE* f = fopen(dump, "wb");
+    if (f) { fwrite(cubin.data(), 1, sz, f); fclose(f); }
+  }
+  CUmodule mod = nullptr;
+  if (a.cuModuleLoadData(&mod, cubin.data()) != 0) { c.failed = true; return c; }
+  if (a.cuModuleGetFunction(&c.fn, mod, "pw_scan_jit") != 0) { c.failed = true; c.fn = nullptr; }
+  (void)key;
+  return c;
+}
+
+}  // namespace
+
+// Cross-compile check used by build(): NVRTC needs no GPU.  Returns 0 when the specialised source compiles.
+int jit_selftest_compile(const ScanPlan& P, int nc, int kw, bool hot, int threads, std::string* err) {
+  Api& a = api();
+  if (!a.nvrtcCreateProgram) {
+    // driver may be missing on a CPU-only box: resolve NVRTC alone
+    void* rtc = nullptr;
+    for (const char* n : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"})
+      if ((rtc = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!rtc) { *err = "libnvrtc not found"; return 1; }
+    *(void**)(&a.nvrtcCreateProgram) = dlsym(rtc, "nvrtcCreateProgram");
+    *(void**)(&a.nvrtcCompileProgram) = dlsym(rtc, "nvrtcCompileProgram");
+    *(void**)(&a.nvrtcGetProgramLogSize) = dlsym(rtc, "nvrtcGetProgramLogSize");
+    *(void**)(&a.nvrtcGetProgramLog) = dlsym(rtc, "nvrtcGetProgramLog");
+    *(void**)(&a.nvrtcGetCUBINSize) = dlsym(rtc, "nvrtcGetCUBINSize");
+    *(void**)(&a.nvrtcGetCUBIN) = dlsym(rtc, "nvrtcGetCUBIN");
+    *(void**)(&a.nvrtcDestroyProgram) = dlsym(rtc, "nvrtcDestroyProgram");
+  }
+  std::ostringstream src;
+  src << "#include \"pw_scan.cuh\"\nnamespace pw {\n" << jit_ctl(P) << "}\n"
+      << "extern \"C\" __global__ void __launch_bounds__(" << threads << ", 1) pw_scan_jit(const __grid_constant__ pw::ScanPlan P) {\n"
+      << "  pw::scan_body<pw::JitCtl, " << nc << ", " << kw << ", " << (hot ? "true" : "false") << ">(P);\n}\n";
+  const std::string text = src.str();
+  nvrtcProgram prog = nullptr;
+  if (a.nvrtcCreateProgram(&prog, text.c_str(), "pw_scan_jit.cu", 0, nullptr, nullptr) != 0) { *err = "nvrtcCreateProgram failed"; return 2; }
+  const std::string inc = "--include-path=" + csrc_dir();
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", inc.c_str(), "-lineinfo", "--device-as-default-execution-space"};
+  const nvrtcResult rc = a.nvrtcCompileProgram(prog, 5, opts);
+  size_t n = 0;
+  a.nvrtcGetProgramLogSize(prog, &n);
+  std::vector<char> log(n + 1, 0);
+  if (n > 1) a.nvrtcGetProgramLog(prog, log.data());
+  *err = log.data();
+  if (rc == 0) {
+    if (const char* dump = getenv("PW_JIT_DUMP")) {
+      size_t sz = 0;
+      a.nvrtcGetCUBINSize(prog, &sz);
+      std::vector<char> cubin(sz);
+      a.nvrtcGetCUBIN(prog, cubin.data());
+      FILE* f = fopen(dump, "wb");
+      if (f) { fwrite(cubin.data(), 1, sz, f); fclose(f); }
+    }
+  }
+  a.nvrtcDestroyProgram(&prog);
+  return rc == 0 ? 0 : 3;
+}
+
+// returns 0 launched, 1 JIT unavailable (caller falls back to the AOT kernel), <0 error
+int launch_scan_jit(const ScanPlan& P, int nc, int kw, bool hot, int threads, int sm_count, cudaStream_t st) {
+  if (getenv("PW_NO_JIT")) return 1;
+  Api& a = api();
+  if (!a.ok) return 1;
+  const std::string ctl = jit_ctl(P);
+  const std::string key = ctl + "|" + std::to_string(nc) + "|" + std::to_string(kw) + "|" + std::to_string((int)hot) + "|" + std::to_string(threads);
+  Compiled c;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_cache.find(key);
+    if (it == g_cache.end()) {
+      c = compile(key, ctl, nc, kw, hot, threads);
+      g_cache[key] = c;
+    } else c = it->second;
+  }
+  if (c.failed || !c.fn) return 1;
+  const size_t smem = hot ? (size_t)P.hot.total_bytes : 0;
+  if (a.cuFuncSetAttribute(c.fn, 8 /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/, (int)smem) != 0) return 1;
+  int per_sm = 0;
+  if (a.cuOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c.fn, threads, smem) != 0 || per_sm < 1) return 1;
+  const int64_t n_steps = (P.n_rows + ROWS_PER_STEP - 1) / ROWS_PER_STEP;
+  const int64_t n_tiles = (n_steps + (threads / 32) - 1) / (threads / 32);
+  int64_t grid = (int64_t)sm_count * per_sm;
+  if (grid > n_tiles) grid = n_tiles;
+  if (grid < 1) grid = 1;
+  ScanPlan copy = P;
+  void* params[] = {&copy};
+  const CUresult rc = a.cuLaunchKernel(c.fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)smem, (CUstream)st, params, nullptr);
+  if (rc != 0) return fail(PW_ERR_CUDA, "cuLaunchKernel(pw_scan_jit) failed with %d", rc);
+  ctx().timings.kernel_launches++;
+  return 0;
+}
+
+}  // namespace pw

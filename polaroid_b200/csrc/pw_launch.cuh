@@ -9,17 +9,18 @@ namespace pw {
 template <int NC, int KW, bool HOT>
 static int launch_scan_t(const ScanPlan& P, int sm_count, cudaStream_t st) {
   auto kern = scan_kernel<NC, KW, HOT>;
-  size_t smem = HOT ? HotTable<KW>::bytes(P.hot_slots, P.n_acc) : 0;
+  size_t smem = HOT ? (size_t)P.hot.total_bytes : 0;
   if (smem > 48 * 1024) PW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
-  PW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SCAN_THREADS, smem));
+  constexpr int THREADS = ScanCfg<NC>::THREADS;
+  PW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
   if (per_sm < 1) return fail(PW_ERR_CUDA, "scan kernel does not fit on an SM (smem %zu)", smem);
   const int64_t n_steps = (P.n_rows + ROWS_PER_STEP - 1) / ROWS_PER_STEP;
-  const int64_t n_tiles = (n_steps + (SCAN_THREADS / 32) - 1) / (SCAN_THREADS / 32);
+  const int64_t n_tiles = (n_steps + (THREADS / 32) - 1) / (THREADS / 32);
   int64_t grid = (int64_t)sm_count * per_sm;  // one wave of resident CTAs, each owning a contiguous row range
   if (grid > n_tiles) grid = n_tiles;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, SCAN_THREADS, smem, st>>>(P);
+  kern<<<(unsigned)grid, THREADS, smem, st>>>(P);
   PW_CUDA(cudaGetLastError());
   ctx().timings.kernel_launches++;
   return 0;

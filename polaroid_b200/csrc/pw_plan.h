@@ -10,7 +10,18 @@
 // Everything is runtime data so one compiled kernel serves every query of a given shape class
 // (template parameters: number of raw slots, number of key words, hot table on/off).
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
+#else
+// NVRTC (pw_jit.cu): no host headers
+typedef signed char int8_t; typedef unsigned char uint8_t; typedef short int16_t; typedef unsigned short uint16_t;
+typedef int int32_t; typedef unsigned int uint32_t; typedef long long int64_t; typedef unsigned long long uint64_t;
+typedef unsigned long long uintptr_t;
+#ifndef INT64_MIN
+#define INT64_MIN (-9223372036854775807ll - 1)
+#define INT64_MAX 9223372036854775807ll
+#endif
+#endif
 
 namespace pw {
 
@@ -30,8 +41,8 @@ enum AccSrc : int32_t {
   SRC_BITS = 0,   // raw 64-bit value (int sum / int min / int max); skipped when null
   SRC_F64,        // value as f64 (f64 sum, mean numerator); skipped when null
   SRC_F64_ORD,    // order-preserving int64 image of the f64 value (float min/max); null and NaN skipped
+                  // (an accumulator still at its init value with count > 0 means "all NaN" -> NaN)
   SRC_VALID,      // 1 when the value is non-null (count, mean denominator, min/max validity)
-  SRC_NOT_NAN,    // 1 when non-null and not NaN (float min/max: all-NaN group -> NaN)
   SRC_ONE,        // 1 per row (len)
   SRC_ROWIDX,     // (global_row << 1) | valid   (first = MIN, last = MAX; nulls included)
   SRC_ROW,        // global row index (group first occurrence for maintain_order / key gather)
@@ -66,10 +77,22 @@ struct KeyCol {
 };
 
 struct Factor { double a, b; int32_t slot, pad; };
+// aggregates requested over one value expression.  Their accumulator words are consecutive, starting at
+// acc_base, in this order (only the requested ones exist).
+enum VFlag : int32_t {
+  VF_SUM_I = 1,   // ADD_I64 of the raw integer value
+  VF_SUM_F = 2,   // ADD_F64 of the value as f64 (f64 sum, mean numerator)
+  VF_COUNT = 4,   // ADD_I64 of "non-null" (only when the expression is nullable; otherwise GF_LEN is shared)
+  VF_MIN = 8, VF_MAX = 16,      // class-dependent: ordered-f64 / i64 / u64
+  VF_FIRST = 32, VF_LAST = 64   // MIN/MAX_U64 over (global_row << 1 | valid)
+};
+enum GFlag : int32_t { GF_LEN = 1, GF_ROW = 2, GF_TMIN = 4 };  // per-group words not tied to a value expression
 struct VExpr {
   int32_t n_factors;  // 0 => plain column `slot`
   int32_t slot;
   int32_t cls;        // class of the result (plain: class of the column; product: F64)
+  int32_t flags;      // VFlag set
+  int32_t acc_base;
   int32_t pad;
   Factor f[MAX_FACTORS];
 };
@@ -91,6 +114,22 @@ struct Table {
   unsigned long long* spilled; // rows that bypassed the hot table
 };
 
+// shared-memory hot table geometry (host-computed; see pw_scan.cuh)
+enum HotKind : int32_t {
+  HOT_SHARED_MM = 0,  // CTA-shared min/max word, atomic only when a row improves it
+  HOT_PRIV64 = 1,     // warp-private 64-bit word (any op), plain read-modify-write under a claim
+  HOT_PRIV32 = 2      // warp-private 32-bit counter (len / count)
+};
+struct HotGeom {
+  int32_t idx_slots;   // key index slots (power of two), 0 = hot table off
+  int32_t gcap;        // dense group ids
+  int32_t replicas;    // R: replicas of every private cell inside a warp (power of two, <= 32)
+  int32_t n_mm;        // number of CTA-shared min/max arrays
+  int32_t keys_off, mm_off, count_off, warp_off, warp_bytes, claim_off, total_bytes, pad;
+  int32_t acc_kind[MAX_ACC];
+  int32_t acc_off[MAX_ACC];  // HOT_SHARED_MM: array index; private kinds: byte offset inside the warp region
+};
+
 struct ScanPlan {
   int64_t n_rows;          // logical rows scanned by this launch
   int64_t row_begin;       // physical row of logical row 0
@@ -99,8 +138,10 @@ struct ScanPlan {
   int32_t n_slots, n_preds, n_keys, n_kw, n_vexpr, n_acc;
   int32_t has_null_word;   // last key word = null mask
   int32_t vec_ok;          // every slot pointer 16-byte aligned -> 128-bit loads
-  int32_t hot_slots;       // shared-memory hot table capacity (power of two) or 0
+  int32_t hot_slots;       // != 0: use the shared-memory hot table described by `hot`
   int32_t check_sorted;    // dynamic without keys: flag descending index
+  int32_t gflags;          // GFlag set; their words follow the value expressions' words: LEN, ROW, TMIN
+  int32_t acc_gbase;
   RawSlot slots[MAX_SLOTS];
   Pred preds[MAX_PREDS];
   KeyCol keys[MAX_KEYS];
@@ -109,6 +150,7 @@ struct ScanPlan {
   Dyn dyn;
   Table table;
   int32_t* not_sorted;     // device flag
+  HotGeom hot;
 };
 
 constexpr uint64_t KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;  // n_kw == 1 occupancy sentinel

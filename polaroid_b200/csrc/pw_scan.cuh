@@ -5,21 +5,39 @@
 // perfectly coalesced 128-bit load per half (narrower types use the matching narrower vector load and
 // keep the same row<->lane map).  The predicate is applied in registers (no mask, no compaction), the
 // key words are hashed, and the row is aggregated either
-//   * into the CTA's shared-memory hot table (the GPU analogue of the reference's FixedIndexTable hot
-//     grouper, polars-expr/src/hot_groups/fixed_index_table.rs) which is flushed into the HBM table
-//     when it fills up and at the end of the CTA's contiguous row range, or
+//   * into the CTA's shared-memory HOT TABLE — the GPU analogue of the reference's FixedIndexTable hot
+//     grouper (polars-expr/src/hot_groups/fixed_index_table.rs) — or
 //   * straight into the HBM open-addressing table (the cold / spill tier: rows whose key does not fit
-//     the hot table, and the whole input when the estimated cardinality is high).
-// CTAs take contiguous row ranges so that time-sorted inputs keep few live groups per CTA.
+//     the hot table, and the whole input when consecutive rows do not share groups).
+//
+// Hot table layout (why it looks the way it does: a shared-memory atomic costs ~64 cycles per warp on
+// this part, a plain LDS/STS 2-6, so the per-row updates must not be atomics):
+//   CTA-shared  key index   buckets of four 32-bit tags (fingerprint | dense id) read with one LDS.128,
+//                           keys stored per dense id -> a probe costs ~1 iteration for every lane (linear
+//                           probing cost the max chain length over the 32 lanes, ~6.5 iterations)
+//   CTA-shared  min/max     one 64-bit word per (acc, id): read, compare, atomic only when it improves
+//                           (used for min/max words when private copies would not fit)
+//   warp-private words      R replicas per (acc, id): replica = lane % R.  A row's lane first CLAIMS
+//                           (id, replica) by writing its lane number and reading it back; winners do a
+//                           plain read-modify-write, losers retry.  R = 32 (tiny group counts, e.g.
+//                           TPC-H Q1's 4 groups) makes every lane its own replica: no claims at all.
+// The hot table is flushed into the HBM table when it fills up (time-sorted inputs drift through
+// groups) and at the end of the CTA's contiguous row range.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 
+#include "pw_ctl.h"
 #include "pw_plan.h"
 
 namespace pw {
 
-constexpr int SCAN_THREADS = 256;
+// CTA size per raw-slot class: the narrow class (<= 4 slots, ~125 registers) runs 12 warps so that one
+// CTA per SM still hides HBM latency when the hot table needs most of the shared memory; the wide class
+// (<= 12 slots, ~240 registers) is register-limited to 8 warps.
+template <int NC> struct ScanCfg { static constexpr int THREADS = NC <= 4 ? 384 : 256; };
 constexpr int ROWS_PER_STEP = 128;  // per warp
 
 // ---------------------------------------------------------------------------------------------------
@@ -87,16 +105,24 @@ __device__ __forceinline__ void put(uint64_t (&a)[N], int idx, uint64_t x) {
   for (int i = 0; i < N; ++i) { const uint64_t m = mask64(idx == i); a[i] = (a[i] & ~m) | (x & m); }
 }
 
-template <int V> struct IC { static constexpr int value = V; };
-
 __device__ __forceinline__ int64_t floor_div(int64_t a, int64_t b) {
   int64_t q = a / b, r = a % b;
   return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q;
 }
 
 // ---------------------------------------------------------------------------------------------------
-// accumulator application (shared and global memory)
+// accumulator application
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t acc_combine(int op, uint64_t a, uint64_t b) {
+  switch (op) {
+    case OP_ADD_F64: return (uint64_t)__double_as_longlong(__longlong_as_double((long long)a) + __longlong_as_double((long long)b));
+    case OP_ADD_I64: return a + b;
+    case OP_MIN_I64: return (int64_t)b < (int64_t)a ? b : a;
+    case OP_MAX_I64: return (int64_t)b > (int64_t)a ? b : a;
+    case OP_MIN_U64: return b < a ? b : a;
+    default: return b > a ? b : a;
+  }
+}
 __device__ __forceinline__ void acc_apply_global(uint64_t* p, int op, uint64_t x) {
   switch (op) {
     case OP_ADD_F64: atomicAdd((double*)p, __longlong_as_double((long long)x)); break;
@@ -107,10 +133,9 @@ __device__ __forceinline__ void acc_apply_global(uint64_t* p, int op, uint64_t x
     default: if (x > __ldcg((const unsigned long long*)p)) atomicMax((unsigned long long*)p, (unsigned long long)x); break;
   }
 }
-__device__ __forceinline__ void acc_apply_shared(uint64_t* p, int op, uint64_t x) {
+// shared-memory min/max word: read, compare, atomic only when the row improves the extremum
+__device__ __forceinline__ void minmax_apply_shared(uint64_t* p, int op, uint64_t x) {
   switch (op) {
-    case OP_ADD_F64: atomicAdd((double*)p, __longlong_as_double((long long)x)); break;
-    case OP_ADD_I64: atomicAdd((unsigned long long*)p, (unsigned long long)x); break;
     case OP_MIN_I64: if ((long long)x < *(volatile long long*)p) atomicMin((long long*)p, (long long)x); break;
     case OP_MAX_I64: if ((long long)x > *(volatile long long*)p) atomicMax((long long*)p, (long long)x); break;
     case OP_MIN_U64: if (x < *(volatile unsigned long long*)p) atomicMin((unsigned long long*)p, (unsigned long long)x); break;
@@ -123,8 +148,8 @@ __device__ __forceinline__ void acc_apply_shared(uint64_t* p, int op, uint64_t x
 // n_kw == 1: the key word itself is the occupancy marker (CAS from KEY_EMPTY); a real key equal to a
 //            sentinel lives in an escape slot past `cap`.
 // n_kw  > 1: per-slot state word 0 -> 1 (busy, keys being written) -> 2 (ready).  A reader that finds a
-//            busy slot retries on the next iteration of a warp-convergent loop (no lane ever waits on
-//            another lane inside a divergent branch).
+//            busy slot retries on the next iteration of its loop (it never waits inside a branch that
+//            the slot owner has to leave first).
 // ---------------------------------------------------------------------------------------------------
 template <int KW>
 __device__ __forceinline__ uint64_t table_upsert(const Table& T, const uint64_t (&k)[KW], uint64_t h, bool key0_is_sentinel_free) {
@@ -180,84 +205,143 @@ __device__ __forceinline__ uint64_t table_upsert(const Table& T, const uint64_t 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// shared-memory hot table
-// layout (bytes): keys[KW][S] u64 | accs[n_acc][S] u64 | state[S] u32 | count u32
+// shared-memory hot table (see the header comment).  Geometry comes from ScanPlan::hot via CT:
+//   [tag u32 x S (buckets of 4)][keys u64 x KW x G][minmax u64 x n_mm x G][count, full-flag]   CTA-shared
+//   per warp: [private words: G x R x (8|4) bytes each][claim u8 x G x R]                      warp-private
 // ---------------------------------------------------------------------------------------------------
-template <int KW>
+constexpr uint32_t TAG_BUSY = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint4 lds128_volatile(const uint32_t* p) {
+  uint4 v;
+  asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  return v;
+}
+
+template <class CT, int KW>
 struct HotTable {
+  uint32_t* tag;
   uint64_t* keys;
-  uint64_t* accs;
-  uint32_t* state;
-  uint32_t* count;
-  int S;
-  __device__ __forceinline__ void bind(unsigned char* smem, int slots, int n_acc) {
-    S = slots;
-    keys = (uint64_t*)smem;
-    accs = keys + (size_t)KW * S;
-    state = (uint32_t*)(accs + (size_t)n_acc * S);
-    count = state + S;
+  uint64_t* mm;
+  uint32_t* count;       // [0] dense ids handed out, [1] "a row found the table full"
+  unsigned char* wbase;  // this warp's private region
+  unsigned char* wall;   // warp 0's private region
+
+  __device__ __forceinline__ void bind(unsigned char* smem, const ScanPlan& P, int warp) {
+    tag = (uint32_t*)smem;
+    keys = (uint64_t*)(smem + CT::h_keys_off(P));
+    mm = (uint64_t*)(smem + CT::h_mm_off(P));
+    count = (uint32_t*)(smem + CT::h_count_off(P));
+    wall = smem + CT::h_warp_off(P);
+    wbase = wall + (size_t)warp * CT::h_warp_bytes(P);
   }
-  static __host__ __device__ size_t bytes(int slots, int n_acc) {
-    return (size_t)slots * (KW * 8 + n_acc * 8 + 4) + 16;
-  }
+  // reset everything (CTA-wide; caller syncs)
   __device__ __forceinline__ void clear(const ScanPlan& P) {
-    for (int s = threadIdx.x; s < S; s += blockDim.x) {
-      state[s] = 0u;
-      for (int a = 0; a < P.n_acc; ++a) accs[(size_t)a * S + s] = acc_init(P.accs[a].op);
+    const int S = CT::h_slots(P), G = CT::h_gcap(P), R = CT::h_rep(P), W = blockDim.x >> 5;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) tag[s] = 0u;
+    for (int a = 0; a < CT::n_acc(P); ++a) {
+      const uint64_t init = acc_init(CT::acc_op(P, a));
+      const int kind = CT::h_kind(P, a);
+      if (kind == HOT_SHARED_MM) {
+        uint64_t* p = mm + (size_t)CT::h_off(P, a) * G;
+        for (int i = threadIdx.x; i < G; i += blockDim.x) p[i] = init;
+      } else {
+        const int cells = G * R;
+        for (int w = 0; w < W; ++w) {
+          unsigned char* base = wall + (size_t)w * CT::h_warp_bytes(P) + CT::h_off(P, a);
+          for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+            if (kind == HOT_PRIV64) ((uint64_t*)base)[i] = init;
+            else ((uint32_t*)base)[i] = 0u;
+          }
+        }
+      }
     }
-    if (threadIdx.x == 0) *count = 0u;
+    if (threadIdx.x == 0) { count[0] = 0u; count[1] = 0u; }
   }
-  // returns slot or -1 when the table is at its load limit / probe limit (row goes to the spill tier)
-  __device__ __forceinline__ int upsert(const uint64_t (&k)[KW], uint64_t h) {
-    int slot = (int)(h & (uint64_t)(S - 1));
+  __device__ __forceinline__ bool key_equals(const ScanPlan& P, int id, const uint64_t (&k)[KW]) const {
+    const int G = CT::h_gcap(P);
+    bool eq = true;
+#pragma unroll
+    for (int w = 0; w < KW; ++w) eq &= (*(volatile uint64_t*)&keys[(size_t)w * G + id] == k[w]);
+    return eq;
+  }
+  // key -> dense group id; -1 when the table is full or the probe budget is spent (row goes cold)
+  __device__ __forceinline__ int upsert(const ScanPlan& P, const uint64_t (&k)[KW], uint64_t h) {
+    const int S = CT::h_slots(P), G = CT::h_gcap(P);
+    const uint32_t fp = (uint32_t)(h >> 48) << 16;
+    int bucket = (int)(h & (uint64_t)((S >> 2) - 1));
     int probes = 0;
     int result = -1;
     bool done = false;
-    const uint32_t limit = (uint32_t)(S - (S >> 2));  // 75 % load
     while (!done) {
-      uint32_t s = ld_volatile_u32(&state[slot]);
-      if (s == 0u) {
-        if (*(volatile uint32_t*)count >= limit) { done = true; continue; }
-        s = atomicCAS(&state[slot], 0u, 1u) == 0u ? 3u : 1u;
-      }
-      if (s == 3u) {
+      uint32_t* tb = tag + bucket * 4;
+      const uint4 t4 = lds128_volatile(tb);
+      const uint32_t t[4] = {t4.x, t4.y, t4.z, t4.w};
+      bool busy = false;
+      int empty = -1;
 #pragma unroll
-        for (int w = 0; w < KW; ++w) keys[(size_t)w * S + slot] = k[w];
-        __threadfence_block();
-        st_volatile_u32(&state[slot], 2u);
-        atomicAdd(count, 1u);
-        result = slot; done = true;
-      } else if (s == 2u) {
-        __threadfence_block();
-        bool eq = true;
-#pragma unroll
-        for (int w = 0; w < KW; ++w) eq &= (*(volatile uint64_t*)&keys[(size_t)w * S + slot] == k[w]);
-        if (eq) { result = slot; done = true; }
-        else {
-          slot = (slot + 1) & (S - 1);
-          if (++probes >= 16) done = true;
+      for (int i = 3; i >= 0; --i) {
+        if (t[i] == TAG_BUSY) busy = true;
+        else if (t[i] == 0u) empty = i;
+        else if ((t[i] & 0xFFFF0000u) == fp && result < 0) {
+          const int id = (int)(t[i] & 0xFFFFu) - 1;
+          if (key_equals(P, id, k)) result = id;
         }
+      }
+      if (result >= 0) { done = true; }
+      else if (busy) { /* someone is inserting into this bucket (maybe our key): look again */ }
+      else if (empty >= 0) {
+        if (*(volatile uint32_t*)count >= (uint32_t)G) { count[1] = 1u; done = true; }  // full: ask for an eviction
+        else if (atomicCAS(&tb[empty], 0u, TAG_BUSY) == 0u) {
+          const uint32_t id = atomicAdd(count, 1u);
+          if (id < (uint32_t)G) {
+#pragma unroll
+            for (int w = 0; w < KW; ++w) keys[(size_t)w * G + id] = k[w];
+            __threadfence_block();
+            st_volatile_u32(&tb[empty], fp | (id + 1u));
+            result = (int)id;
+          } else {
+            st_volatile_u32(&tb[empty], 0u);  // lost the race for the last ids: give the slot back
+            count[1] = 1u;
+          }
+          done = true;
+        }
+        // CAS lost: look again
+      } else {
+        bucket = (bucket + 1) & ((S >> 2) - 1);
+        if (++probes >= 8) done = true;
       }
     }
     return result;
   }
-  // move every group into the HBM table and reset (CTA-wide; callers bracket with __syncthreads)
-  __device__ __forceinline__ void flush(const ScanPlan& P, bool sentinel_free) {
-    for (int s = threadIdx.x; s < S; s += blockDim.x) {
-      if (state[s] != 2u) continue;
+  // move every group into the HBM table (CTA-wide; callers bracket with __syncthreads and clear())
+  __device__ __forceinline__ void flush(const ScanPlan& P) {
+    const int G = CT::h_gcap(P), R = CT::h_rep(P), W = blockDim.x >> 5;
+    const int n = min((int)count[0], G);
+    for (int id = threadIdx.x; id < n; id += blockDim.x) {
       uint64_t k[KW];
 #pragma unroll
-      for (int w = 0; w < KW; ++w) k[w] = keys[(size_t)w * S + s];
-      uint64_t g = table_upsert<KW>(P.table, k, hash_words<KW>(k), sentinel_free);
-      for (int a = 0; a < P.n_acc; ++a) {
-        uint64_t v = accs[(size_t)a * S + s];
-        int op = P.accs[a].op;
-        if (g != ~0ull && v != acc_init(op)) acc_apply_global(&P.table.accs[(uint64_t)a * (P.table.cap + 2) + g], op, v);
-        accs[(size_t)a * S + s] = acc_init(op);
+      for (int w = 0; w < KW; ++w) k[w] = keys[(size_t)w * G + id];
+      // a hot KEY_NULL is always a true null (raw sentinel-valued keys bypass the hot table)
+      const uint64_t gs = table_upsert<KW>(P.table, k, hash_words<KW>(k), true);
+      for (int a = 0; a < CT::n_acc(P); ++a) {
+        const int op = CT::acc_op(P, a);
+        const int kind = CT::h_kind(P, a);
+        uint64_t v;
+        if (kind == HOT_SHARED_MM) {
+          v = mm[(size_t)CT::h_off(P, a) * G + id];
+        } else {
+          v = acc_init(op);  // combine the replicas of every warp
+          for (int w = 0; w < W; ++w) {
+            const unsigned char* base = wall + (size_t)w * CT::h_warp_bytes(P) + CT::h_off(P, a);
+            for (int r = 0; r < R; ++r) {
+              if (kind == HOT_PRIV64) v = acc_combine(op, v, ((const uint64_t*)base)[(size_t)id * R + r]);
+              else v += ((const uint32_t*)base)[(size_t)id * R + r];
+            }
+          }
+        }
+        if (gs != ~0ull && v != acc_init(op)) acc_apply_global(&P.table.accs[(uint64_t)a * (P.table.cap + 2) + gs], op, v);
       }
-      state[s] = 0u;
     }
-    if (threadIdx.x == 0) *count = 0u;
   }
 };
 
@@ -276,10 +360,9 @@ __device__ __forceinline__ int dtype_width(int dt) {
 
 // p = even LOGICAL row index (pair base); logical rows p and p+1 map to physical rows rb + p*rs.
 // `full` = both rows exist, the stride is 1 and vector loads are legal.
-__device__ __forceinline__ uint4 load_pair(const RawSlot& s, int64_t p, int64_t n_rows, bool full, int64_t rb = 0, int64_t rs = 1) {
+__device__ __forceinline__ uint4 load_pair(const void* values, int dt, int64_t p, int64_t n_rows, bool full, int64_t rb = 0, int64_t rs = 1) {
   uint4 r = make_uint4(0u, 0u, 0u, 0u);
-  const unsigned char* base = (const unsigned char*)s.values;
-  const int dt = s.dtype;
+  const unsigned char* base = (const unsigned char*)values;
   if (dt == DT_VIEW || dt == DT_VIEW_HI) {
     const int64_t lrow = p + (dt == DT_VIEW_HI ? 1 : 0);
     if (lrow < n_rows) {
@@ -321,8 +404,11 @@ __device__ __forceinline__ uint4 load_pair(const RawSlot& s, int64_t p, int64_t 
   }
   return r;
 }
+__device__ __forceinline__ uint4 load_pair(const RawSlot& s, int64_t p, int64_t n_rows, bool full, int64_t rb = 0, int64_t rs = 1) {
+  return load_pair(s.values, s.dtype, p, n_rows, full, rb, rs);
+}
 
-// validity bits of rows p, p+1 -> bit0, bit1
+// validity bits of logical rows p, p+1 -> bit0, bit1
 __device__ __forceinline__ uint32_t load_valid_pair(const RawSlot& s, int64_t p, int64_t n_rows, int64_t rb = 0, int64_t rs = 1) {
   if (s.validity == nullptr) return 3u;
   uint32_t out = 0;
@@ -376,188 +462,355 @@ __device__ __forceinline__ int slot_class(int dt) {
     default: return CLS_I64;
   }
 }
-
-// ---------------------------------------------------------------------------------------------------
-// one row: predicate -> key words -> probe -> aggregate.  hf/j are compile-time so that the raw
-// register arrays are never indexed dynamically (they must stay in registers).
-// ---------------------------------------------------------------------------------------------------
-template <int NC, int KW, bool HOT, int hf, int j>
-__device__ __forceinline__ void process_row(const ScanPlan& P, const uint4 (&raw)[2][NC], const uint32_t (&vbits)[2][NC],
-                                            HotTable<KW>& hot, const int64_t base, const int lane, const int64_t n_rows,
-                                            unsigned long long& spilled) {
-  const bool single_key_sentinel_guard = (KW == 1);
-    const int64_t row = base + hf * 64 + 2 * lane + j;
-    bool alive = row < n_rows;
-    // canonical inputs
-    uint64_t in[NC];
-    uint32_t in_valid = 0;  // bit per slot
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int dt = (c < P.n_slots) ? P.slots[c].dtype : DT_I64;
-      in[c] = decode(raw[hf][c], dt, j);
-      in_valid |= ((vbits[hf][c] >> j) & 1u) << c;
-    }
-    // predicate: conjunction, null => false   (polars-compute/src/filter/mod.rs:18-28)
-    for (int q = 0; q < P.n_preds && alive; ++q) {
-      const Pred& pr = P.preds[q];
-      const bool ok = (in_valid >> pr.slot) & 1u;
-      alive = ok && compare(pick<NC>(in, pr.slot), pr.scalar, pr.cls, pr.op);
-    }
-    // key words
-    uint64_t k[KW];
-#pragma unroll
-    for (int w = 0; w < KW; ++w) k[w] = 0;
-    uint64_t nullmask = 0;
-    bool sentinel_free = true;
-    {
-      int w = 0;
-      for (int q = 0; q < P.n_keys; ++q) {
-        const KeyCol& kc = P.keys[q];
-        uint64_t w0, w1 = 0;
-        bool ok;
-        if (kc.dtype == DT_VIEW) {
-          // row j of the pair lives in slot kc.slot + j (even / odd view)
-          const uint4 v = pick128<NC>(raw[hf], kc.slot + j);
-          w0 = (uint64_t)v.y << 32 | v.x;
-          w1 = (uint64_t)v.w << 32 | v.z;
-          const uint32_t vb = pick32<NC>(vbits[hf], kc.slot);
-          ok = (vb >> j) & 1u;
-          if ((uint32_t)w0 > 12u) { if (alive && ok) *P.table.overflow = 2; }  // long string: unsupported here
-        } else {
-          w0 = pick<NC>(in, kc.slot);
-          ok = (in_valid >> kc.slot) & 1u;
-          if (kc.dtype == DT_F64 || kc.dtype == DT_F32) {
-            double d = __longlong_as_double((long long)w0);
-            if (d == 0.0) w0 = 0;                                  // -0.0 == 0.0
-            if (d != d) w0 = 0x7FF8000000000000ull;               // one NaN
-          }
-        }
-        if (!ok) { w0 = 0; w1 = 0; nullmask |= 1ull << q; }
-put<KW>(k, w, w0);
-        if (kc.n_words == 2) put<KW>(k, w + 1, w1);
-        w += kc.n_words;
-      }
-      if (P.dyn.enabled) {
-        // tumbling window index (each row belongs to at most one window on this path)
-        const int64_t t = (int64_t)pick<NC>(in, P.dyn.slot);
-        const int64_t rel = t - P.dyn.origin;
-        int64_t kk;
-        bool member;
-        if (P.dyn.closed == 1) {  // right: (s, s+period]
-          kk = floor_div(rel - 1, P.dyn.every);
-          member = rel - kk * P.dyn.every <= P.dyn.period;
-        } else {
-          kk = floor_div(rel, P.dyn.every);
-          const int64_t off = rel - kk * P.dyn.every;
-          if (P.dyn.closed == 0) member = off < P.dyn.period;              // left  [s, s+period)
-          else if (P.dyn.closed == 3) member = off > 0 && off < P.dyn.period;  // none (s, s+period)
-          else member = off <= P.dyn.period;                               // both [s, s+period], period < every
-        }
-        alive = alive && member;
-put<KW>(k, w, (uint64_t)kk);
-        w += 1;
-      }
-      if (P.has_null_word) {
-put<KW>(k, w, nullmask);
-      } else if (KW == 1 && P.n_keys == 1 && !P.dyn.enabled) {
-        if (nullmask) k[0] = KEY_NULL;
-        else if (k[0] >= KEY_NULL) sentinel_free = false;
-      } else if (KW == 1) {
-        if (k[0] >= KEY_NULL) sentinel_free = false;
-      }
-    }
-    if (!alive) return;
-    const uint64_t h = hash_words<KW>(k);
-    // value expressions
-    uint64_t v[MAX_VEXPR];
-    uint32_t v_valid = 0;
-#pragma unroll
-    for (int e = 0; e < MAX_VEXPR; ++e) {
-      v[e] = 0;
-      if (e < P.n_vexpr) {
-        const VExpr& ve = P.vexprs[e];
-        if (ve.n_factors == 0) {
-          v[e] = pick<NC>(in, ve.slot);
-          v_valid |= ((in_valid >> ve.slot) & 1u) << e;
-        } else {
-          double prod = 1.0;
-          bool ok = true;
-          for (int f = 0; f < ve.n_factors; ++f) {
-            const Factor& fc = ve.f[f];
-            const uint64_t xb = pick<NC>(in, fc.slot);
-            const int cls = slot_class(P.slots[fc.slot].dtype);
-            double x = cls == CLS_F64 ? __longlong_as_double((long long)xb)
-                                      : (cls == CLS_U64 ? __ull2double_rn(xb) : __ll2double_rn((long long)xb));
-            ok = ok && ((in_valid >> fc.slot) & 1u);
-            double t = fc.b == 1.0 ? x : __dmul_rn(fc.b, x);
-            double u = fc.a == 0.0 ? t : __dadd_rn(fc.a, t);
-            prod = f == 0 ? u : __dmul_rn(prod, u);
-          }
-          v[e] = (uint64_t)__double_as_longlong(prod);
-          v_valid |= (ok ? 1u : 0u) << e;
-        }
-      }
-    }
-    // probe
-    int hslot = -1;
-    uint64_t gslot = ~0ull;
-    // rows whose raw key aliases a sentinel bypass the hot table so that a hot KEY_NULL is always a
-    // true null
-    if (HOT && sentinel_free) hslot = hot.upsert(k, h);
-    if (hslot < 0) {
-      gslot = table_upsert<KW>(P.table, k, h, sentinel_free || !single_key_sentinel_guard);
-      if (HOT) ++spilled;
-      if (gslot == ~0ull) return;
-    }
-    // accumulate
-    const uint64_t grow = (uint64_t)(P.row_begin + row * P.row_stride + P.row_offset);
-    for (int a = 0; a < P.n_acc; ++a) {
-      const Acc& ac = P.accs[a];
-      const uint64_t bits = pick<MAX_VEXPR>(v, ac.vexpr);
-      const bool ok = (v_valid >> ac.vexpr) & 1u;
-      uint64_t x = 0;
-      bool apply = true;
-      switch (ac.src) {
-        case SRC_BITS: x = bits; apply = ok; break;
-        case SRC_F64: {
-          const int cls = P.vexprs[ac.vexpr].cls;
-          double d = cls == CLS_F64 ? __longlong_as_double((long long)bits)
-                                    : (cls == CLS_U64 ? __ull2double_rn(bits) : __ll2double_rn((long long)bits));
-          x = (uint64_t)__double_as_longlong(d); apply = ok; break; }
-        case SRC_F64_ORD: {
-          double d = __longlong_as_double((long long)bits);
-          apply = ok && (d == d);
-          x = (uint64_t)f64_to_ordered(d); break; }
-        case SRC_VALID: x = ok ? 1ull : 0ull; apply = ok; break;
-        case SRC_NOT_NAN: {
-          double d = __longlong_as_double((long long)bits);
-          apply = ok && (d == d); x = 1ull; break; }
-        case SRC_ONE: x = 1ull; break;
-        case SRC_ROWIDX: x = (grow << 1) | (ok ? 1ull : 0ull); break;
-        case SRC_ROW: x = grow; break;
-        default: x = pick<NC>(in, P.dyn.slot); break;  // SRC_INDEX_T
-      }
-      if (!apply) continue;
-      if (hslot >= 0) acc_apply_shared(&hot.accs[(size_t)a * hot.S + hslot], ac.op, x);
-      else acc_apply_global(&P.table.accs[(uint64_t)a * (P.table.cap + 2) + gslot], ac.op, x);
-    }
+__device__ __forceinline__ double bits_to_f64(uint64_t b, int cls) {
+  return cls == CLS_F64 ? __longlong_as_double((long long)b) : (cls == CLS_U64 ? __ull2double_rn(b) : __ll2double_rn((long long)b));
 }
 
 // ---------------------------------------------------------------------------------------------------
-// the scan kernel
+// row evaluation shared by the scan, slice and segmented kernels.
+//
+// FRONT END (one copy): select the row's raw registers, decode, apply the predicate, build the key words,
+// evaluate the value expressions -> RowOut (a handful of scalars).
+// BACK END (one copy): hash, probe, and one pass over the per-expression aggregate flags.  Every register
+// array is indexed with compile-time constants only.  History: the first version selected operands per
+// accumulator with runtime indices and inlined the whole row four times; it executed ~57 warp instructions
+// per ROW and stalled on instruction fetch (profiles/r01_*.txt).
 // ---------------------------------------------------------------------------------------------------
-template <int NC, int KW, bool HOT>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const __grid_constant__ ScanPlan P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  HotTable<KW> hot;
+template <int NC> struct NVof { static constexpr int value = NC <= 4 ? 2 : MAX_VEXPR; };
+
+template <int NC>
+struct Row {
+  uint64_t in[NC];      // canonical inputs per raw slot
+  uint32_t in_valid;    // bit per slot
+};
+
+template <int KW, int NV>
+struct RowOut {
+  uint64_t k[KW];
+  uint64_t v[NV];
+  uint32_t v_valid;
+  bool alive, sentinel_free;
+  int64_t row;    // logical row
+  uint64_t tval;  // dynamic index value
+};
+
+template <class CT, int NC>
+__device__ __forceinline__ void row_decode(const ScanPlan& P, const uint4 (&raw)[NC], const uint32_t (&vbits)[NC], int j, Row<NC>& r) {
+  r.in_valid = 0;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    if (c < CT::n_slots(P)) {
+      r.in[c] = decode(raw[c], CT::slot_dtype(P, c), j);
+      r.in_valid |= ((vbits[c] >> j) & 1u) << c;
+    } else r.in[c] = 0;
+  }
+}
+
+// predicate: conjunction, null => false   (polars-compute/src/filter/mod.rs:18-28)
+template <class CT, int NC>
+__device__ __forceinline__ bool row_predicate(const ScanPlan& P, const Row<NC>& r) {
+  bool alive = true;
+#pragma unroll
+  for (int q = 0; q < MAX_PREDS; ++q) {
+    if (q >= CT::n_preds(P)) break;
+    const int slot = CT::pred_slot(P, q);
+    const bool ok = (r.in_valid >> slot) & 1u;
+    alive = alive && ok && compare(pick<NC>(r.in, slot), P.preds[q].scalar, CT::pred_cls(P, q), CT::pred_op(P, q));
+  }
+  return alive;
+}
+
+template <class CT, int NC, int NV>
+__device__ __forceinline__ void row_vexprs(const ScanPlan& P, const Row<NC>& r, uint64_t (&v)[NV], uint32_t& v_valid) {
+  v_valid = 0;
+#pragma unroll
+  for (int e = 0; e < NV; ++e) {
+    v[e] = 0;
+    if (e < CT::n_vexpr(P)) {
+      if (CT::ve_nf(P, e) == 0) {
+        const int slot = CT::ve_slot(P, e);
+        v[e] = pick<NC>(r.in, slot);
+        v_valid |= ((r.in_valid >> slot) & 1u) << e;
+      } else {
+        double prod = 1.0;
+        bool ok = true;
+#pragma unroll
+        for (int f = 0; f < MAX_FACTORS; ++f) {
+          if (f >= CT::ve_nf(P, e)) break;
+          const int slot = CT::fac_slot(P, e, f);
+          const double x = bits_to_f64(pick<NC>(r.in, slot), slot_class(CT::slot_dtype(P, slot)));
+          ok = ok && ((r.in_valid >> slot) & 1u);
+          // one rounding per operation, no FMA contraction (matches the CPU engines bit for bit)
+          const double fb = CT::fac_b(P, e, f), fa = CT::fac_a(P, e, f);
+          const double t = fb == 1.0 ? x : __dmul_rn(fb, x);
+          const double u = fa == 0.0 ? t : __dadd_rn(fa, t);
+          prod = f == 0 ? u : __dmul_rn(prod, u);
+        }
+        v[e] = (uint64_t)__double_as_longlong(prod);
+        v_valid |= (ok ? 1u : 0u) << e;
+      }
+    }
+  }
+}
+
+// tumbling window index of t and membership (each row belongs to at most one window on this path)
+__device__ __forceinline__ bool window_of(const Dyn& d, int closed, int64_t t, int64_t& kk) {
+  const int64_t rel = t - d.origin;
+  if (closed == 1) {  // right: (s, s+period]
+    kk = floor_div(rel - 1, d.every);
+    return rel - kk * d.every <= d.period;
+  }
+  kk = floor_div(rel, d.every);
+  const int64_t off = rel - kk * d.every;
+  if (closed == 0) return off < d.period;               // left  [s, s+period)
+  if (closed == 3) return off > 0 && off < d.period;    // none  (s, s+period)
+  return off <= d.period;                               // both  [s, s+period], period < every
+}
+
+// key words of the row; returns false when the row belongs to no window (dynamic)
+template <class CT, int NC, int KW>
+__device__ __forceinline__ bool row_keys(const ScanPlan& P, const Row<NC>& r, const uint4 (&raw)[NC], const uint32_t (&vbits)[NC], int j,
+                                         bool alive, uint64_t (&k)[KW], bool& sentinel_free) {
+#pragma unroll
+  for (int w = 0; w < KW; ++w) k[w] = 0;
+  uint64_t nullmask = 0;
+  sentinel_free = true;
+  bool member = true;
+  int w = 0;
+#pragma unroll
+  for (int q = 0; q < MAX_KEYS; ++q) {
+    if (q >= CT::n_keys(P)) break;
+    const int kslot = CT::key_slot(P, q), kdt = CT::key_dtype(P, q);
+    uint64_t w0, w1 = 0;
+    bool ok;
+    if (kdt == DT_VIEW) {
+      // row j of the pair lives in slot kslot + j (even / odd view)
+      const uint4 v = pick128<NC>(raw, kslot + j);
+      w0 = (uint64_t)v.y << 32 | v.x;
+      w1 = (uint64_t)v.w << 32 | v.z;
+      ok = (pick32<NC>(vbits, kslot) >> j) & 1u;
+      if ((uint32_t)w0 > 12u && alive && ok) *P.table.overflow = 2;  // long string: unsupported here
+    } else {
+      w0 = pick<NC>(r.in, kslot);
+      ok = (r.in_valid >> kslot) & 1u;
+      if (kdt == DT_F64 || kdt == DT_F32) {
+        const double d = __longlong_as_double((long long)w0);
+        if (d == 0.0) w0 = 0;                     // -0.0 == 0.0
+        if (d != d) w0 = 0x7FF8000000000000ull;   // one NaN
+      }
+    }
+    if (!ok) { w0 = 0; w1 = 0; nullmask |= 1ull << q; }
+    put<KW>(k, w, w0);
+    if (CT::key_words(P, q) == 2) put<KW>(k, w + 1, w1);
+    w += CT::key_words(P, q);
+  }
+  if (CT::dyn_enabled(P)) {
+    int64_t kk;
+    member = window_of(P.dyn, CT::dyn_closed(P), (int64_t)pick<NC>(r.in, CT::dyn_slot(P)), kk);
+    put<KW>(k, w, (uint64_t)kk);
+    w += 1;
+  }
+  if (CT::has_null_word(P)) put<KW>(k, w, nullmask);
+  else if (KW == 1) {
+    if (CT::n_keys(P) == 1 && !CT::dyn_enabled(P) && nullmask) k[0] = KEY_NULL;
+    else if (k[0] >= KEY_NULL) sentinel_free = false;
+  }
+  return member;
+}
+
+// FRONT END for row position rs (0..3) of this lane: half = rs >> 1, pair element = rs & 1.  The half is
+// chosen with mask arithmetic over both halves so that ONE copy of the front end serves all four rows and
+// the raw arrays still see compile-time indices only.
+template <class CT, int NC, int KW, int NV>
+__device__ __forceinline__ void row_front(const ScanPlan& P, const uint4 (&raw)[2][NC], const uint32_t (&vbits)[2][NC],
+                                          int rs, int64_t base, int lane, int64_t n_rows, RowOut<KW, NV>& o) {
+  const int j = rs & 1;
+  const uint32_t m1 = mask32((rs & 2) != 0), m0 = ~m1;
+  uint4 rsel[NC];
+  uint32_t vsel[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    if (c < CT::n_slots(P)) {
+      rsel[c].x = (raw[0][c].x & m0) | (raw[1][c].x & m1);
+      rsel[c].y = (raw[0][c].y & m0) | (raw[1][c].y & m1);
+      rsel[c].z = (raw[0][c].z & m0) | (raw[1][c].z & m1);
+      rsel[c].w = (raw[0][c].w & m0) | (raw[1][c].w & m1);
+      vsel[c] = (vbits[0][c] & m0) | (vbits[1][c] & m1);
+    } else { rsel[c] = make_uint4(0u, 0u, 0u, 0u); vsel[c] = 0u; }
+  }
+  o.row = base + (rs >> 1) * 64 + 2 * lane + j;
+  Row<NC> r;
+  row_decode<CT, NC>(P, rsel, vsel, j, r);
+  bool alive = o.row < n_rows && row_predicate<CT, NC>(P, r);
+  alive = row_keys<CT, NC, KW>(P, r, rsel, vsel, j, alive, o.k, o.sentinel_free) && alive;
+  o.alive = alive;
+  row_vexprs<CT, NC, NV>(P, r, o.v, o.v_valid);
+  o.tval = CT::dyn_enabled(P) ? pick<NC>(r.in, CT::dyn_slot(P)) : 0ull;
+}
+
+// ---- accumulator sinks ------------------------------------------------------------------------------------
+struct ColdSink {  // HBM table, atomics
+  const Table& T;
+  uint64_t slot;
+  template <int OP>
+  __device__ __forceinline__ void add(const ScanPlan&, int a, uint64_t x) const { acc_apply_global(&T.accs[(uint64_t)a * (T.cap + 2) + slot], OP, x); }
+};
+template <class CT, int KW>
+struct HotSink {  // shared-memory hot table: private cells under a claim, shared min/max words
+  const HotTable<CT, KW>& hot;
+  int id, cell;
+  template <int OP>
+  __device__ __forceinline__ void add(const ScanPlan& P, int a, uint64_t x) const {
+    const int kind = CT::h_kind(P, a);
+    if (kind == HOT_PRIV64) {
+      uint64_t* q = (uint64_t*)(hot.wbase + CT::h_off(P, a)) + cell;
+      *q = acc_combine(OP, *q, x);
+    } else if (kind == HOT_PRIV32) {
+      uint32_t* q = (uint32_t*)(hot.wbase + CT::h_off(P, a)) + cell;
+      *q += (uint32_t)x;
+    } else {
+      minmax_apply_shared(&hot.mm[(size_t)CT::h_off(P, a) * CT::h_gcap(P) + id], OP, x);
+    }
+  }
+};
+
+// one pass over the aggregate flags of every value expression; accumulator words are consecutive per
+// expression in VFlag order (host: lower_query), then LEN, ROW, TMIN
+template <class CT, int NV, int KW, class Sink>
+__device__ __forceinline__ void accumulate_row(const ScanPlan& P, const RowOut<KW, NV>& o, uint64_t grow, const Sink& s) {
+#pragma unroll
+  for (int e = 0; e < NV; ++e) {
+    if (e >= CT::n_vexpr(P)) break;
+    const int fl = CT::ve_flags(P, e), cls = CT::ve_cls(P, e);
+    int a = CT::ve_acc(P, e);
+    const uint64_t bits = o.v[e];
+    const bool ok = (o.v_valid >> e) & 1u;
+    if (fl & VF_SUM_I) { if (ok) s.template add<OP_ADD_I64>(P, a, bits); ++a; }
+    if (fl & VF_SUM_F) { if (ok) s.template add<OP_ADD_F64>(P, a, (uint64_t)__double_as_longlong(bits_to_f64(bits, cls))); ++a; }
+    if (fl & VF_COUNT) { if (ok) s.template add<OP_ADD_I64>(P, a, 1ull); ++a; }
+    if (fl & (VF_MIN | VF_MAX)) {
+      uint64_t x = bits;
+      bool use = ok;
+      if (cls == CLS_F64) {
+        const double d = __longlong_as_double((long long)bits);
+        use = ok && (d == d);  // NaN is skipped; an all-NaN group keeps the init word -> NaN at emit time
+        x = (uint64_t)f64_to_ordered(d);
+      }
+      if (fl & VF_MIN) { if (use) { if (cls == CLS_U64) s.template add<OP_MIN_U64>(P, a, x); else s.template add<OP_MIN_I64>(P, a, x); } ++a; }
+      if (fl & VF_MAX) { if (use) { if (cls == CLS_U64) s.template add<OP_MAX_U64>(P, a, x); else s.template add<OP_MAX_I64>(P, a, x); } ++a; }
+    }
+    if (fl & VF_FIRST) { s.template add<OP_MIN_U64>(P, a, (grow << 1) | (ok ? 1ull : 0ull)); ++a; }
+    if (fl & VF_LAST) { s.template add<OP_MAX_U64>(P, a, (grow << 1) | (ok ? 1ull : 0ull)); ++a; }
+  }
+  int a = CT::acc_gbase(P);
+  const int gf = CT::gflags(P);
+  if (gf & GF_LEN) { s.template add<OP_ADD_I64>(P, a, 1ull); ++a; }
+  if (gf & GF_ROW) { s.template add<OP_MIN_U64>(P, a, grow); ++a; }
+  if (gf & GF_TMIN) { s.template add<OP_MIN_I64>(P, a, o.tval); ++a; }
+}
+
+// BACK END: probe + aggregate one row per lane.  Called convergently by all 32 lanes (dead rows keep
+// `alive == false`) because the claim loop uses warp-wide votes.
+template <class CT, int KW, int NV, bool HOT>
+__device__ __forceinline__ void row_back(const ScanPlan& P, HotTable<CT, KW>& hot, const RowOut<KW, NV>& o, int lane, unsigned long long& spilled) {
+  const uint64_t h = hash_words<KW>(o.k);
+  const uint64_t grow = (uint64_t)(P.row_begin + o.row * P.row_stride + P.row_offset);
+  int id = -1;
   if (HOT) {
-    hot.bind(smem_raw, P.hot_slots, P.n_acc);
+    // rows whose raw key aliases a sentinel bypass the hot table so that a hot KEY_NULL is always a true null
+    if (o.alive && o.sentinel_free) id = hot.upsert(P, o.k, h);
+    const int R = CT::h_rep(P);
+    const int cell = id * R + (lane & (R - 1));
+    bool pending = id >= 0;
+    unsigned char* claim = hot.wbase + CT::h_claim_off(P);
+    const bool need_claim = R < 32;
+    while (__any_sync(0xffffffffu, pending)) {
+      bool win = pending;
+      if (need_claim) {
+        if (pending) claim[cell] = (unsigned char)lane;
+        __syncwarp();
+        win = pending && claim[cell] == (unsigned char)lane;
+      }
+      if (win) {
+        const HotSink<CT, KW> sink{hot, id, cell};
+        accumulate_row<CT, NV, KW>(P, o, grow, sink);
+        pending = false;
+      }
+      if (need_claim) __syncwarp();
+    }
+  }
+  if (o.alive && id < 0) {
+    // cold / spill tier: straight into the HBM table
+    const uint64_t gslot = table_upsert<KW>(P.table, o.k, h, o.sentinel_free || KW != 1);
+    if (HOT) ++spilled;
+    if (gslot != ~0ull) {
+      const ColdSink sink{P.table, gslot};
+      accumulate_row<CT, NV, KW>(P, o, grow, sink);
+    }
+  }
+}
+
+// sortedness of the dynamic index over one warp step (every adjacent row pair plus the row before the
+// step) — polars-time/src/group_by/dynamic.rs:77-80 raises when it is violated
+template <class CT, int NC>
+__device__ __forceinline__ void check_sorted_step(const ScanPlan& P, const uint4 (&raw)[2][NC], int64_t base, int lane, int64_t n_rows) {
+  int64_t carry = INT64_MIN;  // t of the row just before this half (lane 0)
+  const int tslot = CT::dyn_slot(P), tdt = CT::slot_dtype(P, tslot);
+  if (lane == 0 && base > 0) {
+    const uint4 r1 = load_pair(P.slots[tslot].values, tdt, base - 1, n_rows, false, P.row_begin, P.row_stride);
+    carry = (int64_t)decode(r1, tdt, 0);
+  }
+  bool bad = false;
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    const int64_t p = base + hf * 64 + 2 * lane;
+    const uint4 r = pick128<NC>(raw[hf], tslot);
+    const int64_t t0 = (int64_t)decode(r, tdt, 0), t1 = (int64_t)decode(r, tdt, 1);
+    int64_t prev = __shfl_up_sync(0xffffffffu, t1, 1);
+    if (lane == 0) prev = carry;
+    if (p < n_rows && t0 < prev) bad = true;
+    if (p + 1 < n_rows && t1 < t0) bad = true;
+    carry = __shfl_sync(0xffffffffu, (p + 1 < n_rows) ? t1 : ((p < n_rows) ? t0 : prev), 31);
+  }
+  if (bad) *P.not_sorted = 1;
+}
+
+// phase 1 of a warp step: issue every load (two halves x NC slots)
+template <class CT, int NC>
+__device__ __forceinline__ void load_step(const ScanPlan& P, int64_t base, int lane, int64_t n_rows, uint4 (&raw)[2][NC], uint32_t (&vbits)[2][NC]) {
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    const int64_t p = base + hf * 64 + 2 * lane;
+    const bool full = CT::vec_ok(P) && (p + 1 < n_rows);  // host clears vec_ok unless stride == 1 and row_begin is even
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if (c < CT::n_slots(P) && p < n_rows) {
+        raw[hf][c] = load_pair(P.slots[c].values, CT::slot_dtype(P, c), p, n_rows, full, P.row_begin, P.row_stride);
+        vbits[hf][c] = CT::slot_nullable(P, c) ? load_valid_pair(P.slots[c], p, n_rows, P.row_begin, P.row_stride) : 3u;
+      } else {
+        raw[hf][c] = make_uint4(0u, 0u, 0u, 0u);
+        vbits[hf][c] = 0u;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the scan kernel body: CTAs take contiguous row ranges (time-sorted inputs keep few live groups per CTA)
+// ---------------------------------------------------------------------------------------------------
+template <class CT, int NC, int KW, bool HOT>
+__device__ __forceinline__ void scan_body(const ScanPlan& P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NV = NVof<NC>::value;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int warps = blockDim.x >> 5;
+  HotTable<CT, KW> hot;
+  if (HOT) {
+    hot.bind(smem_raw, P, warp);
     hot.clear(P);
     __syncthreads();
   }
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int warps = SCAN_THREADS / 32;
   const int64_t n_rows = P.n_rows;
   const int64_t n_steps = (n_rows + ROWS_PER_STEP - 1) / ROWS_PER_STEP;
   const int64_t n_tiles = (n_steps + warps - 1) / warps;
@@ -569,70 +822,44 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const __grid_constan
     const int64_t step = tile * warps + warp;
     const int64_t base = step * ROWS_PER_STEP;
     if (step < n_steps) {
-      // ---- phase 1: issue every load of this step (two halves x NC slots) -------------------------
       uint4 raw[2][NC];
       uint32_t vbits[2][NC];
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        const int64_t p = base + hf * 64 + 2 * lane;
-        const bool full = P.vec_ok && (p + 1 < n_rows);  // host clears vec_ok unless stride == 1 and row_begin is even
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          if (c < P.n_slots && p < n_rows) {
-            raw[hf][c] = load_pair(P.slots[c], p, n_rows, full, P.row_begin, P.row_stride);
-            vbits[hf][c] = load_valid_pair(P.slots[c], p, n_rows, P.row_begin, P.row_stride);
-          } else {
-            raw[hf][c] = make_uint4(0u, 0u, 0u, 0u);
-            vbits[hf][c] = 0u;
-          }
-        }
+      load_step<CT, NC>(P, base, lane, n_rows, raw, vbits);
+      if (CT::check_sorted(P)) check_sorted_step<CT, NC>(P, raw, base, lane, n_rows);
+      // four rows per lane through ONE copy of the front end and of the probe/aggregate back end
+#pragma unroll 1
+      for (int rs = 0; rs < 4; ++rs) {
+        RowOut<KW, NV> o;
+        row_front<CT, NC, KW, NV>(P, raw, vbits, rs, base, lane, n_rows, o);
+        row_back<CT, KW, NV, HOT>(P, hot, o, lane, spilled);
       }
-      // ---- sortedness of the dynamic index (every adjacent row pair of this step, plus the row
-      //      before the step) — polars-time/src/group_by/dynamic.rs:77-80 raises when it is violated
-      if (P.check_sorted) {
-        int64_t carry = INT64_MIN;  // t of the row just before this half (lane 0)
-        if (lane == 0 && base > 0) {
-          const RawSlot& ts = P.slots[P.dyn.slot];
-          uint4 r1 = load_pair(ts, base - 1, n_rows, false, P.row_begin, P.row_stride);
-          carry = (int64_t)decode(r1, ts.dtype, 0);
-        }
-        bool bad = false;
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const int64_t p = base + hf * 64 + 2 * lane;
-          const uint4 r = pick128<NC>(raw[hf], P.dyn.slot);
-          const int dt = P.slots[P.dyn.slot].dtype;
-          const int64_t t0 = (int64_t)decode(r, dt, 0), t1 = (int64_t)decode(r, dt, 1);
-          int64_t prev = __shfl_up_sync(0xffffffffu, t1, 1);
-          if (lane == 0) prev = carry;
-          if (p < n_rows && t0 < prev) bad = true;
-          if (p + 1 < n_rows && t1 < t0) bad = true;
-          carry = __shfl_sync(0xffffffffu, (p + 1 < n_rows) ? t1 : ((p < n_rows) ? t0 : prev), 31);
-        }
-        if (bad) *P.not_sorted = 1;
-      }
-      // ---- phase 2: per row: predicate -> key -> probe -> aggregate ---------------------------------
-      process_row<NC, KW, HOT, 0, 0>(P, raw, vbits, hot, base, lane, n_rows, spilled);
-      process_row<NC, KW, HOT, 0, 1>(P, raw, vbits, hot, base, lane, n_rows, spilled);
-      process_row<NC, KW, HOT, 1, 0>(P, raw, vbits, hot, base, lane, n_rows, spilled);
-      process_row<NC, KW, HOT, 1, 1>(P, raw, vbits, hot, base, lane, n_rows, spilled);
     }
-    if (HOT) {
-      // evict everything when the hot table is getting full (time-sorted inputs drift through groups)
+    if (HOT && ((tile - tile_lo) & 3) == 3) {
       __syncthreads();
-      const bool need_flush = *(volatile uint32_t*)hot.count >= (uint32_t)(hot.S >> 1);
+      // a row found the table full since the last check: evict everything (FixedIndexTable evicts per
+      // slot; a wholesale flush keeps the per-row path free of eviction logic)
+      const bool need_flush = *(volatile uint32_t*)(hot.count + 1) != 0u;
       __syncthreads();
       if (need_flush && tile + 1 < tile_hi) {
-        hot.flush(P, true);
+        hot.flush(P);
+        __syncthreads();
+        hot.clear(P);
         __syncthreads();
       }
     }
   }
   if (HOT) {
     __syncthreads();
-    hot.flush(P, true);
+    hot.flush(P);
     if (spilled) atomicAdd(P.table.spilled, spilled);
   }
 }
+
+#ifndef __CUDACC_RTC__
+template <int NC, int KW, bool HOT>
+__global__ void __launch_bounds__(ScanCfg<NC>::THREADS, 1) scan_kernel(const __grid_constant__ ScanPlan P) {
+  scan_body<RtCtl, NC, KW, HOT>(P);
+}
+#endif
 
 }  // namespace pw

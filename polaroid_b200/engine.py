@@ -140,29 +140,96 @@ def last_timings() -> dict:
 
 
 # ---- Arrow export / import ---------------------------------------------------------------------------
+def _is_stringlike(t) -> bool:
+    return (pa.types.is_string(t) or pa.types.is_large_string(t) or pa.types.is_binary(t) or pa.types.is_large_binary(t)
+            or pa.types.is_string_view(t) or pa.types.is_binary_view(t))
+
+
 def _to_abi_array(col) -> pa.Array:
-    """One contiguous array in a format the C ABI reads: strings become Utf8View (what Polars itself
-    exports, polars-ffi/src/version_0.rs:64)."""
+    """One contiguous array.  String columns stay as they are here and are turned into Utf8View buffers
+    (what Polars itself exports, polars-ffi/src/version_0.rs:64) by ``_ViewColumn``."""
     if isinstance(col, pa.ChunkedArray):
         col = col.combine_chunks() if col.num_chunks != 1 else col.chunk(0)
-    t = col.type
-    if pa.types.is_string(t) or pa.types.is_large_string(t):
-        col = col.cast(pa.string_view())
-    elif pa.types.is_binary(t) or pa.types.is_large_binary(t):
-        col = col.cast(pa.binary_view())
     return col
 
 
+class _ViewColumn:
+    """A string/binary column laid out as Arrow Utf8View buffers [validity, views, data, variadic sizes],
+    built with numpy.  (pyarrow 24's own C export of a view array that has no data buffer segfaults, so the
+    struct is filled in by hand; the layout is the one polars-arrow/src/array/binview/view.rs:19-55 defines.)"""
+
+    def __init__(self, arr: pa.Array):
+        import numpy as np
+        t = arr.type
+        if pa.types.is_string_view(t) or pa.types.is_binary_view(t):
+            arr = arr.cast(pa.large_binary() if pa.types.is_binary_view(t) else pa.large_string())
+            t = arr.type
+        self.is_binary = pa.types.is_binary(t) or pa.types.is_large_binary(t)
+        if arr.offset != 0 or not (pa.types.is_large_string(t) or pa.types.is_large_binary(t)):
+            arr = pa.concat_arrays([arr]).cast(pa.large_binary() if self.is_binary else pa.large_string())
+            if arr.offset != 0:
+                arr = pa.array(arr.to_pylist(), type=arr.type)
+        n = len(arr)
+        bufs = arr.buffers()
+        off = np.frombuffer(bufs[1], dtype=np.int64, count=n + 1) if n else np.zeros(1, dtype=np.int64)
+        data = np.frombuffer(bufs[2], dtype=np.uint8) if bufs[2] is not None and bufs[2].size else np.zeros(1, dtype=np.uint8)
+        lens = (off[1:] - off[:-1]).astype(np.int64)
+        if arr.null_count:
+            valid = np.asarray(arr.is_valid().to_numpy(zero_copy_only=False))
+            lens = np.where(valid, lens, 0)
+            self.validity = np.packbits(valid, bitorder="little")
+        else:
+            self.validity = None
+        views = np.zeros((n, 16), dtype=np.uint8)
+        if n:
+            views[:, 0:4] = lens.astype("<u4").view(np.uint8).reshape(n, 4)
+            j = np.arange(12, dtype=np.int64)
+            idx = np.minimum(off[:-1, None] + j[None, :], max(len(data) - 1, 0))
+            inline = lens <= 12
+            take = (j[None, :] < lens[:, None]) & inline[:, None]
+            views[:, 4:16] = np.where(take, data[idx], 0)
+            longm = ~inline
+            if longm.any():
+                pre = (j[None, :4] < lens[:, None])
+                views[longm, 4:8] = np.where(pre[longm], data[idx[longm, :4]], 0)
+                views[longm, 8:12] = 0  # buffer index 0
+                views[longm, 12:16] = off[:-1][longm].astype("<u4").view(np.uint8).reshape(-1, 4)
+        self.views = np.ascontiguousarray(views)
+        self.data = np.ascontiguousarray(data)
+        self.sizes = np.array([len(self.data)], dtype=np.int64)
+        self.length = n
+        self.null_count = arr.null_count
+        self._bufs = (C.c_void_p * 4)(self.validity.ctypes.data if self.validity is not None else None,
+                                      self.views.ctypes.data, self.data.ctypes.data, self.sizes.ctypes.data)
+
+    def fill(self, c_array: "ArrowArray", c_schema: "ArrowSchema"):
+        c_array.length = self.length
+        c_array.null_count = self.null_count
+        c_array.offset = 0
+        c_array.n_buffers = 4
+        c_array.n_children = 0
+        c_array.buffers = C.cast(self._bufs, C.POINTER(C.c_void_p))
+        c_array.release = None
+        c_schema.format = b"vz" if self.is_binary else b"vu"
+        c_schema.flags = 2
+        c_schema.release = None
+
+
 class _Exported:
-    """Keeps the exported ArrowArray/ArrowSchema structs (and their pyarrow owners) alive for a call."""
+    """Keeps the exported ArrowArray/ArrowSchema structs (and their owners) alive for a call."""
 
     def __init__(self, arrays):
         n = len(arrays)
         self.arrays = arrays
         self.c_arrays = (ArrowArray * n)()
         self.c_schemas = (ArrowSchema * n)()
+        self.views = {}
         for i, a in enumerate(arrays):
-            a._export_to_c(C.addressof(self.c_arrays[i]), C.addressof(self.c_schemas[i]))
+            if _is_stringlike(a.type):
+                self.views[i] = _ViewColumn(a)
+                self.views[i].fill(self.c_arrays[i], self.c_schemas[i])
+            else:
+                a._export_to_c(C.addressof(self.c_arrays[i]), C.addressof(self.c_schemas[i]))
         self.arr_ptrs = (C.c_void_p * n)(*[C.addressof(self.c_arrays[i]) for i in range(n)])
         self.sch_ptrs = (C.c_void_p * n)(*[C.addressof(self.c_schemas[i]) for i in range(n)])
         self.n = n
@@ -179,11 +246,41 @@ class _Exported:
                     C.CFUNCTYPE(None, C.c_void_p)(st.release)(C.addressof(st))
 
 
+def _import_view_array(c_array: "ArrowArray", c_schema: "ArrowSchema") -> pa.Array:
+    """Inline-only Utf8View result (library output) -> pyarrow large_string, then release the C structs."""
+    import numpy as np
+    n = int(c_array.length)
+    binary = c_schema.format == b"vz"
+    if n:
+        views = np.ctypeslib.as_array(C.cast(c_array.buffers[1], C.POINTER(C.c_uint8)), shape=(n, 16)).copy()
+        lens = views[:, 0:4].copy().view("<u4").reshape(n).astype(np.int64)
+        valid = None
+        if c_array.null_count and c_array.buffers[0]:
+            vb = np.ctypeslib.as_array(C.cast(c_array.buffers[0], C.POINTER(C.c_uint8)), shape=((n + 7) // 8,)).copy()
+            valid = np.unpackbits(vb, bitorder="little")[:n].astype(bool)
+        take = np.arange(12)[None, :] < lens[:, None]
+        data = views[:, 4:16][take]
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        arr = pa.Array.from_buffers(pa.large_binary() if binary else pa.large_string(), n,
+                                    [None, pa.py_buffer(off.tobytes()), pa.py_buffer(data.tobytes())])
+        if valid is not None:
+            arr = pa.array(arr.to_pylist(), type=arr.type, mask=~valid) if n < 1_000_000 else pa.compute.if_else(pa.array(valid), arr, None)
+    else:
+        arr = pa.array([], type=pa.large_binary() if binary else pa.large_string())
+    for st in (c_array, c_schema):
+        if st.release:
+            C.CFUNCTYPE(None, C.c_void_p)(st.release)(C.addressof(st))
+    return arr
+
+
 def _import_columns(out_arrays, out_schemas, n) -> tuple:
     names, cols = [], []
     for i in range(n):
         name = out_schemas[i].name.decode() if out_schemas[i].name else ""
-        arr = pa.Array._import_from_c(C.addressof(out_arrays[i]), C.addressof(out_schemas[i]))
+        if out_schemas[i].format in (b"vu", b"vz"):
+            arr = _import_view_array(out_arrays[i], out_schemas[i])
+        else:
+            arr = pa.Array._import_from_c(C.addressof(out_arrays[i]), C.addressof(out_schemas[i]))
         names.append(name)
         cols.append(arr)
     return names, cols
@@ -323,7 +420,6 @@ class DeviceFrame:
         finally:
             ex.release()
         self.handle = h
-        self.abi_schema = pa.schema([pa.field(n, a.type) for n, a in zip(table.column_names, arrays)])
         self.num_rows = table.num_rows
 
     def free(self):
@@ -355,8 +451,7 @@ def _restore_string_types(names, cols, schema: pa.Schema, key_names) -> list:
     for n, c in zip(names, cols):
         if n in key_names and n in schema.names:
             t = schema.field(n).type
-            if c.type != t and (pa.types.is_string(t) or pa.types.is_large_string(t) or pa.types.is_binary(t)
-                                or pa.types.is_large_binary(t)):
+            if c.type != t and _is_stringlike(t):
                 c = c.cast(t)
         out.append(c)
     return out
