@@ -264,11 +264,29 @@ struct HotTable {
     for (int w = 0; w < KW; ++w) eq &= (*(volatile uint64_t*)&keys[(size_t)w * G + id] == k[w]);
     return eq;
   }
-  // key -> dense group id; -1 when the table is full or the probe budget is spent (row goes cold)
+  // key -> dense group id; -1 when the table is full or the probe budget is spent (row goes cold).
+  // Fast path (every row once its group exists): one LDS.128 of the bucket's four tags, a branch-free
+  // fingerprint match, one key compare.  Fingerprints live in [1, 0xFFFE] so that neither an empty (0) nor a
+  // busy (all ones) tag can match.
   __device__ __forceinline__ int upsert(const ScanPlan& P, const uint64_t (&k)[KW], uint64_t h) {
     const int S = CT::h_slots(P), G = CT::h_gcap(P);
-    const uint32_t fp = (uint32_t)(h >> 48) << 16;
+    uint32_t f16 = (uint32_t)(h >> 48);
+    f16 = f16 == 0u ? 1u : (f16 == 0xFFFFu ? 0xFFFEu : f16);
+    const uint32_t fp = f16 << 16;
     int bucket = (int)(h & (uint64_t)((S >> 2) - 1));
+    {
+      const uint4 t4 = lds128_volatile(tag + bucket * 4);
+      uint32_t cand = 0;
+      cand = ((t4.w >> 16) == f16) ? t4.w : cand;
+      cand = ((t4.z >> 16) == f16) ? t4.z : cand;
+      cand = ((t4.y >> 16) == f16) ? t4.y : cand;
+      cand = ((t4.x >> 16) == f16) ? t4.x : cand;
+      if (cand != 0u) {
+        const int id = (int)(cand & 0xFFFFu) - 1;
+        if (key_equals(P, id, k)) return id;
+      }
+    }
+    // slow path: insertion, fingerprint collisions, overflowing buckets
     int probes = 0;
     int result = -1;
     bool done = false;
@@ -618,31 +636,16 @@ __device__ __forceinline__ bool row_keys(const ScanPlan& P, const Row<NC>& r, co
   return member;
 }
 
-// FRONT END for row position rs (0..3) of this lane: half = rs >> 1, pair element = rs & 1.  The half is
-// chosen with mask arithmetic over both halves so that ONE copy of the front end serves all four rows and
-// the raw arrays still see compile-time indices only.
-template <class CT, int NC, int KW, int NV>
+// FRONT END for the row at (half HF, pair element j) of this lane.  The half is a template parameter (two
+// copies of the front end) so that the raw arrays see compile-time indices only; j stays a run-time value.
+template <class CT, int NC, int KW, int NV, int HF>
 __device__ __forceinline__ void row_front(const ScanPlan& P, const uint4 (&raw)[2][NC], const uint32_t (&vbits)[2][NC],
-                                          int rs, int64_t base, int lane, int64_t n_rows, RowOut<KW, NV>& o) {
-  const int j = rs & 1;
-  const uint32_t m1 = mask32((rs & 2) != 0), m0 = ~m1;
-  uint4 rsel[NC];
-  uint32_t vsel[NC];
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    if (c < CT::n_slots(P)) {
-      rsel[c].x = (raw[0][c].x & m0) | (raw[1][c].x & m1);
-      rsel[c].y = (raw[0][c].y & m0) | (raw[1][c].y & m1);
-      rsel[c].z = (raw[0][c].z & m0) | (raw[1][c].z & m1);
-      rsel[c].w = (raw[0][c].w & m0) | (raw[1][c].w & m1);
-      vsel[c] = (vbits[0][c] & m0) | (vbits[1][c] & m1);
-    } else { rsel[c] = make_uint4(0u, 0u, 0u, 0u); vsel[c] = 0u; }
-  }
-  o.row = base + (rs >> 1) * 64 + 2 * lane + j;
+                                          int j, int64_t base, int lane, int64_t n_rows, RowOut<KW, NV>& o) {
+  o.row = base + HF * 64 + 2 * lane + j;
   Row<NC> r;
-  row_decode<CT, NC>(P, rsel, vsel, j, r);
+  row_decode<CT, NC>(P, raw[HF], vbits[HF], j, r);
   bool alive = o.row < n_rows && row_predicate<CT, NC>(P, r);
-  alive = row_keys<CT, NC, KW>(P, r, rsel, vsel, j, alive, o.k, o.sentinel_free) && alive;
+  alive = row_keys<CT, NC, KW>(P, r, raw[HF], vbits[HF], j, alive, o.k, o.sentinel_free) && alive;
   o.alive = alive;
   row_vexprs<CT, NC, NV>(P, r, o.v, o.v_valid);
   o.tval = CT::dyn_enabled(P) ? pick<NC>(r.in, CT::dyn_slot(P)) : 0ull;
@@ -826,11 +829,17 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
       uint32_t vbits[2][NC];
       load_step<CT, NC>(P, base, lane, n_rows, raw, vbits);
       if (CT::check_sorted(P)) check_sorted_step<CT, NC>(P, raw, base, lane, n_rows);
-      // four rows per lane through ONE copy of the front end and of the probe/aggregate back end
+      // four rows per lane: the half is unrolled (compile-time raw indices), the pair element is a real loop
 #pragma unroll 1
-      for (int rs = 0; rs < 4; ++rs) {
+      for (int j = 0; j < 2; ++j) {
         RowOut<KW, NV> o;
-        row_front<CT, NC, KW, NV>(P, raw, vbits, rs, base, lane, n_rows, o);
+        row_front<CT, NC, KW, NV, 0>(P, raw, vbits, j, base, lane, n_rows, o);
+        row_back<CT, KW, NV, HOT>(P, hot, o, lane, spilled);
+      }
+#pragma unroll 1
+      for (int j = 0; j < 2; ++j) {
+        RowOut<KW, NV> o;
+        row_front<CT, NC, KW, NV, 1>(P, raw, vbits, j, base, lane, n_rows, o);
         row_back<CT, KW, NV, HOT>(P, hot, o, lane, spilled);
       }
     }
