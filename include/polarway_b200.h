@@ -230,6 +230,8 @@ typedef struct PwPartial PwPartial;
 int pw_b200_frame_groupby_partial(const PwQuery* q, const PwFrame* frame, int32_t n_parts, PwPartial** out);
 int64_t pw_b200_partial_row_bytes(const PwPartial* p);
 const void* pw_b200_partial_device_rows(const PwPartial* p);
+/* device-to-device copy of all packed rows into a caller-owned buffer (e.g. a torch tensor handed to NCCL) */
+int pw_b200_partial_copy_rows(const PwPartial* p, void* dst_device);
 int pw_b200_partial_offsets(const PwPartial* p, int64_t* part_offsets /* n_parts+1 */);
 int pw_b200_partial_free(PwPartial* p);
 /* Phase 2 on the owner: merge packed rows received from every peer (device pointer, n_rows rows of

@@ -644,6 +644,36 @@ static double solve_groups(double d, double n) {
   return hi;
 }
 
+// order the compacted group list by the plan's sort words (LSD radix passes, least significant first)
+int order_groups(const Lowered& L, const Table& T, int kw, uint32_t** slots_io, uint64_t G) {
+  ThreadCtx& c = ctx();
+  PwTimings& tm = c.timings;
+  uint32_t* slots = *slots_io;
+  if (G > 1 && !L.sort.empty()) {
+    uint64_t *k_in = nullptr, *k_out = nullptr;
+    uint32_t *v_out = nullptr;
+    void* p = nullptr;
+    PW_TRY(dev_alloc(&p, G * 8)); k_in = (uint64_t*)p;
+    PW_TRY(dev_alloc(&p, G * 8)); k_out = (uint64_t*)p;
+    PW_TRY(dev_alloc(&p, G * 4)); v_out = (uint32_t*)p;
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, slots, v_out, (int64_t)G, 0, 64, c.stream);
+    void* tmp = nullptr;
+    PW_TRY(dev_alloc(&tmp, tmp_bytes));
+    const int grid = (int)((G + 255) / 256);
+    for (const SortSpec& sp : L.sort) {  // LSD: least significant word first, every pass stable
+      sort_key_kernel<<<grid, 256, 0, c.stream>>>(T, kw, L.null_word, sp, slots, G, k_in);
+      PW_CUDA(cudaGetLastError());
+      PW_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, slots, v_out, (int64_t)G, 0, 64, c.stream));
+      std::swap(slots, v_out);
+      tm.kernel_launches += 2;
+    }
+    dev_free(tmp); dev_free(k_in); dev_free(k_out); dev_free(v_out);
+  }
+  *slots_io = slots;
+  return 0;
+}
+
 int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out, uint32_t** slot_list_out, uint64_t* n_groups_out) {
   ThreadCtx& c = ctx();
   ScanPlan& P = L.plan;
@@ -741,27 +771,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
   const uint64_t G = hctl.counter;
   tm.n_groups = (int64_t)G;
 
-  if (G > 1 && !L.sort.empty()) {
-    uint64_t *k_in = nullptr, *k_out = nullptr;
-    uint32_t *v_out = nullptr;
-    void* p = nullptr;
-    PW_TRY(dev_alloc(&p, G * 8)); k_in = (uint64_t*)p;
-    PW_TRY(dev_alloc(&p, G * 8)); k_out = (uint64_t*)p;
-    PW_TRY(dev_alloc(&p, G * 4)); v_out = (uint32_t*)p;
-    size_t tmp_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, slots, v_out, (int64_t)G, 0, 64, c.stream);
-    void* tmp = nullptr;
-    PW_TRY(dev_alloc(&tmp, tmp_bytes));
-    const int grid = (int)((G + 255) / 256);
-    for (const SortSpec& sp : L.sort) {  // LSD: least significant word first, every pass stable
-      sort_key_kernel<<<grid, 256, 0, c.stream>>>(T, padded_kw(P.n_kw), L.null_word, sp, slots, G, k_in);
-      PW_CUDA(cudaGetLastError());
-      PW_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, slots, v_out, (int64_t)G, 0, 64, c.stream));
-      std::swap(slots, v_out);
-      tm.kernel_launches += 2;
-    }
-    dev_free(tmp); dev_free(k_in); dev_free(k_out); dev_free(v_out);
-  }
+  PW_TRY(order_groups(L, T, padded_kw(P.n_kw), &slots, G));
   dev_free(dctl);
   *table_out = T;
   *slot_list_out = slots;

@@ -89,6 +89,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
 int emit_results(const Lowered& L, const Table& T, const uint32_t* slot_list, uint64_t n_groups,
                  struct ArrowArray* out_cols, struct ArrowSchema* out_schemas, size_t* n_out);
 void free_table(Table& T);
+int order_groups(const Lowered& L, const Table& T, int kw, uint32_t** slots_io, uint64_t G);
 
 // segmented (sorted-run) dynamic path, pw_segmented.cu
 int run_dynamic_segmented(const PwQuery* q, const PwFrame* f, struct ArrowArray* out_cols, struct ArrowSchema* out_schemas,

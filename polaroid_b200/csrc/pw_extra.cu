@@ -2,13 +2,6 @@
 #include "pw_engine.h"
 using namespace pw;
 
-namespace pw {
-int run_dynamic_segmented(const PwQuery*, const PwFrame*, struct ArrowArray*, struct ArrowSchema*, size_t*, bool* handled) {
-  *handled = false;
-  return 0;
-}
-}  // namespace pw
-
 extern "C" {
 int pw_b200_filter(const PwPredicate*, int32_t, const struct ArrowArray* const*, const struct ArrowSchema* const*, size_t,
                    struct ArrowArray*, struct ArrowSchema*) { return fail(PW_ERR_UNSUPPORTED, "pw_b200_filter: not built yet"); }
@@ -16,13 +9,6 @@ int pw_b200_frame_filter_select(const PwPredicate*, int32_t, const PwFrame*, str
   return fail(PW_ERR_UNSUPPORTED, "pw_b200_frame_filter_select: not built yet"); }
 int pw_b200_frame_group_tuples(const PwFrame*, const int32_t*, int32_t, int32_t, struct ArrowArray*, struct ArrowArray*,
                                struct ArrowArray*, struct ArrowSchema*) { return fail(PW_ERR_UNSUPPORTED, "pw_b200_frame_group_tuples: not built yet"); }
-int pw_b200_frame_groupby_partial(const PwQuery*, const PwFrame*, int32_t, PwPartial**) { return fail(PW_ERR_UNSUPPORTED, "partial: not built yet"); }
-int64_t pw_b200_partial_row_bytes(const PwPartial*) { return -1; }
-const void* pw_b200_partial_device_rows(const PwPartial*) { return nullptr; }
-int pw_b200_partial_offsets(const PwPartial*, int64_t*) { return fail(PW_ERR_UNSUPPORTED, "partial: not built yet"); }
-int pw_b200_partial_free(PwPartial*) { return 0; }
-int pw_b200_merge_partials(const PwQuery*, const PwFrame*, const void*, int64_t, struct ArrowArray*, struct ArrowSchema*, size_t*) {
-  return fail(PW_ERR_UNSUPPORTED, "merge: not built yet"); }
 uint32_t _polars_plugin_get_version(void) { return (0u << 16) | 1u; }
 const char* _polars_plugin_get_last_error_message(void) { return pw_b200_last_error(); }
 void _polars_plugin_filter_groupby_agg(const SeriesExport*, size_t, const uint8_t*, size_t, SeriesExport* rv, const CallerContext*) {

@@ -118,6 +118,7 @@ struct EmitDesc {
   int32_t src_cls;        // class of the aggregated values (mean of u64 etc.)
   int32_t pad;
   RawSlot src;            // FIRST/LAST gather source
+  const uint64_t* fl_values;  // FIRST/LAST after a multi-GPU merge: value bits per table slot (else nullptr)
   int64_t row_offset;
   int64_t every, period, origin;
   void* out_values;
@@ -197,8 +198,11 @@ static __global__ void emit_kernel(Table T, int n_kw, EmitDesc d, const uint32_t
         const int64_t row = (int64_t)(packed >> 1) - d.row_offset;
         uint64_t b = 0;
         if (valid) {
-          uint4 r = load_pair(d.src, row, row + 1, false);  // scalar path, row only
-          b = decode(r, d.src.dtype, 0);
+          if (d.fl_values) b = d.fl_values[slot];
+          else {
+            uint4 r = load_pair(d.src, row, row + 1, false);  // scalar path, row only
+            b = decode(r, d.src.dtype, 0);
+          }
         }
         store_typed(d.out_values, i, d.out_dtype, b);
         break; }

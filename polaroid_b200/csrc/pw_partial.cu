@@ -1,0 +1,263 @@
+// pw_partial.cu — multi-GPU partial aggregates.
+//
+// Rows are sharded contiguously over the GPUs of one box.  Phase 1 (every GPU): the ordinary fused scan
+// builds the local aggregate table; it is exported as fixed-width packed rows
+//     [flags][key words][accumulator words][first/last value words]
+// counting-sorted by owner = (mix(hash(key)) * n_parts) >> 64 — the same multiply-shift routing as the
+// reference's HashPartitioner (polars-utils/src/hashing.rs:100-109).  The host side exchanges the slices with
+// one NCCL all-to-all (polaroid_b200/multigpu.py).  Phase 2 (owner): packed rows are merged into a fresh table
+// with the accumulators' own associative ops — GroupedReduction::combine semantics
+// (polars-expr/src/reduce/mod.rs:94-105): sums add, min/max/first/last keep the better (row-index, value) pair —
+// and finalised by the same emit kernels.
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "pw_engine.h"
+#include "pw_scan.cuh"
+
+struct PwPartial {
+  void* rows = nullptr;
+  int64_t row_words = 0;
+  int64_t n_rows = 0;
+  std::vector<int64_t> offsets;  // n_parts + 1
+};
+
+namespace pw {
+
+struct PackLayout {
+  int32_t kw, n_acc, n_fl;
+  int32_t fl_acc[MAX_ACC];  // accumulator index of each first/last word
+  RawSlot fl_src[MAX_ACC];  // its source column (phase 1 gather)
+  int32_t row_words;        // 1 + kw + n_acc + n_fl
+};
+
+static PackLayout make_layout(const Lowered& L, int kw) {
+  PackLayout pl{};
+  pl.kw = kw; pl.n_acc = L.plan.n_acc;
+  for (int a = 0; a < L.plan.n_acc; ++a)
+    if (L.plan.accs[a].src == SRC_ROWIDX) {
+      pl.fl_acc[pl.n_fl] = a;
+      pl.fl_src[pl.n_fl] = L.plan.slots[L.plan.vexprs[L.plan.accs[a].vexpr].slot];
+      pl.n_fl++;
+    }
+  pl.row_words = 1 + pl.kw + pl.n_acc + pl.n_fl;
+  return pl;
+}
+
+__device__ __forceinline__ uint32_t owner_of(const uint64_t* k, int kw, int n_parts) {
+  uint64_t h = mix64(k[0]);
+  for (int w = 1; w < kw; ++w) h = mix64(h ^ (k[w] + 0x9E3779B97F4A7C15ull * (uint64_t)w));
+  return (uint32_t)__umul64hi(mix64(h ^ 0x5851F42D4C957F2Dull), (uint64_t)n_parts);
+}
+
+// pass 1: owner histogram; pass 2: scatter packed rows
+static __global__ void export_kernel(Table T, PackLayout pl, const uint32_t* slot_list, uint64_t n, int n_parts, int64_t row_offset,
+                                     unsigned long long* part_count, const unsigned long long* part_base, uint64_t* rows, int pass) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t slot = slot_list[i];
+  const uint64_t stride = T.cap + 2;
+  uint64_t k[MAX_KW];
+  for (int w = 0; w < pl.kw; ++w) k[w] = T.keys[(uint64_t)w * stride + slot];
+  const uint32_t owner = owner_of(k, pl.kw, n_parts);
+  if (pass == 0) { atomicAdd(&part_count[owner], 1ull); return; }
+  const unsigned long long pos = part_base[owner] + atomicAdd(&part_count[owner], 1ull);
+  uint64_t* r = rows + pos * (uint64_t)pl.row_words;
+  r[0] = (pl.kw == 1 && slot >= T.cap) ? 1ull : 0ull;  // escape slot: the key word is raw data that aliases a sentinel
+  for (int w = 0; w < pl.kw; ++w) r[1 + w] = k[w];
+  for (int a = 0; a < pl.n_acc; ++a) r[1 + pl.kw + a] = T.accs[(uint64_t)a * stride + slot];
+  for (int f = 0; f < pl.n_fl; ++f) {
+    const uint64_t packed = T.accs[(uint64_t)pl.fl_acc[f] * stride + slot];
+    uint64_t bits = 0;
+    if (packed & 1ull) {
+      const int64_t row = (int64_t)(packed >> 1) - row_offset;
+      bits = decode(load_pair(pl.fl_src[f].values, pl.fl_src[f].dtype, row, row + 1, false), pl.fl_src[f].dtype, 0);
+    }
+    r[1 + pl.kw + pl.n_acc + f] = bits;
+  }
+}
+
+struct AccOpsK { int32_t n; int32_t op[MAX_ACC]; };
+
+template <int KW>
+static __global__ void merge_kernel(Table T, PackLayout pl, AccOpsK ops, const uint64_t* rows, uint64_t n, uint32_t* row_slot) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t* r = rows + i * (uint64_t)pl.row_words;
+  uint64_t k[KW];
+#pragma unroll
+  for (int w = 0; w < KW; ++w) k[w] = w < pl.kw ? r[1 + w] : 0ull;
+  const uint64_t slot = table_upsert<KW>(T, k, hash_words<KW>(k), r[0] == 0ull);
+  row_slot[i] = slot == ~0ull ? 0xFFFFFFFFu : (uint32_t)slot;
+  if (slot == ~0ull) return;
+  const uint64_t stride = T.cap + 2;
+  for (int a = 0; a < pl.n_acc; ++a) {
+    const uint64_t v = r[1 + pl.kw + a];
+    if (v != acc_init(ops.op[a])) acc_apply_global(&T.accs[(uint64_t)a * stride + slot], ops.op[a], v);
+  }
+}
+
+// second phase of first/last: the row whose packed index won the merge publishes its value word
+static __global__ void merge_values_kernel(Table T, PackLayout pl, const uint64_t* rows, uint64_t n, const uint32_t* row_slot, uint64_t* fl_values) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t slot = row_slot[i];
+  if (slot == 0xFFFFFFFFu) return;
+  const uint64_t* r = rows + i * (uint64_t)pl.row_words;
+  const uint64_t stride = T.cap + 2;
+  for (int f = 0; f < pl.n_fl; ++f) {
+    const uint64_t mine = r[1 + pl.kw + pl.fl_acc[f]];
+    if (T.accs[(uint64_t)pl.fl_acc[f] * stride + slot] == mine) fl_values[(uint64_t)f * stride + slot] = r[1 + pl.kw + pl.n_acc + f];
+  }
+}
+
+static int kw_class(int n_kw) { return n_kw <= 1 ? 1 : (n_kw <= 2 ? 2 : (n_kw <= 4 ? 4 : 6)); }
+
+}  // namespace pw
+
+using namespace pw;
+
+extern "C" {
+
+int pw_b200_frame_groupby_partial(const PwQuery* q, const PwFrame* frame, int32_t n_parts, PwPartial** out) {
+  PW_TRY(ensure_device());
+  if (!q || !frame || !out || n_parts < 1) return fail(PW_ERR_INVALID, "bad argument");
+  ThreadCtx& c = ctx();
+  memset(&c.timings, 0, sizeof c.timings);
+  PW_CUDA(cudaEventRecord(c.ev[0], c.stream));
+  Lowered L;
+  PW_TRY(lower_query(q, frame, &L));
+  if (q->dynamic && !L.tumbling) return fail(PW_ERR_UNSUPPORTED, "overlapping windows are not shardable by row range");
+  L.sort.clear();  // ordering happens after the merge
+  Table T{};
+  uint32_t* slots = nullptr;
+  uint64_t G = 0;
+  PW_TRY(run_groupby(q, frame, L, &T, &slots, &G));
+  const int kw = kw_class(L.plan.n_kw);
+  PackLayout pl = make_layout(L, kw);
+  PwPartial* p = new PwPartial();
+  p->row_words = pl.row_words; p->n_rows = (int64_t)G; p->offsets.assign(n_parts + 1, 0);
+  unsigned long long *d_count = nullptr, *d_base = nullptr;
+  void* v = nullptr;
+  PW_TRY(dev_alloc(&v, (size_t)n_parts * 8)); d_count = (unsigned long long*)v;
+  PW_TRY(dev_alloc(&v, (size_t)n_parts * 8)); d_base = (unsigned long long*)v;
+  PW_TRY(dev_alloc(&v, std::max<uint64_t>(G, 1) * pl.row_words * 8)); p->rows = v;
+  PW_CUDA(cudaMemsetAsync(d_count, 0, (size_t)n_parts * 8, c.stream));
+  std::vector<unsigned long long> h_count(n_parts, 0), h_base(n_parts, 0);
+  if (G) {
+    const int grid = (int)((G + 255) / 256);
+    export_kernel<<<grid, 256, 0, c.stream>>>(T, pl, slots, G, n_parts, q->row_offset, d_count, d_base, (uint64_t*)p->rows, 0);
+    PW_CUDA(cudaGetLastError());
+    PW_CUDA(cudaMemcpyAsync(h_count.data(), d_count, (size_t)n_parts * 8, cudaMemcpyDeviceToHost, c.stream));
+    PW_CUDA(cudaStreamSynchronize(c.stream));
+    for (int i = 0; i < n_parts; ++i) { p->offsets[i + 1] = p->offsets[i] + (int64_t)h_count[i]; h_base[i] = (unsigned long long)p->offsets[i]; }
+    PW_CUDA(cudaMemcpyAsync(d_base, h_base.data(), (size_t)n_parts * 8, cudaMemcpyHostToDevice, c.stream));
+    PW_CUDA(cudaMemsetAsync(d_count, 0, (size_t)n_parts * 8, c.stream));
+    export_kernel<<<grid, 256, 0, c.stream>>>(T, pl, slots, G, n_parts, q->row_offset, d_count, d_base, (uint64_t*)p->rows, 1);
+    PW_CUDA(cudaGetLastError());
+    c.timings.kernel_launches += 2;
+  }
+  PW_CUDA(cudaEventRecord(c.ev[5], c.stream));
+  PW_CUDA(cudaStreamSynchronize(c.stream));
+  float ms;
+  if (cudaEventElapsedTime(&ms, c.ev[0], c.ev[5]) == cudaSuccess) c.timings.total_device_ms = ms;
+  if (cudaEventElapsedTime(&ms, c.ev[8], c.ev[9]) == cudaSuccess) c.timings.scan_kernel_ms = ms;
+  dev_free(d_count); dev_free(d_base); dev_free(slots);
+  free_table(T);
+  *out = p;
+  return 0;
+}
+
+int64_t pw_b200_partial_row_bytes(const PwPartial* p) { return p ? p->row_words * 8 : -1; }
+const void* pw_b200_partial_device_rows(const PwPartial* p) { return p ? p->rows : nullptr; }
+int pw_b200_partial_copy_rows(const PwPartial* p, void* dst_device) {
+  if (!p || !dst_device) return fail(PW_ERR_INVALID, "null argument");
+  if (p->n_rows) PW_CUDA(cudaMemcpyAsync(dst_device, p->rows, (size_t)p->n_rows * p->row_words * 8, cudaMemcpyDeviceToDevice, ctx().stream));
+  PW_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+int pw_b200_partial_offsets(const PwPartial* p, int64_t* part_offsets) {
+  if (!p || !part_offsets) return fail(PW_ERR_INVALID, "null argument");
+  for (size_t i = 0; i < p->offsets.size(); ++i) part_offsets[i] = p->offsets[i];
+  return 0;
+}
+int pw_b200_partial_free(PwPartial* p) {
+  if (!p) return 0;
+  dev_free(p->rows);
+  delete p;
+  return 0;
+}
+
+int pw_b200_merge_partials(const PwQuery* q, const PwFrame* schema_from, const void* device_rows, int64_t n_rows,
+                           struct ArrowArray* out_cols, struct ArrowSchema* out_schemas, size_t* n_out) {
+  PW_TRY(ensure_device());
+  if (!q || !schema_from || !out_cols || !out_schemas || !n_out || n_rows < 0) return fail(PW_ERR_INVALID, "bad argument");
+  ThreadCtx& c = ctx();
+  Lowered L;
+  PW_TRY(lower_query(q, schema_from, &L));
+  const int kw = kw_class(L.plan.n_kw);
+  PackLayout pl = make_layout(L, kw);
+  struct Ctl { int32_t overflow; int32_t pad; unsigned long long spilled; unsigned long long counter; } hctl{};
+  Ctl* dctl = nullptr;
+  void* v = nullptr;
+  PW_TRY(dev_alloc(&v, sizeof(Ctl))); dctl = (Ctl*)v;
+  PW_CUDA(cudaMemsetAsync(dctl, 0, sizeof(Ctl), c.stream));
+  Table T{};
+  const uint64_t cap = (uint64_t)std::max<int64_t>(2 * n_rows, 64);
+  const uint64_t nn = cap + 2;
+  PW_TRY(dev_alloc(&v, nn * 8 * (uint64_t)kw)); T.keys = (uint64_t*)v;
+  PW_TRY(dev_alloc(&v, nn * 4)); T.state = (uint32_t*)v;
+  PW_TRY(dev_alloc(&v, nn * 8 * (uint64_t)std::max(1, L.plan.n_acc))); T.accs = (uint64_t*)v;
+  T.cap = cap; T.overflow = &dctl->overflow; T.spilled = &dctl->spilled;
+  AccOps ops{};
+  AccOpsK opsk{};
+  ops.n = opsk.n = L.plan.n_acc;
+  for (int a = 0; a < L.plan.n_acc; ++a) ops.op[a] = opsk.op[a] = L.plan.accs[a].op;
+  table_init_kernel<<<(int)std::min<uint64_t>((nn + 255) / 256, 148 * 8), 256, 0, c.stream>>>(T, kw, ops);
+  PW_CUDA(cudaGetLastError());
+  uint32_t* row_slot = nullptr;
+  uint64_t* fl_values = nullptr;
+  PW_TRY(dev_alloc(&v, (size_t)std::max<int64_t>(n_rows, 1) * 4)); row_slot = (uint32_t*)v;
+  PW_TRY(dev_alloc(&v, nn * 8 * (uint64_t)std::max(1, pl.n_fl))); fl_values = (uint64_t*)v;
+  if (n_rows) {
+    const int grid = (int)((n_rows + 255) / 256);
+    const uint64_t* rows = (const uint64_t*)device_rows;
+    switch (kw) {
+      case 1: merge_kernel<1><<<grid, 256, 0, c.stream>>>(T, pl, opsk, rows, (uint64_t)n_rows, row_slot); break;
+      case 2: merge_kernel<2><<<grid, 256, 0, c.stream>>>(T, pl, opsk, rows, (uint64_t)n_rows, row_slot); break;
+      case 4: merge_kernel<4><<<grid, 256, 0, c.stream>>>(T, pl, opsk, rows, (uint64_t)n_rows, row_slot); break;
+      default: merge_kernel<6><<<grid, 256, 0, c.stream>>>(T, pl, opsk, rows, (uint64_t)n_rows, row_slot); break;
+    }
+    PW_CUDA(cudaGetLastError());
+    if (pl.n_fl) {
+      merge_values_kernel<<<grid, 256, 0, c.stream>>>(T, pl, rows, (uint64_t)n_rows, row_slot, fl_values);
+      PW_CUDA(cudaGetLastError());
+    }
+    c.timings.kernel_launches += 3;
+  }
+  // compact + order + emit (first/last values come from fl_values instead of a column gather)
+  uint32_t* slots = nullptr;
+  PW_TRY(dev_alloc(&v, nn * 4)); slots = (uint32_t*)v;
+  compact_kernel<<<(int)std::min<uint64_t>((nn + 255) / 256, 148 * 8), 256, 0, c.stream>>>(T, kw, slots, &dctl->counter);
+  PW_CUDA(cudaGetLastError());
+  PW_CUDA(cudaMemcpyAsync(&hctl, dctl, sizeof(Ctl), cudaMemcpyDeviceToHost, c.stream));
+  PW_CUDA(cudaStreamSynchronize(c.stream));
+  if (hctl.overflow) { return fail(PW_ERR_INTERNAL, "merge table overflow"); }
+  const uint64_t G = hctl.counter;
+  PW_TRY(order_groups(L, T, kw, &slots, G));
+  int f_idx = 0;
+  for (OutCol& o : L.outs)
+    if (o.emit.kind == EMIT_FIRSTLAST) {
+      for (int f = 0; f < pl.n_fl; ++f) if (pl.fl_acc[f] == o.emit.acc) f_idx = f;
+      o.emit.fl_values = fl_values + (uint64_t)f_idx * nn;
+    }
+  int rc = emit_results(L, T, slots, G, out_cols, out_schemas, n_out);
+  dev_free(slots); dev_free(row_slot); dev_free(fl_values); dev_free(dctl);
+  free_table(T);
+  return rc;
+}
+
+}  // extern "C"

@@ -15,6 +15,7 @@ STRATEGIES = {
     "hot_tiny": {"flags": engine.FLAG_FORCE_HOT, "hot_table_slots": 16},   # forces evictions + spill tier
     "global": {"flags": engine.FLAG_FORCE_GLOBAL},
     "global_tiny": {"flags": engine.FLAG_FORCE_GLOBAL, "initial_table_slots": 4},  # forces table growth retries
+    "hash_dynamic": {"flags": engine.FLAG_NO_SEGMENTED},  # keys-less tumbling windows through the hash path
 }
 
 
