@@ -463,6 +463,14 @@ int lower_query(const PwQuery* q, const PwFrame* f, Lowered* L) {
 // ------------------------------------------------------------------------------------------------------
 
 // the narrow kernel class holds <= 4 raw slots and <= 2 value expressions in registers
+static bool narrow_class(const ScanPlan& P);
+// ahead-of-time kernels only (the group_tuples lookup pass carries per-call pointers that must not enter the JIT key)
+int launch_scan_aot(ScanPlan P, int sm, cudaStream_t st) {
+  if (P.n_kw == 3) P.n_kw = 4;
+  if (P.n_kw == 5) P.n_kw = 6;
+  if (narrow_class(P)) return launch_scan_nc4(P, sm, st);
+  return launch_scan_nc12(P, sm, st);
+}
 static bool narrow_class(const ScanPlan& P) { return P.n_slots <= 4 && P.n_vexpr <= NVof<4>::value; }
 static int launch_scan(ScanPlan P, int sm, cudaStream_t st) {
   // the kernel is compiled for a few (slots, key words) classes; round the key width up (extra words are 0)

@@ -80,6 +80,7 @@ int launch_scan_nc4(const ScanPlan& P, int sm, cudaStream_t st);
 int launch_scan_nc12(const ScanPlan& P, int sm, cudaStream_t st);
 int launch_scan_jit(const ScanPlan& P, int nc, int kw, bool hot, int threads, int sm_count, cudaStream_t st);
 int jit_selftest_compile(const ScanPlan& P, int nc, int kw, bool hot, int threads, std::string* err);
+int launch_scan_aot(ScanPlan P, int sm, cudaStream_t st);
 int ensure_device();
 int dev_alloc(void** p, size_t bytes);
 void dev_free(void* p);

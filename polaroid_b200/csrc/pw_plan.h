@@ -150,6 +150,9 @@ struct ScanPlan {
   Dyn dyn;
   Table table;
   int32_t* not_sorted;     // device flag
+  // group_tuples second pass (GroupsIdx construction): look every row's group up and record its rank
+  uint32_t* row_group_out; // [n_rows] or nullptr
+  const uint32_t* slot_rank; // [cap + 2] rank of every occupied slot in the ordered group list
   HotGeom hot;
 };
 

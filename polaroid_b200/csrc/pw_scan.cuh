@@ -747,10 +747,13 @@ __device__ __forceinline__ void row_back(const ScanPlan& P, HotTable<CT, KW>& ho
     const uint64_t gslot = table_upsert<KW>(P.table, o.k, h, o.sentinel_free || KW != 1);
     if (HOT) ++spilled;
     if (gslot != ~0ull) {
-      const ColdSink sink{P.table, gslot};
-      accumulate_row<CT, NV, KW>(P, o, grow, sink);
+      if (P.row_group_out) P.row_group_out[o.row] = P.slot_rank[gslot];  // lookup pass of group_tuples
+      else {
+        const ColdSink sink{P.table, gslot};
+        accumulate_row<CT, NV, KW>(P, o, grow, sink);
+      }
     }
-  }
+  } else if (!o.alive && P.row_group_out && o.row < P.n_rows) P.row_group_out[o.row] = 0xFFFFFFFFu;
 }
 
 // sortedness of the dynamic index over one warp step (every adjacent row pair plus the row before the

@@ -121,6 +121,7 @@ def lib():
         L.pw_b200_partial_device_rows.restype = C.c_void_p
         L.pw_b200_partial_device_rows.argtypes = [C.c_void_p]
         L.pw_b200_partial_offsets.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.pw_b200_partial_copy_rows.argtypes = [C.c_void_p, C.c_void_p]
         L.pw_b200_partial_free.argtypes = [C.c_void_p]
         L.pw_b200_merge_partials.argtypes = [C.POINTER(PwQuery), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                              C.POINTER(C.c_size_t)]
@@ -520,3 +521,34 @@ def run_filter(table: pa.Table, preds) -> pa.Table:
     names, cols = _import_columns(out_arrays, out_schemas, n)
     cols = _restore_string_types(names, cols, table.schema, table.column_names)
     return pa.Table.from_arrays(cols, names=names)
+
+
+def filter_select(table: pa.Table, preds) -> "pa.Array":
+    """predicate -> compacted selection vector (ascending UInt32 row ids): ``pw_b200_frame_filter_select``."""
+    L = lib()
+    frame = DeviceFrame(table)
+    try:
+        plan = P.GroupByPlan(predicates=list(preds))
+        bq = _BuiltQuery(table.schema, plan)
+        oa, os_ = (ArrowArray * 1)(), (ArrowSchema * 1)()
+        n_sel = C.c_int64(0)
+        _check(L.pw_b200_frame_filter_select(bq.preds, len(preds), frame.handle, oa, os_, C.byref(n_sel)))
+        _, cols = _import_columns(oa, os_, 1)
+        return cols[0]
+    finally:
+        frame.free()
+
+
+def group_tuples(table: pa.Table, keys, maintain_order: bool = True):
+    """GroupsIdx: (first[g], offsets[g+1], row_ids) — ``pw_b200_frame_group_tuples``."""
+    L = lib()
+    frame = DeviceFrame(table)
+    try:
+        kc = (C.c_int32 * max(1, len(keys)))(*[table.column_names.index(k) for k in keys])
+        oa, os_ = (ArrowArray * 3)(), (ArrowSchema * 3)()
+        _check(L.pw_b200_frame_group_tuples(frame.handle, kc, len(keys), int(maintain_order), C.byref(oa[0]), C.byref(oa[1]),
+                                            C.byref(oa[2]), os_))
+        _, cols = _import_columns(oa, os_, 3)
+        return cols[0], cols[1], cols[2]
+    finally:
+        frame.free()

@@ -1,0 +1,78 @@
+"""Rows sharded over the GPUs of one box: local partial aggregates -> key-hash all-to-all -> merge.
+
+One process per GPU (torchrun); ``torch.distributed`` (NCCL over NVLink/NVSwitch) is only the plumbing for the
+single exchange step this path has:
+
+    phase 1  every rank:  pw_b200_frame_groupby_partial   local fused scan -> packed partial rows, counting-sorted
+                                                          by owner = hash(key) -> rank (HashPartitioner semantics,
+                                                          polars-utils/src/hashing.rs:100-109)
+    exchange              one all_to_all of row counts + one all_to_all_single of the packed rows
+    phase 2  every rank:  pw_b200_merge_partials          combine rows of equal keys (GroupedReduction::combine,
+                                                          polars-expr/src/reduce/mod.rs:94-105) and finalise
+
+Every rank ends up with the groups it owns; the full result is the concatenation over ranks, exactly like the
+reference's per-partition DataFrames (polars-stream/src/nodes/group_by.rs:554-563).
+
+``exchange_rows`` is backend-agnostic (works on CPU tensors with gloo) so that the routing logic is covered by the
+world_size-2 CPU tests.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List
+
+import torch
+import torch.distributed as dist
+
+
+def exchange_counts(send_counts: List[int], device) -> List[int]:
+    """all-to-all of one int64 per peer: how many rows every peer will send me."""
+    world = dist.get_world_size()
+    send = torch.tensor(send_counts, dtype=torch.int64, device=device)
+    recv = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_to_all_single(recv, send)
+    return [int(x) for x in recv.tolist()]
+
+
+def exchange_rows(rows: torch.Tensor, send_counts: List[int], row_words: int) -> torch.Tensor:
+    """rows: flat int64 tensor of packed rows already grouped by destination rank (send_counts[r] rows for rank r).
+    Returns the rows this rank receives (flat int64), in source-rank order."""
+    recv_counts = exchange_counts(send_counts, rows.device)
+    in_split = [c * row_words for c in send_counts]
+    out_split = [c * row_words for c in recv_counts]
+    recv = torch.empty(sum(out_split), dtype=rows.dtype, device=rows.device)
+    dist.all_to_all_single(recv, rows, output_split_sizes=out_split, input_split_sizes=in_split)
+    return recv
+
+
+def group_by_sharded(frame, plan, rank: int, world: int, row_offset: int = 0, **opts):
+    """frame: engine.DeviceFrame holding this rank's shard.  Returns the pyarrow Table of the groups this rank owns."""
+    import pyarrow as pa
+    from . import engine
+    L = engine.lib()
+    bq = engine._BuiltQuery(frame.table_schema, plan, row_offset=row_offset, **opts)
+    part = C.c_void_p()
+    engine._check(L.pw_b200_frame_groupby_partial(C.byref(bq.q), frame.handle, world, C.byref(part)))
+    try:
+        row_words = L.pw_b200_partial_row_bytes(part) // 8
+        offs = (C.c_int64 * (world + 1))()
+        engine._check(L.pw_b200_partial_offsets(part, offs))
+        counts = [offs[i + 1] - offs[i] for i in range(world)]
+        n_rows = offs[world]
+        dev = torch.device("cuda", torch.cuda.current_device())
+        send = torch.empty(max(1, n_rows * row_words), dtype=torch.int64, device=dev)
+        engine._check(L.pw_b200_partial_copy_rows(part, C.c_void_p(send.data_ptr())))
+    finally:
+        L.pw_b200_partial_free(part)
+    recv = exchange_rows(send[: n_rows * row_words], counts, row_words)
+    torch.cuda.synchronize()
+    n_recv = recv.numel() // row_words
+    cap = len(plan.keys) + len(plan.aggs) + 4
+    out_arrays = (engine.ArrowArray * cap)()
+    out_schemas = (engine.ArrowSchema * cap)()
+    n_out = C.c_size_t(cap)
+    engine._check(L.pw_b200_merge_partials(C.byref(bq.q), frame.handle, C.c_void_p(recv.data_ptr() if n_recv else 0), n_recv,
+                                           out_arrays, out_schemas, C.byref(n_out)))
+    names, cols = engine._import_columns(out_arrays, out_schemas, n_out.value)
+    cols = engine._restore_string_types(names, cols, frame.table_schema, plan.keys)
+    return pa.Table.from_arrays(cols, names=names)

@@ -1,0 +1,52 @@
+"""group_by_dynamic on the GPU vs the oracle's literal restatement of the reference's window sweep (C4 shapes)."""
+import numpy as np
+import pyarrow as pa
+import pytest
+
+import polaroid_b200 as pw
+from oracle import oracle
+from polaroid_b200 import engine
+from tests import golden_util as G
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("by_symbol", [True, False])
+@pytest.mark.parametrize("n", [1, 1000, 250_000])
+def test_ohlcv_one_minute_bars(n, by_symbol):
+    t = synth.ohlcv(n, n_symbols=17, seed=4, mean_gap_us=200_000)
+    q = synth.ohlcv_query(t, by_symbol=by_symbol)
+    got = engine.run_group_by(q.table, q.plan)
+    G.assert_tables_equal(got, oracle.collect(q), rtol=1e-12)   # row order included: keys ascending, windows ascending
+
+
+@pytest.mark.parametrize("closed", ["left", "right", "both", "none"])
+@pytest.mark.parametrize("every,period,offset", [("1m", None, None), ("1m", "3m", None), ("2m", "1m", "30s"), ("1m", "1m", "-90s")])
+def test_window_shapes_no_keys(closed, every, period, offset):
+    t = synth.ohlcv(60_000, n_symbols=3, seed=8, mean_gap_us=90_000)
+    c = pw.col
+    q = (pw.LazyFrame(t).group_by_dynamic("ts", every=every, period=period, offset=offset, closed=closed, include_boundaries=True)
+         .agg(c("price").first().alias("open"), c("price").max().alias("high"), c("price").min().alias("low"),
+              c("price").last().alias("close"), c("volume").sum().alias("volume"), c("price").mean().alias("vwap_ish"),
+              pw.len().alias("n")))
+    got = engine.run_group_by(q.table, q.plan)
+    G.assert_tables_equal(got, oracle.collect(q), rtol=1e-12)
+
+
+@pytest.mark.parametrize("opts", [{}, {"flags": engine.FLAG_NO_SEGMENTED}, {"flags": engine.FLAG_NO_SEGMENTED | engine.FLAG_FORCE_HOT, "hot_table_slots": 16}])
+def test_tumbling_hash_and_segmented_agree(opts):
+    t = synth.ohlcv(120_000, n_symbols=5, seed=9, mean_gap_us=50_000)
+    q = synth.ohlcv_query(t, by_symbol=False, every="10s")
+    got = engine.run_group_by(q.table, q.plan, **opts)
+    G.assert_tables_equal(got, oracle.collect(q), rtol=1e-12)
+
+
+def test_unsorted_index_is_an_error():
+    t = pa.table({"ts": pa.array([5, 3, 9, 1], type=pa.int64()), "v": pa.array([1, 2, 3, 4])})
+    q = pw.LazyFrame(t).group_by_dynamic("ts", every="2i").agg(pw.col("v").sum())
+    with pytest.raises(engine.PolarwayError) as e:
+        engine.run_group_by(q.table, q.plan)
+    assert e.value.code == -4
+    with pytest.raises(ValueError):
+        oracle.collect(q)
