@@ -1,0 +1,81 @@
+"""CPU-side checks of the drop-in boundary (no compute): the C-ABI library loads and exports every symbol
+include/polarway_b200.h declares, fails loudly without a GPU, the plugin shim's version / error / output-field
+functions behave as the reference's loader expects, and the NVRTC specialisation of the scan kernel compiles."""
+import ctypes as C
+import os
+import re
+
+import pyarrow as pa
+import pytest
+
+import polaroid_b200 as pw
+from polaroid_b200 import engine, plugin_loader
+from tests import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "polarway_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pw_b200_\w+|_polars_plugin_\w+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported():
+    L = engine.lib()
+    syms = declared_symbols()
+    assert len(syms) >= 24, syms
+    for s in syms:
+        assert hasattr(L, s), f"{s} is declared in include/polarway_b200.h but not exported"
+
+
+def test_abi_version_and_plugin_version():
+    L = engine.lib()
+    assert L.pw_b200_abi_version() == 1
+    assert plugin_loader._check_version(L) == (0, 1)   # polars-ffi/src/lib.rs:12-17
+
+
+def test_no_gpu_means_a_loud_error_not_a_fallback():
+    L = engine.lib()
+    if L.pw_b200_device_count() > 0:
+        pytest.skip("a GPU is present")
+    t = pa.table({"k": [1, 2, 1], "v": [1.0, 2.0, 3.0]})
+    with pytest.raises(engine.PolarwayError) as e:
+        pw.LazyFrame(t).group_by("k").agg(pw.col("v").sum()).collect()
+    assert e.value.code == -3 and "no CPU fallback" in str(e.value)
+
+
+def test_plugin_field_function_infers_the_output_schema():
+    t = synth.lineitem(10, seed=1)
+    q = synth.q1_query(t, maintain_order=True)
+    sub = t.select(["l_shipdate", "l_returnflag", "l_linestatus", "l_quantity", "l_extendedprice", "l_discount", "l_tax"])
+    fields = plugin_loader.plugin_field(sub.schema, plugin_loader.plan_to_kwargs(sub.schema, q.plan))
+    assert fields == [("l_returnflag", "vu"), ("l_linestatus", "vu"), ("sum_qty", "l"), ("sum_base_price", "g"),
+                      ("sum_disc_price", "g"), ("sum_charge", "g"), ("avg_qty", "g"), ("avg_price", "g"), ("avg_disc", "g"),
+                      ("count_order", "I")]
+
+
+def test_plugin_field_dtype_rules():
+    # sum of i8/i16/u8/u16 -> Int64, i32 stays (sum.rs:40-47); mean of Date -> Datetime[us] (mean.rs:62-69); count -> u32
+    t = pa.table({"k": pa.array([1], type=pa.int32()), "a": pa.array([1], type=pa.int8()), "b": pa.array([1], type=pa.int32()),
+                  "d": pa.array([1], type=pa.int32()).cast(pa.date32())})
+    q = pw.LazyFrame(t).group_by("k").agg(pw.col("a").sum().alias("sa"), pw.col("b").sum().alias("sb"), pw.col("d").mean().alias("md"),
+                                          pw.col("a").count().alias("c"), pw.col("a").mean().alias("ma"))
+    fields = plugin_loader.plugin_field(t.schema, plugin_loader.plan_to_kwargs(t.schema, q.plan))
+    assert fields == [("k", "i"), ("sa", "l"), ("sb", "i"), ("md", "tsu:"), ("c", "I"), ("ma", "g")]
+
+
+def test_plugin_bad_kwargs_sets_the_error_message():
+    t = pa.table({"k": [1]})
+    with pytest.raises(engine.PolarwayError) as e:
+        plugin_loader.plugin_field(t.schema, {"keys": [0], "aggs": [("x", 0, 5, None)]})   # column 5 does not exist
+    assert "the plugin failed with message" in str(e.value)
+
+
+def test_jit_specialisation_compiles_without_a_gpu():
+    L = engine.lib()
+    buf = C.create_string_buffer(1 << 16)
+    rc = L.pw_b200_jit_selftest(buf, C.c_size_t(len(buf)))
+    if rc == 1:
+        pytest.skip("libnvrtc is not installed on this machine")
+    assert rc == 0, buf.value.decode()

@@ -141,3 +141,15 @@ def test_long_string_key_is_refused_loudly():
     q = pw.LazyFrame(t).group_by("s").agg(pw.col("v").sum())
     with pytest.raises(engine.PolarwayError):
         engine.run_group_by(q.table, q.plan)
+
+
+def test_plugin_shim_end_to_end_multi_chunk():
+    # the very call sequence of the reference's plugin loader (plugin.rs:75-142), chunked inputs included
+    from polaroid_b200 import plugin_loader
+    t = synth.lineitem(30_000, seed=6)
+    t = pa.concat_tables([t.slice(0, 11_111), t.slice(11_111, 7), t.slice(11_118)])
+    q = synth.q1_query(t, maintain_order=True)
+    got = plugin_loader.call_plugin(t, plugin_loader.plan_to_kwargs(t.schema, q.plan))
+    want = oracle.collect(q)
+    got = got.set_column(0, "l_returnflag", got["l_returnflag"].cast(pa.string())).set_column(1, "l_linestatus", got["l_linestatus"].cast(pa.string()))
+    G.assert_tables_equal(got, want, rtol=1e-12)
