@@ -143,6 +143,7 @@ std::string jit_ctl(const ScanPlan& P) {
   g.table1("int", "acc_op", P.n_acc, [&](int i) { return P.accs[i].op; });
   g.scalar("bool", "vec_ok", P.vec_ok);
   g.scalar("bool", "check_sorted", P.check_sorted);
+  g.scalar("bool", "unit_stride", P.row_begin == 0 && P.row_stride == 1);
   g.scalar("int", "h_slots", P.hot.idx_slots);
   g.scalar("int", "h_gcap", P.hot.gcap);
   g.scalar("int", "h_rep", P.hot.replicas > 0 ? P.hot.replicas : 1);

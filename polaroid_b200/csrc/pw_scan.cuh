@@ -49,8 +49,12 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   x ^= x >> 32;
   return x;
 }
+// One key word: a single multiply, consumers take the TOP bits (bucket = bits 32.., fingerprint = bits 48..,
+// HBM slot = umulhi(h, cap)) — the reference's DirtyHash + hash_to_partition construction
+// (polars-utils/src/hashing.rs:62-69, 124-151).  Several words: a full mix per word.
 template <int KW>
 __device__ __forceinline__ uint64_t hash_words(const uint64_t (&k)[KW]) {
+  if (KW == 1) return k[0] * 0x55fbfd6bfc5458e9ull;
   uint64_t h = mix64(k[0]);
 #pragma unroll
   for (int w = 1; w < KW; ++w) h = mix64(h ^ (k[w] + 0x9E3779B97F4A7C15ull * (uint64_t)w));
@@ -271,11 +275,13 @@ struct HotTable {
   __device__ __forceinline__ int upsert(const ScanPlan& P, const uint64_t (&k)[KW], uint64_t h) {
     const int S = CT::h_slots(P), G = CT::h_gcap(P);
     uint32_t f16 = (uint32_t)(h >> 48);
-    f16 = f16 == 0u ? 1u : (f16 == 0xFFFFu ? 0xFFFEu : f16);
+    f16 = min(max(f16, 1u), 0xFFFEu);
     const uint32_t fp = f16 << 16;
-    int bucket = (int)(h & (uint64_t)((S >> 2) - 1));
-    {
-      const uint4 t4 = lds128_volatile(tag + bucket * 4);
+    const int bmask = (S >> 2) - 1;
+    int bucket = (int)((uint32_t)(h >> 32) & (uint32_t)bmask);
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {  // home bucket, then its neighbour (where an overflowing bucket spills to)
+      const uint4 t4 = lds128_volatile(tag + ((bucket + t) & bmask) * 4);
       uint32_t cand = 0;
       cand = ((t4.w >> 16) == f16) ? t4.w : cand;
       cand = ((t4.z >> 16) == f16) ? t4.z : cand;
@@ -325,7 +331,7 @@ struct HotTable {
         }
         // CAS lost: look again
       } else {
-        bucket = (bucket + 1) & ((S >> 2) - 1);
+        bucket = (bucket + 1) & bmask;
         if (++probes >= 8) done = true;
       }
     }
@@ -717,7 +723,7 @@ __device__ __forceinline__ void accumulate_row(const ScanPlan& P, const RowOut<K
 template <class CT, int KW, int NV, bool HOT>
 __device__ __forceinline__ void row_back(const ScanPlan& P, HotTable<CT, KW>& hot, const RowOut<KW, NV>& o, int lane, unsigned long long& spilled) {
   const uint64_t h = hash_words<KW>(o.k);
-  const uint64_t grow = (uint64_t)(P.row_begin + o.row * P.row_stride + P.row_offset);
+  const uint64_t grow = CT::unit_stride(P) ? (uint64_t)(o.row + P.row_offset) : (uint64_t)(P.row_begin + o.row * P.row_stride + P.row_offset);
   int id = -1;
   if (HOT) {
     // rows whose raw key aliases a sentinel bypass the hot table so that a hot KEY_NULL is always a true null
@@ -763,7 +769,7 @@ __device__ __forceinline__ void check_sorted_step(const ScanPlan& P, const uint4
   int64_t carry = INT64_MIN;  // t of the row just before this half (lane 0)
   const int tslot = CT::dyn_slot(P), tdt = CT::slot_dtype(P, tslot);
   if (lane == 0 && base > 0) {
-    const uint4 r1 = load_pair(P.slots[tslot].values, tdt, base - 1, n_rows, false, P.row_begin, P.row_stride);
+    const uint4 r1 = load_pair(P.slots[tslot].values, tdt, base - 1, n_rows, false, P.row_begin, P.row_stride);  // (rare path)
     carry = (int64_t)decode(r1, tdt, 0);
   }
   bool bad = false;
@@ -791,8 +797,13 @@ __device__ __forceinline__ void load_step(const ScanPlan& P, int64_t base, int l
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       if (c < CT::n_slots(P) && p < n_rows) {
-        raw[hf][c] = load_pair(P.slots[c].values, CT::slot_dtype(P, c), p, n_rows, full, P.row_begin, P.row_stride);
-        vbits[hf][c] = CT::slot_nullable(P, c) ? load_valid_pair(P.slots[c], p, n_rows, P.row_begin, P.row_stride) : 3u;
+        if (CT::unit_stride(P)) {
+          raw[hf][c] = load_pair(P.slots[c].values, CT::slot_dtype(P, c), p, n_rows, full, 0, 1);
+          vbits[hf][c] = CT::slot_nullable(P, c) ? load_valid_pair(P.slots[c], p, n_rows, 0, 1) : 3u;
+        } else {
+          raw[hf][c] = load_pair(P.slots[c].values, CT::slot_dtype(P, c), p, n_rows, full, P.row_begin, P.row_stride);
+          vbits[hf][c] = CT::slot_nullable(P, c) ? load_valid_pair(P.slots[c], p, n_rows, P.row_begin, P.row_stride) : 3u;
+        }
       } else {
         raw[hf][c] = make_uint4(0u, 0u, 0u, 0u);
         vbits[hf][c] = 0u;
