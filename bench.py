@@ -32,6 +32,13 @@ import numpy as np  # noqa: E402
 WORKLOADS = {
     "c2": dict(rows=100_000_000, groups=1_000, bytes_per_row=16.0,
                name="C2 low-cardinality group_by: 1e8 rows, int64 key x 1e3 groups, f64 sum/mean/min/max"),
+    # the other BASELINE configs: parity-test shapes, runnable here for the per-config table in profiles/
+    "c1": dict(rows=6_001_215, groups=4, bytes_per_row=72.0,
+               name="C1 TPC-H Q1 shape, synthetic lineitem SF1: filter shipdate + group_by(returnflag, linestatus) 8 aggregates"),
+    "c3": dict(rows=100_000_000, groups=10_000_000, bytes_per_row=16.125,
+               name="C3 high-cardinality group_by: 1e8 rows, 1e7 int64 keys, 5% null f64, sum/mean/min/max/count/first/last"),
+    "c4": dict(rows=200_000_000, groups=None, bytes_per_row=28.0,
+               name="C4 OHLCV group_by_dynamic 1m by symbol: 2e8 sorted ticks (1e9 in BASELINE; reduced for host RAM), 100 symbols"),
 }
 
 
@@ -99,6 +106,27 @@ def c2_plan():
     return P.GroupByPlan(keys=["key"], aggs=[a.spec() for a in aggs], maintain_order=False)
 
 
+def make_workload(name: str, rows: int, rank: int):
+    """-> (pyarrow table in pageable host memory, plan)"""
+    import pyarrow as pa
+    import polaroid_b200 as pw
+    from tests import synth
+    if name == "c1":
+        t = synth.lineitem(rows, seed=1 + rank)
+        return t, synth.q1_query(t).plan
+    if name == "c3":
+        t = synth.c3_table(rows, 10_000_000 if rows >= 10_000_000 else max(rows // 10, 1), seed=3 + rank)
+        q = pw.LazyFrame(t).group_by("key").agg(
+            pw.col("value").sum().alias("sum"), pw.col("value").mean().alias("mean"), pw.col("value").min().alias("min"),
+            pw.col("value").max().alias("max"), pw.col("value").count().alias("count"), pw.col("value").first().alias("first"),
+            pw.col("value").last().alias("last"))
+        return t, q.plan
+    if name == "c4":
+        t = synth.ohlcv(rows, n_symbols=100, seed=4 + rank, mean_gap_us=1000)
+        return t, synth.ohlcv_query(t, by_symbol=True).plan
+    raise ValueError(name)
+
+
 def pinned_table(keys: np.ndarray, vals: np.ndarray):
     """pyarrow Table whose buffers live in pinned host memory (so H2D runs at PCIe speed)."""
     import pyarrow as pa
@@ -151,6 +179,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default: the workload's)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -176,11 +205,15 @@ def main():
     stream = torch.cuda.Stream()
     L.pw_b200_set_stream(stream.cuda_stream)
 
-    w = WORKLOADS["c2"]
+    w = WORKLOADS[args.workload]
     rows = args.rows or w["rows"]
-    keys, vals = make_c2_numpy(rows, w["groups"], seed=2 + rank)
-    host_table, _pins = pinned_table(keys, vals)
-    plan = c2_plan()
+    if args.workload == "c2":
+        keys, vals = make_c2_numpy(rows, w["groups"], seed=2 + rank)
+        host_table, _pins = pinned_table(keys, vals)
+        plan = c2_plan()
+    else:
+        host_table, plan = make_workload(args.workload, rows, rank)
+        args.no_cpu_baseline = True   # the CPU baseline leg is defined for the headline workload
     warm = max(args.warmup, 3)
 
     def barrier():
@@ -236,13 +269,13 @@ def main():
         te = torch.tensor([e2e_s], device="cuda")
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te.item())
-    h2d = rows * 16
+    h2d = int(rows * w["bytes_per_row"])
     d2h = sum(b.size for c in res.columns for ch in c.chunks for b in ch.buffers() if b is not None)
 
     # ---------------- roofline of the dominant kernel ----------------
     peak, peak_src = measured_peak_gbs()
     k_ms = float(np.mean(scan_ms))
-    algo_bytes = rows * w["bytes_per_row"] + w["groups"] * 40
+    algo_bytes = rows * w["bytes_per_row"] + (w["groups"] or tm["n_groups"]) * 40
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9
 
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
@@ -267,8 +300,8 @@ def main():
             "metric": "rows_per_sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["name"], "rows_per_gpu": rows, "groups": w["groups"],
-                       "l2": "inputs (1.6 GB per step) are larger than the 126 MB L2; no explicit flush",
+            "config": {"workload": w["name"], "rows_per_gpu": rows, "groups": w["groups"] or int(tm["n_groups"]),
+                       "l2": f"inputs ({rows * w['bytes_per_row'] / 1e9:.2f} GB per step) are larger than the 126 MB L2; no explicit flush",
                        "strategy": {1: "hot table + spill tier", 2: "HBM table", 3: "segmented"}.get(tm["strategy"]),
                        "parallelism": f"rows sharded over {world} GPU(s); partial aggregates merged by key hash"},
             "clocks": clocks,
@@ -282,6 +315,7 @@ def main():
             "cpu_baseline": cpu,
             "phases_ms": {k: tm[k] for k in ("estimate_ms", "scan_ms", "scan_kernel_ms", "finalize_ms", "d2h_ms", "total_device_ms")},
             "spilled_rows": tm["spilled_rows"], "table_slots": tm["table_slots"], "n_groups": tm["n_groups"],
+            "jit": bool(tm["reserved"]), "retries": tm["retries"],
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -120,7 +120,6 @@ static __global__ void __launch_bounds__(256) slice_agg_kernel(const __grid_cons
   using CT = RtCtl;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   uint64_t* cells = (uint64_t*)smem_raw + (size_t)warp * P.n_acc * 32;
-  const uint64_t stride = P.table.cap + 2;
   for (int64_t x = (int64_t)blockIdx.x * warps + warp; x < n_out; x += (int64_t)gridDim.x * warps) {
     for (int a = 0; a < P.n_acc; ++a) cells[a * 32 + lane] = acc_init(P.accs[a].op);
     __syncwarp();
@@ -150,7 +149,7 @@ static __global__ void __launch_bounds__(256) slice_agg_kernel(const __grid_cons
       uint64_t v = cells[a * 32 + lane];
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) v = acc_combine(op, v, __shfl_xor_sync(0xffffffffu, v, d));
-      if (lane == 0) P.table.accs[(uint64_t)a * stride + x] = v;
+      if (lane == 0) tacc(P.table, a, (uint64_t)x) = v;
     }
     __syncwarp();
   }
@@ -255,6 +254,7 @@ int run_dynamic_segmented(const PwQuery* q, const PwFrame* f, struct ArrowArray*
     PW_TRY(dev_alloc(&p, (n_win + 2) * 4)); T.state = (uint32_t*)p;
     PW_TRY(dev_alloc(&p, (n_win + 2) * 8 * (uint64_t)P.n_acc)); T.accs = (uint64_t*)p;
     T.overflow = &dctl->not_sorted; T.spilled = &dctl->total;
+    T.key_sw = T.acc_sw = n_win + 2; T.key_ss = T.acc_ss = 1;  // dense, sequentially written: struct of arrays
     if (n_win) {
       dyn_emit_kernel<<<grid_n, 256, 0, c.stream>>>(ts, n, w, counts, offsets, win_index, win_start);
       PW_CUDA(cudaGetLastError());
@@ -277,6 +277,7 @@ int run_dynamic_segmented(const PwQuery* q, const PwFrame* f, struct ArrowArray*
     PW_TRY(dev_alloc(&p, 16)); T.keys = (uint64_t*)p;
     PW_TRY(dev_alloc(&p, 8)); T.state = (uint32_t*)p;
     PW_TRY(dev_alloc(&p, 16 * (uint64_t)std::max(1, P.n_acc))); T.accs = (uint64_t*)p;
+    T.key_sw = T.acc_sw = 2; T.key_ss = T.acc_ss = 1;
   }
   { void* p = nullptr; PW_TRY(dev_alloc(&p, std::max<uint64_t>(n_win, 1) * 4)); slots = (uint32_t*)p; }
   if (n_win) {

@@ -506,16 +506,17 @@ static bool plan_hot(ScanPlan& P, int64_t groups_hint, int requested_gcap) {
     const size_t shared = (size_t)S * 4 + (size_t)gcap * 8 * kw + 32;
     auto per_warp = [&](int R, int mmp) { return (((size_t)gcap * R * ((size_t)(n_priv64 + mmp) * 8 + (size_t)n_priv32 * 4 + 1)) + 15) & ~(size_t)15; };
     auto total = [&](int R, int mmp) { return shared + (size_t)(n_mm - mmp) * gcap * 8 + per_warp(R, mmp) * warps; };
-    // prefer two CTAs per SM; accept one when the table needs the room
+    // Preference order: every word warp-private (plain read-modify-write; first/last words improve on almost every
+    // row, so CTA-shared atomics for them are very slow) with two CTAs per SM, then with one CTA per SM, then
+    // min/max words CTA-shared (2 CTAs, 1 CTA), else fewer dense ids.
     const size_t budget2 = 110 * 1024, budget1 = 224 * 1024;
     int mmp = n_mm;
     size_t budget = budget2;
-    if (total(1, n_mm) > budget2) {
-      if (total(1, 0) <= budget2) mmp = 0;
-      else if (total(1, n_mm) <= budget1) budget = budget1;
-      else if (total(1, 0) <= budget1) { mmp = 0; budget = budget1; }
-      else continue;  // fewer ids
-    }
+    if (total(1, n_mm) <= budget2) { mmp = n_mm; budget = budget2; }
+    else if (total(1, n_mm) <= budget1) { mmp = n_mm; budget = budget1; }
+    else if (total(1, 0) <= budget2) { mmp = 0; budget = budget2; }
+    else if (total(1, 0) <= budget1) { mmp = 0; budget = budget1; }
+    else continue;  // fewer ids
     int R = 32;
     while (R > 1 && total(R, mmp) > budget) R >>= 1;
     if (requested_gcap > 0 && requested_gcap <= 64) R = std::min(R, 2);  // test hook: exercise the claim path
@@ -577,19 +578,29 @@ struct Control {  // device control block (zeroed per run)
   unsigned long long null_counts[64];
 };
 
-static int alloc_table(Table* T, int n_kw, int n_acc, uint64_t cap, Control* dctl) {
+// Array-of-structs hash table: one row [key words | accumulator words | pad] per slot, padded to 4/8/16/32 words
+int alloc_table_raw(Table* T, int n_kw, int n_acc, uint64_t cap, int32_t* overflow, unsigned long long* spilled) {
   const uint64_t n = cap + 2;
+  int row = 4;
+  while (row < n_kw + n_acc) row <<= 1;
   void* p = nullptr;
-  PW_TRY(dev_alloc(&p, n * 8 * (uint64_t)n_kw)); T->keys = (uint64_t*)p;
+  PW_TRY(dev_alloc(&p, n * 8 * (uint64_t)row));
+  T->keys = (uint64_t*)p;
+  T->accs = T->keys + n_kw;
   PW_TRY(dev_alloc(&p, n * 4)); T->state = (uint32_t*)p;
-  PW_TRY(dev_alloc(&p, n * 8 * (uint64_t)n_acc)); T->accs = (uint64_t*)p;
   T->cap = cap;
-  T->overflow = &dctl->overflow;
-  T->spilled = &dctl->spilled;
+  T->key_sw = T->acc_sw = 1; T->key_ss = T->acc_ss = (uint64_t)row;
+  T->overflow = overflow;
+  T->spilled = spilled;
   return 0;
 }
+static int alloc_table(Table* T, int n_kw, int n_acc, uint64_t cap, Control* dctl) {
+  return alloc_table_raw(T, n_kw, n_acc, cap, &dctl->overflow, &dctl->spilled);
+}
 void free_table(Table& T) {
-  dev_free(T.keys); dev_free(T.state); dev_free(T.accs);
+  const bool aos = T.key_ss != 1;  // accs points into the row buffer
+  dev_free(T.keys); dev_free(T.state);
+  if (!aos) dev_free(T.accs);
   T.keys = nullptr; T.state = nullptr; T.accs = nullptr;
 }
 static int init_table(const Table& T, const ScanPlan& P, cudaStream_t st) {
@@ -824,8 +835,8 @@ int emit_results(const Lowered& L, const Table& T, const uint32_t* slot_list, ui
   PW_CUDA(cudaMemcpyAsync(h_nulls, d_nulls, 64 * 8, cudaMemcpyDeviceToHost, c.stream));
   std::vector<void*> h_vals(ncol, nullptr), h_valid(ncol, nullptr);
   for (size_t i = 0; i < ncol; ++i) {
-    h_vals[i] = malloc(val_bytes[i] + 64);
-    h_valid[i] = malloc(valid_bytes[i] + 64);
+    h_vals[i] = host_alloc(val_bytes[i]);
+    h_valid[i] = host_alloc(valid_bytes[i]);
     if (!h_vals[i] || !h_valid[i]) return fail(PW_ERR_INTERNAL, "out of host memory");
     if (G) {
       PW_CUDA(cudaMemcpyAsync(h_vals[i], d_vals[i], val_bytes[i], cudaMemcpyDeviceToHost, c.stream));

@@ -90,6 +90,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
 int emit_results(const Lowered& L, const Table& T, const uint32_t* slot_list, uint64_t n_groups,
                  struct ArrowArray* out_cols, struct ArrowSchema* out_schemas, size_t* n_out);
 void free_table(Table& T);
+int alloc_table_raw(Table* T, int n_kw, int n_acc, uint64_t cap, int32_t* overflow, unsigned long long* spilled);
 int order_groups(const Lowered& L, const Table& T, int kw, uint32_t** slots_io, uint64_t G);
 
 // segmented (sorted-run) dynamic path, pw_segmented.cu
@@ -98,6 +99,7 @@ int run_dynamic_segmented(const PwQuery* q, const PwFrame* f, struct ArrowArray*
 
 // Arrow helpers (pw_arrow.cpp)
 int parse_format(const char* fmt, int32_t* dtype);
+void* host_alloc(size_t bytes);  // free() compatible
 int make_host_array(int64_t length, int64_t null_count, void* validity, void* values, size_t n_extra_buffers,
                     struct ArrowArray* out);
 int make_schema(const char* format, const char* name, bool nullable, struct ArrowSchema* out);

@@ -96,9 +96,9 @@ static __global__ void gather_kernel(RawSlot src, int width, const uint32_t* ids
 }
 
 // rank of every slot in the ordered group list + group sizes in rank order (sizes[G] = 0 closes the scan)
-static __global__ void rank_kernel(const uint32_t* slots, uint32_t* slot_rank, uint64_t* sizes, const uint64_t* lens, uint64_t G) {
+static __global__ void rank_kernel(const uint32_t* slots, uint32_t* slot_rank, uint64_t* sizes, Table T, int acc_len, uint64_t G) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < G) { const uint32_t s = slots[i]; slot_rank[s] = (uint32_t)i; sizes[i] = lens[s]; }
+  if (i < G) { const uint32_t s = slots[i]; slot_rank[s] = (uint32_t)i; sizes[i] = tacc(T, acc_len, s); }
   else if (i == G) sizes[i] = 0;
 }
 static __global__ void first_kernel(const uint32_t* row_ids_sorted, const uint64_t* offsets, uint32_t* first, uint64_t G) {
@@ -171,8 +171,8 @@ static int select_rows(const PredPlan& pp, int64_t n, uint32_t** ids_out, int64_
 static int device_to_arrow(const void* d_vals, size_t val_bytes, const void* d_valid, size_t valid_bytes, int64_t n, int64_t nulls,
                            bool is_view, const char* format, const char* name, struct ArrowArray* out, struct ArrowSchema* schema) {
   ThreadCtx& c = ctx();
-  void* hv = malloc(val_bytes + 64);
-  void* hb = malloc(valid_bytes + 64);
+  void* hv = host_alloc(val_bytes);
+  void* hb = host_alloc(valid_bytes);
   if (!hv || !hb) return fail(PW_ERR_INTERNAL, "out of host memory");
   if (val_bytes) PW_CUDA(cudaMemcpyAsync(hv, d_vals, val_bytes, cudaMemcpyDeviceToHost, c.stream));
   if (valid_bytes && d_valid) PW_CUDA(cudaMemcpyAsync(hb, d_valid, valid_bytes, cudaMemcpyDeviceToHost, c.stream));
@@ -274,7 +274,7 @@ int pw_b200_frame_group_tuples(const PwFrame* frame, const int32_t* key_columns,
   PW_TRY(dev_alloc(&v, (G + 1) * 8)); offsets = (uint64_t*)v;
   int acc_len = -1;
   for (int a = 0; a < L.plan.n_acc; ++a) if (L.plan.accs[a].src == SRC_ONE) acc_len = a;
-  rank_kernel<<<(unsigned)std::max<uint64_t>(1, (G + 1 + 255) / 256), 256, 0, c.stream>>>(slots, slot_rank, sizes, T.accs + (uint64_t)acc_len * nn, G);
+  rank_kernel<<<(unsigned)std::max<uint64_t>(1, (G + 1 + 255) / 256), 256, 0, c.stream>>>(slots, slot_rank, sizes, T, acc_len, G);
   PW_CUDA(cudaGetLastError());
   size_t tmp_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, sizes, offsets, (int)(G + 1), c.stream);

@@ -15,14 +15,14 @@ struct AccOps { int32_t n; int32_t op[MAX_ACC]; };
 static __global__ void table_init_kernel(Table T, int n_kw, AccOps ops) {
   const uint64_t n = T.cap + 2;
   for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (uint64_t)gridDim.x * blockDim.x) {
-    if (n_kw == 1) T.keys[s] = KEY_EMPTY;
+    if (n_kw == 1) tkey(T, 0, s) = KEY_EMPTY;
     T.state[s] = 0u;
-    for (int a = 0; a < ops.n; ++a) T.accs[(uint64_t)a * n + s] = acc_init(ops.op[a]);
+    for (int a = 0; a < ops.n; ++a) tacc(T, a, s) = acc_init(ops.op[a]);
   }
 }
 
 __device__ __forceinline__ bool slot_occupied(const Table& T, int n_kw, uint64_t s) {
-  if (n_kw == 1 && s < T.cap) return T.keys[s] != KEY_EMPTY;
+  if (n_kw == 1 && s < T.cap) return tkey(T, 0, s) != KEY_EMPTY;
   return T.state[s] == 2u;
 }
 
@@ -59,8 +59,8 @@ __device__ __forceinline__ uint64_t bswap64(uint64_t x) {
 }
 
 __device__ __forceinline__ bool key_is_null(const Table& T, int n_kw, uint64_t slot, int null_word, int nullbit, int single_key_null) {
-  if (null_word >= 0) return (T.keys[(uint64_t)null_word * (T.cap + 2) + slot] >> nullbit) & 1ull;
-  if (single_key_null) return slot < T.cap && T.keys[slot] == KEY_NULL;
+  if (null_word >= 0) return (tkey(T, null_word, slot) >> nullbit) & 1ull;
+  if (single_key_null) return slot < T.cap && tkey(T, 0, slot) == KEY_NULL;
   return false;
 }
 
@@ -68,23 +68,22 @@ static __global__ void sort_key_kernel(Table T, int n_kw, int null_word, SortSpe
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t slot = slot_list[i];
-  const uint64_t stride = T.cap + 2;
   uint64_t v = 0;
   const bool isnull = key_is_null(T, n_kw, slot, null_word, sp.nullbit, sp.single_key_null);
   switch (sp.src) {
-    case SORT_ACC_U64: v = T.accs[(uint64_t)sp.acc * stride + slot]; break;
-    case SORT_WORD_I64: v = isnull ? 0 : (T.keys[(uint64_t)sp.word * stride + slot] ^ 0x8000000000000000ull); break;
-    case SORT_WORD_U64: v = isnull ? 0 : T.keys[(uint64_t)sp.word * stride + slot]; break;
+    case SORT_ACC_U64: v = tacc(T, sp.acc, slot); break;
+    case SORT_WORD_I64: v = isnull ? 0 : (tkey(T, sp.word, slot) ^ 0x8000000000000000ull); break;
+    case SORT_WORD_U64: v = isnull ? 0 : tkey(T, sp.word, slot); break;
     case SORT_WORD_F64: {
-      uint64_t b = T.keys[(uint64_t)sp.word * stride + slot];
+      uint64_t b = tkey(T, sp.word, slot);
       int64_t o = (int64_t)b ^ (((int64_t)b >> 63) & 0x7FFFFFFFFFFFFFFFll);
       v = isnull ? 0 : ((uint64_t)o ^ 0x8000000000000000ull); break; }
     case SORT_VIEW_HI: {
-      uint64_t w0 = T.keys[(uint64_t)sp.word * stride + slot], w1 = T.keys[(uint64_t)(sp.word + 1) * stride + slot];
+      uint64_t w0 = tkey(T, sp.word, slot), w1 = tkey(T, sp.word + 1, slot);
       uint64_t first8 = (w0 >> 32) | (w1 << 32);  // string bytes 0..7 (little endian in memory)
       v = isnull ? 0 : bswap64(first8); break; }
     case SORT_VIEW_LO: {
-      uint64_t w0 = T.keys[(uint64_t)sp.word * stride + slot], w1 = T.keys[(uint64_t)(sp.word + 1) * stride + slot];
+      uint64_t w0 = tkey(T, sp.word, slot), w1 = tkey(T, sp.word + 1, slot);
       uint64_t last4 = w1 >> 32;  // bytes 8..11
       v = isnull ? 0 : ((bswap64(last4) & 0xFFFFFFFF00000000ull) | (w0 & 0xFFFFFFFFull)); break; }
     default: v = isnull ? 0 : 1; break;
@@ -138,7 +137,6 @@ __device__ __forceinline__ void store_typed(void* base, uint64_t i, int dt, uint
 
 static __global__ void emit_kernel(Table T, int n_kw, EmitDesc d, const uint32_t* slot_list, uint64_t n) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t stride = T.cap + 2;
   bool valid = true;
   if (i < n) {
     const uint64_t slot = slot_list[i];
@@ -146,54 +144,54 @@ static __global__ void emit_kernel(Table T, int n_kw, EmitDesc d, const uint32_t
     switch (d.kind) {
       case EMIT_KEY_INT:
         valid = !key_is_null(T, n_kw, slot, d.null_word, d.nullbit, d.single_key_null);
-        bits = valid ? T.keys[(uint64_t)d.word * stride + slot] : 0;
+        bits = valid ? tkey(T, d.word, slot) : 0;
         store_typed(d.out_values, i, d.out_dtype, bits);
         break;
       case EMIT_KEY_VIEW: {
         valid = !key_is_null(T, n_kw, slot, d.null_word, d.nullbit, d.single_key_null);
-        uint64_t w0 = valid ? T.keys[(uint64_t)d.word * stride + slot] : 0;
-        uint64_t w1 = valid ? T.keys[(uint64_t)(d.word + 1) * stride + slot] : 0;
+        uint64_t w0 = valid ? tkey(T, d.word, slot) : 0;
+        uint64_t w1 = valid ? tkey(T, d.word + 1, slot) : 0;
         ((uint64_t*)d.out_values)[2 * i] = w0;
         ((uint64_t*)d.out_values)[2 * i + 1] = w1;
         break; }
       case EMIT_SUM_INT: case EMIT_ACC_I64:
-        store_typed(d.out_values, i, d.out_dtype, T.accs[(uint64_t)d.acc * stride + slot]);
+        store_typed(d.out_values, i, d.out_dtype, tacc(T, d.acc, slot));
         break;
       case EMIT_SUM_F64:
-        store_typed(d.out_values, i, d.out_dtype, T.accs[(uint64_t)d.acc * stride + slot]);
+        store_typed(d.out_values, i, d.out_dtype, tacc(T, d.acc, slot));
         break;
       case EMIT_MEAN: {
-        const uint64_t cnt = T.accs[(uint64_t)d.acc_cnt * stride + slot];
+        const uint64_t cnt = tacc(T, d.acc_cnt, slot);
         valid = cnt != 0;
-        double m = valid ? __longlong_as_double((long long)T.accs[(uint64_t)d.acc * stride + slot]) / (double)cnt : 0.0;
+        double m = valid ? __longlong_as_double((long long)tacc(T, d.acc, slot)) / (double)cnt : 0.0;
         switch (d.mean_out) {
           case MEAN_F64: ((double*)d.out_values)[i] = m; break;
           case MEAN_F32: ((float*)d.out_values)[i] = (float)m; break;
           case MEAN_DATE_US: {
             // (s * US_IN_DAY / c) as i64   (mean.rs:62-69)
-            double s = __longlong_as_double((long long)T.accs[(uint64_t)d.acc * stride + slot]);
+            double s = __longlong_as_double((long long)tacc(T, d.acc, slot));
             double us = valid ? __dmul_rn(s, 86400000000.0) / (double)cnt : 0.0;
             ((int64_t*)d.out_values)[i] = (int64_t)us; break; }
           default: ((int64_t*)d.out_values)[i] = (int64_t)m; break;
         }
         break; }
       case EMIT_MINMAX_INT:
-        valid = T.accs[(uint64_t)d.acc_cnt * stride + slot] != 0;
-        store_typed(d.out_values, i, d.out_dtype, valid ? T.accs[(uint64_t)d.acc * stride + slot] : 0);
+        valid = tacc(T, d.acc_cnt, slot) != 0;
+        store_typed(d.out_values, i, d.out_dtype, valid ? tacc(T, d.acc, slot) : 0);
         break;
       case EMIT_MINMAX_F64: {
-        valid = T.accs[(uint64_t)d.acc_cnt * stride + slot] != 0;
+        valid = tacc(T, d.acc_cnt, slot) != 0;
         // the ordered image of a real value never equals the init sentinel (INT64_MAX/MIN map to NaN payloads)
-        const uint64_t raw = T.accs[(uint64_t)d.acc * stride + slot];
+        const uint64_t raw = tacc(T, d.acc, slot);
         const bool any_num = raw != (uint64_t)d.every;  // d.every carries acc_init(op) for this emit kind
         uint64_t b = any_num ? ordered_to_f64_bits((int64_t)raw) : 0x7FF8000000000000ull;
         store_typed(d.out_values, i, d.out_dtype, valid ? b : 0);
         break; }
       case EMIT_COUNT:
-        ((uint32_t*)d.out_values)[i] = (uint32_t)T.accs[(uint64_t)d.acc * stride + slot];
+        ((uint32_t*)d.out_values)[i] = (uint32_t)tacc(T, d.acc, slot);
         break;
       case EMIT_FIRSTLAST: {
-        const uint64_t packed = T.accs[(uint64_t)d.acc * stride + slot];
+        const uint64_t packed = tacc(T, d.acc, slot);
         valid = packed & 1ull;
         const int64_t row = (int64_t)(packed >> 1) - d.row_offset;
         uint64_t b = 0;
@@ -207,7 +205,7 @@ static __global__ void emit_kernel(Table T, int n_kw, EmitDesc d, const uint32_t
         store_typed(d.out_values, i, d.out_dtype, b);
         break; }
       case EMIT_DYN_LOWER: case EMIT_DYN_UPPER: {
-        const int64_t k = (int64_t)T.keys[(uint64_t)d.word * stride + slot];
+        const int64_t k = (int64_t)tkey(T, d.word, slot);
         int64_t t = d.origin + k * d.every + (d.kind == EMIT_DYN_UPPER ? d.period : 0);
         store_typed(d.out_values, i, d.out_dtype, (uint64_t)t);
         break; }

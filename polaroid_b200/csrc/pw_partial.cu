@@ -61,16 +61,16 @@ static __global__ void export_kernel(Table T, PackLayout pl, const uint32_t* slo
   const uint64_t slot = slot_list[i];
   const uint64_t stride = T.cap + 2;
   uint64_t k[MAX_KW];
-  for (int w = 0; w < pl.kw; ++w) k[w] = T.keys[(uint64_t)w * stride + slot];
+  for (int w = 0; w < pl.kw; ++w) k[w] = tkey(T, w, slot);
   const uint32_t owner = owner_of(k, pl.kw, n_parts);
   if (pass == 0) { atomicAdd(&part_count[owner], 1ull); return; }
   const unsigned long long pos = part_base[owner] + atomicAdd(&part_count[owner], 1ull);
   uint64_t* r = rows + pos * (uint64_t)pl.row_words;
   r[0] = (pl.kw == 1 && slot >= T.cap) ? 1ull : 0ull;  // escape slot: the key word is raw data that aliases a sentinel
   for (int w = 0; w < pl.kw; ++w) r[1 + w] = k[w];
-  for (int a = 0; a < pl.n_acc; ++a) r[1 + pl.kw + a] = T.accs[(uint64_t)a * stride + slot];
+  for (int a = 0; a < pl.n_acc; ++a) r[1 + pl.kw + a] = tacc(T, a, slot);
   for (int f = 0; f < pl.n_fl; ++f) {
-    const uint64_t packed = T.accs[(uint64_t)pl.fl_acc[f] * stride + slot];
+    const uint64_t packed = tacc(T, pl.fl_acc[f], slot);
     uint64_t bits = 0;
     if (packed & 1ull) {
       const int64_t row = (int64_t)(packed >> 1) - row_offset;
@@ -96,7 +96,7 @@ static __global__ void merge_kernel(Table T, PackLayout pl, AccOpsK ops, const u
   const uint64_t stride = T.cap + 2;
   for (int a = 0; a < pl.n_acc; ++a) {
     const uint64_t v = r[1 + pl.kw + a];
-    if (v != acc_init(ops.op[a])) acc_apply_global(&T.accs[(uint64_t)a * stride + slot], ops.op[a], v);
+    if (v != acc_init(ops.op[a])) acc_apply_global(&tacc(T, a, slot), ops.op[a], v);
   }
 }
 
@@ -110,7 +110,7 @@ static __global__ void merge_values_kernel(Table T, PackLayout pl, const uint64_
   const uint64_t stride = T.cap + 2;
   for (int f = 0; f < pl.n_fl; ++f) {
     const uint64_t mine = r[1 + pl.kw + pl.fl_acc[f]];
-    if (T.accs[(uint64_t)pl.fl_acc[f] * stride + slot] == mine) fl_values[(uint64_t)f * stride + slot] = r[1 + pl.kw + pl.n_acc + f];
+    if (tacc(T, pl.fl_acc[f], slot) == mine) fl_values[(uint64_t)f * (T.cap + 2) + slot] = r[1 + pl.kw + pl.n_acc + f];
   }
 }
 
@@ -208,10 +208,7 @@ int pw_b200_merge_partials(const PwQuery* q, const PwFrame* schema_from, const v
   Table T{};
   const uint64_t cap = (uint64_t)std::max<int64_t>(2 * n_rows, 64);
   const uint64_t nn = cap + 2;
-  PW_TRY(dev_alloc(&v, nn * 8 * (uint64_t)kw)); T.keys = (uint64_t*)v;
-  PW_TRY(dev_alloc(&v, nn * 4)); T.state = (uint32_t*)v;
-  PW_TRY(dev_alloc(&v, nn * 8 * (uint64_t)std::max(1, L.plan.n_acc))); T.accs = (uint64_t*)v;
-  T.cap = cap; T.overflow = &dctl->overflow; T.spilled = &dctl->spilled;
+  PW_TRY(alloc_table_raw(&T, kw, L.plan.n_acc, cap, &dctl->overflow, &dctl->spilled));
   AccOps ops{};
   AccOpsK opsk{};
   ops.n = opsk.n = L.plan.n_acc;

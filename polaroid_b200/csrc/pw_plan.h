@@ -105,14 +105,22 @@ struct Dyn {
 };
 
 // HBM open-addressing table (also the partial-aggregate state exchanged between GPUs)
+// Layout: hash tables are ARRAY OF STRUCTS — one row [key words | accumulator words | pad] of 4/8/16/32 words per
+// slot, so a probe plus the updates of one input row touch one or two 32-byte sectors (the first, struct-of-arrays
+// layout touched one sector per word: ~7 random sectors per row on the high-cardinality path).  The window list of
+// the sorted dynamic path is a dense, sequentially written table and stays struct-of-arrays.  Both are addressed
+// through tkey()/tacc() with (word stride, slot stride).
 struct Table {
-  uint64_t* keys;    // [n_kw][cap + 2] SoA; word 0 doubles as the occupancy marker when n_kw == 1
-  uint32_t* state;   // [cap + 2]: 0 empty, 1 busy, 2 ready   (n_kw > 1)
-  uint64_t* accs;    // [n_acc][cap + 2] SoA
+  uint64_t* keys;    // word 0 doubles as the occupancy marker when n_kw == 1
+  uint32_t* state;   // [cap + 2]: 0 empty, 1 busy, 2 ready   (n_kw > 1, and the escape slots)
+  uint64_t* accs;
   uint64_t cap;      // probe range; slots cap and cap+1 are the escape slots for sentinel-valued keys
   int32_t* overflow; // set to 1 when a probe sequence exhausts the table (host retries bigger)
   unsigned long long* spilled; // rows that bypassed the hot table
+  uint64_t key_sw, key_ss, acc_sw, acc_ss;  // strides (in words) per word index / per slot
 };
+__host__ __device__ inline uint64_t& tkey(const Table& T, int w, uint64_t slot) { return T.keys[(uint64_t)w * T.key_sw + slot * T.key_ss]; }
+__host__ __device__ inline uint64_t& tacc(const Table& T, int a, uint64_t slot) { return T.accs[(uint64_t)a * T.acc_sw + slot * T.acc_ss]; }
 
 // shared-memory hot table geometry (host-computed; see pw_scan.cuh)
 enum HotKind : int32_t {

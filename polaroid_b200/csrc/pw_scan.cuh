@@ -162,15 +162,15 @@ __device__ __forceinline__ uint64_t table_upsert(const Table& T, const uint64_t 
     const uint64_t k0 = k[0];
     if (!key0_is_sentinel_free) {
       // k0 is a raw data value that collides with a sentinel -> escape slots
-      if (k0 == KEY_EMPTY) { st_volatile_u32(&T.state[cap], 2u); T.keys[cap] = k0; return cap; }
-      if (k0 == KEY_NULL) { st_volatile_u32(&T.state[cap + 1], 2u); T.keys[cap + 1] = k0; return cap + 1; }
+      if (k0 == KEY_EMPTY) { st_volatile_u32(&T.state[cap], 2u); tkey(T, 0, cap) = k0; return cap; }
+      if (k0 == KEY_NULL) { st_volatile_u32(&T.state[cap + 1], 2u); tkey(T, 0, cap + 1) = k0; return cap + 1; }
     }
     uint64_t slot = __umul64hi(h, cap);
     for (uint64_t probes = 0; probes < cap; ++probes) {
-      unsigned long long old = __ldcg((const unsigned long long*)&T.keys[slot]);
+      unsigned long long old = __ldcg((const unsigned long long*)&tkey(T, 0, slot));
       if (old == k0) return slot;
       if (old == KEY_EMPTY) {
-        old = atomicCAS((unsigned long long*)&T.keys[slot], (unsigned long long)KEY_EMPTY, (unsigned long long)k0);
+        old = atomicCAS((unsigned long long*)&tkey(T, 0, slot), (unsigned long long)KEY_EMPTY, (unsigned long long)k0);
         if (old == KEY_EMPTY || old == k0) return slot;
       }
       slot = (slot + 1 == cap) ? 0 : slot + 1;
@@ -187,7 +187,7 @@ __device__ __forceinline__ uint64_t table_upsert(const Table& T, const uint64_t 
       if (s == 0u) s = atomicCAS(&T.state[slot], 0u, 1u) == 0u ? 3u : 1u;  // 3: we own the slot
       if (s == 3u) {
 #pragma unroll
-        for (int w = 0; w < KW; ++w) T.keys[(uint64_t)w * (cap + 2) + slot] = k[w];
+        for (int w = 0; w < KW; ++w) tkey(T, w, slot) = k[w];
         __threadfence();
         st_volatile_u32(&T.state[slot], 2u);
         result = slot; done = true;
@@ -195,7 +195,7 @@ __device__ __forceinline__ uint64_t table_upsert(const Table& T, const uint64_t 
         __threadfence();
         bool eq = true;
 #pragma unroll
-        for (int w = 0; w < KW; ++w) eq &= (__ldcg((const unsigned long long*)&T.keys[(uint64_t)w * (cap + 2) + slot]) == k[w]);
+        for (int w = 0; w < KW; ++w) eq &= (__ldcg((const unsigned long long*)&tkey(T, w, slot)) == k[w]);
         if (eq) { result = slot; done = true; }
         else {
           slot = (slot + 1 == cap) ? 0 : slot + 1;
@@ -364,7 +364,7 @@ struct HotTable {
             }
           }
         }
-        if (gs != ~0ull && v != acc_init(op)) acc_apply_global(&P.table.accs[(uint64_t)a * (P.table.cap + 2) + gs], op, v);
+        if (gs != ~0ull && v != acc_init(op)) acc_apply_global(&tacc(P.table, a, gs), op, v);
       }
     }
   }
@@ -663,7 +663,7 @@ struct ColdSink {  // HBM table, atomics
   const Table& T;
   uint64_t slot;
   template <int OP>
-  __device__ __forceinline__ void add(const ScanPlan&, int a, uint64_t x) const { acc_apply_global(&T.accs[(uint64_t)a * (T.cap + 2) + slot], OP, x); }
+  __device__ __forceinline__ void add(const ScanPlan&, int a, uint64_t x) const { acc_apply_global(&tacc(T, a, slot), OP, x); }
 };
 template <class CT, int KW>
 struct HotSink {  // shared-memory hot table: private cells under a claim, shared min/max words
@@ -845,6 +845,8 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
   const int64_t tile_lo = n_tiles * blockIdx.x / gridDim.x;
   const int64_t tile_hi = n_tiles * (blockIdx.x + 1) / gridDim.x;
   unsigned long long spilled = 0;
+  bool stable_set = false, flushed_once = false;  // eviction heuristics (CTA-uniform)
+  int tiles_since_flush = 0;
 
   for (int64_t tile = tile_lo; tile < tile_hi; ++tile) {
     const int64_t step = tile * warps + warp;
@@ -894,17 +896,28 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
         }
       }
     }
-    if (HOT && ((tile - tile_lo) & 3) == 3) {
+    if (HOT && ((tile - tile_lo) & 3) == 3) {  // every 4 tiles (6144 rows at 12 warps): two CTA barriers
       __syncthreads();
-      // a row found the table full since the last check: evict everything (FixedIndexTable evicts per
-      // slot; a wholesale flush keeps the per-row path free of eviction logic)
-      const bool need_flush = *(volatile uint32_t*)(hot.count + 1) != 0u;
+      // Evict everything (FixedIndexTable evicts per slot; a wholesale flush keeps the per-row path free of
+      // eviction logic) when a row found the table full, or — for group sets that drift (time-sorted input) —
+      // before that happens: at 7/8 full, unless the table refilled right after the previous eviction (a stable
+      // group set that simply needs most of the table: then only a full table evicts).
+      const uint32_t cnt = *(volatile uint32_t*)hot.count;
+      const bool full = *(volatile uint32_t*)(hot.count + 1) != 0u;
+      const uint32_t G = (uint32_t)CT::h_gcap(P);
+      const bool nearly = cnt >= G - (G >> 3) && !stable_set;
       __syncthreads();
-      if (need_flush && tile + 1 < tile_hi) {
-        hot.flush(P);
-        __syncthreads();
-        hot.clear(P);
-        __syncthreads();
+      ++tiles_since_flush;
+      if ((full || nearly) && tile + 1 < tile_hi) {
+        if (!full && flushed_once && tiles_since_flush <= 2) stable_set = true;  // refilled at once: same groups again
+        else {
+          hot.flush(P);
+          __syncthreads();
+          hot.clear(P);
+          __syncthreads();
+          flushed_once = true;
+          tiles_since_flush = 0;
+        }
       }
     }
   }
