@@ -37,6 +37,8 @@ WORKLOADS = {
                name="C1 TPC-H Q1 shape, synthetic lineitem SF1: filter shipdate + group_by(returnflag, linestatus) 8 aggregates"),
     "c3": dict(rows=100_000_000, groups=10_000_000, bytes_per_row=16.125,
                name="C3 high-cardinality group_by: 1e8 rows, 1e7 int64 keys, 5% null f64, sum/mean/min/max/count/first/last"),
+    "c4e": dict(rows=200_000_000, groups=None, bytes_per_row=24.0,
+                name="C4 keys-empty variant (what polars-timeseries calls): group_by_dynamic 1m over 2e8 sorted ticks, no group_by"),
     "c4": dict(rows=200_000_000, groups=None, bytes_per_row=28.0,
                name="C4 OHLCV group_by_dynamic 1m by symbol: 2e8 sorted ticks (1e9 in BASELINE; reduced for host RAM), 100 symbols"),
 }
@@ -121,9 +123,9 @@ def make_workload(name: str, rows: int, rank: int):
             pw.col("value").max().alias("max"), pw.col("value").count().alias("count"), pw.col("value").first().alias("first"),
             pw.col("value").last().alias("last"))
         return t, q.plan
-    if name == "c4":
+    if name in ("c4", "c4e"):
         t = synth.ohlcv(rows, n_symbols=100, seed=4 + rank, mean_gap_us=1000)
-        return t, synth.ohlcv_query(t, by_symbol=True).plan
+        return t, synth.ohlcv_query(t, by_symbol=(name == "c4")).plan
     raise ValueError(name)
 
 

@@ -12,6 +12,8 @@
 //   costs nothing); the end row is a binary search; one warp then reduces each [start,end) slice with the
 //   same row evaluation as the hash path and warp shuffles.
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 #include <stdio.h>
 #include <string.h>
 
@@ -19,6 +21,7 @@
 
 #include "pw_engine.h"
 #include "pw_scan.cuh"
+#include "pw_segmented.cuh"
 
 namespace pw {
 
@@ -155,9 +158,121 @@ static __global__ void __launch_bounds__(256) slice_agg_kernel(const __grid_cons
   }
 }
 
+
 static int64_t floor_div_h(int64_t a, int64_t b) {
   int64_t q = a / b, r = a % b;
   return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q;
+}
+
+// dense window table helpers of the tumbling fast path
+static __global__ void seg_fill_keys_kernel(uint64_t* keys, int64_t k0, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keys[i] = (uint64_t)(k0 + (int64_t)i);
+}
+static __global__ void seg_flags_kernel(Table T, int acc_len, uint64_t n, unsigned char* flags) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = tacc(T, acc_len, i) != 0ull;
+}
+
+// Tumbling windows (every row in at most one window) and a dense window range that fits memory: the one-pass
+// segmented kernel of pw_segmented.cuh.  Returns handled = false when the shape does not qualify.
+static int run_segmented_fast(const PwQuery* q, const PwFrame* f, Lowered& L, struct ArrowArray* out_cols, struct ArrowSchema* out_schemas,
+                              size_t* n_out, bool* handled) {
+  *handled = false;
+  ThreadCtx& c = ctx();
+  ScanPlan& P = L.plan;
+  const PwDynamic& d = *q->dynamic;
+  const int64_t n = f->n_rows;
+  if (n == 0) return 0;
+  const RawSlot ts = P.slots[P.dyn.slot];
+  int64_t t_first = 0, t_last = 0;
+  {
+    const int w = ts.dtype == DT_I32 ? 4 : 8;
+    int64_t a = 0, b = 0;
+    PW_CUDA(cudaMemcpyAsync(&a, (const char*)ts.values, w, cudaMemcpyDeviceToHost, c.stream));
+    PW_CUDA(cudaMemcpyAsync(&b, (const char*)ts.values + (size_t)(n - 1) * w, w, cudaMemcpyDeviceToHost, c.stream));
+    PW_CUDA(cudaStreamSynchronize(c.stream));
+    t_first = w == 4 ? (int64_t)(int32_t)a : a;
+    t_last = w == 4 ? (int64_t)(int32_t)b : b;
+  }
+  if (t_last < t_first) return fail(PW_ERR_NOT_SORTED, "argument in operation 'group_by_dynamic' is not sorted, please sort the 'expr/series/column' first");
+  // a window that contains t has index floor((t - origin) / every) or one less (right-closed edges)
+  const int64_t k_lo = floor_div_h(t_first - d.offset, d.every) - 1;
+  const int64_t k_hi = floor_div_h(t_last - d.offset, d.every) + 1;
+  const int64_t n_dense = k_hi - k_lo + 1;
+  if (n_dense > (int64_t)1 << 25 || n_dense > 4 * n + 1024) return 0;  // sparse index: the general path lists only non-empty windows
+  *handled = true;
+  PwTimings& tm = c.timings;
+  tm.n_rows = n; tm.strategy = 3;
+  struct Ctl { int32_t not_sorted; int32_t overflow; unsigned long long spilled; int32_t n_sel; int32_t pad; } hctl{};
+  Ctl* dctl = nullptr;
+  void* p = nullptr;
+  PW_TRY(dev_alloc(&p, sizeof(Ctl))); dctl = (Ctl*)p;
+  PW_CUDA(cudaMemsetAsync(dctl, 0, sizeof(Ctl), c.stream));
+  PW_CUDA(cudaEventRecord(c.ev[2], c.stream));
+  Table T{};
+  const uint64_t nn = (uint64_t)n_dense + 2;
+  PW_TRY(dev_alloc(&p, nn * 8)); T.keys = (uint64_t*)p;
+  PW_TRY(dev_alloc(&p, nn * 4)); T.state = (uint32_t*)p;
+  PW_TRY(dev_alloc(&p, nn * 8 * (uint64_t)P.n_acc)); T.accs = (uint64_t*)p;
+  T.cap = (uint64_t)n_dense; T.key_sw = T.acc_sw = nn; T.key_ss = T.acc_ss = 1;
+  T.overflow = &dctl->overflow; T.spilled = &dctl->spilled;
+  AccOps ops{};
+  ops.n = P.n_acc;
+  for (int a = 0; a < P.n_acc; ++a) ops.op[a] = P.accs[a].op;
+  table_init_kernel<<<(int)std::min<uint64_t>((nn + 255) / 256, 148 * 8), 256, 0, c.stream>>>(T, 2 /*no key sentinel*/, ops);
+  PW_CUDA(cudaGetLastError());
+  seg_fill_keys_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, c.stream>>>(T.keys, k_lo, nn);
+  PW_CUDA(cudaGetLastError());
+  P.table = T; P.not_sorted = &dctl->not_sorted; P.check_sorted = 1; P.hot_slots = 0;
+  SegParams sp{k_lo, n_dense};
+  const size_t smem = (size_t)8 * P.n_acc * 32 * 8;
+  const bool narrow = P.n_slots <= 4 && P.n_vexpr <= NVof<4>::value;
+  int per_sm = 1;
+  if (narrow) PW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seg_kernel<4>, 256, smem));
+  else PW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seg_kernel<12>, 256, smem));
+  const int64_t n_steps = (n + ROWS_PER_STEP - 1) / ROWS_PER_STEP;
+  int64_t grid = std::min<int64_t>((int64_t)c.sm_count * std::max(per_sm, 1), (n_steps + 7) / 8);
+  if (grid < 1) grid = 1;
+  PW_CUDA(cudaEventRecord(c.ev[8], c.stream));
+  if (narrow) seg_kernel<4><<<(unsigned)grid, 256, smem, c.stream>>>(P, sp);
+  else seg_kernel<12><<<(unsigned)grid, 256, smem, c.stream>>>(P, sp);
+  PW_CUDA(cudaGetLastError());
+  PW_CUDA(cudaEventRecord(c.ev[9], c.stream));
+  // non-empty windows, ascending
+  int acc_len = -1;
+  for (int a = 0; a < P.n_acc; ++a) if (P.accs[a].src == SRC_ONE) acc_len = a;
+  unsigned char* flags = nullptr; uint32_t* slots = nullptr;
+  PW_TRY(dev_alloc(&p, (size_t)n_dense)); flags = (unsigned char*)p;
+  PW_TRY(dev_alloc(&p, (size_t)n_dense * 4)); slots = (uint32_t*)p;
+  seg_flags_kernel<<<(unsigned)((n_dense + 255) / 256), 256, 0, c.stream>>>(T, acc_len, (uint64_t)n_dense, flags);
+  PW_CUDA(cudaGetLastError());
+  cub::CountingInputIterator<uint32_t> iota(0u);
+  size_t tmp_bytes = 0;
+  cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, flags, slots, &dctl->n_sel, (int)n_dense, c.stream);
+  void* tmp = nullptr;
+  PW_TRY(dev_alloc(&tmp, tmp_bytes));
+  PW_CUDA(cub::DeviceSelect::Flagged(tmp, tmp_bytes, iota, flags, slots, &dctl->n_sel, (int)n_dense, c.stream));
+  PW_CUDA(cudaMemcpyAsync(&hctl, dctl, sizeof(Ctl), cudaMemcpyDeviceToHost, c.stream));
+  PW_CUDA(cudaStreamSynchronize(c.stream));
+  tm.kernel_launches += 6;
+  dev_free(tmp); dev_free(flags);
+  int rc = 0;
+  if (hctl.not_sorted) rc = fail(PW_ERR_NOT_SORTED, "argument in operation 'group_by_dynamic' is not sorted, please sort the 'expr/series/column' first");
+  const uint64_t n_win = (uint64_t)hctl.n_sel;
+  tm.n_groups = (int64_t)n_win; tm.table_slots = n_dense;
+  PW_CUDA(cudaEventRecord(c.ev[3], c.stream));
+  if (!rc) rc = emit_results(L, T, slots, n_win, out_cols, out_schemas, n_out);
+  dev_free(slots); dev_free(dctl);
+  free_table(T);
+  if (rc) return rc;
+  float ms;
+  if (cudaEventElapsedTime(&ms, c.ev[2], c.ev[3]) == cudaSuccess) tm.scan_ms = ms;
+  if (cudaEventElapsedTime(&ms, c.ev[3], c.ev[4]) == cudaSuccess) tm.finalize_ms = ms;
+  if (cudaEventElapsedTime(&ms, c.ev[4], c.ev[5]) == cudaSuccess) tm.d2h_ms = ms;
+  if (cudaEventElapsedTime(&ms, c.ev[0], c.ev[5]) == cudaSuccess) tm.total_device_ms = ms;
+  if (cudaEventElapsedTime(&ms, c.ev[8], c.ev[9]) == cudaSuccess) tm.scan_kernel_ms = ms;
+  return 0;
 }
 
 int run_dynamic_segmented(const PwQuery* q, const PwFrame* f, struct ArrowArray* out_cols, struct ArrowSchema* out_schemas,
@@ -167,13 +282,17 @@ int run_dynamic_segmented(const PwQuery* q, const PwFrame* f, struct ArrowArray*
   const PwDynamic& d = *q->dynamic;
   const bool overlapping = d.closed == PW_CLOSED_BOTH ? d.period >= d.every : d.period > d.every;
   if (!overlapping && (q->flags & PW_FLAG_NO_SEGMENTED)) return 0;       // tumbling windows through the hash path (test hook)
-  if (q->n_predicates > 0) {
-    if (!overlapping) return 0;  // hash path applies the predicate in registers
+  if (q->n_predicates > 0 && overlapping)
     return fail(PW_ERR_UNSUPPORTED, "filter + overlapping dynamic windows (needs a compacted index; SURVEY 8f rank 4)");
-  }
   ThreadCtx& c = ctx();
   Lowered L;
   PW_TRY(lower_query(q, f, &L));
+  if (!overlapping && !(q->flags & PW_FLAG_FORCE_SEGMENTED)) {
+    // (PW_FLAG_FORCE_SEGMENTED here means: use the general window-list path even for tumbling windows — test hook)
+    int rc = run_segmented_fast(q, f, L, out_cols, out_schemas, n_out, handled);
+    if (rc || *handled) return rc;
+  }
+  if (q->n_predicates > 0) return 0;  // tumbling + filter that did not qualify: the hash path applies the predicate in registers
   ScanPlan& P = L.plan;
   const int64_t n = f->n_rows;
   *handled = true;

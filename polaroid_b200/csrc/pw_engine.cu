@@ -370,6 +370,7 @@ int lower_query(const PwQuery* q, const PwFrame* f, Lowered* L) {
     o.emit.out_dtype = o.out_dtype; o.emit.src_cls = cls;
     tmp.push_back(t);
   }
+  if (dyn) gflags |= GF_LEN;  // the sorted fast path finds the non-empty windows through the row counter
   const bool want_row = !dyn && q->maintain_order;
   const bool want_tmin = dyn && dyn->label == PW_LABEL_DATAPOINT;
   if (want_row) gflags |= GF_ROW;

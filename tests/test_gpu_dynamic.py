@@ -34,7 +34,7 @@ def test_window_shapes_no_keys(closed, every, period, offset):
     G.assert_tables_equal(got, oracle.collect(q), rtol=1e-12)
 
 
-@pytest.mark.parametrize("opts", [{}, {"flags": engine.FLAG_NO_SEGMENTED}, {"flags": engine.FLAG_NO_SEGMENTED | engine.FLAG_FORCE_HOT, "hot_table_slots": 16}])
+@pytest.mark.parametrize("opts", [{}, {"flags": engine.FLAG_FORCE_SEGMENTED}, {"flags": engine.FLAG_NO_SEGMENTED}, {"flags": engine.FLAG_NO_SEGMENTED | engine.FLAG_FORCE_HOT, "hot_table_slots": 16}])
 def test_tumbling_hash_and_segmented_agree(opts):
     t = synth.ohlcv(120_000, n_symbols=5, seed=9, mean_gap_us=50_000)
     q = synth.ohlcv_query(t, by_symbol=False, every="10s")
@@ -50,3 +50,12 @@ def test_unsorted_index_is_an_error():
     assert e.value.code == -4
     with pytest.raises(ValueError):
         oracle.collect(q)
+
+
+def test_filter_fused_into_sorted_windows():
+    t = synth.ohlcv(150_000, n_symbols=5, seed=10, mean_gap_us=40_000)
+    c = pw.col
+    q = (pw.LazyFrame(t).filter(c("volume") > 500).group_by_dynamic("ts", every="30s")
+         .agg(c("price").first().alias("open"), c("price").last().alias("close"), c("volume").sum().alias("v"), pw.len().alias("n")))
+    got = engine.run_group_by(q.table, q.plan)
+    G.assert_tables_equal(got, oracle.collect(q), rtol=1e-12)

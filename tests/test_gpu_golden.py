@@ -16,6 +16,7 @@ STRATEGIES = {
     "global": {"flags": engine.FLAG_FORCE_GLOBAL},
     "global_tiny": {"flags": engine.FLAG_FORCE_GLOBAL, "initial_table_slots": 4},  # forces table growth retries
     "hash_dynamic": {"flags": engine.FLAG_NO_SEGMENTED},  # keys-less tumbling windows through the hash path
+    "window_list": {"flags": engine.FLAG_FORCE_SEGMENTED},  # keys-less tumbling windows through the general window-list path
 }
 
 
