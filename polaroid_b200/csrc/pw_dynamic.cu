@@ -235,9 +235,13 @@ static int run_segmented_fast(const PwQuery* q, const PwFrame* f, Lowered& L, st
   int64_t grid = std::min<int64_t>((int64_t)c.sm_count * std::max(per_sm, 1), (n_steps + 7) / 8);
   if (grid < 1) grid = 1;
   PW_CUDA(cudaEventRecord(c.ev[8], c.stream));
-  if (narrow) seg_kernel<4><<<(unsigned)grid, 256, smem, c.stream>>>(P, sp);
-  else seg_kernel<12><<<(unsigned)grid, 256, smem, c.stream>>>(P, sp);
-  PW_CUDA(cudaGetLastError());
+  const int jrc = launch_seg_jit(P, sp, narrow ? 4 : 12, 256, smem, c.sm_count, c.stream);  // query-shape specialised (NVRTC)
+  if (jrc < 0) return jrc;
+  if (jrc > 0) {
+    if (narrow) seg_kernel<4><<<(unsigned)grid, 256, smem, c.stream>>>(P, sp);
+    else seg_kernel<12><<<(unsigned)grid, 256, smem, c.stream>>>(P, sp);
+    PW_CUDA(cudaGetLastError());
+  }
   PW_CUDA(cudaEventRecord(c.ev[9], c.stream));
   // non-empty windows, ascending
   int acc_len = -1;

@@ -163,14 +163,23 @@ struct Compiled { CUfunction fn = nullptr; bool failed = false; };
 std::mutex g_mu;
 std::map<std::string, Compiled> g_cache;
 
-Compiled compile(const std::string& key, const std::string& ctl, int nc, int kw, bool hot, int threads) {
+std::string scan_entry(int nc, int kw, bool hot, int threads) {
+  std::ostringstream src;
+  src << "extern \"C\" __global__ void __launch_bounds__(" << threads << ", 1) pw_scan_jit(const __grid_constant__ pw::ScanPlan P) {\n"
+      << "  pw::scan_body<pw::JitCtl, " << nc << ", " << kw << ", " << (hot ? "true" : "false") << ">(P);\n}\n";
+  return src.str();
+}
+std::string seg_entry(int nc, int threads) {
+  std::ostringstream src;
+  src << "extern \"C\" __global__ void __launch_bounds__(" << threads << ") pw_seg_jit(const __grid_constant__ pw::ScanPlan P, const pw::SegParams sp) {\n"
+      << "  pw::seg_body<pw::JitCtl, " << nc << ">(P, sp);\n}\n";
+  return src.str();
+}
+
+Compiled compile(const std::string& ctl, const std::string& entry, const char* entry_name) {
   Api& a = api();
   Compiled c;
-  std::ostringstream src;
-  src << "#include \"pw_scan.cuh\"\nnamespace pw {\n" << ctl << "}\n"
-      << "extern \"C\" __global__ void __launch_bounds__(" << threads << ", 1) pw_scan_jit(const __grid_constant__ pw::ScanPlan P) {\n"
-      << "  pw::scan_body<pw::JitCtl, " << nc << ", " << kw << ", " << (hot ? "true" : "false") << ">(P);\n}\n";
-  const std::string text = src.str();
+  const std::string text = "#include \"pw_segmented.cuh\"\nnamespace pw {\n" + ctl + "}\n" + entry;
   nvrtcProgram prog = nullptr;
   if (a.nvrtcCreateProgram(&prog, text.c_str(), "pw_scan_jit.cu", 0, nullptr, nullptr) != 0) { c.failed = true; return c; }
   const std::string inc = "--include-path=" + csrc_dir();
@@ -184,7 +193,7 @@ Compiled compile(const std::string& key, const std::string& ctl, int nc, int kw,
       a.nvrtcGetProgramLog(prog, log.data());
       if (rc != 0 || n > 2) fprintf(stderr, "[pw jit] nvrtc rc=%d\n%s\n", rc, log.data());
     }
-    if (getenv("PW_DEBUG") && rc == 0) fprintf(stderr, "[pw jit] compiled shape (nc=%d kw=%d hot=%d):\n%s", nc, kw, (int)hot, ctl.c_str());
+    if (getenv("PW_DEBUG") && rc == 0) fprintf(stderr, "[pw jit] compiled %s for shape:\n%s", entry_name, ctl.c_str());
   }
   if (rc != 0) { a.nvrtcDestroyProgram(&prog); c.failed = true; return c; }
   size_t sz = 0;
@@ -198,8 +207,7 @@ Compiled compile(const std::string& key, const std::string& ctl, int nc, int kw,
   }
   CUmodule mod = nullptr;
   if (a.cuModuleLoadData(&mod, cubin.data()) != 0) { c.failed = true; return c; }
-  if (a.cuModuleGetFunction(&c.fn, mod, "pw_scan_jit") != 0) { c.failed = true; c.fn = nullptr; }
-  (void)key;
+  if (a.cuModuleGetFunction(&c.fn, mod, entry_name) != 0) { c.failed = true; c.fn = nullptr; }
   return c;
 }
 
@@ -222,11 +230,7 @@ int jit_selftest_compile(const ScanPlan& P, int nc, int kw, bool hot, int thread
     *(void**)(&a.nvrtcGetCUBIN) = dlsym(rtc, "nvrtcGetCUBIN");
     *(void**)(&a.nvrtcDestroyProgram) = dlsym(rtc, "nvrtcDestroyProgram");
   }
-  std::ostringstream src;
-  src << "#include \"pw_scan.cuh\"\nnamespace pw {\n" << jit_ctl(P) << "}\n"
-      << "extern \"C\" __global__ void __launch_bounds__(" << threads << ", 1) pw_scan_jit(const __grid_constant__ pw::ScanPlan P) {\n"
-      << "  pw::scan_body<pw::JitCtl, " << nc << ", " << kw << ", " << (hot ? "true" : "false") << ">(P);\n}\n";
-  const std::string text = src.str();
+  const std::string text = "#include \"pw_segmented.cuh\"\nnamespace pw {\n" + jit_ctl(P) + "}\n" + scan_entry(nc, kw, hot, threads) + seg_entry(nc, 256);
   nvrtcProgram prog = nullptr;
   if (a.nvrtcCreateProgram(&prog, text.c_str(), "pw_scan_jit.cu", 0, nullptr, nullptr) != 0) { *err = "nvrtcCreateProgram failed"; return 2; }
   const std::string inc = "--include-path=" + csrc_dir();
@@ -263,7 +267,7 @@ int launch_scan_jit(const ScanPlan& P, int nc, int kw, bool hot, int threads, in
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_cache.find(key);
     if (it == g_cache.end()) {
-      c = compile(key, ctl, nc, kw, hot, threads);
+      c = compile(ctl, scan_entry(nc, kw, hot, threads), "pw_scan_jit");
       g_cache[key] = c;
     } else c = it->second;
   }
@@ -282,6 +286,39 @@ int launch_scan_jit(const ScanPlan& P, int nc, int kw, bool hot, int threads, in
   const CUresult rc = a.cuLaunchKernel(c.fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)smem, (CUstream)st, params, nullptr);
   if (rc != 0) return fail(PW_ERR_CUDA, "cuLaunchKernel(pw_scan_jit) failed with %d", rc);
   ctx().timings.kernel_launches++;
+  return 0;
+}
+
+// the sorted-window kernel, specialised the same way; returns 0 launched, 1 unavailable
+int launch_seg_jit(const ScanPlan& P, const SegParams& sp, int nc, int threads, size_t smem, int sm_count, cudaStream_t st) {
+  if (getenv("PW_NO_JIT")) return 1;
+  Api& a = api();
+  if (!a.ok) return 1;
+  const std::string ctl = jit_ctl(P);
+  const std::string key = ctl + "|seg|" + std::to_string(nc) + "|" + std::to_string(threads);
+  Compiled c;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_cache.find(key);
+    if (it == g_cache.end()) {
+      c = compile(ctl, seg_entry(nc, threads), "pw_seg_jit");
+      g_cache[key] = c;
+    } else c = it->second;
+  }
+  if (c.failed || !c.fn) return 1;
+  if (smem > 48 * 1024 && a.cuFuncSetAttribute(c.fn, 8, (int)smem) != 0) return 1;
+  int per_sm = 0;
+  if (a.cuOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c.fn, threads, smem) != 0 || per_sm < 1) return 1;
+  const int64_t n_steps = (P.n_rows + ROWS_PER_STEP - 1) / ROWS_PER_STEP;
+  int64_t grid = std::min<int64_t>((int64_t)sm_count * per_sm, (n_steps + (threads / 32) - 1) / (threads / 32));
+  if (grid < 1) grid = 1;
+  ScanPlan copy = P;
+  SegParams spc = sp;
+  void* params[] = {&copy, &spc};
+  const CUresult rc = a.cuLaunchKernel(c.fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)smem, (CUstream)st, params, nullptr);
+  if (rc != 0) return fail(PW_ERR_CUDA, "cuLaunchKernel(pw_seg_jit) failed with %d", rc);
+  ctx().timings.kernel_launches++;
+  ctx().timings.reserved = 1.0f;
   return 0;
 }
 
