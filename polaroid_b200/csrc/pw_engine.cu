@@ -617,8 +617,14 @@ static int init_table(const Table& T, const ScanPlan& P, cudaStream_t st) {
 }
 
 // distinct keys among `n_sample` rows starting at row_begin with the given stride (pilot launch)
-static int sample_distinct(const Lowered& L, int64_t row_begin, int64_t stride, int64_t n_sample, Control* dctl,
-                           Control* hctl, uint64_t* distinct) {
+// distinct keys among `n_sample` rows starting at row_begin with the given stride (pilot launch).  Launch and
+// collect are split so that both pilots of a query run back to back with ONE host synchronisation.
+struct Pilot {
+  Table T{};
+  Control* dctl = nullptr;
+  uint32_t* dummy = nullptr;
+};
+static int pilot_launch(const Lowered& L, int64_t row_begin, int64_t stride, int64_t n_sample, Pilot* pl) {
   ThreadCtx& c = ctx();
   ScanPlan P = L.plan;
   P.n_rows = n_sample; P.row_begin = row_begin; P.row_stride = stride;
@@ -627,26 +633,23 @@ static int sample_distinct(const Lowered& L, int64_t row_begin, int64_t stride, 
   // only group identity matters: one len accumulator
   P.n_acc = 1; P.accs[0].op = OP_ADD_I64; P.accs[0].src = SRC_ONE; P.accs[0].vexpr = 0; P.n_vexpr = 0;
   P.gflags = GF_LEN; P.acc_gbase = 0;
-  Table T{};
-  PW_TRY(alloc_table(&T, padded_kw(P.n_kw), 1, (uint64_t)n_sample * 2 + 64, dctl));
-  PW_TRY(init_table(T, P, c.stream));
-  P.table = T; P.not_sorted = &dctl->not_sorted;
-  PW_CUDA(cudaMemsetAsync(dctl, 0, sizeof(Control), c.stream));
-  PW_TRY(launch_scan(P, c.sm_count, c.stream));
-  uint32_t* dummy = nullptr;
   void* p = nullptr;
-  PW_TRY(dev_alloc(&p, (T.cap + 2) * 4)); dummy = (uint32_t*)p;
-  int grid = (int)std::min<uint64_t>((T.cap + 2 + 255) / 256, 148 * 8);
-  compact_kernel<<<grid, 256, 0, c.stream>>>(T, padded_kw(P.n_kw), dummy, &dctl->counter);
+  PW_TRY(dev_alloc(&p, sizeof(Control))); pl->dctl = (Control*)p;
+  PW_CUDA(cudaMemsetAsync(pl->dctl, 0, sizeof(Control), c.stream));
+  PW_TRY(alloc_table(&pl->T, padded_kw(P.n_kw), 1, (uint64_t)n_sample * 2 + 64, pl->dctl));
+  PW_TRY(init_table(pl->T, P, c.stream));
+  P.table = pl->T; P.not_sorted = &pl->dctl->not_sorted;
+  PW_TRY(launch_scan(P, c.sm_count, c.stream));
+  PW_TRY(dev_alloc(&p, (pl->T.cap + 2) * 4)); pl->dummy = (uint32_t*)p;
+  int grid = (int)std::min<uint64_t>((pl->T.cap + 2 + 255) / 256, 148 * 8);
+  compact_kernel<<<grid, 256, 0, c.stream>>>(pl->T, padded_kw(P.n_kw), pl->dummy, &pl->dctl->counter);
   PW_CUDA(cudaGetLastError());
   c.timings.kernel_launches++;
-  PW_CUDA(cudaMemcpyAsync(hctl, dctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream));
-  PW_CUDA(cudaStreamSynchronize(c.stream));
-  *distinct = hctl->counter;
-  dev_free(dummy);
-  free_table(T);
-  if (hctl->overflow == 2) return fail(PW_ERR_UNSUPPORTED, "string key longer than 12 bytes (long views need the data buffers: SURVEY 8f rank 1)");
   return 0;
+}
+static void pilot_free(Pilot* pl) {
+  dev_free(pl->dummy); dev_free(pl->dctl);
+  if (pl->T.keys) free_table(pl->T);
 }
 
 // d distinct values seen in a uniform sample of n rows -> number of groups, assuming equally likely
@@ -715,21 +718,29 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
   if (N <= SMALL) {
     if (!cap) cap = (uint64_t)std::max<int64_t>(2 * N, 64);
   } else if (!cap || !(q->flags & (PW_FLAG_FORCE_HOT_TABLE | PW_FLAG_FORCE_GLOBAL_TABLE))) {
-    // (1) strided sample over the whole input -> table size
-    const int64_t n_s = SMALL;
-    uint64_t d = 0;
-    PW_TRY(sample_distinct(L, 0, N / n_s, n_s, dctl, &hctl, &d));
-    double g = solve_groups((double)d, (double)n_s);
-    if (P.n_preds == 0 || true) g = std::min(g, (double)N);
-    if (!cap) cap = (uint64_t)std::max(1024.0, std::min(2.0 * (double)N + 64.0, 2.5 * g + 1024.0));
-    // (2) a contiguous block from the middle -> do consecutive rows share few groups? (hot table pays)
+    // (1) strided sample over the whole input -> table size; (2) a contiguous block from the middle -> do
+    // consecutive rows share few groups (then the hot table pays)?  Both pilots are queued, then one sync.
+    const int64_t n_s = N >= (32ll << 20) ? SMALL : (1 << 16);
     const int64_t n_b = 1 << 16;
     int64_t mid = ((N / 2) / ROWS_PER_STEP) * ROWS_PER_STEP;
     if (mid + n_b > N) mid = 0;
-    uint64_t dl = 0;
-    PW_TRY(sample_distinct(L, mid, 1, n_b, dctl, &hctl, &dl));
-    live_groups = (int64_t)dl;
-    use_hot = dl <= 2048;
+    Pilot p1, p2;
+    int prc = pilot_launch(L, 0, N / n_s, n_s, &p1);
+    if (!prc) prc = pilot_launch(L, mid, 1, n_b, &p2);
+    Control h1{}, h2{};
+    if (!prc) {
+      cudaMemcpyAsync(&h1, p1.dctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream);
+      cudaMemcpyAsync(&h2, p2.dctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream);
+      if (cudaStreamSynchronize(c.stream) != cudaSuccess) prc = fail(PW_ERR_CUDA, "pilot failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    pilot_free(&p1); pilot_free(&p2);
+    if (prc) { dev_free(dctl); return prc; }
+    if (h1.overflow == 2 || h2.overflow == 2) { dev_free(dctl); return fail(PW_ERR_UNSUPPORTED, "string key longer than 12 bytes (long views need the data buffers: SURVEY 8f rank 1)"); }
+    double g = solve_groups((double)h1.counter, (double)n_s);
+    g = std::min(g, (double)N);
+    if (!cap) cap = (uint64_t)std::max(1024.0, std::min(2.0 * (double)N + 64.0, 2.5 * g + 1024.0));
+    live_groups = (int64_t)h2.counter;
+    use_hot = h2.counter <= 2048;
   }
   if (q->flags & PW_FLAG_FORCE_HOT_TABLE) use_hot = true;
   if (q->flags & PW_FLAG_FORCE_GLOBAL_TABLE) use_hot = false;
@@ -744,6 +755,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
 
   // ---- scan (with growth retries) ------------------------------------------------------------------
   Table T{};
+  uint32_t* slots = nullptr;
   tm.retries = 0;
   for (;;) {
     PW_TRY(alloc_table(&T, padded_kw(P.n_kw), P.n_acc, cap, dctl));
@@ -755,11 +767,19 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     PW_CUDA(cudaEventRecord(c.ev[8], c.stream));
     if (N > 0) PW_TRY(launch_scan(P, c.sm_count, c.stream));
     PW_CUDA(cudaEventRecord(c.ev[9], c.stream));
+    // queue the compaction right behind the scan: its result is simply discarded when the scan overflowed
+    { void* p = nullptr; PW_TRY(dev_alloc(&p, (cap + 2) * 4)); slots = (uint32_t*)p; }
+    {
+      int grid = (int)std::min<uint64_t>((cap + 2 + 255) / 256, 148 * 8);
+      compact_kernel<<<grid, 256, 0, c.stream>>>(T, padded_kw(P.n_kw), slots, &dctl->counter);
+      PW_CUDA(cudaGetLastError());
+      tm.kernel_launches++;
+    }
     PW_CUDA(cudaMemcpyAsync(&hctl, dctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream));
     PW_CUDA(cudaStreamSynchronize(c.stream));
-    if (hctl.overflow == 2) { free_table(T); dev_free(dctl); return fail(PW_ERR_UNSUPPORTED, "string key longer than 12 bytes (long views need the data buffers: SURVEY 8f rank 1)"); }
+    if (hctl.overflow == 2) { free_table(T); dev_free(slots); dev_free(dctl); return fail(PW_ERR_UNSUPPORTED, "string key longer than 12 bytes (long views need the data buffers: SURVEY 8f rank 1)"); }
     if (hctl.overflow == 1) {
-      free_table(T);
+      free_table(T); dev_free(slots); slots = nullptr;
       if (cap >= (uint64_t)2 * (uint64_t)N + 64) { dev_free(dctl); return fail(PW_ERR_INTERNAL, "hash table overflow at maximum size"); }
       cap = std::min<uint64_t>(cap * 4, (uint64_t)2 * (uint64_t)N + 64);
       tm.retries++;
@@ -768,29 +788,15 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     break;
   }
   if (hctl.not_sorted) {
-    free_table(T); dev_free(dctl);
+    free_table(T); dev_free(slots); dev_free(dctl);
     return fail(PW_ERR_NOT_SORTED, "argument in operation 'group_by_dynamic' is not sorted, please sort the 'expr/series/column' first");
   }
   tm.strategy = use_hot ? 1 : 2;
   tm.spilled_rows = (int64_t)hctl.spilled;
   tm.table_slots = (int64_t)cap;
   PW_CUDA(cudaEventRecord(c.ev[3], c.stream));
-
-  // ---- compact + order --------------------------------------------------------------------------------
-  uint32_t* slots = nullptr;
-  { void* p = nullptr; PW_TRY(dev_alloc(&p, (cap + 2) * 4)); slots = (uint32_t*)p; }
-  PW_CUDA(cudaMemsetAsync(&dctl->counter, 0, sizeof(unsigned long long), c.stream));
-  {
-    int grid = (int)std::min<uint64_t>((cap + 2 + 255) / 256, 148 * 8);
-    compact_kernel<<<grid, 256, 0, c.stream>>>(T, padded_kw(P.n_kw), slots, &dctl->counter);
-    PW_CUDA(cudaGetLastError());
-    tm.kernel_launches++;
-  }
-  PW_CUDA(cudaMemcpyAsync(&hctl, dctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream));
-  PW_CUDA(cudaStreamSynchronize(c.stream));
   const uint64_t G = hctl.counter;
   tm.n_groups = (int64_t)G;
-
   PW_TRY(order_groups(L, T, padded_kw(P.n_kw), &slots, G));
   dev_free(dctl);
   *table_out = T;
@@ -808,51 +814,67 @@ int emit_results(const Lowered& L, const Table& T, const uint32_t* slot_list, ui
   const size_t ncol = L.outs.size();
   if (*n_out < ncol) return fail(PW_ERR_INVALID, "output capacity %zu < %zu result columns", *n_out, ncol);
   if (ncol > 64) return fail(PW_ERR_UNSUPPORTED, "more than 64 result columns");
-  unsigned long long* d_nulls = nullptr;
-  { void* p = nullptr; PW_TRY(dev_alloc(&p, 64 * 8)); d_nulls = (unsigned long long*)p; }
-  PW_CUDA(cudaMemsetAsync(d_nulls, 0, 64 * 8, c.stream));
-  std::vector<void*> d_vals(ncol, nullptr), d_valid(ncol, nullptr);
-  std::vector<size_t> val_bytes(ncol), valid_bytes(ncol);
-  const int grid = (int)std::max<uint64_t>(1, (G + 255) / 256);
   const int kw = padded_kw(L.plan.n_kw);
+  const int grid = (int)std::max<uint64_t>(1, (G + 255) / 256);
+  std::vector<size_t> val_bytes(ncol), valid_bytes(ncol), val_off(ncol), valid_off(ncol);
+  // one device block: [null counts: 64 x u64][values 0][validity 0][values 1] ... every piece 256-byte aligned
+  size_t total = 64 * 8;
+  auto place = [&](size_t bytes) { size_t o = total; total += (bytes + 255) / 256 * 256; return o; };
   for (size_t i = 0; i < ncol; ++i) {
-    const OutCol& o = L.outs[i];
-    val_bytes[i] = (size_t)G * dtype_bytes(o.out_dtype);
+    val_bytes[i] = (size_t)G * dtype_bytes(L.outs[i].out_dtype);
     valid_bytes[i] = ((G + 31) / 32) * 4;
-    PW_TRY(dev_alloc(&d_vals[i], val_bytes[i]));
-    PW_TRY(dev_alloc(&d_valid[i], valid_bytes[i]));
-    EmitDesc d = o.emit;
-    d.out_values = d_vals[i];
-    d.out_validity = (uint32_t*)d_valid[i];
+    val_off[i] = place(val_bytes[i]);
+    valid_off[i] = place(valid_bytes[i]);
+  }
+  char* d_block = nullptr;
+  { void* p = nullptr; PW_TRY(dev_alloc(&p, total)); d_block = (char*)p; }
+  unsigned long long* d_nulls = (unsigned long long*)d_block;
+  PW_CUDA(cudaMemsetAsync(d_nulls, 0, 64 * 8, c.stream));
+  for (size_t i = 0; i < ncol && G; ++i) {
+    EmitDesc d = L.outs[i].emit;
+    d.out_values = d_block + val_off[i];
+    d.out_validity = (uint32_t*)(d_block + valid_off[i]);
     d.null_count = d_nulls + i;
-    if (G) {
-      emit_kernel<<<grid, 256, 0, c.stream>>>(T, kw, d, slot_list, G);
-      PW_CUDA(cudaGetLastError());
-      c.timings.kernel_launches++;
-    }
+    emit_kernel<<<grid, 256, 0, c.stream>>>(T, kw, d, slot_list, G);
+    PW_CUDA(cudaGetLastError());
+    c.timings.kernel_launches++;
   }
   PW_CUDA(cudaEventRecord(c.ev[4], c.stream));
   unsigned long long h_nulls[64] = {0};
-  PW_CUDA(cudaMemcpyAsync(h_nulls, d_nulls, 64 * 8, cudaMemcpyDeviceToHost, c.stream));
   std::vector<void*> h_vals(ncol, nullptr), h_valid(ncol, nullptr);
   for (size_t i = 0; i < ncol; ++i) {
     h_vals[i] = host_alloc(val_bytes[i]);
     h_valid[i] = host_alloc(valid_bytes[i]);
     if (!h_vals[i] || !h_valid[i]) return fail(PW_ERR_INTERNAL, "out of host memory");
-    if (G) {
-      PW_CUDA(cudaMemcpyAsync(h_vals[i], d_vals[i], val_bytes[i], cudaMemcpyDeviceToHost, c.stream));
-      PW_CUDA(cudaMemcpyAsync(h_valid[i], d_valid[i], valid_bytes[i], cudaMemcpyDeviceToHost, c.stream));
-    }
   }
-  PW_CUDA(cudaEventRecord(c.ev[5], c.stream));
-  PW_CUDA(cudaStreamSynchronize(c.stream));
+  if (total <= STAGING_BYTES) {
+    // small result: ONE copy into this thread's pinned staging block, then split on the host.  Copies into
+    // pageable memory cost a driver round trip each (~10 us x 2 x columns: most of a Q1-sized query).
+    if (!c.staging) PW_CUDA(cudaHostAlloc(&c.staging, STAGING_BYTES, cudaHostAllocPortable));
+    PW_CUDA(cudaMemcpyAsync(c.staging, d_block, total, cudaMemcpyDeviceToHost, c.stream));
+    PW_CUDA(cudaEventRecord(c.ev[5], c.stream));
+    PW_CUDA(cudaStreamSynchronize(c.stream));
+    const char* h = (const char*)c.staging;
+    memcpy(h_nulls, h, 64 * 8);
+    for (size_t i = 0; i < ncol; ++i) {
+      memcpy(h_vals[i], h + val_off[i], val_bytes[i]);
+      memcpy(h_valid[i], h + valid_off[i], valid_bytes[i]);
+    }
+  } else {
+    PW_CUDA(cudaMemcpyAsync(h_nulls, d_nulls, 64 * 8, cudaMemcpyDeviceToHost, c.stream));
+    for (size_t i = 0; i < ncol; ++i) {
+      PW_CUDA(cudaMemcpyAsync(h_vals[i], d_block + val_off[i], val_bytes[i], cudaMemcpyDeviceToHost, c.stream));
+      PW_CUDA(cudaMemcpyAsync(h_valid[i], d_block + valid_off[i], valid_bytes[i], cudaMemcpyDeviceToHost, c.stream));
+    }
+    PW_CUDA(cudaEventRecord(c.ev[5], c.stream));
+    PW_CUDA(cudaStreamSynchronize(c.stream));
+  }
   for (size_t i = 0; i < ncol; ++i) {
     const OutCol& o = L.outs[i];
     PW_TRY(make_host_array((int64_t)G, (int64_t)h_nulls[i], h_valid[i], h_vals[i], o.out_dtype == DT_VIEW ? 1 : 0, &out_cols[i]));
     PW_TRY(make_schema(o.format.c_str(), o.name.c_str(), true, &out_schemas[i]));
-    dev_free(d_vals[i]); dev_free(d_valid[i]);
   }
-  dev_free(d_nulls);
+  dev_free(d_block);
   *n_out = ncol;
   return 0;
 }

@@ -22,7 +22,9 @@ struct ThreadCtx {
   bool ev_ready = false;
   int sm_count = 0;
   bool pool_ready = false;
+  void* staging = nullptr;  // pinned host block for small results (one D2H copy per query), lives with the thread
 };
+static const size_t STAGING_BYTES = 1u << 20;
 ThreadCtx& ctx();
 int fail(int code, const char* fmt, ...);
 

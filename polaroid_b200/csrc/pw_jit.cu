@@ -163,9 +163,9 @@ struct Compiled { CUfunction fn = nullptr; bool failed = false; };
 std::mutex g_mu;
 std::map<std::string, Compiled> g_cache;
 
-std::string scan_entry(int nc, int kw, bool hot, int threads) {
+std::string scan_entry(int nc, int kw, bool hot, int threads, int min_blocks = 1) {
   std::ostringstream src;
-  src << "extern \"C\" __global__ void __launch_bounds__(" << threads << ", 1) pw_scan_jit(const __grid_constant__ pw::ScanPlan P) {\n"
+  src << "extern \"C\" __global__ void __launch_bounds__(" << threads << ", " << min_blocks << ") pw_scan_jit(const __grid_constant__ pw::ScanPlan P) {\n"
       << "  pw::scan_body<pw::JitCtl, " << nc << ", " << kw << ", " << (hot ? "true" : "false") << ">(P);\n}\n";
   return src.str();
 }
@@ -261,13 +261,16 @@ int launch_scan_jit(const ScanPlan& P, int nc, int kw, bool hot, int threads, in
   Api& a = api();
   if (!a.ok) return 1;
   const std::string ctl = jit_ctl(P);
-  const std::string key = ctl + "|" + std::to_string(nc) + "|" + std::to_string(kw) + "|" + std::to_string((int)hot) + "|" + std::to_string(threads);
+  // two resident CTAs per SM when the hot table leaves room for them: the register allocator is told so
+  const size_t smem_need = hot ? (size_t)P.hot.total_bytes : 0;
+  const int min_blocks = (2 * (smem_need + 1024) <= 227 * 1024 && 2 * threads <= 1024) ? 2 : 1;
+  const std::string key = ctl + "|" + std::to_string(nc) + "|" + std::to_string(kw) + "|" + std::to_string((int)hot) + "|" + std::to_string(threads) + "|" + std::to_string(min_blocks);
   Compiled c;
   {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_cache.find(key);
     if (it == g_cache.end()) {
-      c = compile(ctl, scan_entry(nc, kw, hot, threads), "pw_scan_jit");
+      c = compile(ctl, scan_entry(nc, kw, hot, threads, min_blocks), "pw_scan_jit");
       g_cache[key] = c;
     } else c = it->second;
   }
