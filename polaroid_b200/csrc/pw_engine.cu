@@ -498,37 +498,50 @@ static bool plan_hot(ScanPlan& P, int64_t groups_hint, int requested_gcap) {
   auto is_add = [&](int a) { return P.accs[a].op == OP_ADD_F64 || P.accs[a].op == OP_ADD_I64; };
   auto is_count = [&](int a) { return P.accs[a].op == OP_ADD_I64 && (P.accs[a].src == SRC_ONE || P.accs[a].src == SRC_VALID); };
   for (int a = 0; a < P.n_acc; ++a) { if (is_count(a)) n_priv32++; else if (is_add(a)) n_priv64++; else n_mm++; }
-  // dense ids: a little head-room over the live-group estimate; the key index has >= 2x as many slots
+  // dense ids: a little head-room over the live-group estimate
   int gcap = requested_gcap > 0 ? requested_gcap : (int)std::min<int64_t>(4096, std::max<int64_t>(8, groups_hint + groups_hint / 8 + 4));
+  const int mm_stride_all = n_mm > 1 ? ((n_mm + 1) & ~1) : n_mm;
   for (;; gcap = gcap * 3 / 4) {
     if (gcap < 4) return false;
-    int S = 8;
-    while (S < 2 * gcap) S <<= 1;  // tag buckets of 4 at <= 50 % load: a full bucket is rare
-    const size_t shared = (size_t)S * 4 + (size_t)gcap * 8 * kw + 32;
-    auto per_warp = [&](int R, int mmp) { return (((size_t)gcap * R * ((size_t)(n_priv64 + mmp) * 8 + (size_t)n_priv32 * 4 + 1)) + 15) & ~(size_t)15; };
-    auto total = [&](int R, int mmp) { return shared + (size_t)(n_mm - mmp) * gcap * 8 + per_warp(R, mmp) * warps; };
+    // key index: buckets of four tags.  At 4 slots per id (25 % load) a row finds its key in the HOME bucket with
+    // probability > 0.999, so the probe is one LDS.128 + one key compare and the neighbour bucket is only looked at
+    // on the (rare, warp-uniformly branched) slow path; 2 slots per id is the fallback when memory is short.
+    int S2 = 8;
+    while (S2 < 2 * gcap) S2 <<= 1;
+    // private bytes per cell: 8 per sum-like word (+ min/max words when they are private), 4 per counter; the claim
+    // byte lives in the top byte of the first counter (a dedicated 4-byte word when the query has no counter)
+    auto cell_bytes = [&](int mmp) { return (size_t)(n_priv64 + mmp) * 8 + (size_t)n_priv32 * 4 + (n_priv32 ? 0 : 4); };
+    auto per_warp = [&](int R, int mmp) { return (((size_t)gcap * R * cell_bytes(mmp)) + 15) & ~(size_t)15; };
+    auto total = [&](int S, int R, int mmp) {
+      const size_t shared = (size_t)S * 4 + (size_t)gcap * 8 * kw + 32;
+      return shared + (size_t)(mmp ? 0 : mm_stride_all) * gcap * 8 + per_warp(R, mmp) * warps;
+    };
     // Preference order: every word warp-private (plain read-modify-write; first/last words improve on almost every
     // row, so CTA-shared atomics for them are very slow) with two CTAs per SM, then with one CTA per SM, then
-    // min/max words CTA-shared (2 CTAs, 1 CTA), else fewer dense ids.
+    // min/max words CTA-shared (2 CTAs, 1 CTA), else fewer dense ids.  Inside a tier the larger key index wins.
     const size_t budget2 = 110 * 1024, budget1 = 224 * 1024;
-    int mmp = n_mm;
-    size_t budget = budget2;
-    if (total(1, n_mm) <= budget2) { mmp = n_mm; budget = budget2; }
-    else if (total(1, n_mm) <= budget1) { mmp = n_mm; budget = budget1; }
-    else if (total(1, 0) <= budget2) { mmp = 0; budget = budget2; }
-    else if (total(1, 0) <= budget1) { mmp = 0; budget = budget1; }
-    else continue;  // fewer ids
+    int mmp = -1, S = 0;
+    size_t budget = 0;
+    for (int tier = 0; tier < 4 && mmp < 0; ++tier) {
+      const int cand_mmp = tier < 2 ? n_mm : 0;
+      const size_t cand_budget = (tier & 1) ? budget1 : budget2;
+      for (int mult = 2; mult >= 1; --mult)
+        if (total(S2 * mult, 1, cand_mmp) <= cand_budget) { mmp = cand_mmp; budget = cand_budget; S = S2 * mult; break; }
+    }
+    if (mmp < 0) continue;  // fewer ids
     int R = 32;
-    while (R > 1 && total(R, mmp) > budget) R >>= 1;
+    while (R > 1 && total(S, R, mmp) > budget) R >>= 1;
     if (requested_gcap > 0 && requested_gcap <= 64) R = std::min(R, 2);  // test hook: exercise the claim path
     g.idx_slots = S; g.gcap = gcap; g.replicas = R; g.n_mm = n_mm - mmp;
+    g.mm_stride = mmp ? 0 : mm_stride_all;
     size_t off = (size_t)S * 4;
     off = (off + 15) & ~(size_t)15; g.keys_off = (int32_t)off; off += (size_t)gcap * 8 * kw;
-    g.mm_off = (int32_t)off; off += (size_t)g.n_mm * gcap * 8;
+    off = (off + 15) & ~(size_t)15; g.mm_off = (int32_t)off; off += (size_t)g.mm_stride * gcap * 8;
     g.count_off = (int32_t)off; off += 16;
     g.warp_off = (int32_t)off;
     size_t woff = 0;
     int mm_idx = 0;
+    g.claim_acc = -1;
     for (int pass = 0; pass < 2; ++pass) {  // 8-byte words first, then 4-byte counters
       for (int a = 0; a < P.n_acc; ++a) {
         if (pass == 0) {
@@ -537,10 +550,11 @@ static bool plan_hot(ScanPlan& P, int64_t groups_hint, int requested_gcap) {
           g.acc_kind[a] = HOT_PRIV64; g.acc_off[a] = (int32_t)woff; woff += (size_t)gcap * R * 8;
         } else if (is_count(a)) {
           g.acc_kind[a] = HOT_PRIV32; g.acc_off[a] = (int32_t)woff; woff += (size_t)gcap * R * 4;
+          if (g.claim_acc < 0) { g.claim_acc = a; g.claim_off = g.acc_off[a]; }
         }
       }
     }
-    g.claim_off = (int32_t)woff; woff += (size_t)gcap * R;
+    if (g.claim_acc < 0) { g.claim_off = (int32_t)woff; woff += (size_t)gcap * R * 4; }
     woff = (woff + 15) & ~(size_t)15;
     g.warp_bytes = (int32_t)woff;
     g.total_bytes = (int32_t)(off + woff * warps);

@@ -132,10 +132,13 @@ struct HotGeom {
   int32_t idx_slots;   // key index slots (power of two), 0 = hot table off
   int32_t gcap;        // dense group ids
   int32_t replicas;    // R: replicas of every private cell inside a warp (power of two, <= 32)
-  int32_t n_mm;        // number of CTA-shared min/max arrays
-  int32_t keys_off, mm_off, count_off, warp_off, warp_bytes, claim_off, total_bytes, pad;
+  int32_t n_mm;        // number of CTA-shared min/max words per group
+  int32_t keys_off, mm_off, count_off, warp_off, warp_bytes, claim_off, total_bytes;
+  int32_t mm_stride;   // words per group in the CTA-shared min/max block (n_mm rounded up to even: 16-byte pairs)
+  int32_t claim_acc;   // accumulator whose 32-bit private counter hosts the claim byte (bits 24..31), -1 = dedicated words
+  int32_t pad;
   int32_t acc_kind[MAX_ACC];
-  int32_t acc_off[MAX_ACC];  // HOT_SHARED_MM: array index; private kinds: byte offset inside the warp region
+  int32_t acc_off[MAX_ACC];  // HOT_SHARED_MM: word inside the group's min/max block; private kinds: byte offset inside the warp region
 };
 
 struct ScanPlan {

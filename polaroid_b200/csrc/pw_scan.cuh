@@ -246,8 +246,8 @@ struct HotTable {
       const uint64_t init = acc_init(CT::acc_op(P, a));
       const int kind = CT::h_kind(P, a);
       if (kind == HOT_SHARED_MM) {
-        uint64_t* p = mm + (size_t)CT::h_off(P, a) * G;
-        for (int i = threadIdx.x; i < G; i += blockDim.x) p[i] = init;
+        uint64_t* p = mm + CT::h_off(P, a);
+        for (int i = threadIdx.x; i < G; i += blockDim.x) p[(size_t)i * CT::h_mm_stride(P)] = init;
       } else {
         const int cells = G * R;
         for (int w = 0; w < W; ++w) {
@@ -268,32 +268,47 @@ struct HotTable {
     for (int w = 0; w < KW; ++w) eq &= (*(volatile uint64_t*)&keys[(size_t)w * G + id] == k[w]);
     return eq;
   }
-  // key -> dense group id; -1 when the table is full or the probe budget is spent (row goes cold).
-  // Fast path (every row once its group exists): one LDS.128 of the bucket's four tags, a branch-free
-  // fingerprint match, one key compare.  Fingerprints live in [1, 0xFFFE] so that neither an empty (0) nor a
-  // busy (all ones) tag can match.
-  __device__ __forceinline__ int upsert(const ScanPlan& P, const uint64_t (&k)[KW], uint64_t h) {
+  // key -> dense group id.  FAST PATH (every row once its group exists): one LDS.128 of the home bucket's four
+  // tags, a branch-free fingerprint match, one key compare; -1 = not there (caller takes the slow path for the
+  // warp's missing rows).  Fingerprints live in [1, 0xFFFE] so that neither an empty (0) nor a busy (all ones)
+  // tag can match.
+  // The lookup is split in two so that a lane's rows can issue all their tag loads, then all their key loads
+  // (volatile shared-memory loads keep program order: back-to-back whole lookups would serialise the round trips).
+  __device__ __forceinline__ uint4 lookup_tags(const ScanPlan& P, uint64_t h) const {
+    const int bmask = (CT::h_slots(P) >> 2) - 1;
+    const int bucket = (int)((uint32_t)(h >> 32) & (uint32_t)bmask);
+    return lds128_volatile(tag + bucket * 4);
+  }
+  __device__ __forceinline__ int lookup_match(const uint4& ta, uint64_t h) const {  // -> dense id or -1
+    uint32_t f16 = (uint32_t)(h >> 48);
+    f16 = min(max(f16, 1u), 0xFFFEu);
+    uint32_t ca = 0;
+    ca = ((ta.w >> 16) == f16) ? ta.w : ca; ca = ((ta.z >> 16) == f16) ? ta.z : ca;
+    ca = ((ta.y >> 16) == f16) ? ta.y : ca; ca = ((ta.x >> 16) == f16) ? ta.x : ca;
+    return (int)(ca & 0xFFFFu) - 1;
+  }
+  // SLOW PATH: insertion, fingerprint collisions, keys that live in a neighbour of an overflowing bucket.
+  // -1 when the table is full or the probe budget is spent (row goes cold).
+  struct Key { uint64_t w[KW]; };  // by value: a reference would force the caller's key registers onto the stack
+  __device__ __forceinline__ int upsert_slow(const ScanPlan& P, const uint64_t (&k)[KW], uint64_t h) const {
+    Key kv;
+#pragma unroll
+    for (int w = 0; w < KW; ++w) kv.w[w] = k[w];
+    return upsert_slow_fn(*this, P, kv, h);
+  }
+  static __device__ __noinline__ int upsert_slow_fn(HotTable hot, const ScanPlan& P, Key kv, uint64_t h) {
+    uint32_t* const tag = hot.tag;
+    uint64_t* const keys = hot.keys;
+    uint32_t* const count = hot.count;
+    uint64_t k[KW];
+#pragma unroll
+    for (int w = 0; w < KW; ++w) k[w] = kv.w[w];
     const int S = CT::h_slots(P), G = CT::h_gcap(P);
     uint32_t f16 = (uint32_t)(h >> 48);
     f16 = min(max(f16, 1u), 0xFFFEu);
     const uint32_t fp = f16 << 16;
     const int bmask = (S >> 2) - 1;
     int bucket = (int)((uint32_t)(h >> 32) & (uint32_t)bmask);
-    {
-      // home bucket and its neighbour (where an overflowing bucket spills to), both read unconditionally and
-      // resolved without branches so that the probes of several rows can overlap
-      const uint4 ta = lds128_volatile(tag + bucket * 4);
-      const uint4 tb = lds128_volatile(tag + ((bucket + 1) & bmask) * 4);
-      uint32_t ca = 0, cb = 0;
-      ca = ((ta.w >> 16) == f16) ? ta.w : ca; ca = ((ta.z >> 16) == f16) ? ta.z : ca;
-      ca = ((ta.y >> 16) == f16) ? ta.y : ca; ca = ((ta.x >> 16) == f16) ? ta.x : ca;
-      cb = ((tb.w >> 16) == f16) ? tb.w : cb; cb = ((tb.z >> 16) == f16) ? tb.z : cb;
-      cb = ((tb.y >> 16) == f16) ? tb.y : cb; cb = ((tb.x >> 16) == f16) ? tb.x : cb;
-      const int ia = ca ? (int)(ca & 0xFFFFu) - 1 : 0, ib = cb ? (int)(cb & 0xFFFFu) - 1 : 0;
-      const bool ha = key_equals(P, ia, k) && ca != 0u, hb = key_equals(P, ib, k) && cb != 0u;
-      if (ha || hb) return ha ? ia : ib;
-    }
-    // slow path: insertion, fingerprint collisions, overflowing buckets
     int probes = 0;
     int result = -1;
     bool done = false;
@@ -309,7 +324,7 @@ struct HotTable {
         else if (t[i] == 0u) empty = i;
         else if ((t[i] & 0xFFFF0000u) == fp && result < 0) {
           const int id = (int)(t[i] & 0xFFFFu) - 1;
-          if (key_equals(P, id, k)) result = id;
+          if (hot.key_equals(P, id, k)) result = id;
         }
       }
       if (result >= 0) { done = true; }
@@ -353,14 +368,14 @@ struct HotTable {
         const int kind = CT::h_kind(P, a);
         uint64_t v;
         if (kind == HOT_SHARED_MM) {
-          v = mm[(size_t)CT::h_off(P, a) * G + id];
+          v = mm[(size_t)id * CT::h_mm_stride(P) + CT::h_off(P, a)];
         } else {
           v = acc_init(op);  // combine the replicas of every warp
           for (int w = 0; w < W; ++w) {
             const unsigned char* base = wall + (size_t)w * CT::h_warp_bytes(P) + CT::h_off(P, a);
             for (int r = 0; r < R; ++r) {
               if (kind == HOT_PRIV64) v = acc_combine(op, v, ((const uint64_t*)base)[(size_t)id * R + r]);
-              else v += ((const uint32_t*)base)[(size_t)id * R + r];
+              else v += ((const uint32_t*)base)[(size_t)id * R + r] & (a == CT::h_claim_acc(P) ? 0x00FFFFFFu : 0xFFFFFFFFu);
             }
           }
         }
@@ -526,7 +541,9 @@ __device__ __forceinline__ void row_decode(const ScanPlan& P, const uint4 (&raw)
   for (int c = 0; c < NC; ++c) {
     if (c < CT::n_slots(P)) {
       r.in[c] = decode(raw[c], CT::slot_dtype(P, c), j);
-      r.in_valid |= ((vbits[c] >> j) & 1u) << c;
+      // a slot without a validity bitmap is valid by construction (rows past the end are never alive), which lets
+      // the compiler drop every null check downstream
+      r.in_valid |= (CT::slot_nullable(P, c) ? ((vbits[c] >> j) & 1u) : 1u) << c;
     } else r.in[c] = 0;
   }
 }
@@ -665,24 +682,144 @@ struct ColdSink {  // HBM table, atomics
   template <int OP>
   __device__ __forceinline__ void add(const ScanPlan&, int a, uint64_t x) const { acc_apply_global(&tacc(T, a, slot), OP, x); }
 };
-template <class CT, int KW>
-struct HotSink {  // shared-memory hot table: private cells under a claim, shared min/max words
+// Shared-memory hot table, B rows of one lane at a time: private cells under a claim, shared min/max words.
+// Every accumulator word is updated for all B rows together — B independent loads, then B stores — so that the
+// shared-memory round trips of a lane's rows overlap (the caller guarantees that enabled rows of one lane hit
+// DISTINCT cells).  `cw` = the cell's claim/counter word as read under the claim.
+template <class CT, int KW, int B>
+struct HotSinkB {
   const HotTable<CT, KW>& hot;
-  int id, cell;
+  const int (&id)[B];
+  const int (&cell)[B];
+  const uint32_t (&cw)[B];
   template <int OP>
-  __device__ __forceinline__ void add(const ScanPlan& P, int a, uint64_t x) const {
+  __device__ __forceinline__ void add(const ScanPlan& P, int a, const uint64_t (&x)[B], const bool (&en)[B]) const {
     const int kind = CT::h_kind(P, a);
     if (kind == HOT_PRIV64) {
-      uint64_t* q = (uint64_t*)(hot.wbase + CT::h_off(P, a)) + cell;
-      *q = acc_combine(OP, *q, x);
+      uint64_t* base = (uint64_t*)(hot.wbase + CT::h_off(P, a));
+      uint64_t old[B];
+#pragma unroll
+      for (int i = 0; i < B; ++i) old[i] = en[i] ? base[cell[i]] : 0ull;
+#pragma unroll
+      for (int i = 0; i < B; ++i) if (en[i]) base[cell[i]] = acc_combine(OP, old[i], x[i]);
     } else if (kind == HOT_PRIV32) {
-      uint32_t* q = (uint32_t*)(hot.wbase + CT::h_off(P, a)) + cell;
-      *q += (uint32_t)x;
+      uint32_t* base = (uint32_t*)(hot.wbase + CT::h_off(P, a));
+      if (CT::h_rep(P) < 32 && a == CT::h_claim_acc(P)) {
+        // the counter that hosts the claim byte was read by the claim check: store only (count < 2^24 between
+        // flushes, so the add never carries into the claim byte)
+#pragma unroll
+        for (int i = 0; i < B; ++i) if (en[i]) base[cell[i]] = cw[i] + (uint32_t)x[i];
+      } else {
+        uint32_t old[B];
+#pragma unroll
+        for (int i = 0; i < B; ++i) old[i] = en[i] ? base[cell[i]] : 0u;
+#pragma unroll
+        for (int i = 0; i < B; ++i) if (en[i]) base[cell[i]] = old[i] + (uint32_t)x[i];
+      }
     } else {
-      minmax_apply_shared(&hot.mm[(size_t)CT::h_off(P, a) * CT::h_gcap(P) + id], OP, x);
+#pragma unroll
+      for (int i = 0; i < B; ++i)
+        if (en[i]) minmax_apply_shared(&hot.mm[(size_t)id[i] * CT::h_mm_stride(P) + CT::h_off(P, a)], OP, x[i]);
+    }
+  }
+  // min word at accumulator a, max word at a + 1, same operand: when both are CTA-shared and form an aligned
+  // 16-byte pair, one LDS.128 reads both extrema
+  template <int OPMIN, int OPMAX>
+  __device__ __forceinline__ void minmax(const ScanPlan& P, int a, const uint64_t (&x)[B], const bool (&en)[B]) const {
+    if (CT::h_kind(P, a) == HOT_SHARED_MM && CT::h_kind(P, a + 1) == HOT_SHARED_MM && (CT::h_off(P, a) & 1) == 0 &&
+        CT::h_off(P, a + 1) == CT::h_off(P, a) + 1 && (CT::h_mm_stride(P) & 1) == 0) {
+      uint4 cur[B];
+#pragma unroll
+      for (int i = 0; i < B; ++i) {
+        const uint64_t* q = &hot.mm[(size_t)(en[i] ? id[i] : 0) * CT::h_mm_stride(P) + CT::h_off(P, a)];
+        cur[i] = lds128_volatile((const uint32_t*)q);
+      }
+#pragma unroll
+      for (int i = 0; i < B; ++i) {
+        uint64_t* q = &hot.mm[(size_t)id[i] * CT::h_mm_stride(P) + CT::h_off(P, a)];
+        const uint64_t lo = (uint64_t)cur[i].y << 32 | cur[i].x, hi = (uint64_t)cur[i].w << 32 | cur[i].z;
+        if (OPMIN == OP_MIN_I64) {
+          if (en[i] && (long long)x[i] < (long long)lo) atomicMin((long long*)q, (long long)x[i]);
+          if (en[i] && (long long)x[i] > (long long)hi) atomicMax((long long*)(q + 1), (long long)x[i]);
+        } else {
+          if (en[i] && x[i] < lo) atomicMin((unsigned long long*)q, (unsigned long long)x[i]);
+          if (en[i] && x[i] > hi) atomicMax((unsigned long long*)(q + 1), (unsigned long long)x[i]);
+        }
+      }
+    } else {
+      add<OPMIN>(P, a, x, en);
+      add<OPMAX>(P, a + 1, x, en);
     }
   }
 };
+
+// B-row form of accumulate_row (same walk over the aggregate flags; `en` = rows that take part)
+template <class CT, int NV, int KW, int B, class Sink>
+__device__ __forceinline__ void accumulate_rows(const ScanPlan& P, const RowOut<KW, NV> (&o)[B], const uint64_t (&grow)[B],
+                                                const bool (&en)[B], const Sink& s) {
+  uint64_t ones[B];
+#pragma unroll
+  for (int i = 0; i < B; ++i) ones[i] = 1ull;
+#pragma unroll
+  for (int e = 0; e < NV; ++e) {
+    if (e >= CT::n_vexpr(P)) break;
+    const int fl = CT::ve_flags(P, e), cls = CT::ve_cls(P, e);
+    int a = CT::ve_acc(P, e);
+    uint64_t bits[B];
+    bool ok[B];
+#pragma unroll
+    for (int i = 0; i < B; ++i) { bits[i] = o[i].v[e]; ok[i] = en[i] && ((o[i].v_valid >> e) & 1u); }
+    if (fl & VF_SUM_I) { s.template add<OP_ADD_I64>(P, a, bits, ok); ++a; }
+    if (fl & VF_SUM_F) {
+      uint64_t xs[B];
+#pragma unroll
+      for (int i = 0; i < B; ++i) xs[i] = (uint64_t)__double_as_longlong(bits_to_f64(bits[i], cls));
+      s.template add<OP_ADD_F64>(P, a, xs, ok); ++a;
+    }
+    if (fl & VF_COUNT) { s.template add<OP_ADD_I64>(P, a, ones, ok); ++a; }
+    if (fl & (VF_MIN | VF_MAX)) {
+      uint64_t x[B];
+      bool use[B];
+#pragma unroll
+      for (int i = 0; i < B; ++i) {
+        x[i] = bits[i]; use[i] = ok[i];
+        if (cls == CLS_F64) {
+          const double d = __longlong_as_double((long long)bits[i]);
+          use[i] = ok[i] && (d == d);  // NaN is skipped; an all-NaN group keeps the init word -> NaN at emit time
+          x[i] = (uint64_t)f64_to_ordered(d);
+        }
+      }
+      if ((fl & VF_MIN) && (fl & VF_MAX)) {
+        if (cls == CLS_U64) s.template minmax<OP_MIN_U64, OP_MAX_U64>(P, a, x, use);
+        else s.template minmax<OP_MIN_I64, OP_MAX_I64>(P, a, x, use);
+        a += 2;
+      } else if (fl & VF_MIN) {
+        if (cls == CLS_U64) s.template add<OP_MIN_U64>(P, a, x, use); else s.template add<OP_MIN_I64>(P, a, x, use);
+        ++a;
+      } else {
+        if (cls == CLS_U64) s.template add<OP_MAX_U64>(P, a, x, use); else s.template add<OP_MAX_I64>(P, a, x, use);
+        ++a;
+      }
+    }
+    if (fl & (VF_FIRST | VF_LAST)) {
+      uint64_t x[B];
+#pragma unroll
+      for (int i = 0; i < B; ++i) x[i] = (grow[i] << 1) | (ok[i] ? 1ull : 0ull);
+      if (fl & VF_FIRST) { s.template add<OP_MIN_U64>(P, a, x, en); ++a; }
+      if (fl & VF_LAST) { s.template add<OP_MAX_U64>(P, a, x, en); ++a; }
+    }
+  }
+  int a = CT::acc_gbase(P);
+  const int gf = CT::gflags(P);
+  if (gf & GF_LEN) { s.template add<OP_ADD_I64>(P, a, ones, en); ++a; }
+  if (gf & GF_ROW) { s.template add<OP_MIN_U64>(P, a, grow, en); ++a; }
+  if (gf & GF_TMIN) {
+    uint64_t t[B];
+#pragma unroll
+    for (int i = 0; i < B; ++i) t[i] = o[i].tval;
+    s.template add<OP_MIN_I64>(P, a, t, en); ++a;
+  }
+}
 
 // one pass over the aggregate flags of every value expression; accumulator words are consecutive per
 // expression in VFlag order (host: lower_query), then LEN, ROW, TMIN
@@ -719,58 +856,120 @@ __device__ __forceinline__ void accumulate_row(const ScanPlan& P, const RowOut<K
   if (gf & GF_TMIN) { s.template add<OP_MIN_I64>(P, a, o.tval); ++a; }
 }
 
-// BACK END, phase 1: hash + hot-table probe (independent per row: several rows are probed back to back so
-// that their shared-memory round trips overlap)
-template <class CT, int KW, int NV, bool HOT>
-__device__ __forceinline__ void row_probe(const ScanPlan& P, HotTable<CT, KW>& hot, const RowOut<KW, NV>& o, uint64_t& h, int& id) {
-  h = hash_words<KW>(o.k);
-  id = -1;
-  // rows whose raw key aliases a sentinel bypass the hot table so that a hot KEY_NULL is always a true null
-  if (HOT && o.alive && o.sentinel_free) id = hot.upsert(P, o.k, h);
+template <class CT>
+__device__ __forceinline__ uint64_t global_row(const ScanPlan& P, int64_t row) {
+  return CT::unit_stride(P) ? (uint64_t)(row + P.row_offset) : (uint64_t)(P.row_begin + row * P.row_stride + P.row_offset);
 }
 
-// BACK END, phase 2: aggregate one row per lane.  Called convergently by all 32 lanes (dead rows keep
-// `alive == false`) because the claim loop uses warp-wide votes.
-template <class CT, int KW, int NV, bool HOT>
-__device__ __forceinline__ void row_accumulate(const ScanPlan& P, HotTable<CT, KW>& hot, const RowOut<KW, NV>& o, uint64_t h, int id,
-                                               int lane, unsigned long long& spilled) {
-  const uint64_t grow = CT::unit_stride(P) ? (uint64_t)(o.row + P.row_offset) : (uint64_t)(P.row_begin + o.row * P.row_stride + P.row_offset);
+// BACK END, phase 1: hash + hot-table probe of B rows per lane.  The home-bucket lookups are branch-free and
+// independent, so their shared-memory round trips overlap; rows that miss (first sight of a group, keys that
+// live next to an overflowing bucket) take the slow path under one warp-uniform branch.  Called convergently.
+template <class CT, int KW, int NV, bool HOT, int B>
+__device__ __forceinline__ void rows_probe(const ScanPlan& P, HotTable<CT, KW>& hot, const RowOut<KW, NV> (&o)[B], uint64_t (&h)[B], int (&id)[B]) {
+  bool miss = false;
+#pragma unroll
+  for (int i = 0; i < B; ++i) { h[i] = hash_words<KW>(o[i].k); id[i] = -1; }
   if (HOT) {
-    const int R = CT::h_rep(P);
-    const int cell = id * R + (lane & (R - 1));
-    // lanes of this warp that target the same private cell: each writes its lane number into the cell's claim
-    // byte and reads it back; the winner does a plain read-modify-write, losers retry.  (A MATCH.ANY based ranking
-    // was measured 15 % slower on B200: 1.93 ms vs 1.68 ms on C2.)  R == 32 gives every lane its own replica.
-    bool pending = id >= 0;
-    unsigned char* claim = hot.wbase + CT::h_claim_off(P);
-    const bool need_claim = R < 32;
-    while (__any_sync(0xffffffffu, pending)) {
-      bool win = pending;
-      if (need_claim) {
-        if (pending) claim[cell] = (unsigned char)lane;
-        __syncwarp();
-        win = pending && claim[cell] == (unsigned char)lane;
-      }
-      if (win) {
-        const HotSink<CT, KW> sink{hot, id, cell};
-        accumulate_row<CT, NV, KW>(P, o, grow, sink);
-        pending = false;
-      }
-      if (need_claim) __syncwarp();
+    uint4 tags[B];
+    int cand[B];
+    bool eq[B];
+#pragma unroll
+    for (int i = 0; i < B; ++i) tags[i] = hot.lookup_tags(P, h[i]);
+#pragma unroll
+    for (int i = 0; i < B; ++i) cand[i] = hot.lookup_match(tags[i], h[i]);
+#pragma unroll
+    for (int i = 0; i < B; ++i) eq[i] = hot.key_equals(P, max(cand[i], 0), o[i].k);
+#pragma unroll
+    for (int i = 0; i < B; ++i) {
+      // rows whose raw key aliases a sentinel bypass the hot table so that a hot KEY_NULL is always a true null
+      const bool want = o[i].alive && o[i].sentinel_free;
+      const bool hit = eq[i] && cand[i] >= 0;
+      id[i] = (want && hit) ? cand[i] : -1;
+      miss = miss || (want && !hit);
     }
   }
-  if (o.alive && id < 0) {
-    // cold / spill tier: straight into the HBM table
-    const uint64_t gslot = table_upsert<KW>(P.table, o.k, h, o.sentinel_free || KW != 1);
-    if (HOT) ++spilled;
-    if (gslot != ~0ull) {
-      if (P.row_group_out) P.row_group_out[o.row] = P.slot_rank[gslot];  // lookup pass of group_tuples
-      else {
-        const ColdSink sink{P.table, gslot};
-        accumulate_row<CT, NV, KW>(P, o, grow, sink);
+  if (HOT && __any_sync(0xffffffffu, miss)) {
+#pragma unroll
+    for (int i = 0; i < B; ++i)
+      if (o[i].alive && o[i].sentinel_free && id[i] < 0) id[i] = hot.upsert_slow(P, o[i].k, h[i]);
+  }
+}
+
+// BACK END, phase 2: aggregate B rows per lane.  Called convergently by all 32 lanes (dead rows keep
+// `alive == false`) because the claim loop uses warp-wide votes.
+template <class CT, int KW, int NV, bool HOT, int B>
+__device__ __forceinline__ void rows_accumulate(const ScanPlan& P, HotTable<CT, KW>& hot, const RowOut<KW, NV> (&o)[B], const uint64_t (&h)[B],
+                                                const int (&id)[B], int lane, unsigned long long& spilled) {
+  uint64_t grow[B];
+#pragma unroll
+  for (int i = 0; i < B; ++i) grow[i] = global_row<CT>(P, o[i].row);
+  if (HOT) {
+    const int R = CT::h_rep(P);
+    int cell[B];
+    uint32_t cw[B];
+    bool pend[B];
+#pragma unroll
+    for (int i = 0; i < B; ++i) { pend[i] = id[i] >= 0; cell[i] = pend[i] ? id[i] * R + (lane & (R - 1)) : 0; cw[i] = 0u; }
+    const HotSinkB<CT, KW, B> sink{hot, id, cell, cw};
+    if (R == 32) {
+      // every lane owns its replica: no claims.  Two rows of one lane may share a cell -> one row at a time.
+#pragma unroll
+      for (int i = 0; i < B; ++i) {
+        bool en[B];
+#pragma unroll
+        for (int j = 0; j < B; ++j) en[j] = (j == i) && pend[j];
+        accumulate_rows<CT, NV, KW, B>(P, o, grow, en, sink);
+      }
+    } else {
+      // Lanes of this warp that target the same private cell: every pending row writes its lane number into the
+      // cell's claim byte (top byte of the cell's counter word), the warp syncs, and the row whose lane number
+      // survived owns the cell for this round: plain read-modify-write, no atomics.  Losers (and a lane's second row
+      // for the same cell) go again.  All B rows of a lane claim in the same round.  (A MATCH.ANY based ranking was
+      // measured 15 % slower on B200: 1.93 ms vs 1.68 ms on C2.)
+      uint32_t* cwords = (uint32_t*)(hot.wbase + CT::h_claim_off(P));
+      bool any = false;
+#pragma unroll
+      for (int i = 0; i < B; ++i) any = any || pend[i];
+      while (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+        for (int i = 0; i < B; ++i)
+          if (pend[i]) ((volatile unsigned char*)(cwords + cell[i]))[3] = (unsigned char)lane;
+        __syncwarp();
+        bool win[B];
+#pragma unroll
+        for (int i = 0; i < B; ++i) {
+          cw[i] = pend[i] ? ld_volatile_u32(cwords + cell[i]) : 0u;
+          win[i] = pend[i] && (cw[i] >> 24) == (uint32_t)lane;
+#pragma unroll
+          for (int j = 0; j < i; ++j) win[i] = win[i] && !(win[j] && cell[j] == cell[i]);
+        }
+        accumulate_rows<CT, NV, KW, B>(P, o, grow, win, sink);
+        any = false;
+#pragma unroll
+        for (int i = 0; i < B; ++i) { pend[i] = pend[i] && !win[i]; any = any || pend[i]; }
       }
     }
-  } else if (!o.alive && P.row_group_out && o.row < P.n_rows) P.row_group_out[o.row] = 0xFFFFFFFFu;
+  }
+  bool cold = CT::group_out(P);
+#pragma unroll
+  for (int i = 0; i < B; ++i) cold = cold || (o[i].alive && id[i] < 0);
+  if (cold) {
+#pragma unroll
+    for (int i = 0; i < B; ++i) {
+      if (o[i].alive && id[i] < 0) {
+        // cold / spill tier: straight into the HBM table
+        const uint64_t gslot = table_upsert<KW>(P.table, o[i].k, h[i], o[i].sentinel_free || KW != 1);
+        if (HOT) ++spilled;
+        if (gslot != ~0ull) {
+          if (CT::group_out(P)) P.row_group_out[o[i].row] = P.slot_rank[gslot];  // lookup pass of group_tuples
+          else {
+            const ColdSink sink{P.table, gslot};
+            accumulate_row<CT, NV, KW>(P, o[i], grow[i], sink);
+          }
+        }
+      } else if (!o[i].alive && CT::group_out(P) && o[i].row < P.n_rows) P.row_group_out[o[i].row] = 0xFFFFFFFFu;
+    }
+  }
 }
 
 // sortedness of the dynamic index over one warp step (every adjacent row pair plus the row before the
@@ -857,42 +1056,36 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
       load_step<CT, NC>(P, base, lane, n_rows, raw, vbits);
       if (CT::check_sorted(P)) check_sorted_step<CT, NC>(P, raw, base, lane, n_rows);
       if (NC <= 4) {
-        // narrow class: evaluate and PROBE all four rows first (independent chains -> instruction-level
-        // parallelism), then aggregate them one after the other
-        RowOut<KW, NV> o0, o1, o2, o3;
-        uint64_t h0, h1, h2, h3;
-        int i0, i1, i2, i3;
-        row_front<CT, NC, KW, NV, 0>(P, raw, vbits, 0, base, lane, n_rows, o0);
-        row_front<CT, NC, KW, NV, 0>(P, raw, vbits, 1, base, lane, n_rows, o1);
-        row_front<CT, NC, KW, NV, 1>(P, raw, vbits, 0, base, lane, n_rows, o2);
-        row_front<CT, NC, KW, NV, 1>(P, raw, vbits, 1, base, lane, n_rows, o3);
-        row_probe<CT, KW, NV, HOT>(P, hot, o0, h0, i0);
-        row_probe<CT, KW, NV, HOT>(P, hot, o1, h1, i1);
-        row_probe<CT, KW, NV, HOT>(P, hot, o2, h2, i2);
-        row_probe<CT, KW, NV, HOT>(P, hot, o3, h3, i3);
-        row_accumulate<CT, KW, NV, HOT>(P, hot, o0, h0, i0, lane, spilled);
-        row_accumulate<CT, KW, NV, HOT>(P, hot, o1, h1, i1, lane, spilled);
-        row_accumulate<CT, KW, NV, HOT>(P, hot, o2, h2, i2, lane, spilled);
-        row_accumulate<CT, KW, NV, HOT>(P, hot, o3, h3, i3, lane, spilled);
+        // narrow class: evaluate, PROBE and AGGREGATE the lane's four rows together (independent chains ->
+        // instruction-level parallelism; one claim round for all four)
+        RowOut<KW, NV> o[4];
+        uint64_t h[4];
+        int id[4];
+        row_front<CT, NC, KW, NV, 0>(P, raw, vbits, 0, base, lane, n_rows, o[0]);
+        row_front<CT, NC, KW, NV, 0>(P, raw, vbits, 1, base, lane, n_rows, o[1]);
+        row_front<CT, NC, KW, NV, 1>(P, raw, vbits, 0, base, lane, n_rows, o[2]);
+        row_front<CT, NC, KW, NV, 1>(P, raw, vbits, 1, base, lane, n_rows, o[3]);
+        rows_probe<CT, KW, NV, HOT, 4>(P, hot, o, h, id);
+        rows_accumulate<CT, KW, NV, HOT, 4>(P, hot, o, h, id, lane, spilled);
       } else {
         // wide class (register-bound): one row at a time; the half is unrolled, the pair element is a real loop
 #pragma unroll 1
         for (int j = 0; j < 2; ++j) {
-          RowOut<KW, NV> o;
-          uint64_t h;
-          int id;
-          row_front<CT, NC, KW, NV, 0>(P, raw, vbits, j, base, lane, n_rows, o);
-          row_probe<CT, KW, NV, HOT>(P, hot, o, h, id);
-          row_accumulate<CT, KW, NV, HOT>(P, hot, o, h, id, lane, spilled);
+          RowOut<KW, NV> o[1];
+          uint64_t h[1];
+          int id[1];
+          row_front<CT, NC, KW, NV, 0>(P, raw, vbits, j, base, lane, n_rows, o[0]);
+          rows_probe<CT, KW, NV, HOT, 1>(P, hot, o, h, id);
+          rows_accumulate<CT, KW, NV, HOT, 1>(P, hot, o, h, id, lane, spilled);
         }
 #pragma unroll 1
         for (int j = 0; j < 2; ++j) {
-          RowOut<KW, NV> o;
-          uint64_t h;
-          int id;
-          row_front<CT, NC, KW, NV, 1>(P, raw, vbits, j, base, lane, n_rows, o);
-          row_probe<CT, KW, NV, HOT>(P, hot, o, h, id);
-          row_accumulate<CT, KW, NV, HOT>(P, hot, o, h, id, lane, spilled);
+          RowOut<KW, NV> o[1];
+          uint64_t h[1];
+          int id[1];
+          row_front<CT, NC, KW, NV, 1>(P, raw, vbits, j, base, lane, n_rows, o[0]);
+          rows_probe<CT, KW, NV, HOT, 1>(P, hot, o, h, id);
+          rows_accumulate<CT, KW, NV, HOT, 1>(P, hot, o, h, id, lane, spilled);
         }
       }
     }
@@ -908,8 +1101,9 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
       const bool nearly = cnt >= G - (G >> 3) && !stable_set;
       __syncthreads();
       ++tiles_since_flush;
-      if ((full || nearly) && tile + 1 < tile_hi) {
-        if (!full && flushed_once && tiles_since_flush <= 2) stable_set = true;  // refilled at once: same groups again
+      const bool wrap = tiles_since_flush >= 30000;  // private counters share their word with the claim byte: 24 bits
+      if ((full || nearly || wrap) && tile + 1 < tile_hi) {
+        if (!full && !wrap && flushed_once && tiles_since_flush <= 2) stable_set = true;  // refilled at once: same groups again
         else {
           hot.flush(P);
           __syncthreads();
