@@ -1047,13 +1047,19 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
   bool stable_set = false, flushed_once = false;  // eviction heuristics (CTA-uniform)
   int tiles_since_flush = 0;
 
+  // narrow class: the loads of the NEXT tile are issued before the current tile is processed (software pipeline;
+  // 12 warps per SM cannot hide an HBM round trip per tile otherwise).  The wide class has no registers to spare.
+  constexpr bool PREFETCH = NC <= 4;
+  uint4 raw[2][NC], nraw[2][NC];
+  uint32_t vbits[2][NC], nvbits[2][NC];
+  if (PREFETCH && tile_lo < tile_hi) load_step<CT, NC>(P, (tile_lo * warps + warp) * ROWS_PER_STEP, lane, n_rows, raw, vbits);
+
   for (int64_t tile = tile_lo; tile < tile_hi; ++tile) {
     const int64_t step = tile * warps + warp;
     const int64_t base = step * ROWS_PER_STEP;
+    if (PREFETCH) load_step<CT, NC>(P, base + (int64_t)warps * ROWS_PER_STEP, lane, tile + 1 < tile_hi ? n_rows : 0, nraw, nvbits);
     if (step < n_steps) {
-      uint4 raw[2][NC];
-      uint32_t vbits[2][NC];
-      load_step<CT, NC>(P, base, lane, n_rows, raw, vbits);
+      if (!PREFETCH) load_step<CT, NC>(P, base, lane, n_rows, raw, vbits);
       if (CT::check_sorted(P)) check_sorted_step<CT, NC>(P, raw, base, lane, n_rows);
       if (NC <= 4) {
         // narrow class: evaluate, PROBE and AGGREGATE the lane's four rows together (independent chains ->
@@ -1088,6 +1094,12 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
           rows_accumulate<CT, KW, NV, HOT, 1>(P, hot, o, h, id, lane, spilled);
         }
       }
+    }
+    if (PREFETCH) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { raw[hf][c] = nraw[hf][c]; vbits[hf][c] = nvbits[hf][c]; }
     }
     if (HOT && ((tile - tile_lo) & 3) == 3) {  // every 4 tiles (6144 rows at 12 warps): two CTA barriers
       __syncthreads();
