@@ -686,7 +686,10 @@ struct ColdSink {  // HBM table, atomics
 // Every accumulator word is updated for all B rows together — B independent loads, then B stores — so that the
 // shared-memory round trips of a lane's rows overlap (the caller guarantees that enabled rows of one lane hit
 // DISTINCT cells).  `cw` = the cell's claim/counter word as read under the claim.
-template <class CT, int KW, int B>
+// PART selects which words a pass touches: the CTA-shared min/max words need no claim, so they are updated once,
+// outside the claim loop (whose every extra round would otherwise repeat them).
+enum HotPart : int { PART_ALL = 0, PART_PRIVATE = 1, PART_SHARED = 2 };
+template <class CT, int KW, int B, int PART>
 struct HotSinkB {
   const HotTable<CT, KW>& hot;
   const int (&id)[B];
@@ -695,6 +698,8 @@ struct HotSinkB {
   template <int OP>
   __device__ __forceinline__ void add(const ScanPlan& P, int a, const uint64_t (&x)[B], const bool (&en)[B]) const {
     const int kind = CT::h_kind(P, a);
+    if (PART == PART_PRIVATE && kind == HOT_SHARED_MM) return;
+    if (PART == PART_SHARED && kind != HOT_SHARED_MM) return;
     if (kind == HOT_PRIV64) {
       uint64_t* base = (uint64_t*)(hot.wbase + CT::h_off(P, a));
       uint64_t old[B];
@@ -728,6 +733,18 @@ struct HotSinkB {
   __device__ __forceinline__ void minmax(const ScanPlan& P, int a, const uint64_t (&x)[B], const bool (&en)[B]) const {
     if (CT::h_kind(P, a) == HOT_SHARED_MM && CT::h_kind(P, a + 1) == HOT_SHARED_MM && (CT::h_off(P, a) & 1) == 0 &&
         CT::h_off(P, a + 1) == CT::h_off(P, a) + 1 && (CT::h_mm_stride(P) & 1) == 0) {
+      minmax_pair<OPMIN>(P, a, x, en, part_tag<PART != PART_PRIVATE>{});
+    } else {
+      add<OPMIN>(P, a, x, en);
+      add<OPMAX>(P, a + 1, x, en);
+    }
+  }
+  template <bool ON> struct part_tag {};
+  template <int OPMIN>
+  __device__ __forceinline__ void minmax_pair(const ScanPlan&, int, const uint64_t (&)[B], const bool (&)[B], part_tag<false>) const {}
+  template <int OPMIN>
+  __device__ __forceinline__ void minmax_pair(const ScanPlan& P, int a, const uint64_t (&x)[B], const bool (&en)[B], part_tag<true>) const {
+    {
       uint4 cur[B];
 #pragma unroll
       for (int i = 0; i < B; ++i) {
@@ -746,9 +763,6 @@ struct HotSinkB {
           if (en[i] && x[i] > hi) atomicMax((unsigned long long*)(q + 1), (unsigned long long)x[i]);
         }
       }
-    } else {
-      add<OPMIN>(P, a, x, en);
-      add<OPMAX>(P, a + 1, x, en);
     }
   }
 };
@@ -910,7 +924,9 @@ __device__ __forceinline__ void rows_accumulate(const ScanPlan& P, HotTable<CT, 
     bool pend[B];
 #pragma unroll
     for (int i = 0; i < B; ++i) { pend[i] = id[i] >= 0; cell[i] = pend[i] ? id[i] * R + (lane & (R - 1)) : 0; cw[i] = 0u; }
-    const HotSinkB<CT, KW, B> sink{hot, id, cell, cw};
+    const HotSinkB<CT, KW, B, PART_ALL> sink{hot, id, cell, cw};
+    const HotSinkB<CT, KW, B, PART_PRIVATE> sink_private{hot, id, cell, cw};
+    const HotSinkB<CT, KW, B, PART_SHARED> sink_shared{hot, id, cell, cw};
     if (R == 32) {
       // every lane owns its replica: no claims.  Two rows of one lane may share a cell -> one row at a time.
 #pragma unroll
@@ -930,6 +946,7 @@ __device__ __forceinline__ void rows_accumulate(const ScanPlan& P, HotTable<CT, 
       bool any = false;
 #pragma unroll
       for (int i = 0; i < B; ++i) any = any || pend[i];
+      if (CT::h_n_mm(P) > 0) accumulate_rows<CT, NV, KW, B>(P, o, grow, pend, sink_shared);
       while (__any_sync(0xffffffffu, any)) {
 #pragma unroll
         for (int i = 0; i < B; ++i)
@@ -943,7 +960,7 @@ __device__ __forceinline__ void rows_accumulate(const ScanPlan& P, HotTable<CT, 
 #pragma unroll
           for (int j = 0; j < i; ++j) win[i] = win[i] && !(win[j] && cell[j] == cell[i]);
         }
-        accumulate_rows<CT, NV, KW, B>(P, o, grow, win, sink);
+        accumulate_rows<CT, NV, KW, B>(P, o, grow, win, sink_private);
         any = false;
 #pragma unroll
         for (int i = 0; i < B; ++i) { pend[i] = pend[i] && !win[i]; any = any || pend[i]; }
