@@ -947,7 +947,9 @@ __device__ __forceinline__ void rows_accumulate(const ScanPlan& P, HotTable<CT, 
 #pragma unroll
       for (int i = 0; i < B; ++i) any = any || pend[i];
       if (CT::h_n_mm(P) > 0) accumulate_rows<CT, NV, KW, B>(P, o, grow, pend, sink_shared);
-      while (__any_sync(0xffffffffu, any)) {
+      // first round: all B rows of the lane
+      bool go = __any_sync(0xffffffffu, any);
+      while (go) {
 #pragma unroll
         for (int i = 0; i < B; ++i)
           if (pend[i]) ((volatile unsigned char*)(cwords + cell[i]))[3] = (unsigned char)lane;
@@ -964,6 +966,36 @@ __device__ __forceinline__ void rows_accumulate(const ScanPlan& P, HotTable<CT, 
         any = false;
 #pragma unroll
         for (int i = 0; i < B; ++i) { pend[i] = pend[i] && !win[i]; any = any || pend[i]; }
+        go = (B == 1) && __any_sync(0xffffffffu, any);
+      }
+      if (B > 1) {
+        // later rounds: few rows are left (the losers of a collision), so each lane retries ONE row per round — its
+        // first pending one — through a single-row body that costs a fraction of the B-wide round
+        while (__any_sync(0xffffffffu, any)) {
+          RowOut<KW, NV> so[1];
+          uint64_t sgrow[1];
+          int sid[1], scell[1];
+          uint32_t scw[1];
+          so[0] = o[B - 1]; sgrow[0] = grow[B - 1]; sid[0] = id[B - 1]; scell[0] = cell[B - 1];
+#pragma unroll
+          for (int i = B - 2; i >= 0; --i)
+            if (pend[i]) { so[0] = o[i]; sgrow[0] = grow[i]; sid[0] = id[i]; scell[0] = cell[i]; }
+          if (any) ((volatile unsigned char*)(cwords + scell[0]))[3] = (unsigned char)lane;
+          __syncwarp();
+          scw[0] = any ? ld_volatile_u32(cwords + scell[0]) : 0u;
+          const bool swin[1] = {any && (scw[0] >> 24) == (uint32_t)lane};
+          const HotSinkB<CT, KW, 1, PART_PRIVATE> s1{hot, sid, scell, scw};
+          accumulate_rows<CT, NV, KW, 1>(P, so, sgrow, swin, s1);
+          bool found = false;  // passed the lane's first pending row?
+          any = false;
+#pragma unroll
+          for (int i = 0; i < B; ++i) {
+            const bool is_first = pend[i] && !found;
+            found = found || pend[i];
+            if (is_first && swin[0]) pend[i] = false;
+            any = any || pend[i];
+          }
+        }
       }
     }
   }
