@@ -53,18 +53,59 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region."""
+    """SM clock + throttle reasons sampled DURING the timed region.
+
+    NVML in-process (nvidia_ml_py) at ~1 kHz so that even a 20 ms timed region gets samples; falls back to an
+    `nvidia-smi -lms` child process when NVML cannot be loaded."""
+
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index: int):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+        self.idx, self.rows, self.proc, self.h, self.stop_flag = gpu_index, [], None, None, False
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(gpu_index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    @staticmethod
+    def _physical_index(i: int) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[i])
+            except Exception:
+                return i
+        return i
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for name, bit in self.BAD.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                break
+            time.sleep(0.001)
 
     def start(self):
+        if self.h is not None:
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -75,6 +116,11 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self) -> dict:
+        if self.h is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1.0)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -90,7 +136,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def make_c2_numpy(rows: int, groups: int, seed: int):
@@ -175,7 +221,7 @@ def run_reference(args, rank: int, world: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default: the workload's)")
@@ -315,7 +361,7 @@ def main():
                          "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
                          "whole_step_frac": (algo_bytes / (ms * 1e-3) / 1e9) / peak},
             "cpu_baseline": cpu,
-            "phases_ms": {k: tm[k] for k in ("estimate_ms", "scan_ms", "scan_kernel_ms", "finalize_ms", "d2h_ms", "total_device_ms")},
+            "phases_ms": {k: tm[k] for k in ("estimate_ms", "scan_ms", "scan_kernel_ms", "finalize_ms", "d2h_ms", "total_device_ms", "host_ms")},
             "spilled_rows": tm["spilled_rows"], "table_slots": tm["table_slots"], "n_groups": tm["n_groups"],
             "jit": bool(tm["reserved"]), "retries": tm["retries"],
         }

@@ -171,7 +171,9 @@ typedef struct PwTimings {
   int64_t kernel_launches; /* launches of this library's kernels in the last call */
   int64_t spilled_rows;  /* rows that bypassed the hot table (spill tier) */
   float scan_kernel_ms;  /* the dominant kernel alone (events immediately around its launch) */
-  float reserved;
+  float reserved;         /* 1 = the query-shape specialised (NVRTC) kernel ran, 0 = the ahead-of-time kernel */
+  float host_ms;          /* wall-clock time spent inside the last pw_b200_frame_groupby call (host + device) */
+  float pad;
 } PwTimings;
 int pw_b200_last_timings(PwTimings* out);
 

@@ -3,6 +3,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
+
 #include "pw_engine.h"
 
 using namespace pw;
@@ -118,6 +120,8 @@ int pw_b200_frame_groupby(const PwQuery* q, const PwFrame* frame, struct ArrowAr
   PW_TRY(ensure_device());
   if (!q || !frame || !out_cols || !out_schemas || !n_out) return fail(PW_ERR_INVALID, "null argument");
   ThreadCtx& c = ctx();
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto host_ms = [&]() { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
   const float h2d = c.timings.h2d_ms;
   memset(&c.timings, 0, sizeof c.timings);
   c.timings.h2d_ms = h2d;
@@ -126,7 +130,7 @@ int pw_b200_frame_groupby(const PwQuery* q, const PwFrame* frame, struct ArrowAr
     bool handled = false;
     int rc = run_dynamic_segmented(q, frame, out_cols, out_schemas, n_out, &handled);
     if (rc) return rc;
-    if (handled) return 0;
+    if (handled) { c.timings.host_ms = host_ms(); return 0; }
   }
   Lowered L;
   PW_TRY(lower_query(q, frame, &L));
@@ -147,6 +151,7 @@ int pw_b200_frame_groupby(const PwQuery* q, const PwFrame* frame, struct ArrowAr
   if (cudaEventElapsedTime(&ms, c.ev[4], c.ev[5]) == cudaSuccess) c.timings.d2h_ms = ms;
   if (cudaEventElapsedTime(&ms, c.ev[0], c.ev[5]) == cudaSuccess) c.timings.total_device_ms = ms;
   if (cudaEventElapsedTime(&ms, c.ev[8], c.ev[9]) == cudaSuccess) c.timings.scan_kernel_ms = ms;
+  c.timings.host_ms = host_ms();
   return 0;
 }
 

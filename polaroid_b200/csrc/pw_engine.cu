@@ -739,11 +739,13 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     int64_t mid = ((N / 2) / ROWS_PER_STEP) * ROWS_PER_STEP;
     if (mid + n_b > N) mid = 0;
     Pilot p1, p2;
-    int prc = pilot_launch(L, 0, N / n_s, n_s, &p1);
-    if (!prc) prc = pilot_launch(L, mid, 1, n_b, &p2);
     Control h1{}, h2{};
+    int prc = pilot_launch(L, 0, N / n_s, n_s, &p1);
     if (!prc) {
       cudaMemcpyAsync(&h1, p1.dctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream);
+      prc = pilot_launch(L, mid, 1, n_b, &p2);
+    }
+    if (!prc) {
       cudaMemcpyAsync(&h2, p2.dctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream);
       if (cudaStreamSynchronize(c.stream) != cudaSuccess) prc = fail(PW_ERR_CUDA, "pilot failed: %s", cudaGetErrorString(cudaGetLastError()));
     }

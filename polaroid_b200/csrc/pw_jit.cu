@@ -163,7 +163,7 @@ std::string jit_ctl(const ScanPlan& P) {
   return g.o.str();
 }
 
-struct Compiled { CUfunction fn = nullptr; bool failed = false; };
+struct Compiled { CUfunction fn = nullptr; bool failed = false; int per_sm = 0; };
 std::mutex g_mu;
 std::map<std::string, Compiled> g_cache;
 
@@ -260,32 +260,63 @@ int jit_selftest_compile(const ScanPlan& P, int nc, int kw, bool hot, int thread
 }
 
 // returns 0 launched, 1 JIT unavailable (caller falls back to the AOT kernel), <0 error
+// Binary cache key: exactly the fields jit_ctl() turns into constants (the text itself is only generated on a miss —
+// building it costs more than a small kernel launch).
+static std::string plan_key(const ScanPlan& P) {
+  std::string k;
+  k.reserve(1024);
+  auto put = [&](const void* p, size_t n) { k.append((const char*)p, n); };
+  auto i32 = [&](int32_t v) { put(&v, 4); };
+  i32(P.n_slots);
+  for (int i = 0; i < P.n_slots; ++i) { i32(P.slots[i].dtype); i32(P.slots[i].validity != nullptr); }
+  i32(P.n_preds);
+  for (int i = 0; i < P.n_preds; ++i) { i32(P.preds[i].slot); i32(P.preds[i].op); i32(P.preds[i].cls); }
+  i32(P.n_keys);
+  for (int i = 0; i < P.n_keys; ++i) { i32(P.keys[i].slot); i32(P.keys[i].dtype); i32(P.keys[i].n_words); }
+  i32(P.has_null_word); i32(P.dyn.enabled); i32(P.dyn.slot); i32(P.dyn.closed);
+  i32(P.n_vexpr);
+  for (int e = 0; e < P.n_vexpr; ++e) {
+    const VExpr& v = P.vexprs[e];
+    i32(v.n_factors); i32(v.slot); i32(v.cls); i32(v.flags); i32(v.acc_base);
+    for (int f = 0; f < v.n_factors; ++f) { i32(v.f[f].slot); put(&v.f[f].a, 8); put(&v.f[f].b, 8); }
+  }
+  i32(P.gflags); i32(P.acc_gbase); i32(P.n_acc);
+  for (int a = 0; a < P.n_acc; ++a) i32(P.accs[a].op);
+  i32(P.vec_ok); i32(P.check_sorted); i32(P.row_begin == 0 && P.row_stride == 1); i32(P.row_group_out != nullptr);
+  put(&P.hot, sizeof P.hot);
+  return k;
+}
+
+// returns 0 launched, 1 JIT unavailable (caller falls back to the AOT kernel), <0 error
 int launch_scan_jit(const ScanPlan& P, int nc, int kw, bool hot, int threads, int sm_count, cudaStream_t st) {
-  if (getenv("PW_NO_JIT")) return 1;
+  static const bool disabled = getenv("PW_NO_JIT") != nullptr;
+  if (disabled) return 1;
   Api& a = api();
   if (!a.ok) return 1;
-  const std::string ctl = jit_ctl(P);
   // two resident CTAs per SM when the hot table leaves room for them: the register allocator is told so
-  const size_t smem_need = hot ? (size_t)P.hot.total_bytes : 0;
-  const int min_blocks = (2 * (smem_need + 1024) <= 227 * 1024 && 2 * threads <= 1024) ? 2 : 1;
-  const std::string key = ctl + "|" + std::to_string(nc) + "|" + std::to_string(kw) + "|" + std::to_string((int)hot) + "|" + std::to_string(threads) + "|" + std::to_string(min_blocks);
+  const size_t smem = hot ? (size_t)P.hot.total_bytes : 0;
+  const int min_blocks = (2 * (smem + 1024) <= 227 * 1024 && 2 * threads <= 1024) ? 2 : 1;
+  std::string key = plan_key(P);
+  const int32_t tail[5] = {nc, kw, (int32_t)hot, threads, min_blocks};
+  key.append((const char*)tail, sizeof tail);
   Compiled c;
   {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_cache.find(key);
     if (it == g_cache.end()) {
-      c = compile(ctl, scan_entry(nc, kw, hot, threads, min_blocks), "pw_scan_jit");
+      c = compile(jit_ctl(P), scan_entry(nc, kw, hot, threads, min_blocks), "pw_scan_jit");
+      if (!c.failed && c.fn) {
+        if (a.cuFuncSetAttribute(c.fn, 8 /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/, (int)smem) != 0 ||
+            a.cuOccupancyMaxActiveBlocksPerMultiprocessor(&c.per_sm, c.fn, threads, smem) != 0 || c.per_sm < 1)
+          c.failed = true;
+      }
       g_cache[key] = c;
     } else c = it->second;
   }
   if (c.failed || !c.fn) return 1;
-  const size_t smem = hot ? (size_t)P.hot.total_bytes : 0;
-  if (a.cuFuncSetAttribute(c.fn, 8 /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/, (int)smem) != 0) return 1;
-  int per_sm = 0;
-  if (a.cuOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c.fn, threads, smem) != 0 || per_sm < 1) return 1;
   const int64_t n_steps = (P.n_rows + ROWS_PER_STEP - 1) / ROWS_PER_STEP;
   const int64_t n_tiles = (n_steps + (threads / 32) - 1) / (threads / 32);
-  int64_t grid = (int64_t)sm_count * per_sm;
+  int64_t grid = (int64_t)sm_count * c.per_sm;
   if (grid > n_tiles) grid = n_tiles;
   if (grid < 1) grid = 1;
   ScanPlan copy = P;
@@ -298,24 +329,29 @@ int launch_scan_jit(const ScanPlan& P, int nc, int kw, bool hot, int threads, in
 
 // the sorted-window kernel, specialised the same way; returns 0 launched, 1 unavailable
 int launch_seg_jit(const ScanPlan& P, const SegParams& sp, int nc, int threads, size_t smem, int sm_count, cudaStream_t st) {
-  if (getenv("PW_NO_JIT")) return 1;
+  static const bool disabled = getenv("PW_NO_JIT") != nullptr;
+  if (disabled) return 1;
   Api& a = api();
   if (!a.ok) return 1;
-  const std::string ctl = jit_ctl(P);
-  const std::string key = ctl + "|seg|" + std::to_string(nc) + "|" + std::to_string(threads);
+  std::string key = plan_key(P);
+  const int32_t tail[4] = {-1 /* seg */, nc, threads, (int32_t)smem};
+  key.append((const char*)tail, sizeof tail);
   Compiled c;
   {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_cache.find(key);
     if (it == g_cache.end()) {
-      c = compile(ctl, seg_entry(nc, threads), "pw_seg_jit");
+      c = compile(jit_ctl(P), seg_entry(nc, threads), "pw_seg_jit");
+      if (!c.failed && c.fn) {
+        if ((smem > 48 * 1024 && a.cuFuncSetAttribute(c.fn, 8, (int)smem) != 0) ||
+            a.cuOccupancyMaxActiveBlocksPerMultiprocessor(&c.per_sm, c.fn, threads, smem) != 0 || c.per_sm < 1)
+          c.failed = true;
+      }
       g_cache[key] = c;
     } else c = it->second;
   }
   if (c.failed || !c.fn) return 1;
-  if (smem > 48 * 1024 && a.cuFuncSetAttribute(c.fn, 8, (int)smem) != 0) return 1;
-  int per_sm = 0;
-  if (a.cuOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c.fn, threads, smem) != 0 || per_sm < 1) return 1;
+  const int per_sm = c.per_sm;
   const int64_t n_steps = (P.n_rows + ROWS_PER_STEP - 1) / ROWS_PER_STEP;
   int64_t grid = std::min<int64_t>((int64_t)sm_count * per_sm, (n_steps + (threads / 32) - 1) / (threads / 32));
   if (grid < 1) grid = 1;

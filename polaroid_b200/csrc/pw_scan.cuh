@@ -279,13 +279,15 @@ struct HotTable {
     const int bucket = (int)((uint32_t)(h >> 32) & (uint32_t)bmask);
     return lds128_volatile(tag + bucket * 4);
   }
-  __device__ __forceinline__ int lookup_match(const uint4& ta, uint64_t h) const {  // -> dense id or -1
-    uint32_t f16 = (uint32_t)(h >> 48);
-    f16 = min(max(f16, 1u), 0xFFFEu);
+  // fingerprint of a hash: 15 bits + 1, i.e. [1, 0x8000] — never an empty (0) or busy (all ones) tag
+  static __device__ __forceinline__ uint32_t fingerprint(uint64_t h) { return (uint32_t)(h >> 49) + 1u; }
+  // -> matching tag (fingerprint << 16 | dense id) or 0
+  __device__ __forceinline__ uint32_t lookup_match(const uint4& ta, uint64_t h) const {
+    const uint32_t f16 = fingerprint(h);
     uint32_t ca = 0;
     ca = ((ta.w >> 16) == f16) ? ta.w : ca; ca = ((ta.z >> 16) == f16) ? ta.z : ca;
     ca = ((ta.y >> 16) == f16) ? ta.y : ca; ca = ((ta.x >> 16) == f16) ? ta.x : ca;
-    return (int)(ca & 0xFFFFu) - 1;
+    return ca;
   }
   // SLOW PATH: insertion, fingerprint collisions, keys that live in a neighbour of an overflowing bucket.
   // -1 when the table is full or the probe budget is spent (row goes cold).
@@ -304,9 +306,7 @@ struct HotTable {
 #pragma unroll
     for (int w = 0; w < KW; ++w) k[w] = kv.w[w];
     const int S = CT::h_slots(P), G = CT::h_gcap(P);
-    uint32_t f16 = (uint32_t)(h >> 48);
-    f16 = min(max(f16, 1u), 0xFFFEu);
-    const uint32_t fp = f16 << 16;
+    const uint32_t fp = fingerprint(h) << 16;
     const int bmask = (S >> 2) - 1;
     int bucket = (int)((uint32_t)(h >> 32) & (uint32_t)bmask);
     int probes = 0;
@@ -323,7 +323,7 @@ struct HotTable {
         if (t[i] == TAG_BUSY) busy = true;
         else if (t[i] == 0u) empty = i;
         else if ((t[i] & 0xFFFF0000u) == fp && result < 0) {
-          const int id = (int)(t[i] & 0xFFFFu) - 1;
+          const int id = (int)(t[i] & 0xFFFFu);
           if (hot.key_equals(P, id, k)) result = id;
         }
       }
@@ -337,7 +337,7 @@ struct HotTable {
 #pragma unroll
             for (int w = 0; w < KW; ++w) keys[(size_t)w * G + id] = k[w];
             __threadfence_block();
-            st_volatile_u32(&tb[empty], fp | (id + 1u));
+            st_volatile_u32(&tb[empty], fp | id);
             result = (int)id;
           } else {
             st_volatile_u32(&tb[empty], 0u);  // lost the race for the last ids: give the slot back
@@ -664,11 +664,12 @@ __device__ __forceinline__ bool row_keys(const ScanPlan& P, const Row<NC>& r, co
 // copies of the front end) so that the raw arrays see compile-time indices only; j stays a run-time value.
 template <class CT, int NC, int KW, int NV, int HF>
 __device__ __forceinline__ void row_front(const ScanPlan& P, const uint4 (&raw)[2][NC], const uint32_t (&vbits)[2][NC],
-                                          int j, int64_t base, int lane, int64_t n_rows, RowOut<KW, NV>& o) {
+                                          int j, int64_t base, int lane, int rem, RowOut<KW, NV>& o) {
+  // rem = rows of this warp step that exist (<= ROWS_PER_STEP): bounds checks stay in 32 bits
   o.row = base + HF * 64 + 2 * lane + j;
   Row<NC> r;
   row_decode<CT, NC>(P, raw[HF], vbits[HF], j, r);
-  bool alive = o.row < n_rows && row_predicate<CT, NC>(P, r);
+  bool alive = (HF * 64 + 2 * lane + j) < rem && row_predicate<CT, NC>(P, r);
   alive = row_keys<CT, NC, KW>(P, r, raw[HF], vbits[HF], j, alive, o.k, o.sentinel_free) && alive;
   o.alive = alive;
   row_vexprs<CT, NC, NV>(P, r, o.v, o.v_valid);
@@ -885,20 +886,20 @@ __device__ __forceinline__ void rows_probe(const ScanPlan& P, HotTable<CT, KW>& 
   for (int i = 0; i < B; ++i) { h[i] = hash_words<KW>(o[i].k); id[i] = -1; }
   if (HOT) {
     uint4 tags[B];
-    int cand[B];
+    uint32_t cand[B];
     bool eq[B];
 #pragma unroll
     for (int i = 0; i < B; ++i) tags[i] = hot.lookup_tags(P, h[i]);
 #pragma unroll
     for (int i = 0; i < B; ++i) cand[i] = hot.lookup_match(tags[i], h[i]);
 #pragma unroll
-    for (int i = 0; i < B; ++i) eq[i] = hot.key_equals(P, max(cand[i], 0), o[i].k);
+    for (int i = 0; i < B; ++i) eq[i] = hot.key_equals(P, (int)(cand[i] & 0xFFFFu), o[i].k);  // no match: id 0, ignored
 #pragma unroll
     for (int i = 0; i < B; ++i) {
       // rows whose raw key aliases a sentinel bypass the hot table so that a hot KEY_NULL is always a true null
       const bool want = o[i].alive && o[i].sentinel_free;
-      const bool hit = eq[i] && cand[i] >= 0;
-      id[i] = (want && hit) ? cand[i] : -1;
+      const bool hit = eq[i] && cand[i] != 0u;
+      id[i] = (want && hit) ? (int)(cand[i] & 0xFFFFu) : -1;
       miss = miss || (want && !hit);
     }
   }
@@ -1049,6 +1050,24 @@ __device__ __forceinline__ void check_sorted_step(const ScanPlan& P, const uint4
 // phase 1 of a warp step: issue every load (two halves x NC slots)
 template <class CT, int NC>
 __device__ __forceinline__ void load_step(const ScanPlan& P, int64_t base, int lane, int64_t n_rows, uint4 (&raw)[2][NC], uint32_t (&vbits)[2][NC]) {
+  if (CT::vec_ok(P) && CT::unit_stride(P) && base + ROWS_PER_STEP <= n_rows) {
+    // the whole step exists (every step but the last): no per-lane bounds logic, straight vector loads
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int64_t p = base + hf * 64 + 2 * lane;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        if (c < CT::n_slots(P)) {
+          raw[hf][c] = load_pair(P.slots[c].values, CT::slot_dtype(P, c), p, n_rows, true, 0, 1);
+          vbits[hf][c] = CT::slot_nullable(P, c) ? load_valid_pair(P.slots[c], p, n_rows, 0, 1) : 3u;
+        } else {
+          raw[hf][c] = make_uint4(0u, 0u, 0u, 0u);
+          vbits[hf][c] = 0u;
+        }
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int hf = 0; hf < 2; ++hf) {
     const int64_t p = base + hf * 64 + 2 * lane;
@@ -1108,6 +1127,8 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
     const int64_t base = step * ROWS_PER_STEP;
     if (PREFETCH) load_step<CT, NC>(P, base + (int64_t)warps * ROWS_PER_STEP, lane, tile + 1 < tile_hi ? n_rows : 0, nraw, nvbits);
     if (step < n_steps) {
+      const int64_t left = n_rows - base;
+      const int rem = left >= ROWS_PER_STEP ? ROWS_PER_STEP : (int)left;
       if (!PREFETCH) load_step<CT, NC>(P, base, lane, n_rows, raw, vbits);
       if (CT::check_sorted(P)) check_sorted_step<CT, NC>(P, raw, base, lane, n_rows);
       if (NC <= 4) {
@@ -1116,10 +1137,10 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
         RowOut<KW, NV> o[4];
         uint64_t h[4];
         int id[4];
-        row_front<CT, NC, KW, NV, 0>(P, raw, vbits, 0, base, lane, n_rows, o[0]);
-        row_front<CT, NC, KW, NV, 0>(P, raw, vbits, 1, base, lane, n_rows, o[1]);
-        row_front<CT, NC, KW, NV, 1>(P, raw, vbits, 0, base, lane, n_rows, o[2]);
-        row_front<CT, NC, KW, NV, 1>(P, raw, vbits, 1, base, lane, n_rows, o[3]);
+        row_front<CT, NC, KW, NV, 0>(P, raw, vbits, 0, base, lane, rem, o[0]);
+        row_front<CT, NC, KW, NV, 0>(P, raw, vbits, 1, base, lane, rem, o[1]);
+        row_front<CT, NC, KW, NV, 1>(P, raw, vbits, 0, base, lane, rem, o[2]);
+        row_front<CT, NC, KW, NV, 1>(P, raw, vbits, 1, base, lane, rem, o[3]);
         rows_probe<CT, KW, NV, HOT, 4>(P, hot, o, h, id);
         rows_accumulate<CT, KW, NV, HOT, 4>(P, hot, o, h, id, lane, spilled);
       } else {
@@ -1129,7 +1150,7 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
           RowOut<KW, NV> o[1];
           uint64_t h[1];
           int id[1];
-          row_front<CT, NC, KW, NV, 0>(P, raw, vbits, j, base, lane, n_rows, o[0]);
+          row_front<CT, NC, KW, NV, 0>(P, raw, vbits, j, base, lane, rem, o[0]);
           rows_probe<CT, KW, NV, HOT, 1>(P, hot, o, h, id);
           rows_accumulate<CT, KW, NV, HOT, 1>(P, hot, o, h, id, lane, spilled);
         }
@@ -1138,7 +1159,7 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
           RowOut<KW, NV> o[1];
           uint64_t h[1];
           int id[1];
-          row_front<CT, NC, KW, NV, 1>(P, raw, vbits, j, base, lane, n_rows, o[0]);
+          row_front<CT, NC, KW, NV, 1>(P, raw, vbits, j, base, lane, rem, o[0]);
           rows_probe<CT, KW, NV, HOT, 1>(P, hot, o, h, id);
           rows_accumulate<CT, KW, NV, HOT, 1>(P, hot, o, h, id, lane, spilled);
         }
