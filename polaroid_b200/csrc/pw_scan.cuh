@@ -752,16 +752,26 @@ struct HotSinkB {
         const uint64_t* q = &hot.mm[(size_t)(en[i] ? id[i] : 0) * CT::h_mm_stride(P) + CT::h_off(P, a)];
         cur[i] = lds128_volatile((const uint32_t*)q);
       }
+      // the common case (no row improves an extremum) leaves through ONE branch
+      bool lower[B], higher[B], need = false;
 #pragma unroll
       for (int i = 0; i < B; ++i) {
-        uint64_t* q = &hot.mm[(size_t)id[i] * CT::h_mm_stride(P) + CT::h_off(P, a)];
         const uint64_t lo = (uint64_t)cur[i].y << 32 | cur[i].x, hi = (uint64_t)cur[i].w << 32 | cur[i].z;
-        if (OPMIN == OP_MIN_I64) {
-          if (en[i] && (long long)x[i] < (long long)lo) atomicMin((long long*)q, (long long)x[i]);
-          if (en[i] && (long long)x[i] > (long long)hi) atomicMax((long long*)(q + 1), (long long)x[i]);
-        } else {
-          if (en[i] && x[i] < lo) atomicMin((unsigned long long*)q, (unsigned long long)x[i]);
-          if (en[i] && x[i] > hi) atomicMax((unsigned long long*)(q + 1), (unsigned long long)x[i]);
+        if (OPMIN == OP_MIN_I64) { lower[i] = en[i] && (long long)x[i] < (long long)lo; higher[i] = en[i] && (long long)x[i] > (long long)hi; }
+        else { lower[i] = en[i] && x[i] < lo; higher[i] = en[i] && x[i] > hi; }
+        need = need || lower[i] || higher[i];
+      }
+      if (need) {
+#pragma unroll
+        for (int i = 0; i < B; ++i) {
+          uint64_t* q = &hot.mm[(size_t)id[i] * CT::h_mm_stride(P) + CT::h_off(P, a)];
+          if (OPMIN == OP_MIN_I64) {
+            if (lower[i]) atomicMin((long long*)q, (long long)x[i]);
+            if (higher[i]) atomicMax((long long*)(q + 1), (long long)x[i]);
+          } else {
+            if (lower[i]) atomicMin((unsigned long long*)q, (unsigned long long)x[i]);
+            if (higher[i]) atomicMax((unsigned long long*)(q + 1), (unsigned long long)x[i]);
+          }
         }
       }
     }

@@ -422,6 +422,7 @@ class DeviceFrame:
             ex.release()
         self.handle = h
         self.num_rows = table.num_rows
+        self._queries = {}
 
     def free(self):
         if self.handle:
@@ -436,7 +437,16 @@ class DeviceFrame:
 
     def group_by(self, plan: P.GroupByPlan, **opts) -> pa.Table:
         L = lib()
-        bq = _BuiltQuery(self.table_schema, plan, **opts)
+        # the lowered PwQuery of a plan object is reused across calls (plans are immutable once built)
+        ck = (id(plan), tuple(sorted(opts.items())))
+        cache = self.__dict__.setdefault("_queries", {})
+        hit = cache.get(ck)
+        if hit is None or hit[0] is not plan:
+            if len(cache) > 64:
+                cache.clear()
+            hit = (plan, _BuiltQuery(self.table_schema, plan, **opts))
+            cache[ck] = hit
+        bq = hit[1]
         cap = len(plan.keys) + len(plan.aggs) + 4
         out_arrays = (ArrowArray * cap)()
         out_schemas = (ArrowSchema * cap)()
