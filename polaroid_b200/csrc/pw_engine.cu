@@ -734,7 +734,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
   } else if (!cap || !(q->flags & (PW_FLAG_FORCE_HOT_TABLE | PW_FLAG_FORCE_GLOBAL_TABLE))) {
     // (1) strided sample over the whole input -> table size; (2) a contiguous block from the middle -> do
     // consecutive rows share few groups (then the hot table pays)?  Both pilots are queued, then one sync.
-    const int64_t n_s = N >= (32ll << 20) ? SMALL : (1 << 16);
+    const int64_t n_s = N >= (32ll << 20) ? (1 << 17) : (1 << 16);
     const int64_t n_b = 1 << 16;
     int64_t mid = ((N / 2) / ROWS_PER_STEP) * ROWS_PER_STEP;
     if (mid + n_b > N) mid = 0;
@@ -846,12 +846,17 @@ int emit_results(const Lowered& L, const Table& T, const uint32_t* slot_list, ui
   { void* p = nullptr; PW_TRY(dev_alloc(&p, total)); d_block = (char*)p; }
   unsigned long long* d_nulls = (unsigned long long*)d_block;
   PW_CUDA(cudaMemsetAsync(d_nulls, 0, 64 * 8, c.stream));
-  for (size_t i = 0; i < ncol && G; ++i) {
-    EmitDesc d = L.outs[i].emit;
-    d.out_values = d_block + val_off[i];
-    d.out_validity = (uint32_t*)(d_block + valid_off[i]);
-    d.null_count = d_nulls + i;
-    emit_kernel<<<grid, 256, 0, c.stream>>>(T, kw, d, slot_list, G);
+  for (size_t i0 = 0; i0 < ncol && G; i0 += EMIT_BATCH) {
+    EmitBatch batch;
+    const size_t nb = std::min<size_t>(EMIT_BATCH, ncol - i0);
+    for (size_t j = 0; j < nb; ++j) {
+      EmitDesc d = L.outs[i0 + j].emit;
+      d.out_values = d_block + val_off[i0 + j];
+      d.out_validity = (uint32_t*)(d_block + valid_off[i0 + j]);
+      d.null_count = d_nulls + i0 + j;
+      batch.d[j] = d;
+    }
+    emit_kernel<<<dim3((unsigned)grid, (unsigned)nb), 256, 0, c.stream>>>(T, kw, batch, slot_list, G);
     PW_CUDA(cudaGetLastError());
     c.timings.kernel_launches++;
   }

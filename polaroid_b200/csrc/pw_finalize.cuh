@@ -135,7 +135,11 @@ __device__ __forceinline__ void store_typed(void* base, uint64_t i, int dt, uint
   }
 }
 
-static __global__ void emit_kernel(Table T, int n_kw, EmitDesc d, const uint32_t* slot_list, uint64_t n) {
+// One launch emits up to EMIT_BATCH result columns: blockIdx.y selects the column.
+constexpr int EMIT_BATCH = 16;
+struct EmitBatch { EmitDesc d[EMIT_BATCH]; };
+static __global__ void emit_kernel(Table T, int n_kw, const __grid_constant__ EmitBatch batch, const uint32_t* slot_list, uint64_t n) {
+  const EmitDesc& d = batch.d[blockIdx.y];
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool valid = true;
   if (i < n) {

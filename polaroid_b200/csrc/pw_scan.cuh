@@ -982,30 +982,27 @@ __device__ __forceinline__ void rows_accumulate(const ScanPlan& P, HotTable<CT, 
       if (B > 1) {
         // later rounds: few rows are left (the losers of a collision), so each lane retries ONE row per round — its
         // first pending one — through a single-row body that costs a fraction of the B-wide round
-        while (__any_sync(0xffffffffu, any)) {
+        uint32_t pm = 0;  // pending rows of this lane, one bit each
+#pragma unroll
+        for (int i = 0; i < B; ++i) pm |= (pend[i] ? 1u : 0u) << i;
+        while (__any_sync(0xffffffffu, pm != 0u)) {
+          const int j = __ffs((int)pm) - 1;  // -1: nothing pending in this lane
           RowOut<KW, NV> so[1];
           uint64_t sgrow[1];
           int sid[1], scell[1];
           uint32_t scw[1];
-          so[0] = o[B - 1]; sgrow[0] = grow[B - 1]; sid[0] = id[B - 1]; scell[0] = cell[B - 1];
+          so[0] = o[0]; sgrow[0] = grow[0]; sid[0] = id[0]; scell[0] = cell[0];
 #pragma unroll
-          for (int i = B - 2; i >= 0; --i)
-            if (pend[i]) { so[0] = o[i]; sgrow[0] = grow[i]; sid[0] = id[i]; scell[0] = cell[i]; }
-          if (any) ((volatile unsigned char*)(cwords + scell[0]))[3] = (unsigned char)lane;
+          for (int i = 1; i < B; ++i)
+            if (j == i) { so[0] = o[i]; sgrow[0] = grow[i]; sid[0] = id[i]; scell[0] = cell[i]; }
+          const bool mine = j >= 0;
+          if (mine) ((volatile unsigned char*)(cwords + scell[0]))[3] = (unsigned char)lane;
           __syncwarp();
-          scw[0] = any ? ld_volatile_u32(cwords + scell[0]) : 0u;
-          const bool swin[1] = {any && (scw[0] >> 24) == (uint32_t)lane};
+          scw[0] = mine ? ld_volatile_u32(cwords + scell[0]) : 0u;
+          const bool swin[1] = {mine && (scw[0] >> 24) == (uint32_t)lane};
           const HotSinkB<CT, KW, 1, PART_PRIVATE> s1{hot, sid, scell, scw};
           accumulate_rows<CT, NV, KW, 1>(P, so, sgrow, swin, s1);
-          bool found = false;  // passed the lane's first pending row?
-          any = false;
-#pragma unroll
-          for (int i = 0; i < B; ++i) {
-            const bool is_first = pend[i] && !found;
-            found = found || pend[i];
-            if (is_first && swin[0]) pend[i] = false;
-            any = any || pend[i];
-          }
+          if (swin[0]) pm &= pm - 1u;  // retire the row (lowest set bit)
         }
       }
     }
