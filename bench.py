@@ -325,6 +325,15 @@ def main():
     k_ms = float(np.mean(scan_ms))
     algo_bytes = rows * w["bytes_per_row"] + (w["groups"] or tm["n_groups"]) * 40
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9
+    # DRAM traffic of the same kernel on the same workload from the committed ncu --set full capture (per launch)
+    traffic = None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_c2_traffic.json")) as f:
+            tj = json.load(f)
+        if args.workload == tj["workload"] and rows == tj["rows"]:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    except Exception:
+        traffic = None
 
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None
@@ -357,7 +366,8 @@ def main():
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3},
             "gpu_launches": int(launches) * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "pw::scan_kernel", "kernel_ms": k_ms,
+                         "traffic": traffic, "kernel": ("pw_seg_jit" if tm["strategy"] == 3 else "pw_scan_jit") if tm["reserved"] else "pw::scan_kernel",
+                         "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
                          "whole_step_frac": (algo_bytes / (ms * 1e-3) / 1e9) / peak},
             "cpu_baseline": cpu,
