@@ -359,7 +359,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["name"], "rows_per_gpu": rows, "groups": w["groups"] or int(tm["n_groups"]),
                        "l2": f"inputs ({rows * w['bytes_per_row'] / 1e9:.2f} GB per step) are larger than the 126 MB L2; no explicit flush",
-                       "strategy": {1: "hot table + spill tier", 2: "HBM table", 3: "segmented"}.get(tm["strategy"]),
+                       "strategy": {1: "hot table + spill tier", 2: "HBM table", 3: "segmented", 4: "hot table, dense ids + spill tier"}.get(tm["strategy"]),
                        "parallelism": f"rows sharded over {world} GPU(s); partial aggregates merged by key hash"},
             "clocks": clocks,
             "e2e": {"value": rows * world / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": h2d * world,

@@ -166,7 +166,7 @@ int pw_b200_set_stream(void* cuda_stream);     /* calling thread's cudaStream_t 
 typedef struct PwTimings {
   float h2d_ms, estimate_ms, scan_ms, finalize_ms, d2h_ms, total_device_ms;
   int64_t n_rows, n_groups, table_slots;
-  int32_t strategy;      /* 1 hot table, 2 global table, 3 segmented */
+  int32_t strategy;      /* 1 hot table, 2 global table, 3 segmented, 4 hot table with dense ids (small integer key range) */
   int32_t retries;       /* table growth re-runs */
   int64_t kernel_launches; /* launches of this library's kernels in the last call */
   int64_t spilled_rows;  /* rows that bypassed the hot table (spill tier) */

@@ -489,9 +489,11 @@ static int padded_kw(int n_kw) { return n_kw == 3 ? 4 : (n_kw == 5 ? 6 : n_kw); 
 
 // Shared-memory hot table geometry for `groups_hint` live groups (see pw_scan.cuh).  Returns false when no
 // useful table fits.
-static bool plan_hot(ScanPlan& P, int64_t groups_hint, int requested_gcap) {
+// dense_range > 0: dense ids (id = key - dense_min) over exactly that many ids, no key index.
+static bool plan_hot(ScanPlan& P, int64_t groups_hint, int requested_gcap, int64_t dense_range = 0) {
   HotGeom& g = P.hot;
   memset(&g, 0, sizeof g);
+  const bool dense = dense_range > 0;
   const int kw = padded_kw(P.n_kw);
   const int warps = (narrow_class(P) ? ScanCfg<4>::THREADS : ScanCfg<12>::THREADS) / 32;
   int n_priv64 = 0, n_priv32 = 0, n_mm = 0;
@@ -500,20 +502,22 @@ static bool plan_hot(ScanPlan& P, int64_t groups_hint, int requested_gcap) {
   for (int a = 0; a < P.n_acc; ++a) { if (is_count(a)) n_priv32++; else if (is_add(a)) n_priv64++; else n_mm++; }
   // dense ids: a little head-room over the live-group estimate
   int gcap = requested_gcap > 0 ? requested_gcap : (int)std::min<int64_t>(4096, std::max<int64_t>(8, groups_hint + groups_hint / 8 + 4));
+  if (dense) gcap = (int)dense_range;
   const int mm_stride_all = n_mm > 1 ? ((n_mm + 1) & ~1) : n_mm;
-  for (;; gcap = gcap * 3 / 4) {
-    if (gcap < 4) return false;
+  for (bool first = true;; gcap = gcap * 3 / 4, first = false) {
+    if (gcap < 4 || (dense && !first)) return false;  // a dense range is all or nothing
     // key index: buckets of four tags.  At 4 slots per id (25 % load) a row finds its key in the HOME bucket with
     // probability > 0.999, so the probe is one LDS.128 + one key compare and the neighbour bucket is only looked at
     // on the (rare, warp-uniformly branched) slow path; 2 slots per id is the fallback when memory is short.
     int S2 = 8;
     while (S2 < 2 * gcap) S2 <<= 1;
+    if (dense) S2 = 4;  // one unused bucket keeps the "hot table on" switch (idx_slots != 0)
     // private bytes per cell: 8 per sum-like word (+ min/max words when they are private), 4 per counter; the claim
     // byte lives in the top byte of the first counter (a dedicated 4-byte word when the query has no counter)
     auto cell_bytes = [&](int mmp) { return (size_t)(n_priv64 + mmp) * 8 + (size_t)n_priv32 * 4 + (n_priv32 ? 0 : 4); };
     auto per_warp = [&](int R, int mmp) { return (((size_t)gcap * R * cell_bytes(mmp)) + 15) & ~(size_t)15; };
     auto total = [&](int S, int R, int mmp) {
-      const size_t shared = (size_t)S * 4 + (size_t)gcap * 8 * kw + 32;
+      const size_t shared = (size_t)S * 4 + (dense ? 0 : (size_t)gcap * 8 * kw) + 32;
       return shared + (size_t)(mmp ? 0 : mm_stride_all) * gcap * 8 + per_warp(R, mmp) * warps;
     };
     // Preference order: every word warp-private (plain read-modify-write; first/last words improve on almost every
@@ -525,17 +529,17 @@ static bool plan_hot(ScanPlan& P, int64_t groups_hint, int requested_gcap) {
     for (int tier = 0; tier < 4 && mmp < 0; ++tier) {
       const int cand_mmp = tier < 2 ? n_mm : 0;
       const size_t cand_budget = (tier & 1) ? budget1 : budget2;
-      for (int mult = 2; mult >= 1; --mult)
+      for (int mult = dense ? 1 : 2; mult >= 1; --mult)
         if (total(S2 * mult, 1, cand_mmp) <= cand_budget) { mmp = cand_mmp; budget = cand_budget; S = S2 * mult; break; }
     }
     if (mmp < 0) continue;  // fewer ids
     int R = 32;
     while (R > 1 && total(S, R, mmp) > budget) R >>= 1;
     if (requested_gcap > 0 && requested_gcap <= 64) R = std::min(R, 2);  // test hook: exercise the claim path
-    g.idx_slots = S; g.gcap = gcap; g.replicas = R; g.n_mm = n_mm - mmp;
+    g.idx_slots = S; g.gcap = gcap; g.replicas = R; g.n_mm = n_mm - mmp; g.dense = dense ? 1 : 0;
     g.mm_stride = mmp ? 0 : mm_stride_all;
     size_t off = (size_t)S * 4;
-    off = (off + 15) & ~(size_t)15; g.keys_off = (int32_t)off; off += (size_t)gcap * 8 * kw;
+    off = (off + 15) & ~(size_t)15; g.keys_off = (int32_t)off; off += dense ? 0 : (size_t)gcap * 8 * kw;
     off = (off + 15) & ~(size_t)15; g.mm_off = (int32_t)off; off += (size_t)g.mm_stride * gcap * 8;
     g.count_off = (int32_t)off; off += 16;
     g.warp_off = (int32_t)off;
@@ -576,7 +580,7 @@ extern "C" __attribute__((visibility("default"))) int pw_b200_jit_selftest(char*
   P.accs[0].op = OP_ADD_F64; P.accs[0].src = SRC_F64; P.accs[1].op = OP_MIN_I64; P.accs[1].src = SRC_F64_ORD;
   P.accs[2].op = OP_MAX_I64; P.accs[2].src = SRC_F64_ORD; P.accs[3].op = OP_ADD_I64; P.accs[3].src = SRC_ONE;
   P.n_acc = 4; P.gflags = GF_LEN; P.acc_gbase = 3;
-  if (!plan_hot(P, 1000, 0)) return -1;
+  if (!plan_hot(P, 1000, 0, getenv("PW_SELFTEST_DENSE") ? 1000 : 0)) return -1;
   P.hot_slots = P.hot.idx_slots;
   std::string err;
   const int rc = jit_selftest_compile(P, 4, 1, true, ScanCfg<4>::THREADS, &err);
@@ -591,7 +595,51 @@ struct Control {  // device control block (zeroed per run)
   unsigned long long spilled;
   unsigned long long counter;
   unsigned long long null_counts[64];
+  // key range of the pilot samples, as maxima of order-preserving unsigned images (zero-initialised = empty):
+  // kmax_u = max(key ^ 2^63), kmin_n = max(~(key ^ 2^63))
+  unsigned long long kmax_u, kmin_n;
 };
+
+// value range of a single integer key column over a row sample (row = begin + i * stride): decides whether
+// dense ids apply (the analogue of a perfect-hash / direct-address aggregate over a small key domain)
+__global__ void key_range_kernel(RawSlot key, int64_t begin, int64_t stride, int64_t n, unsigned long long* kmax_u, unsigned long long* kmin_n) {
+  unsigned long long hi = 0, lo = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = begin + i * stride;
+    if (key.validity) {
+      const int64_t b = (int64_t)key.bit_offset + row;
+      if (!((key.validity[b >> 3] >> (b & 7)) & 1)) continue;
+    }
+    int64_t v;
+    switch (key.dtype) {
+      case DT_I8: v = ((const int8_t*)key.values)[row]; break;
+      case DT_U8: v = ((const uint8_t*)key.values)[row]; break;
+      case DT_I16: v = ((const int16_t*)key.values)[row]; break;
+      case DT_U16: v = ((const uint16_t*)key.values)[row]; break;
+      case DT_I32: v = ((const int32_t*)key.values)[row]; break;
+      case DT_U32: v = ((const uint32_t*)key.values)[row]; break;
+      default: v = ((const int64_t*)key.values)[row]; break;
+    }
+    const unsigned long long u = (unsigned long long)v ^ 0x8000000000000000ull;
+    hi = u > hi ? u : hi;
+    lo = ~u > lo ? ~u : lo;
+  }
+  for (int o = 16; o; o >>= 1) {
+    const unsigned long long h2 = __shfl_xor_sync(0xffffffffu, hi, o), l2 = __shfl_xor_sync(0xffffffffu, lo, o);
+    hi = h2 > hi ? h2 : hi;
+    lo = l2 > lo ? l2 : lo;
+  }
+  if ((threadIdx.x & 31) == 0 && (hi | lo)) { atomicMax(kmax_u, hi); atomicMax(kmin_n, lo); }
+}
+// may this query use dense ids at all?  One plain signed (or narrow unsigned) integer key, a per-group row counter
+static bool dense_eligible(const PwQuery* q, const ScanPlan& P) {
+  if (getenv("PW_NO_DENSE")) return false;
+  if (q->n_keys != 1 || P.dyn.enabled || P.n_kw != 1 || !(P.gflags & GF_LEN) || P.row_group_out) return false;
+  switch (P.keys[0].dtype) {
+    case DT_I8: case DT_U8: case DT_I16: case DT_U16: case DT_I32: case DT_U32: case DT_I64: return true;
+    default: return false;
+  }
+}
 
 // Array-of-structs hash table: one row [key words | accumulator words | pad] per slot, padded to 4/8/16/32 words
 int alloc_table_raw(Table* T, int n_kw, int n_acc, uint64_t cap, int32_t* overflow, unsigned long long* spilled) {
@@ -727,10 +775,31 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
   uint64_t cap = 0;
   bool use_hot = true;
   int64_t live_groups = 0;  // distinct keys among consecutive rows (sizes the hot table)
+  int64_t dense_range = 0;  // > 0: single integer key whose sampled values span this many ids
   const int64_t SMALL = 1 << 18;
   if (q->initial_table_slots > 0) cap = (uint64_t)q->initial_table_slots;
+  auto take_range = [&](unsigned long long kmax_u, unsigned long long kmin_n, int64_t live) {
+    if (!(kmax_u | kmin_n)) return;
+    const uint64_t lo = ~kmin_n, hi = kmax_u;  // biased images, lo <= hi
+    const uint64_t range = hi - lo + 1;
+    // dense ids pay when the range is small and mostly populated (rows outside it still aggregate, through the
+    // HBM table)
+    if (range <= 4096 && range <= (uint64_t)std::max<int64_t>(64, 4 * live)) {
+      dense_range = (int64_t)range;
+      P.dense_min = (int64_t)(lo ^ 0x8000000000000000ull);
+    }
+  };
   if (N <= SMALL) {
     if (!cap) cap = (uint64_t)std::max<int64_t>(2 * N, 64);
+    if ((q->flags & PW_FLAG_FORCE_HOT_TABLE) && q->hot_table_slots == 0 && N > 0 && dense_eligible(q, P)) {
+      // unit-sized inputs reach the dense-id path through the force flag: range of ALL keys, one extra sync
+      PW_CUDA(cudaMemsetAsync(dctl, 0, sizeof(Control), c.stream));
+      key_range_kernel<<<64, 256, 0, c.stream>>>(P.slots[P.keys[0].slot], 0, 1, N, &dctl->kmax_u, &dctl->kmin_n);
+      tm.kernel_launches++;
+      PW_CUDA(cudaMemcpyAsync(&hctl, dctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream));
+      PW_CUDA(cudaStreamSynchronize(c.stream));
+      take_range(hctl.kmax_u, hctl.kmin_n, 1024);
+    }
   } else if (!cap || !(q->flags & (PW_FLAG_FORCE_HOT_TABLE | PW_FLAG_FORCE_GLOBAL_TABLE))) {
     // (1) strided sample over the whole input -> table size; (2) a contiguous block from the middle -> do
     // consecutive rows share few groups (then the hot table pays)?  Both pilots are queued, then one sync.
@@ -741,6 +810,12 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     Pilot p1, p2;
     Control h1{}, h2{};
     int prc = pilot_launch(L, 0, N / n_s, n_s, &p1);
+    if (!prc && dense_eligible(q, P)) {
+      const RawSlot& ks = P.slots[P.keys[0].slot];
+      key_range_kernel<<<64, 256, 0, c.stream>>>(ks, 0, N / n_s, n_s, &p1.dctl->kmax_u, &p1.dctl->kmin_n);
+      key_range_kernel<<<64, 256, 0, c.stream>>>(ks, mid, 1, n_b, &p1.dctl->kmax_u, &p1.dctl->kmin_n);
+      tm.kernel_launches += 2;
+    }
     if (!prc) {
       cudaMemcpyAsync(&h1, p1.dctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream);
       prc = pilot_launch(L, mid, 1, n_b, &p2);
@@ -757,16 +832,18 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     if (!cap) cap = (uint64_t)std::max(1024.0, std::min(2.0 * (double)N + 64.0, 2.5 * g + 1024.0));
     live_groups = (int64_t)h2.counter;
     use_hot = h2.counter <= 2048;
+    if (use_hot) take_range(h1.kmax_u, h1.kmin_n, live_groups);
   }
   if (q->flags & PW_FLAG_FORCE_HOT_TABLE) use_hot = true;
   if (q->flags & PW_FLAG_FORCE_GLOBAL_TABLE) use_hot = false;
   if (live_groups == 0) live_groups = std::min<int64_t>(std::max<int64_t>(N, 4), 1024);
-  if (use_hot && !plan_hot(P, live_groups, q->hot_table_slots)) use_hot = false;
+  if (use_hot && dense_range > 0 && q->hot_table_slots == 0 && plan_hot(P, live_groups, 0, dense_range)) { /* dense ids */ }
+  else if (use_hot && !plan_hot(P, live_groups, q->hot_table_slots)) use_hot = false;
   if (cap > 0xFFFFFFF0ull) return fail(PW_ERR_UNSUPPORTED, "table larger than 2^32 slots");
   if (getenv("PW_DEBUG"))
-    fprintf(stderr, "[pw] rows=%lld kw=%d slots=%d accs=%d cap=%llu hot=%d live=%lld gcap=%d S=%d R=%d n_mm=%d smem=%d\n", (long long)N, P.n_kw,
+    fprintf(stderr, "[pw] rows=%lld kw=%d slots=%d accs=%d cap=%llu hot=%d live=%lld gcap=%d S=%d R=%d n_mm=%d smem=%d dense=%d min=%lld\n", (long long)N, P.n_kw,
             P.n_slots, P.n_acc, (unsigned long long)cap, (int)use_hot, (long long)live_groups, P.hot.gcap, P.hot.idx_slots, P.hot.replicas,
-            P.hot.n_mm, P.hot.total_bytes);
+            P.hot.n_mm, P.hot.total_bytes, P.hot.dense, (long long)P.dense_min);
   PW_CUDA(cudaEventRecord(c.ev[2], c.stream));
 
   // ---- scan (with growth retries) ------------------------------------------------------------------
@@ -807,7 +884,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     free_table(T); dev_free(slots); dev_free(dctl);
     return fail(PW_ERR_NOT_SORTED, "argument in operation 'group_by_dynamic' is not sorted, please sort the 'expr/series/column' first");
   }
-  tm.strategy = use_hot ? 1 : 2;
+  tm.strategy = use_hot ? (P.hot.dense ? 4 : 1) : 2;
   tm.spilled_rows = (int64_t)hctl.spilled;
   tm.table_slots = (int64_t)cap;
   PW_CUDA(cudaEventRecord(c.ev[3], c.stream));

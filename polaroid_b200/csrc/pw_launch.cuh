@@ -30,12 +30,4 @@ template <int NC, int KW>
 static int launch_scan_nk(const ScanPlan& P, int sm, cudaStream_t st) {
   return P.hot_slots > 0 ? launch_scan_t<NC, KW, true>(P, sm, st) : launch_scan_t<NC, KW, false>(P, sm, st);
 }
-template <int NC>
-static int launch_scan_n(const ScanPlan& P, int sm, cudaStream_t st) {
-  if (P.n_kw <= 1) return launch_scan_nk<NC, 1>(P, sm, st);
-  if (P.n_kw <= 2) return launch_scan_nk<NC, 2>(P, sm, st);
-  if (P.n_kw <= 4) return launch_scan_nk<NC, 4>(P, sm, st);
-  return launch_scan_nk<NC, 6>(P, sm, st);
-}
-
 }  // namespace pw

@@ -1,0 +1,2 @@
+#include "pw_launch.cuh"
+namespace pw { int launch_scan_nc12_kw2(const ScanPlan& P, int sm, cudaStream_t st) { return launch_scan_nk<12, 2>(P, sm, st); } }

@@ -1,0 +1,2 @@
+#include "pw_launch.cuh"
+namespace pw { int launch_scan_nc4_kw4(const ScanPlan& P, int sm, cudaStream_t st) { return launch_scan_nk<4, 4>(P, sm, st); } }

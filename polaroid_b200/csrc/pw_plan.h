@@ -136,7 +136,8 @@ struct HotGeom {
   int32_t keys_off, mm_off, count_off, warp_off, warp_bytes, claim_off, total_bytes;
   int32_t mm_stride;   // words per group in the CTA-shared min/max block (n_mm rounded up to even: 16-byte pairs)
   int32_t claim_acc;   // accumulator whose 32-bit private counter hosts the claim byte (bits 24..31), -1 = dedicated words
-  int32_t pad;
+  int32_t dense;       // != 0: single integer key with a small value range -> dense id = key - ScanPlan::dense_min
+                       // (no key index, no key compare; the per-group row counter marks the ids that exist)
   int32_t acc_kind[MAX_ACC];
   int32_t acc_off[MAX_ACC];  // HOT_SHARED_MM: word inside the group's min/max block; private kinds: byte offset inside the warp region
 };
@@ -164,6 +165,7 @@ struct ScanPlan {
   // group_tuples second pass (GroupsIdx construction): look every row's group up and record its rank
   uint32_t* row_group_out; // [n_rows] or nullptr
   const uint32_t* slot_rank; // [cap + 2] rank of every occupied slot in the ordered group list
+  int64_t dense_min;       // hot.dense: key value of dense id 0 (data, not part of the JIT shape)
   HotGeom hot;
 };
 

@@ -356,11 +356,24 @@ struct HotTable {
   // move every group into the HBM table (CTA-wide; callers bracket with __syncthreads and clear())
   __device__ __forceinline__ void flush(const ScanPlan& P) {
     const int G = CT::h_gcap(P), R = CT::h_rep(P), W = blockDim.x >> 5;
-    const int n = min((int)count[0], G);
+    const int n = CT::h_dense(P) ? G : min((int)count[0], G);
     for (int id = threadIdx.x; id < n; id += blockDim.x) {
       uint64_t k[KW];
+      if (CT::h_dense(P)) {
+        // dense ids: the id exists iff a row was counted into it (the planner guarantees a LEN word)
+        const int a = CT::acc_gbase(P);
+        uint32_t rows = 0;
+        for (int w = 0; w < W; ++w) {
+          const uint32_t* base = (const uint32_t*)(wall + (size_t)w * CT::h_warp_bytes(P) + CT::h_off(P, a));
+          for (int r = 0; r < R; ++r) rows += base[(size_t)id * R + r] & (a == CT::h_claim_acc(P) ? 0x00FFFFFFu : 0xFFFFFFFFu);
+        }
+        if (rows == 0u) continue;
 #pragma unroll
-      for (int w = 0; w < KW; ++w) k[w] = keys[(size_t)w * G + id];
+        for (int w = 0; w < KW; ++w) k[w] = w == 0 ? (uint64_t)P.dense_min + (uint64_t)id : 0ull;
+      } else {
+#pragma unroll
+        for (int w = 0; w < KW; ++w) k[w] = keys[(size_t)w * G + id];
+      }
       // a hot KEY_NULL is always a true null (raw sentinel-valued keys bypass the hot table)
       const uint64_t gs = table_upsert<KW>(P.table, k, hash_words<KW>(k), true);
       for (int a = 0; a < CT::n_acc(P); ++a) {
@@ -892,6 +905,17 @@ __device__ __forceinline__ uint64_t global_row(const ScanPlan& P, int64_t row) {
 template <class CT, int KW, int NV, bool HOT, int B>
 __device__ __forceinline__ void rows_probe(const ScanPlan& P, HotTable<CT, KW>& hot, const RowOut<KW, NV> (&o)[B], uint64_t (&h)[B], int (&id)[B]) {
   bool miss = false;
+  if (HOT && CT::h_dense(P)) {
+    // dense ids: the key IS the id (minus the range base): no index, no key compare, no insertion.  Null keys and
+    // raw keys that alias a sentinel (>= KEY_NULL) and keys outside the range go to the HBM table.
+#pragma unroll
+    for (int i = 0; i < B; ++i) {
+      const uint64_t d = o[i].k[0] - (uint64_t)P.dense_min;
+      h[i] = 0;  // the cold path hashes on demand
+      id[i] = (o[i].alive && o[i].k[0] < KEY_NULL && d < (uint64_t)CT::h_gcap(P)) ? (int)d : -1;
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < B; ++i) { h[i] = hash_words<KW>(o[i].k); id[i] = -1; }
   if (HOT) {
@@ -1015,7 +1039,8 @@ __device__ __forceinline__ void rows_accumulate(const ScanPlan& P, HotTable<CT, 
     for (int i = 0; i < B; ++i) {
       if (o[i].alive && id[i] < 0) {
         // cold / spill tier: straight into the HBM table
-        const uint64_t gslot = table_upsert<KW>(P.table, o[i].k, h[i], o[i].sentinel_free || KW != 1);
+        const uint64_t hh = (HOT && CT::h_dense(P)) ? hash_words<KW>(o[i].k) : h[i];
+        const uint64_t gslot = table_upsert<KW>(P.table, o[i].k, hh, o[i].sentinel_free || KW != 1);
         if (HOT) ++spilled;
         if (gslot != ~0ull) {
           if (CT::group_out(P)) P.row_group_out[o[i].row] = P.slot_rank[gslot];  // lookup pass of group_tuples
