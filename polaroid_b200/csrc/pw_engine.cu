@@ -473,6 +473,18 @@ int launch_scan_aot(ScanPlan P, int sm, cudaStream_t st) {
   return launch_scan_nc12(P, sm, st);
 }
 static bool narrow_class(const ScanPlan& P) { return P.n_slots <= 4 && P.n_vexpr <= NVof<4>::value; }
+// CTA size of the scan launch (the specialised kernels take it as a launch parameter; PW_SCAN_THREADS overrides the
+// narrow class for experiments)
+static int scan_threads(const ScanPlan& P) {
+  if (P.hot_slots > 0 && P.hot.threads > 0) return P.hot.threads;
+  return narrow_class(P) ? ScanCfg<4>::THREADS : ScanCfg<12>::THREADS;
+}
+// CTA sizes worth trying for the hot table, best first: 16 warps hide the shared-memory round trips of the narrow
+// class better than 12 (C2: 0.674 -> 0.635 ms) when 16 private regions still fit next to the full set of ids
+static int wide_cta_threads() {
+  static const int env = getenv("PW_SCAN_THREADS") ? atoi(getenv("PW_SCAN_THREADS")) : 0;
+  return env >= 64 && env <= 1024 && env % 32 == 0 ? env : 512;
+}
 static int launch_scan(ScanPlan P, int sm, cudaStream_t st) {
   // the kernel is compiled for a few (slots, key words) classes; round the key width up (extra words are 0)
   if (P.n_kw == 3) P.n_kw = 4;
@@ -480,7 +492,7 @@ static int launch_scan(ScanPlan P, int sm, cudaStream_t st) {
   const bool narrow = narrow_class(P);
   // query-shape specialised kernel (NVRTC); falls back to the ahead-of-time kernel of the same class
   const int kwc = P.n_kw <= 1 ? 1 : (P.n_kw <= 2 ? 2 : (P.n_kw <= 4 ? 4 : 6));
-  const int rc = launch_scan_jit(P, narrow ? 4 : 12, kwc, P.hot_slots > 0, narrow ? ScanCfg<4>::THREADS : ScanCfg<12>::THREADS, sm, st);
+  const int rc = launch_scan_jit(P, narrow ? 4 : 12, kwc, P.hot_slots > 0, scan_threads(P), sm, st);
   if (rc <= 0) { if (rc == 0) ctx().timings.reserved = 1.0f; return rc; }
   if (narrow) return launch_scan_nc4(P, sm, st);
   return launch_scan_nc12(P, sm, st);
@@ -490,12 +502,26 @@ static int padded_kw(int n_kw) { return n_kw == 3 ? 4 : (n_kw == 5 ? 6 : n_kw); 
 // Shared-memory hot table geometry for `groups_hint` live groups (see pw_scan.cuh).  Returns false when no
 // useful table fits.
 // dense_range > 0: dense ids (id = key - dense_min) over exactly that many ids, no key index.
+static bool plan_hot_threads(ScanPlan& P, int64_t groups_hint, int requested_gcap, int64_t dense_range, int threads, bool exact);
 static bool plan_hot(ScanPlan& P, int64_t groups_hint, int requested_gcap, int64_t dense_range = 0) {
+  const int base = narrow_class(P) ? ScanCfg<4>::THREADS : ScanCfg<12>::THREADS;
+  if (!plan_hot_threads(P, groups_hint, requested_gcap, dense_range, base, false)) return false;
+  // one CTA per SM anyway (big table): more warps, if their private regions still fit next to the same ids
+  if (narrow_class(P) && wide_cta_threads() != base && P.hot.total_bytes > 110 * 1024 && requested_gcap == 0) {
+    const HotGeom keep = P.hot;
+    if (!plan_hot_threads(P, groups_hint, keep.gcap, dense_range, wide_cta_threads(), true) || P.hot.n_mm != keep.n_mm || P.hot.replicas < keep.replicas)
+      P.hot = keep;
+  }
+  return true;
+}
+// exact: fail instead of shrinking the id capacity
+static bool plan_hot_threads(ScanPlan& P, int64_t groups_hint, int requested_gcap, int64_t dense_range, int threads, bool exact) {
   HotGeom& g = P.hot;
   memset(&g, 0, sizeof g);
+  g.threads = threads;
   const bool dense = dense_range > 0;
   const int kw = padded_kw(P.n_kw);
-  const int warps = (narrow_class(P) ? ScanCfg<4>::THREADS : ScanCfg<12>::THREADS) / 32;
+  const int warps = threads / 32;
   int n_priv64 = 0, n_priv32 = 0, n_mm = 0;
   auto is_add = [&](int a) { return P.accs[a].op == OP_ADD_F64 || P.accs[a].op == OP_ADD_I64; };
   auto is_count = [&](int a) { return P.accs[a].op == OP_ADD_I64 && (P.accs[a].src == SRC_ONE || P.accs[a].src == SRC_VALID); };
@@ -505,7 +531,7 @@ static bool plan_hot(ScanPlan& P, int64_t groups_hint, int requested_gcap, int64
   if (dense) gcap = (int)dense_range;
   const int mm_stride_all = n_mm > 1 ? ((n_mm + 1) & ~1) : n_mm;
   for (bool first = true;; gcap = gcap * 3 / 4, first = false) {
-    if (gcap < 4 || (dense && !first)) return false;  // a dense range is all or nothing
+    if (gcap < 4 || ((dense || exact) && !first)) return false;  // a dense range is all or nothing
     // key index: buckets of four tags.  At 4 slots per id (25 % load) a row finds its key in the HOME bucket with
     // probability > 0.999, so the probe is one LDS.128 + one key compare and the neighbour bucket is only looked at
     // on the (rare, warp-uniformly branched) slow path; 2 slots per id is the fallback when memory is short.
@@ -517,7 +543,7 @@ static bool plan_hot(ScanPlan& P, int64_t groups_hint, int requested_gcap, int64
     auto cell_bytes = [&](int mmp) { return (size_t)(n_priv64 + mmp) * 8 + (size_t)n_priv32 * 4 + (n_priv32 ? 0 : 4); };
     auto per_warp = [&](int R, int mmp) { return (((size_t)gcap * R * cell_bytes(mmp)) + 15) & ~(size_t)15; };
     auto total = [&](int S, int R, int mmp) {
-      const size_t shared = (size_t)S * 4 + (dense ? 0 : (size_t)gcap * 8 * kw) + 32;
+      const size_t shared = (size_t)S * 4 + (dense ? 0 : (size_t)gcap * 8 * kw) + 48;
       return shared + (size_t)(mmp ? 0 : mm_stride_all) * gcap * 8 + per_warp(R, mmp) * warps;
     };
     // Preference order: every word warp-private (plain read-modify-write; first/last words improve on almost every
@@ -541,7 +567,7 @@ static bool plan_hot(ScanPlan& P, int64_t groups_hint, int requested_gcap, int64
     size_t off = (size_t)S * 4;
     off = (off + 15) & ~(size_t)15; g.keys_off = (int32_t)off; off += dense ? 0 : (size_t)gcap * 8 * kw;
     off = (off + 15) & ~(size_t)15; g.mm_off = (int32_t)off; off += (size_t)g.mm_stride * gcap * 8;
-    g.count_off = (int32_t)off; off += 16;
+    g.count_off = (int32_t)off; off += 32;  // [count, full flag, -, -][guard scratch: lo, hi]
     g.warp_off = (int32_t)off;
     size_t woff = 0;
     int mm_idx = 0;
@@ -559,6 +585,18 @@ static bool plan_hot(ScanPlan& P, int64_t groups_hint, int requested_gcap, int64
       }
     }
     if (g.claim_acc < 0) { g.claim_off = (int32_t)woff; woff += (size_t)gcap * R * 4; }
+    // extremum guard: the first CTA-shared (min, max) pair over one value expression that sits in an aligned 16-byte cell
+    g.guard_acc = -1;
+    // measured on C2 (1e3 groups): the guard over ALL groups stays too loose (max over groups of the minima) to pay for
+    // its divergent exact path: 0.715 vs 0.674 ms.  Opt-in for experiments.
+    if (getenv("PW_GUARD"))
+      for (int a = 0; a + 1 < P.n_acc && g.guard_acc < 0; ++a) {
+        const bool pair = (P.accs[a].op == OP_MIN_I64 && P.accs[a + 1].op == OP_MAX_I64) || (P.accs[a].op == OP_MIN_U64 && P.accs[a + 1].op == OP_MAX_U64);
+        if (pair && P.accs[a].vexpr == P.accs[a + 1].vexpr && P.accs[a].src == P.accs[a + 1].src && P.accs[a].src != SRC_ROWIDX && P.accs[a].src != SRC_ROW &&
+            g.acc_kind[a] == HOT_SHARED_MM && g.acc_kind[a + 1] == HOT_SHARED_MM && (g.acc_off[a] & 1) == 0 && g.acc_off[a + 1] == g.acc_off[a] + 1 &&
+            (g.mm_stride & 1) == 0 && a < P.acc_gbase)
+          g.guard_acc = a;
+      }
     woff = (woff + 15) & ~(size_t)15;
     g.warp_bytes = (int32_t)woff;
     g.total_bytes = (int32_t)(off + woff * warps);
@@ -776,6 +814,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
   bool use_hot = true;
   int64_t live_groups = 0;  // distinct keys among consecutive rows (sizes the hot table)
   int64_t dense_range = 0;  // > 0: single integer key whose sampled values span this many ids
+  bool dense_sentinels = false;
   const int64_t SMALL = 1 << 18;
   if (q->initial_table_slots > 0) cap = (uint64_t)q->initial_table_slots;
   auto take_range = [&](unsigned long long kmax_u, unsigned long long kmin_n, int64_t live) {
@@ -787,6 +826,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     if (range <= 4096 && range <= (uint64_t)std::max<int64_t>(64, 4 * live)) {
       dense_range = (int64_t)range;
       P.dense_min = (int64_t)(lo ^ 0x8000000000000000ull);
+      dense_sentinels = P.dense_min <= -1 && P.dense_min + (int64_t)range > -2;  // -1 / -2 inside the range
     }
   };
   if (N <= SMALL) {
@@ -837,7 +877,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
   if (q->flags & PW_FLAG_FORCE_HOT_TABLE) use_hot = true;
   if (q->flags & PW_FLAG_FORCE_GLOBAL_TABLE) use_hot = false;
   if (live_groups == 0) live_groups = std::min<int64_t>(std::max<int64_t>(N, 4), 1024);
-  if (use_hot && dense_range > 0 && q->hot_table_slots == 0 && plan_hot(P, live_groups, 0, dense_range)) { /* dense ids */ }
+  if (use_hot && dense_range > 0 && q->hot_table_slots == 0 && plan_hot(P, live_groups, 0, dense_range)) { if (dense_sentinels) P.hot.dense = 2; }
   else if (use_hot && !plan_hot(P, live_groups, q->hot_table_slots)) use_hot = false;
   if (cap > 0xFFFFFFF0ull) return fail(PW_ERR_UNSUPPORTED, "table larger than 2^32 slots");
   if (getenv("PW_DEBUG"))

@@ -229,6 +229,42 @@ struct HotTable {
   uint32_t* count;       // [0] dense ids handed out, [1] "a row found the table full"
   unsigned char* wbase;  // this warp's private region
   unsigned char* wall;   // warp 0's private region
+  // Extremum guard (registers, refreshed at the periodic CTA barrier): every dense id < g_cov already holds a minimum
+  // <= G_lo and a maximum >= G_hi, so a row whose value lies strictly inside (G_lo, G_hi) cannot improve any of them
+  // and skips the min/max words altogether.  Only the high 32 bits of the 64-bit images are kept (conservative).
+  int32_t g_lo_h, g_hi_h, g_cov;
+  __device__ __forceinline__ void guard_off() { g_lo_h = 0x7FFFFFFF; g_hi_h = (int32_t)0x80000000; g_cov = 0; }
+  __device__ __forceinline__ uint64_t* guard_words() const { return (uint64_t*)(count + 4); }
+  // CTA-wide, between two barriers placed by the caller: reset scratch (before), reduce (here), read back (after)
+  __device__ __forceinline__ void guard_reduce(const ScanPlan& P, int n_ids) {
+    const int a = CT::h_guard_acc(P);
+    const bool uns = CT::acc_op(P, a) == OP_MIN_U64;
+    const uint64_t flip = uns ? 0x8000000000000000ull : 0ull;  // reduce in the signed domain
+    long long lo = (long long)0x8000000000000000ull, hi = 0x7FFFFFFFFFFFFFFFll;  // max of minima, min of maxima
+    for (int id = threadIdx.x; id < n_ids; id += blockDim.x) {
+      const uint64_t* q = &mm[(size_t)id * CT::h_mm_stride(P) + CT::h_off(P, a)];
+      const long long mn = (long long)(q[0] ^ flip), mx = (long long)(q[1] ^ flip);
+      lo = mn > lo ? mn : lo;  // an id without a value yet holds (+inf, -inf): the guard closes
+      hi = mx < hi ? mx : hi;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+      lo = l2 > lo ? l2 : lo;
+      hi = h2 < hi ? h2 : hi;
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMax((long long*)guard_words(), lo);
+      atomicMin((long long*)guard_words() + 1, hi);
+    }
+  }
+  __device__ __forceinline__ void guard_read(const ScanPlan& P, int n_ids) {
+    const volatile uint64_t* g = guard_words();  // signed-domain images (unsigned words are compared after the same flip)
+    g_lo_h = (int32_t)(uint32_t)(g[0] >> 32);
+    g_hi_h = (int32_t)(uint32_t)(g[1] >> 32);
+    g_cov = n_ids;
+    if (g_lo_h >= g_hi_h) guard_off();  // empty interval (an id without a value yet, or a single-valued column)
+  }
 
   __device__ __forceinline__ void bind(unsigned char* smem, const ScanPlan& P, int warp) {
     tag = (uint32_t*)smem;
@@ -237,6 +273,7 @@ struct HotTable {
     count = (uint32_t*)(smem + CT::h_count_off(P));
     wall = smem + CT::h_warp_off(P);
     wbase = wall + (size_t)warp * CT::h_warp_bytes(P);
+    guard_off();
   }
   // reset everything (CTA-wide; caller syncs)
   __device__ __forceinline__ void clear(const ScanPlan& P) {
@@ -743,21 +780,75 @@ struct HotSinkB {
   }
   // min word at accumulator a, max word at a + 1, same operand: when both are CTA-shared and form an aligned
   // 16-byte pair, one LDS.128 reads both extrema
+  // `x` = 64-bit image in the op's order (floats: f64_to_ordered), `ok` = row enabled and value non-null.  With
+  // is_f64 the NaN rows (skipped by min/max) are still in `ok`: they are filtered here, from the image.
+  static __device__ __forceinline__ bool image_is_nan(uint64_t x) {
+    return (long long)x > 0x7FF0000000000000ll || (long long)x < (long long)0x800FFFFFFFFFFFFFull;
+  }
   template <int OPMIN, int OPMAX>
-  __device__ __forceinline__ void minmax(const ScanPlan& P, int a, const uint64_t (&x)[B], const bool (&en)[B]) const {
+  __device__ __forceinline__ void minmax(const ScanPlan& P, int a, const uint64_t (&x)[B], const bool (&ok)[B], bool is_f64) const {
     if (CT::h_kind(P, a) == HOT_SHARED_MM && CT::h_kind(P, a + 1) == HOT_SHARED_MM && (CT::h_off(P, a) & 1) == 0 &&
         CT::h_off(P, a + 1) == CT::h_off(P, a) + 1 && (CT::h_mm_stride(P) & 1) == 0) {
-      minmax_pair<OPMIN>(P, a, x, en, part_tag<PART != PART_PRIVATE>{});
+      minmax_pair<OPMIN>(P, a, x, ok, is_f64, part_tag<PART != PART_PRIVATE>{});
     } else {
+      bool en[B];
+#pragma unroll
+      for (int i = 0; i < B; ++i) en[i] = ok[i] && !(is_f64 && image_is_nan(x[i]));
       add<OPMIN>(P, a, x, en);
       add<OPMAX>(P, a + 1, x, en);
     }
   }
   template <bool ON> struct part_tag {};
   template <int OPMIN>
-  __device__ __forceinline__ void minmax_pair(const ScanPlan&, int, const uint64_t (&)[B], const bool (&)[B], part_tag<false>) const {}
+  __device__ __forceinline__ void minmax_pair(const ScanPlan&, int, const uint64_t (&)[B], const bool (&)[B], bool, part_tag<false>) const {}
   template <int OPMIN>
-  __device__ __forceinline__ void minmax_pair(const ScanPlan& P, int a, const uint64_t (&x)[B], const bool (&en)[B], part_tag<true>) const {
+  __device__ __forceinline__ void minmax_pair(const ScanPlan& P, int a, const uint64_t (&x)[B], const bool (&ok)[B], bool is_f64, part_tag<true>) const {
+    bool en[B];
+    const bool guarded = a == CT::h_guard_acc(P) && B > 1 && hot.g_cov > 0;  // CTA-uniform
+    if (guarded) {
+      // extremum guard: two 32-bit compares per row decide whether the row can matter at all.  NaN images lie outside
+      // every guard interval, so they reach the exact filter below.
+      bool any = false;
+#pragma unroll
+      for (int i = 0; i < B; ++i) {
+        const uint32_t xh = (uint32_t)(x[i] >> 32);
+        const bool outside = OPMIN == OP_MIN_I64 ? ((int32_t)xh <= hot.g_lo_h || (int32_t)xh >= hot.g_hi_h)
+                                                 : ((int32_t)(xh ^ 0x80000000u) <= hot.g_lo_h || (int32_t)(xh ^ 0x80000000u) >= hot.g_hi_h);
+        en[i] = ok[i] && (outside || id[i] >= hot.g_cov);
+        any = any || en[i];
+      }
+      if (!any) return;
+    } else {
+#pragma unroll
+      for (int i = 0; i < B; ++i) en[i] = ok[i];
+    }
+#pragma unroll
+    for (int i = 0; i < B; ++i) en[i] = en[i] && !(is_f64 && image_is_nan(x[i]));
+    if (guarded) {
+      // few rows get here once the guard has tightened: one row per lane per round through a single-row body
+      uint32_t m = 0;
+#pragma unroll
+      for (int i = 0; i < B; ++i) m |= (en[i] ? 1u : 0u) << i;
+      while (m) {
+        const int j = __ffs((int)m) - 1;
+        m &= m - 1u;
+        uint64_t xv = x[0];
+        int idv = id[0];
+#pragma unroll
+        for (int i = 1; i < B; ++i) if (j == i) { xv = x[i]; idv = id[i]; }
+        uint64_t* q = &hot.mm[(size_t)idv * CT::h_mm_stride(P) + CT::h_off(P, a)];
+        const uint4 cur = lds128_volatile((const uint32_t*)q);
+        const uint64_t lo = (uint64_t)cur.y << 32 | cur.x, hi = (uint64_t)cur.w << 32 | cur.z;
+        if (OPMIN == OP_MIN_I64) {
+          if ((long long)xv < (long long)lo) atomicMin((long long*)q, (long long)xv);
+          if ((long long)xv > (long long)hi) atomicMax((long long*)(q + 1), (long long)xv);
+        } else {
+          if (xv < lo) atomicMin((unsigned long long*)q, (unsigned long long)xv);
+          if (xv > hi) atomicMax((unsigned long long*)(q + 1), (unsigned long long)xv);
+        }
+      }
+      return;
+    }
     {
       uint4 cur[B];
 #pragma unroll
@@ -818,18 +909,21 @@ __device__ __forceinline__ void accumulate_rows(const ScanPlan& P, const RowOut<
     if (fl & (VF_MIN | VF_MAX)) {
       uint64_t x[B];
       bool use[B];
+      const bool both = (fl & VF_MIN) && (fl & VF_MAX);
 #pragma unroll
       for (int i = 0; i < B; ++i) {
         x[i] = bits[i]; use[i] = ok[i];
         if (cls == CLS_F64) {
           const double d = __longlong_as_double((long long)bits[i]);
-          use[i] = ok[i] && (d == d);  // NaN is skipped; an all-NaN group keeps the init word -> NaN at emit time
+          // NaN is skipped; an all-NaN group keeps the init word -> NaN at emit time.  (min AND max: the sink filters
+          // NaN from the image, after its cheap guard test)
+          if (!both) use[i] = ok[i] && (d == d);
           x[i] = (uint64_t)f64_to_ordered(d);
         }
       }
-      if ((fl & VF_MIN) && (fl & VF_MAX)) {
-        if (cls == CLS_U64) s.template minmax<OP_MIN_U64, OP_MAX_U64>(P, a, x, use);
-        else s.template minmax<OP_MIN_I64, OP_MAX_I64>(P, a, x, use);
+      if (both) {
+        if (cls == CLS_U64) s.template minmax<OP_MIN_U64, OP_MAX_U64>(P, a, x, use, false);
+        else s.template minmax<OP_MIN_I64, OP_MAX_I64>(P, a, x, use, cls == CLS_F64);
         a += 2;
       } else if (fl & VF_MIN) {
         if (cls == CLS_U64) s.template add<OP_MIN_U64>(P, a, x, use); else s.template add<OP_MIN_I64>(P, a, x, use);
@@ -912,7 +1006,8 @@ __device__ __forceinline__ void rows_probe(const ScanPlan& P, HotTable<CT, KW>& 
     for (int i = 0; i < B; ++i) {
       const uint64_t d = o[i].k[0] - (uint64_t)P.dense_min;
       h[i] = 0;  // the cold path hashes on demand
-      id[i] = (o[i].alive && o[i].k[0] < KEY_NULL && d < (uint64_t)CT::h_gcap(P)) ? (int)d : -1;
+      const bool plain = !CT::h_dense_sentinels(P) || o[i].k[0] < KEY_NULL;  // -1 / -2 inside the range: sentinels go cold
+      id[i] = (o[i].alive && plain && d < (uint64_t)CT::h_gcap(P)) ? (int)d : -1;
     }
     return;
   }
@@ -1213,9 +1308,14 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
       const bool full = *(volatile uint32_t*)(hot.count + 1) != 0u;
       const uint32_t G = (uint32_t)CT::h_gcap(P);
       const bool nearly = cnt >= G - (G >> 3) && !stable_set;
+      if (CT::h_guard_acc(P) >= 0 && threadIdx.x == 0) {  // guard scratch: (max of minima, min of maxima), signed domain
+        hot.guard_words()[0] = 0x8000000000000000ull;
+        hot.guard_words()[1] = 0x7FFFFFFFFFFFFFFFull;
+      }
       __syncthreads();
       ++tiles_since_flush;
       const bool wrap = tiles_since_flush >= 30000;  // private counters share their word with the claim byte: 24 bits
+      bool flushed = false;
       if ((full || nearly || wrap) && tile + 1 < tile_hi) {
         if (!full && !wrap && flushed_once && tiles_since_flush <= 2) stable_set = true;  // refilled at once: same groups again
         else {
@@ -1225,7 +1325,18 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
           __syncthreads();
           flushed_once = true;
           tiles_since_flush = 0;
+          flushed = true;
+          hot.guard_off();
         }
+      }
+      // refresh the extremum guard every 16th check, from the 32nd after a flush on: the interval tightens like 1/rows
+      // seen per group, and a loose guard (most warps still find a row that needs the exact test) costs more than the
+      // branch-free exact path it replaces
+      if (CT::h_guard_acc(P) >= 0 && !flushed && tiles_since_flush >= 32 && (tiles_since_flush & 15) == 0) {
+        const int n_ids = CT::h_dense(P) ? (int)G : (int)min(cnt, G);
+        hot.guard_reduce(P, n_ids);
+        __syncthreads();
+        hot.guard_read(P, n_ids);
       }
     }
   }
