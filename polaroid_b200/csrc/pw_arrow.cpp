@@ -5,6 +5,9 @@
 #include <string.h>
 #include <sys/mman.h>
 
+#include <map>
+#include <mutex>
+
 #include "pw_engine.h"
 
 namespace pw {
@@ -37,15 +40,78 @@ int parse_format(const char* fmt, int32_t* dtype) {
   return fail(PW_ERR_UNSUPPORTED, "Arrow format '%s' is outside this path (SURVEY 8f: long/offset strings, nested types)", fmt);
 }
 
-// Result buffers: large ones are 2 MB aligned and advised to transparent huge pages — the device-to-host copy of
-// a 1e7-group result spent most of its time in first-touch page faults on 4 KB pages (C3: 287 ms for 0.5 GB).
+// Result buffers.  Large ones come from a process-wide pool of PINNED blocks: the device-to-host copy of a
+// 1e7-group result into pageable memory ran at ~5 GB/s (C3: 119 ms for 0.6 GB, most of the query); into pinned
+// memory it runs at PCIe speed.  Pinning is expensive (~0.3 ms per MB), so a released result returns its blocks to the
+// pool instead of unpinning them; the pool is capped (PW_PINNED_POOL_MB, default 8192) and anything beyond the cap is
+// unpinned on release.  Small buffers stay on malloc.
+namespace {
+struct PinnedPool {
+  std::mutex mu;
+  std::multimap<size_t, void*> free_blocks;  // size -> block
+  std::map<void*, size_t> live;              // every pinned block handed out
+  size_t pooled = 0, cap = 0;
+  bool disabled = false;
+  PinnedPool() {
+    const char* e = getenv("PW_PINNED_POOL_MB");
+    cap = (size_t)(e ? atoll(e) : 8192) << 20;
+    disabled = cap == 0;
+  }
+};
+PinnedPool& pinned_pool() { static PinnedPool* p = new PinnedPool(); return *p; }  // never destroyed (library is never unloaded)
+const size_t PINNED_MIN = 1u << 20;
+}  // namespace
+
 void* host_alloc(size_t bytes) {
-  const size_t huge = 2u << 20;
-  if (bytes < huge) return malloc(bytes + 64);
-  const size_t rounded = (bytes + huge - 1) / huge * huge;
-  void* p = aligned_alloc(huge, rounded);
+  if (bytes < PINNED_MIN) return malloc(bytes + 64);
+  PinnedPool& pool = pinned_pool();
+  const size_t gran = 2u << 20;
+  const size_t rounded = (bytes + gran - 1) / gran * gran;
+  if (!pool.disabled) {
+    {
+      std::lock_guard<std::mutex> lk(pool.mu);
+      auto it = pool.free_blocks.lower_bound(rounded);
+      if (it != pool.free_blocks.end() && it->first <= rounded + rounded / 2) {  // best fit, at most 1.5x oversized
+        void* p = it->second;
+        pool.pooled -= it->first;
+        pool.live[p] = it->first;
+        pool.free_blocks.erase(it);
+        return p;
+      }
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, rounded, cudaHostAllocPortable) == cudaSuccess && p) {
+      std::lock_guard<std::mutex> lk(pool.mu);
+      pool.live[p] = rounded;
+      return p;
+    }
+    cudaGetLastError();  // pinning refused (ulimit, no device): plain pages
+  }
+  void* p = aligned_alloc(gran, rounded);
   if (p) madvise(p, rounded, MADV_HUGEPAGE);
   return p;
+}
+
+void host_free(void* p) {
+  if (!p) return;
+  PinnedPool& pool = pinned_pool();
+  size_t size = 0;
+  {
+    std::lock_guard<std::mutex> lk(pool.mu);
+    auto it = pool.live.find(p);
+    if (it == pool.live.end()) { size = 0; }
+    else {
+      size = it->second;
+      pool.live.erase(it);
+      if (pool.pooled + size <= pool.cap) {
+        pool.free_blocks.emplace(size, p);
+        pool.pooled += size;
+        return;
+      }
+    }
+  }
+  if (size) cudaFreeHost(p);
+  else free(p);
 }
 
 namespace {
@@ -57,7 +123,7 @@ void release_array(struct ArrowArray* a) {
   if (!a || !a->release) return;
   ArrayPrivate* p = (ArrayPrivate*)a->private_data;
   if (p) {
-    for (int i = 0; i < 4; ++i) free(p->owned[i]);
+    for (int i = 0; i < 4; ++i) host_free(p->owned[i]);
     free(p);
   }
   a->release = nullptr;

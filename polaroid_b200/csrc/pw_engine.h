@@ -103,7 +103,8 @@ int run_dynamic_segmented(const PwQuery* q, const PwFrame* f, struct ArrowArray*
 
 // Arrow helpers (pw_arrow.cpp)
 int parse_format(const char* fmt, int32_t* dtype);
-void* host_alloc(size_t bytes);  // free() compatible
+void* host_alloc(size_t bytes);  // result buffers: pinned pool for large ones; release with host_free
+void host_free(void* p);
 int make_host_array(int64_t length, int64_t null_count, void* validity, void* values, size_t n_extra_buffers,
                     struct ArrowArray* out);
 int make_schema(const char* format, const char* name, bool nullable, struct ArrowSchema* out);
