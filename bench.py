@@ -359,7 +359,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["name"], "rows_per_gpu": rows, "groups": w["groups"] or int(tm["n_groups"]),
                        "l2": f"inputs ({rows * w['bytes_per_row'] / 1e9:.2f} GB per step) are larger than the 126 MB L2; no explicit flush",
-                       "strategy": {1: "hot table + spill tier", 2: "HBM table", 3: "segmented", 4: "hot table, dense ids + spill tier"}.get(tm["strategy"]),
+                       "strategy": {1: "hot table + spill tier", 2: "HBM table", 3: "segmented", 4: "hot table, dense ids + spill tier", 5: "radix partition + hot table"}.get(tm["strategy"]),
                        "parallelism": f"rows sharded over {world} GPU(s); partial aggregates merged by key hash"},
             "clocks": clocks,
             "e2e": {"value": rows * world / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": h2d * world,
@@ -371,7 +371,7 @@ def main():
                          "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
                          "whole_step_frac": (algo_bytes / (ms * 1e-3) / 1e9) / peak},
             "cpu_baseline": cpu,
-            "phases_ms": {k: tm[k] for k in ("estimate_ms", "scan_ms", "scan_kernel_ms", "finalize_ms", "d2h_ms", "total_device_ms", "host_ms")},
+            "phases_ms": {k: tm[k] for k in ("estimate_ms", "scan_ms", "scan_kernel_ms", "finalize_ms", "d2h_ms", "total_device_ms", "host_ms", "partition_ms")},
             "spilled_rows": tm["spilled_rows"], "table_slots": tm["table_slots"], "n_groups": tm["n_groups"],
             "jit": bool(tm["reserved"]), "retries": tm["retries"],
         }

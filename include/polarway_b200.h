@@ -136,6 +136,8 @@ typedef struct PwDynamic {
 #define PW_FLAG_FORCE_GLOBAL_TABLE (1ull << 1) /* HBM open-addressing table only */
 #define PW_FLAG_FORCE_SEGMENTED (1ull << 2)    /* sorted-run segmented reduction (dynamic, no keys) */
 #define PW_FLAG_NO_SEGMENTED (1ull << 3)       /* dynamic without keys through the hash path */
+#define PW_FLAG_FORCE_PARTITION (1ull << 4)    /* radix-partition the rows by key hash first (high-cardinality tier) */
+#define PW_FLAG_NO_PARTITION (1ull << 5)       /* never partition (POLARS_NO_PARTITION) */
 
 #define PW_ABI_VERSION 1u
 typedef struct PwQuery {
@@ -166,14 +168,14 @@ int pw_b200_set_stream(void* cuda_stream);     /* calling thread's cudaStream_t 
 typedef struct PwTimings {
   float h2d_ms, estimate_ms, scan_ms, finalize_ms, d2h_ms, total_device_ms;
   int64_t n_rows, n_groups, table_slots;
-  int32_t strategy;      /* 1 hot table, 2 global table, 3 segmented, 4 hot table with dense ids (small integer key range) */
+  int32_t strategy;      /* 1 hot table, 2 global table, 3 segmented, 4 hot table with dense ids (small integer key range), 5 partitioned */
   int32_t retries;       /* table growth re-runs */
   int64_t kernel_launches; /* launches of this library's kernels in the last call */
   int64_t spilled_rows;  /* rows that bypassed the hot table (spill tier) */
   float scan_kernel_ms;  /* the dominant kernel alone (events immediately around its launch) */
   float reserved;         /* 1 = the query-shape specialised (NVRTC) kernel ran, 0 = the ahead-of-time kernel */
   float host_ms;          /* wall-clock time spent inside the last pw_b200_frame_groupby call (host + device) */
-  float pad;
+  float partition_ms;     /* strategy 5: histogram + scatter passes (part of scan_ms) */
 } PwTimings;
 int pw_b200_last_timings(PwTimings* out);
 

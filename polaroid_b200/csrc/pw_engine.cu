@@ -4,6 +4,7 @@
 //   polars-mem-engine/src/executors/group_by_streaming.rs:114-244), kernel launches, finalisation and
 //   Arrow result construction.  One process per GPU; every call runs on the calling thread's stream.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -797,6 +798,81 @@ int order_groups(const Lowered& L, const Table& T, int kw, uint32_t** slots_io, 
   return 0;
 }
 
+// ---- high-cardinality tier: radix-partition the rows by key hash, then scan the partitioned copy (pw_partition.cuh)
+struct PartTemp {
+  uint64_t* words = nullptr;
+  uint32_t* hist = nullptr;
+  uint32_t* cursor = nullptr;
+  void* scan_tmp = nullptr;
+};
+static void part_free(PartTemp& t) { dev_free(t.words); dev_free(t.hist); dev_free(t.cursor); dev_free(t.scan_tmp); t = PartTemp{}; }
+static bool part_eligible(const PwQuery* q, const ScanPlan& P) {
+  if ((q->flags & PW_FLAG_NO_PARTITION) || getenv("PW_NO_PARTITION") || !jit_available()) return false;
+  if (P.dyn.enabled || P.row_group_out || P.n_slots + 1 > 4 || !narrow_class(P) || P.n_slots > 8) return false;
+  for (int s = 0; s < P.n_slots; ++s)
+    if (P.slots[s].dtype == DT_VIEW || P.slots[s].dtype == DT_VIEW_HI || P.slots[s].dtype == DT_BOOL) return false;
+  return true;
+}
+// Builds the partitioned copy of the rows that pass the predicate and the plan P2 that scans it.  g_hint = expected
+// number of groups.  Returns PW_OK with P2->n_rows = surviving rows.
+static int partition_input(const ScanPlan& P, double g_hint, ScanPlan* P2out, PartTemp* tmp) {
+  ThreadCtx& c = ctx();
+  const int64_t N = P.n_rows;
+  if (N >= (int64_t)1 << 32) return fail(PW_ERR_UNSUPPORTED, "partitioned path: more than 2^32 rows per device");
+  ScanPlan P2 = P;
+  const uint64_t stride = ((uint64_t)N + 31) & ~(uint64_t)31;
+  { void* p = nullptr; PW_TRY(dev_alloc(&p, (size_t)(P.n_slots + 1) * stride * 8)); tmp->words = (uint64_t*)p; }
+  for (int s = 0; s < P.n_slots; ++s) {
+    RawSlot& d = P2.slots[s];
+    d.values = tmp->words + (uint64_t)s * stride;
+    d.validity = nullptr; d.bit_offset = 0;
+    const int cls = dtype_class(P.slots[s].dtype);
+    d.dtype = cls == CLS_F64 ? DT_F64 : (cls == CLS_U64 ? DT_U64 : DT_I64);  // canonical 64-bit image of the class
+  }
+  RawSlot& rid = P2.slots[P.n_slots];
+  rid.values = tmp->words + (uint64_t)P.n_slots * stride; rid.validity = nullptr; rid.bit_offset = 0; rid.dtype = DT_U64;
+  P2.n_slots = P.n_slots + 1;
+  P2.rowid_slot_p1 = P.n_slots + 1;
+  for (int k = 0; k < P2.n_keys; ++k) P2.keys[k].dtype = P2.slots[P2.keys[k].slot].dtype;
+  P2.n_preds = 0; P2.check_sorted = 0; P2.vec_ok = 1; P2.row_begin = 0; P2.row_stride = 1;
+  // partitions: about a quarter of the hot table's ids each, so that a few of them are resident side by side
+  if (!plan_hot(P2, 4096, 0)) return 1;  // no hot table fits: caller keeps the plain HBM-table path
+  static const double part_div = getenv("PW_PART_DIV") ? atof(getenv("PW_PART_DIV")) : 4.0;
+  const double per_part = std::max(8.0, (double)P2.hot.gcap / part_div);
+  uint64_t n_parts = (uint64_t)std::min(4.0e6, std::max(4.0, ceil(std::max(g_hint, 1.0) * 1.1 / per_part)));
+  if (getenv("PW_DEBUG"))
+    fprintf(stderr, "[pw] partition: rows=%lld groups~%.0f parts=%llu gcap=%d S=%d R=%d n_mm=%d smem=%d threads=%d\n", (long long)N, g_hint,
+            (unsigned long long)n_parts, P2.hot.gcap, P2.hot.idx_slots, P2.hot.replicas, P2.hot.n_mm, P2.hot.total_bytes, P2.hot.threads);
+  { void* p = nullptr; PW_TRY(dev_alloc(&p, n_parts * 4)); tmp->hist = (uint32_t*)p; }
+  { void* p = nullptr; PW_TRY(dev_alloc(&p, n_parts * 4)); tmp->cursor = (uint32_t*)p; }
+  PW_CUDA(cudaMemsetAsync(tmp->hist, 0, n_parts * 4, c.stream));
+  PartParams pp{};
+  pp.hist = tmp->hist; pp.cursor = tmp->cursor; pp.out = tmp->words; pp.out_stride = stride; pp.n_parts = (uint32_t)n_parts;
+  const int kwc = padded_kw(P.n_kw) <= 1 ? 1 : (padded_kw(P.n_kw) <= 2 ? 2 : (padded_kw(P.n_kw) <= 4 ? 4 : 6));
+  ScanPlan PA = P;  // passes 1 and 2 read the original frame
+  PA.n_kw = padded_kw(P.n_kw); PA.hot_slots = 0; memset(&PA.hot, 0, sizeof PA.hot);
+  pp.mode = 1;
+  if (int rc = launch_part_jit(PA, pp, 4, kwc, c.sm_count, c.stream)) return rc;
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, tmp->hist, tmp->cursor, (int)n_parts, c.stream);
+  PW_TRY(dev_alloc(&tmp->scan_tmp, tb));
+  PW_CUDA(cub::DeviceScan::ExclusiveSum(tmp->scan_tmp, tb, tmp->hist, tmp->cursor, (int)n_parts, c.stream));
+  c.timings.kernel_launches++;
+  int64_t n2 = N;
+  if (P.n_preds > 0 || P.n_keys == 0) {  // rows dropped by the predicate never reach the copy: count them
+    uint32_t last[2] = {0, 0};
+    PW_CUDA(cudaMemcpyAsync(&last[0], tmp->cursor + n_parts - 1, 4, cudaMemcpyDeviceToHost, c.stream));
+    PW_CUDA(cudaMemcpyAsync(&last[1], tmp->hist + n_parts - 1, 4, cudaMemcpyDeviceToHost, c.stream));
+    PW_CUDA(cudaStreamSynchronize(c.stream));
+    n2 = (int64_t)last[0] + (int64_t)last[1];
+  }
+  pp.mode = 2;
+  if (int rc = launch_part_jit(PA, pp, 4, kwc, c.sm_count, c.stream)) return rc;
+  P2.n_rows = n2;
+  *P2out = P2;
+  return 0;
+}
+
 int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out, uint32_t** slot_list_out, uint64_t* n_groups_out) {
   ThreadCtx& c = ctx();
   ScanPlan& P = L.plan;
@@ -813,6 +889,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
   uint64_t cap = 0;
   bool use_hot = true;
   int64_t live_groups = 0;  // distinct keys among consecutive rows (sizes the hot table)
+  double g_est = 0;         // estimated number of groups (0: no pilot ran)
   int64_t dense_range = 0;  // > 0: single integer key whose sampled values span this many ids
   bool dense_sentinels = false;
   const int64_t SMALL = 1 << 18;
@@ -869,6 +946,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     if (h1.overflow == 2 || h2.overflow == 2) { dev_free(dctl); return fail(PW_ERR_UNSUPPORTED, "string key longer than 12 bytes (long views need the data buffers: SURVEY 8f rank 1)"); }
     double g = solve_groups((double)h1.counter, (double)n_s);
     g = std::min(g, (double)N);
+    g_est = g;
     if (!cap) cap = (uint64_t)std::max(1024.0, std::min(2.0 * (double)N + 64.0, 2.5 * g + 1024.0));
     live_groups = (int64_t)h2.counter;
     use_hot = h2.counter <= 2048;
@@ -886,6 +964,25 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
             P.hot.n_mm, P.hot.total_bytes, P.hot.dense, (long long)P.dense_min);
   PW_CUDA(cudaEventRecord(c.ev[2], c.stream));
 
+  // ---- high-cardinality tier: many groups, several rows each, no locality -> partition the rows by key hash first
+  // (the analogue of the reference's partitioned group-by; POLARS_FORCE_PARTITION / POLARS_NO_PARTITION = the flags)
+  PartTemp ptmp;
+  ScanPlan PP{};  // plan over the partitioned copy
+  bool partitioned = false;
+  {
+    const bool forced = (q->flags & PW_FLAG_FORCE_PARTITION) != 0;
+    const bool pays = !use_hot && g_est >= 262144.0 && N >= (4ll << 20) && (double)N >= 3.0 * g_est &&
+                      !(q->flags & (PW_FLAG_FORCE_HOT_TABLE | PW_FLAG_FORCE_GLOBAL_TABLE));
+    if ((forced || pays) && N > 0 && part_eligible(q, P)) {
+      PW_CUDA(cudaEventRecord(c.ev[10], c.stream));
+      const int prc = partition_input(P, g_est > 0 ? g_est : std::max<double>((double)N / 4.0, 64.0), &PP, &ptmp);
+      PW_CUDA(cudaEventRecord(c.ev[11], c.stream));
+      if (prc < 0) { part_free(ptmp); dev_free(dctl); return prc; }
+      partitioned = prc == 0;
+      if (!partitioned) part_free(ptmp);
+    }
+  }
+
   // ---- scan (with growth retries) ------------------------------------------------------------------
   Table T{};
   uint32_t* slots = nullptr;
@@ -898,7 +995,10 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     P.not_sorted = &dctl->not_sorted;
     P.hot_slots = use_hot ? P.hot.idx_slots : 0;
     PW_CUDA(cudaEventRecord(c.ev[8], c.stream));
-    if (N > 0) PW_TRY(launch_scan(P, c.sm_count, c.stream));
+    if (partitioned) {
+      PP.table = T; PP.not_sorted = &dctl->not_sorted; PP.hot_slots = PP.hot.idx_slots;
+      if (PP.n_rows > 0) PW_TRY(launch_scan(PP, c.sm_count, c.stream));
+    } else if (N > 0) PW_TRY(launch_scan(P, c.sm_count, c.stream));
     PW_CUDA(cudaEventRecord(c.ev[9], c.stream));
     // queue the compaction right behind the scan: its result is simply discarded when the scan overflowed
     { void* p = nullptr; PW_TRY(dev_alloc(&p, (cap + 2) * 4)); slots = (uint32_t*)p; }
@@ -910,10 +1010,10 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     }
     PW_CUDA(cudaMemcpyAsync(&hctl, dctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream));
     PW_CUDA(cudaStreamSynchronize(c.stream));
-    if (hctl.overflow == 2) { free_table(T); dev_free(slots); dev_free(dctl); return fail(PW_ERR_UNSUPPORTED, "string key longer than 12 bytes (long views need the data buffers: SURVEY 8f rank 1)"); }
+    if (hctl.overflow == 2) { part_free(ptmp); free_table(T); dev_free(slots); dev_free(dctl); return fail(PW_ERR_UNSUPPORTED, "string key longer than 12 bytes (long views need the data buffers: SURVEY 8f rank 1)"); }
     if (hctl.overflow == 1) {
       free_table(T); dev_free(slots); slots = nullptr;
-      if (cap >= (uint64_t)2 * (uint64_t)N + 64) { dev_free(dctl); return fail(PW_ERR_INTERNAL, "hash table overflow at maximum size"); }
+      if (cap >= (uint64_t)2 * (uint64_t)N + 64) { part_free(ptmp); dev_free(dctl); return fail(PW_ERR_INTERNAL, "hash table overflow at maximum size"); }
       cap = std::min<uint64_t>(cap * 4, (uint64_t)2 * (uint64_t)N + 64);
       tm.retries++;
       continue;
@@ -921,10 +1021,13 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     break;
   }
   if (hctl.not_sorted) {
-    free_table(T); dev_free(slots); dev_free(dctl);
+    part_free(ptmp); free_table(T); dev_free(slots); dev_free(dctl);
     return fail(PW_ERR_NOT_SORTED, "argument in operation 'group_by_dynamic' is not sorted, please sort the 'expr/series/column' first");
   }
-  tm.strategy = use_hot ? (P.hot.dense ? 4 : 1) : 2;
+  part_free(ptmp);
+  tm.partition_ms = 0.0f;
+  if (partitioned) { float ms = 0; if (cudaEventElapsedTime(&ms, c.ev[10], c.ev[11]) == cudaSuccess) tm.partition_ms = ms; }
+  tm.strategy = partitioned ? 5 : (use_hot ? (P.hot.dense ? 4 : 1) : 2);
   tm.spilled_rows = (int64_t)hctl.spilled;
   tm.table_slots = (int64_t)cap;
   PW_CUDA(cudaEventRecord(c.ev[3], c.stream));

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "pw_engine.h"
+#include "pw_partition.cuh"
 #include "pw_scan.cuh"
 
 namespace pw {
@@ -155,6 +156,7 @@ std::string jit_ctl(const ScanPlan& P) {
   g.scalar("int", "h_claim_off", P.hot.claim_off);
   g.scalar("int", "h_claim_acc", P.hot.claim_acc);
   g.scalar("int", "h_n_mm", P.hot.n_mm);
+  g.scalar("int", "rowid_slot", P.rowid_slot_p1 - 1);
   g.scalar("bool", "h_dense", P.hot.dense != 0);
   g.scalar("bool", "h_dense_sentinels", P.hot.dense == 2);
   g.scalar("int", "h_guard_acc", P.hot.guard_acc);
@@ -183,10 +185,17 @@ std::string seg_entry(int nc, int threads) {
   return src.str();
 }
 
+std::string part_entry(int nc, int kw, int threads) {
+  std::ostringstream src;
+  src << "extern \"C\" __global__ void __launch_bounds__(" << threads << ") pw_part_jit(const __grid_constant__ pw::ScanPlan P, const pw::PartParams pp) {\n"
+      << "  pw::part_body<pw::JitCtl, " << nc << ", " << kw << ">(P, pp);\n}\n";
+  return src.str();
+}
+
 Compiled compile(const std::string& ctl, const std::string& entry, const char* entry_name) {
   Api& a = api();
   Compiled c;
-  const std::string text = "#include \"pw_segmented.cuh\"\nnamespace pw {\n" + ctl + "}\n" + entry;
+  const std::string text = "#include \"pw_segmented.cuh\"\n#include \"pw_partition.cuh\"\nnamespace pw {\n" + ctl + "}\n" + entry;
   nvrtcProgram prog = nullptr;
   if (a.nvrtcCreateProgram(&prog, text.c_str(), "pw_scan_jit.cu", 0, nullptr, nullptr) != 0) { c.failed = true; return c; }
   const std::string inc = "--include-path=" + csrc_dir();
@@ -237,7 +246,7 @@ int jit_selftest_compile(const ScanPlan& P, int nc, int kw, bool hot, int thread
     *(void**)(&a.nvrtcGetCUBIN) = dlsym(rtc, "nvrtcGetCUBIN");
     *(void**)(&a.nvrtcDestroyProgram) = dlsym(rtc, "nvrtcDestroyProgram");
   }
-  const std::string text = "#include \"pw_segmented.cuh\"\nnamespace pw {\n" + jit_ctl(P) + "}\n" + scan_entry(nc, kw, hot, threads) + seg_entry(nc, 256);
+  const std::string text = "#include \"pw_segmented.cuh\"\n#include \"pw_partition.cuh\"\nnamespace pw {\n" + jit_ctl(P) + "}\n" + scan_entry(nc, kw, hot, threads) + seg_entry(nc, 256) + part_entry(nc, kw, 256);
   nvrtcProgram prog = nullptr;
   if (a.nvrtcCreateProgram(&prog, text.c_str(), "pw_scan_jit.cu", 0, nullptr, nullptr) != 0) { *err = "nvrtcCreateProgram failed"; return 2; }
   const std::string inc = "--include-path=" + csrc_dir();
@@ -285,6 +294,7 @@ static std::string plan_key(const ScanPlan& P) {
   }
   i32(P.gflags); i32(P.acc_gbase); i32(P.n_acc);
   for (int a = 0; a < P.n_acc; ++a) i32(P.accs[a].op);
+  i32(P.rowid_slot_p1);
   i32(P.vec_ok); i32(P.check_sorted); i32(P.row_begin == 0 && P.row_stride == 1); i32(P.row_group_out != nullptr);
   put(&P.hot, sizeof P.hot);
   return k;
@@ -328,6 +338,45 @@ int launch_scan_jit(const ScanPlan& P, int nc, int kw, bool hot, int threads, in
   if (rc != 0) return fail(PW_ERR_CUDA, "cuLaunchKernel(pw_scan_jit) failed with %d", rc);
   ctx().timings.kernel_launches++;
   return 0;
+}
+
+// the partitioning passes (histogram / scatter), specialised the same way; returns 0 launched, 1 unavailable
+int launch_part_jit(const ScanPlan& P, const PartParams& pp, int nc, int kw, int sm_count, cudaStream_t st) {
+  static const bool disabled = getenv("PW_NO_JIT") != nullptr;
+  if (disabled) return 1;
+  Api& a = api();
+  if (!a.ok) return 1;
+  const int threads = 256;
+  std::string key = plan_key(P);
+  const int32_t tail[3] = {-2 /* part */, nc, kw};
+  key.append((const char*)tail, sizeof tail);
+  Compiled c;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_cache.find(key);
+    if (it == g_cache.end()) {
+      c = compile(jit_ctl(P), part_entry(nc, kw, threads), "pw_part_jit");
+      if (!c.failed && c.fn) {
+        if (a.cuOccupancyMaxActiveBlocksPerMultiprocessor(&c.per_sm, c.fn, threads, 0) != 0 || c.per_sm < 1) c.failed = true;
+      }
+      g_cache[key] = c;
+    } else c = it->second;
+  }
+  if (c.failed || !c.fn) return 1;
+  const int64_t n_steps = (P.n_rows + ROWS_PER_STEP - 1) / ROWS_PER_STEP;
+  int64_t grid = std::min<int64_t>((int64_t)sm_count * c.per_sm, (n_steps + (threads / 32) - 1) / (threads / 32));
+  if (grid < 1) grid = 1;
+  ScanPlan copy = P;
+  PartParams ppc = pp;
+  void* params[] = {&copy, &ppc};
+  const CUresult rc = a.cuLaunchKernel(c.fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, 0, (CUstream)st, params, nullptr);
+  if (rc != 0) return fail(PW_ERR_CUDA, "cuLaunchKernel(pw_part_jit) failed with %d", rc);
+  ctx().timings.kernel_launches++;
+  return 0;
+}
+bool jit_available() {
+  static const bool disabled = getenv("PW_NO_JIT") != nullptr;
+  return !disabled && api().ok;
 }
 
 // the sorted-window kernel, specialised the same way; returns 0 launched, 1 unavailable

@@ -169,7 +169,22 @@ struct ScanPlan {
   uint32_t* row_group_out; // [n_rows] or nullptr
   const uint32_t* slot_rank; // [cap + 2] rank of every occupied slot in the ordered group list
   int64_t dense_min;       // hot.dense: key value of dense id 0 (data, not part of the JIT shape)
+  // Partitioned input (high-cardinality path, pw_partition.cuh): the scan runs over a temporary frame whose rows were
+  // scattered into key-hash partitions.  Every slot of that frame is a 64-bit word column; the extra slot
+  // `rowid_slot_p1 - 1` holds (original row << 8) | validity bit of every slot.  0 = plain input.
+  int32_t rowid_slot_p1;
+  int32_t pad3;
   HotGeom hot;
+};
+
+// radix partitioning pass (pw_partition.cuh): mode 1 counts rows per partition, mode 2 scatters them
+struct PartParams {
+  uint32_t* hist;       // [n_parts] mode 1: rows per partition
+  uint32_t* cursor;     // [n_parts] mode 2: next free row of every partition (starts at the partition's offset)
+  uint64_t* out;        // mode 2: (n_slots + 1) word columns, `out_stride` words apart
+  uint64_t out_stride;
+  uint32_t n_parts;
+  int32_t mode;
 };
 
 constexpr uint64_t KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;  // n_kw == 1 occupancy sentinel

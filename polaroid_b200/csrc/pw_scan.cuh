@@ -596,6 +596,8 @@ __device__ __forceinline__ void row_decode(const ScanPlan& P, const uint4 (&raw)
       r.in_valid |= (CT::slot_nullable(P, c) ? ((vbits[c] >> j) & 1u) : 1u) << c;
     } else r.in[c] = 0;
   }
+  // partitioned input: the validity bits of the original row travel in the low byte of the row-id word
+  if (CT::rowid_slot(P) >= 0) r.in_valid = (uint32_t)pick<NC>(r.in, CT::rowid_slot(P)) & 0xFFu;
 }
 
 // predicate: conjunction, null => false   (polars-compute/src/filter/mod.rs:18-28)
@@ -719,6 +721,7 @@ __device__ __forceinline__ void row_front(const ScanPlan& P, const uint4 (&raw)[
   o.row = base + HF * 64 + 2 * lane + j;
   Row<NC> r;
   row_decode<CT, NC>(P, raw[HF], vbits[HF], j, r);
+  if (CT::rowid_slot(P) >= 0) o.row = (int64_t)(pick<NC>(r.in, CT::rowid_slot(P)) >> 8);  // row of the original frame
   bool alive = (HF * 64 + 2 * lane + j) < rem && row_predicate<CT, NC>(P, r);
   alive = row_keys<CT, NC, KW>(P, r, raw[HF], vbits[HF], j, alive, o.k, o.sentinel_free) && alive;
   o.alive = alive;
@@ -1298,7 +1301,10 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) { raw[hf][c] = nraw[hf][c]; vbits[hf][c] = nvbits[hf][c]; }
     }
-    if (HOT && ((tile - tile_lo) & 3) == 3) {  // every 4 tiles (6144 rows at 12 warps): two CTA barriers
+    // every 4 tiles (6144 rows at 12 warps): two CTA barriers.  Partitioned input walks through disjoint group sets
+    // (one per partition, a tile or two long): check every tile and evict at half full, so that the next partitions
+    // always find room
+    if (HOT && (CT::rowid_slot(P) >= 0 || ((tile - tile_lo) & 3) == 3)) {
       __syncthreads();
       // Evict everything (FixedIndexTable evicts per slot; a wholesale flush keeps the per-row path free of
       // eviction logic) when a row found the table full, or — for group sets that drift (time-sorted input) —
@@ -1307,7 +1313,7 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
       const uint32_t cnt = *(volatile uint32_t*)hot.count;
       const bool full = *(volatile uint32_t*)(hot.count + 1) != 0u;
       const uint32_t G = (uint32_t)CT::h_gcap(P);
-      const bool nearly = cnt >= G - (G >> 3) && !stable_set;
+      const bool nearly = CT::rowid_slot(P) >= 0 ? cnt >= (G >> 1) : (cnt >= G - (G >> 3) && !stable_set);
       if (CT::h_guard_acc(P) >= 0 && threadIdx.x == 0) {  // guard scratch: (max of minima, min of maxima), signed domain
         hot.guard_words()[0] = 0x8000000000000000ull;
         hot.guard_words()[1] = 0x7FFFFFFFFFFFFFFFull;
@@ -1317,7 +1323,7 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
       const bool wrap = tiles_since_flush >= 30000;  // private counters share their word with the claim byte: 24 bits
       bool flushed = false;
       if ((full || nearly || wrap) && tile + 1 < tile_hi) {
-        if (!full && !wrap && flushed_once && tiles_since_flush <= 2) stable_set = true;  // refilled at once: same groups again
+        if (!full && !wrap && flushed_once && tiles_since_flush <= 2 && CT::rowid_slot(P) < 0) stable_set = true;  // refilled at once: same groups again
         else {
           hot.flush(P);
           __syncthreads();

@@ -24,6 +24,8 @@ FLAG_FORCE_HOT = 1 << 0
 FLAG_FORCE_GLOBAL = 1 << 1
 FLAG_FORCE_SEGMENTED = 1 << 2
 FLAG_NO_SEGMENTED = 1 << 3
+FLAG_FORCE_PARTITION = 1 << 4
+FLAG_NO_PARTITION = 1 << 5
 
 
 class PolarwayError(RuntimeError):
@@ -68,7 +70,7 @@ class PwTimings(C.Structure):
                 ("d2h_ms", C.c_float), ("total_device_ms", C.c_float), ("n_rows", C.c_int64), ("n_groups", C.c_int64),
                 ("table_slots", C.c_int64), ("strategy", C.c_int32), ("retries", C.c_int32),
                 ("kernel_launches", C.c_int64), ("spilled_rows", C.c_int64), ("scan_kernel_ms", C.c_float),
-                ("reserved", C.c_float), ("host_ms", C.c_float), ("pad", C.c_float)]
+                ("reserved", C.c_float), ("host_ms", C.c_float), ("partition_ms", C.c_float)]
 
 
 class ArrowSchema(C.Structure):

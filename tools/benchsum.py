@@ -14,7 +14,7 @@ def main():
         j = json.loads(line[-1])
         r, ph = j["roofline"], j["phases_ms"]
         print(f"{w:4s} step {j['ms_per_step']:8.3f} ms  kernel {r['kernel_ms']:8.3f} ms  frac {r['frac']:.3f}  e2e {j['e2e']['ms_per_step']:8.2f} ms  "
-              f"call {ph['host_ms']:.3f} est {ph['estimate_ms']:.3f} fin {ph['finalize_ms']:.3f} d2h {ph['d2h_ms']:.3f}  spilled {j['spilled_rows']} groups {j['n_groups']} "
+              f"call {ph['host_ms']:.3f} scan {ph['scan_ms']:.3f} part {ph.get('partition_ms', 0):.3f} est {ph['estimate_ms']:.3f} fin {ph['finalize_ms']:.3f} d2h {ph['d2h_ms']:.3f}  spilled {j['spilled_rows']} groups {j['n_groups']} "
               f"jit {j['jit']} strat {j['config']['strategy']} clocks {j['clocks'].get('sm_mhz')}", flush=True)
 
 if __name__ == "__main__":
