@@ -243,6 +243,15 @@ int pw_b200_partial_free(PwPartial* p);
  * finalise.  `schema_from` supplies dtypes/names (any rank's frame with the same schema). */
 int pw_b200_merge_partials(const PwQuery* q, const PwFrame* schema_from, const void* device_rows, int64_t n_rows,
                            struct ArrowArray* out_cols, struct ArrowSchema* out_schemas, size_t* n_out);
+/* Small-result exchange (one collective, no host round trip between export and merge): every rank writes
+ * [n_rows | cap_rows x (owner, packed row)] into `send_device` (1 + cap_rows * (row_words + 1) 64-bit words), the
+ * buffers are all-gathered, and each rank merges the rows it owns straight from the gathered buffer.
+ * partial_into returns 1 when this rank has more than cap_rows groups (its header then says so to every peer);
+ * merge_gathered returns 1 when any rank overflowed: all ranks then repeat through the general path above. */
+int64_t pw_b200_partial_row_words(const PwQuery* q, const PwFrame* frame);
+int pw_b200_frame_groupby_partial_into(const PwQuery* q, const PwFrame* frame, int32_t n_parts, void* send_device, int64_t cap_rows);
+int pw_b200_merge_gathered(const PwQuery* q, const PwFrame* schema_from, const void* gathered_device, int32_t world, int64_t cap_rows,
+                           int32_t my_rank, struct ArrowArray* out_cols, struct ArrowSchema* out_schemas, size_t* n_out);
 
 /* ---- expression-plugin compatibility shim (polars-ffi/src/version_0.rs, plugin.rs:75-142) ----------- */
 typedef struct SeriesExport {

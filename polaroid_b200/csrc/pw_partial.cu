@@ -80,13 +80,61 @@ static __global__ void export_kernel(Table T, PackLayout pl, const uint32_t* slo
   }
 }
 
+// small-result exchange: rows go straight into the caller's send buffer, unsorted, each tagged with its owner
+static __global__ void export_gather_kernel(Table T, PackLayout pl, const uint32_t* slot_list, uint64_t n, int n_parts, int64_t row_offset,
+                                            uint64_t* buf, uint64_t header) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) buf[0] = header;
+  if (i >= n || header == ~0ull) return;
+  const uint64_t slot = slot_list[i];
+  uint64_t k[MAX_KW];
+  for (int w = 0; w < pl.kw; ++w) k[w] = tkey(T, w, slot);
+  uint64_t* r = buf + 1 + i * (uint64_t)(pl.row_words + 1);
+  r[0] = owner_of(k, pl.kw, n_parts);
+  r[1] = (pl.kw == 1 && slot >= T.cap) ? 1ull : 0ull;
+  for (int w = 0; w < pl.kw; ++w) r[2 + w] = k[w];
+  for (int a = 0; a < pl.n_acc; ++a) r[2 + pl.kw + a] = tacc(T, a, slot);
+  for (int f = 0; f < pl.n_fl; ++f) {
+    const uint64_t packed = tacc(T, pl.fl_acc[f], slot);
+    uint64_t bits = 0;
+    if (packed & 1ull) {
+      const int64_t row = (int64_t)(packed >> 1) - row_offset;
+      bits = decode(load_pair(pl.fl_src[f].values, pl.fl_src[f].dtype, row, row + 1, false), pl.fl_src[f].dtype, 0);
+    }
+    r[2 + pl.kw + pl.n_acc + f] = bits;
+  }
+}
+
 struct AccOpsK { int32_t n; int32_t op[MAX_ACC]; };
 
+// Where the packed rows of a merge live.  Plain: n rows back to back.  Gathered (small-result exchange, one
+// all-gather): `world` segments of [n_rows | cap_rows x (owner, packed row)]; a rank merges the rows it owns.  The row
+// counts stay on the device (no host round trip between the collective and the merge); a segment whose header is
+// GATHER_OVERFLOW (its rank had more than cap_rows groups) raises flag 3 and the caller repeats the exchange through
+// the general two-step path.
+constexpr uint64_t GATHER_OVERFLOW = ~0ull;
+struct RowSrc {
+  const uint64_t* base;
+  uint64_t seg_words, cap_rows;
+  int32_t gathered, my_rank;
+};
+__device__ __forceinline__ const uint64_t* locate_row(const RowSrc& src, const PackLayout& pl, uint64_t i, int32_t* overflow) {
+  if (!src.gathered) return src.base + i * (uint64_t)pl.row_words;
+  const uint64_t seg = i / src.cap_rows, j = i % src.cap_rows;
+  const uint64_t* sb = src.base + seg * src.seg_words;
+  const uint64_t n = sb[0];
+  if (n == GATHER_OVERFLOW) { if (j == 0) *overflow = 3; return nullptr; }
+  if (j >= n) return nullptr;
+  const uint64_t* r = sb + 1 + j * (uint64_t)(pl.row_words + 1);
+  return r[0] == (uint64_t)src.my_rank ? r + 1 : nullptr;
+}
+
 template <int KW>
-static __global__ void merge_kernel(Table T, PackLayout pl, AccOpsK ops, const uint64_t* rows, uint64_t n, uint32_t* row_slot) {
+static __global__ void merge_kernel(Table T, PackLayout pl, AccOpsK ops, RowSrc src, uint64_t n, uint32_t* row_slot) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint64_t* r = rows + i * (uint64_t)pl.row_words;
+  const uint64_t* r = locate_row(src, pl, i, T.overflow);
+  if (!r) { row_slot[i] = 0xFFFFFFFFu; return; }
   uint64_t k[KW];
 #pragma unroll
   for (int w = 0; w < KW; ++w) k[w] = w < pl.kw ? r[1 + w] : 0ull;
@@ -101,12 +149,14 @@ static __global__ void merge_kernel(Table T, PackLayout pl, AccOpsK ops, const u
 }
 
 // second phase of first/last: the row whose packed index won the merge publishes its value word
-static __global__ void merge_values_kernel(Table T, PackLayout pl, const uint64_t* rows, uint64_t n, const uint32_t* row_slot, uint64_t* fl_values) {
+static __global__ void merge_values_kernel(Table T, PackLayout pl, RowSrc src, uint64_t n, const uint32_t* row_slot, uint64_t* fl_values) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t slot = row_slot[i];
   if (slot == 0xFFFFFFFFu) return;
-  const uint64_t* r = rows + i * (uint64_t)pl.row_words;
+  int32_t dummy = 0;
+  const uint64_t* r = locate_row(src, pl, i, &dummy);
+  if (!r) return;
   const uint64_t stride = T.cap + 2;
   for (int f = 0; f < pl.n_fl; ++f) {
     const uint64_t mine = r[1 + pl.kw + pl.fl_acc[f]];
@@ -191,10 +241,72 @@ int pw_b200_partial_free(PwPartial* p) {
   return 0;
 }
 
+static int merge_impl(const PwQuery* q, const PwFrame* schema_from, RowSrc src, int64_t n_rows, uint64_t cap,
+                      struct ArrowArray* out_cols, struct ArrowSchema* out_schemas, size_t* n_out);
+
 int pw_b200_merge_partials(const PwQuery* q, const PwFrame* schema_from, const void* device_rows, int64_t n_rows,
                            struct ArrowArray* out_cols, struct ArrowSchema* out_schemas, size_t* n_out) {
   PW_TRY(ensure_device());
   if (!q || !schema_from || !out_cols || !out_schemas || !n_out || n_rows < 0) return fail(PW_ERR_INVALID, "bad argument");
+  RowSrc src{};
+  src.base = (const uint64_t*)device_rows;
+  return merge_impl(q, schema_from, src, n_rows, (uint64_t)std::max<int64_t>(2 * n_rows, 64), out_cols, out_schemas, n_out);
+}
+
+int64_t pw_b200_partial_row_words(const PwQuery* q, const PwFrame* frame) {
+  if (!q || !frame) return fail(PW_ERR_INVALID, "bad argument");
+  Lowered L;
+  PW_TRY(lower_query(q, frame, &L));
+  return make_layout(L, kw_class(L.plan.n_kw)).row_words;
+}
+
+int pw_b200_frame_groupby_partial_into(const PwQuery* q, const PwFrame* frame, int32_t n_parts, void* send_device, int64_t cap_rows) {
+  PW_TRY(ensure_device());
+  if (!q || !frame || !send_device || n_parts < 1 || cap_rows < 1) return fail(PW_ERR_INVALID, "bad argument");
+  ThreadCtx& c = ctx();
+  memset(&c.timings, 0, sizeof c.timings);
+  PW_CUDA(cudaEventRecord(c.ev[0], c.stream));
+  Lowered L;
+  PW_TRY(lower_query(q, frame, &L));
+  if (q->dynamic && !L.tumbling) return fail(PW_ERR_UNSUPPORTED, "overlapping windows are not shardable by row range");
+  L.sort.clear();
+  Table T{};
+  uint32_t* slots = nullptr;
+  uint64_t G = 0;
+  PW_TRY(run_groupby(q, frame, L, &T, &slots, &G));
+  PackLayout pl = make_layout(L, kw_class(L.plan.n_kw));
+  const bool fits = G <= (uint64_t)cap_rows;
+  const uint64_t n = fits ? G : 0;
+  export_gather_kernel<<<(int)std::max<uint64_t>(1, (n + 255) / 256), 256, 0, c.stream>>>(T, pl, slots, n, n_parts, q->row_offset, (uint64_t*)send_device,
+                                                                                          fits ? G : GATHER_OVERFLOW);
+  PW_CUDA(cudaGetLastError());
+  c.timings.kernel_launches++;
+  float ms;
+  if (cudaEventElapsedTime(&ms, c.ev[8], c.ev[9]) == cudaSuccess) c.timings.scan_kernel_ms = ms;
+  dev_free(slots);
+  free_table(T);
+  return fits ? 0 : 1;
+}
+
+int pw_b200_merge_gathered(const PwQuery* q, const PwFrame* schema_from, const void* gathered_device, int32_t world, int64_t cap_rows,
+                           int32_t my_rank, struct ArrowArray* out_cols, struct ArrowSchema* out_schemas, size_t* n_out) {
+  PW_TRY(ensure_device());
+  if (!q || !schema_from || !gathered_device || !out_cols || !out_schemas || !n_out || world < 1 || cap_rows < 1) return fail(PW_ERR_INVALID, "bad argument");
+  Lowered L;
+  PW_TRY(lower_query(q, schema_from, &L));
+  const int64_t rw = make_layout(L, kw_class(L.plan.n_kw)).row_words;
+  RowSrc src{};
+  src.base = (const uint64_t*)gathered_device;
+  src.seg_words = 1 + (uint64_t)cap_rows * (uint64_t)(rw + 1);
+  src.cap_rows = (uint64_t)cap_rows;
+  src.gathered = 1; src.my_rank = my_rank;
+  return merge_impl(q, schema_from, src, (int64_t)world * cap_rows, (uint64_t)std::max<int64_t>(4 * cap_rows, 64), out_cols, out_schemas, n_out);
+}
+
+// returns 0, an error, or 1 = "repeat through the general exchange" (gathered input only: a rank overflowed its
+// segment, or this rank owns more groups than the optimistic table holds)
+static int merge_impl(const PwQuery* q, const PwFrame* schema_from, RowSrc src, int64_t n_rows, uint64_t cap,
+                      struct ArrowArray* out_cols, struct ArrowSchema* out_schemas, size_t* n_out) {
   ThreadCtx& c = ctx();
   Lowered L;
   PW_TRY(lower_query(q, schema_from, &L));
@@ -206,7 +318,6 @@ int pw_b200_merge_partials(const PwQuery* q, const PwFrame* schema_from, const v
   PW_TRY(dev_alloc(&v, sizeof(Ctl))); dctl = (Ctl*)v;
   PW_CUDA(cudaMemsetAsync(dctl, 0, sizeof(Ctl), c.stream));
   Table T{};
-  const uint64_t cap = (uint64_t)std::max<int64_t>(2 * n_rows, 64);
   const uint64_t nn = cap + 2;
   PW_TRY(alloc_table_raw(&T, kw, L.plan.n_acc, cap, &dctl->overflow, &dctl->spilled));
   AccOps ops{};
@@ -221,16 +332,15 @@ int pw_b200_merge_partials(const PwQuery* q, const PwFrame* schema_from, const v
   PW_TRY(dev_alloc(&v, nn * 8 * (uint64_t)std::max(1, pl.n_fl))); fl_values = (uint64_t*)v;
   if (n_rows) {
     const int grid = (int)((n_rows + 255) / 256);
-    const uint64_t* rows = (const uint64_t*)device_rows;
     switch (kw) {
-      case 1: merge_kernel<1><<<grid, 256, 0, c.stream>>>(T, pl, opsk, rows, (uint64_t)n_rows, row_slot); break;
-      case 2: merge_kernel<2><<<grid, 256, 0, c.stream>>>(T, pl, opsk, rows, (uint64_t)n_rows, row_slot); break;
-      case 4: merge_kernel<4><<<grid, 256, 0, c.stream>>>(T, pl, opsk, rows, (uint64_t)n_rows, row_slot); break;
-      default: merge_kernel<6><<<grid, 256, 0, c.stream>>>(T, pl, opsk, rows, (uint64_t)n_rows, row_slot); break;
+      case 1: merge_kernel<1><<<grid, 256, 0, c.stream>>>(T, pl, opsk, src, (uint64_t)n_rows, row_slot); break;
+      case 2: merge_kernel<2><<<grid, 256, 0, c.stream>>>(T, pl, opsk, src, (uint64_t)n_rows, row_slot); break;
+      case 4: merge_kernel<4><<<grid, 256, 0, c.stream>>>(T, pl, opsk, src, (uint64_t)n_rows, row_slot); break;
+      default: merge_kernel<6><<<grid, 256, 0, c.stream>>>(T, pl, opsk, src, (uint64_t)n_rows, row_slot); break;
     }
     PW_CUDA(cudaGetLastError());
     if (pl.n_fl) {
-      merge_values_kernel<<<grid, 256, 0, c.stream>>>(T, pl, rows, (uint64_t)n_rows, row_slot, fl_values);
+      merge_values_kernel<<<grid, 256, 0, c.stream>>>(T, pl, src, (uint64_t)n_rows, row_slot, fl_values);
       PW_CUDA(cudaGetLastError());
     }
     c.timings.kernel_launches += 3;
@@ -242,7 +352,12 @@ int pw_b200_merge_partials(const PwQuery* q, const PwFrame* schema_from, const v
   PW_CUDA(cudaGetLastError());
   PW_CUDA(cudaMemcpyAsync(&hctl, dctl, sizeof(Ctl), cudaMemcpyDeviceToHost, c.stream));
   PW_CUDA(cudaStreamSynchronize(c.stream));
-  if (hctl.overflow) { return fail(PW_ERR_INTERNAL, "merge table overflow"); }
+  if (hctl.overflow) {
+    dev_free(slots); dev_free(row_slot); dev_free(fl_values); dev_free(dctl);
+    free_table(T);
+    if (src.gathered) return 1;
+    return fail(PW_ERR_INTERNAL, "merge table overflow");
+  }
   const uint64_t G = hctl.counter;
   PW_TRY(order_groups(L, T, kw, &slots, G));
   int f_idx = 0;

@@ -118,6 +118,11 @@ def lib():
         L.pw_b200_frame_group_tuples.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_void_p,
                                                  C.c_void_p, C.c_void_p, C.c_void_p]
         L.pw_b200_frame_groupby_partial.argtypes = [C.POINTER(PwQuery), C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+        L.pw_b200_partial_row_words.restype = C.c_int64
+        L.pw_b200_partial_row_words.argtypes = [C.POINTER(PwQuery), C.c_void_p]
+        L.pw_b200_frame_groupby_partial_into.argtypes = [C.POINTER(PwQuery), C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
+        L.pw_b200_merge_gathered.argtypes = [C.POINTER(PwQuery), C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
+                                             C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]
         L.pw_b200_partial_row_bytes.restype = C.c_int64
         L.pw_b200_partial_row_bytes.argtypes = [C.c_void_p]
         L.pw_b200_partial_device_rows.restype = C.c_void_p

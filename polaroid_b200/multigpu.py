@@ -19,6 +19,7 @@ world_size-2 CPU tests.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List
 
 import torch
@@ -45,12 +46,54 @@ def exchange_rows(rows: torch.Tensor, send_counts: List[int], row_words: int) ->
     return recv
 
 
+GATHER_CAP_ROWS = int(os.environ.get("PW_MGPU_GATHER_ROWS", "8192"))  # 0 disables the single-collective exchange
+_gather_bufs = {}
+
+
+def _gathered_exchange(L, engine, bq, frame, plan, rank: int, world: int):
+    """Small results (<= GATHER_CAP_ROWS groups per rank): ONE all-gather of fixed-size buffers, row counts stay on the
+    device, no host synchronisation between the local aggregation and the merge.  Returns the result table, or None when
+    some rank had too many groups (every rank sees the same headers, so every rank falls back together)."""
+    import pyarrow as pa
+    rw = L.pw_b200_partial_row_words(C.byref(bq.q), frame.handle)
+    if rw <= 0:
+        engine._check(int(rw))
+    words = 1 + GATHER_CAP_ROWS * (rw + 1)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    key = (dev.index, world, words)
+    if key not in _gather_bufs:
+        _gather_bufs[key] = (torch.zeros(words, dtype=torch.int64, device=dev), torch.zeros(world * words, dtype=torch.int64, device=dev))
+    send, gathered = _gather_bufs[key]
+    # the collective is ordered against torch's current stream: the library's launches must be on that stream too
+    L.pw_b200_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    rc = L.pw_b200_frame_groupby_partial_into(C.byref(bq.q), frame.handle, world, C.c_void_p(send.data_ptr()), GATHER_CAP_ROWS)
+    if rc not in (0, 1):
+        engine._check(rc)
+    dist.all_gather_into_tensor(gathered, send)     # same stream as the library's launches: ordered, no sync
+    cap = len(plan.keys) + len(plan.aggs) + 4
+    out_arrays = (engine.ArrowArray * cap)()
+    out_schemas = (engine.ArrowSchema * cap)()
+    n_out = C.c_size_t(cap)
+    rc = L.pw_b200_merge_gathered(C.byref(bq.q), frame.handle, C.c_void_p(gathered.data_ptr()), world, GATHER_CAP_ROWS, rank,
+                                  out_arrays, out_schemas, C.byref(n_out))
+    if rc == 1:
+        return None
+    engine._check(rc)
+    names, cols = engine._import_columns(out_arrays, out_schemas, n_out.value)
+    cols = engine._restore_string_types(names, cols, frame.table_schema, plan.keys)
+    return pa.Table.from_arrays(cols, names=names)
+
+
 def group_by_sharded(frame, plan, rank: int, world: int, row_offset: int = 0, **opts):
     """frame: engine.DeviceFrame holding this rank's shard.  Returns the pyarrow Table of the groups this rank owns."""
     import pyarrow as pa
     from . import engine
     L = engine.lib()
     bq = engine._BuiltQuery(frame.table_schema, plan, row_offset=row_offset, **opts)
+    if GATHER_CAP_ROWS > 0 and dist.is_initialized() and dist.get_backend() == "nccl":
+        got = _gathered_exchange(L, engine, bq, frame, plan, rank, world)
+        if got is not None:
+            return got
     part = C.c_void_p()
     engine._check(L.pw_b200_frame_groupby_partial(C.byref(bq.q), frame.handle, world, C.byref(part)))
     try:
