@@ -531,6 +531,20 @@ static bool plan_hot_threads(ScanPlan& P, int64_t groups_hint, int requested_gca
   int gcap = requested_gcap > 0 ? requested_gcap : (int)std::min<int64_t>(4096, std::max<int64_t>(8, groups_hint + groups_hint / 8 + 4));
   if (dense) gcap = (int)dense_range;
   const int mm_stride_all = n_mm > 1 ? ((n_mm + 1) & ~1) : n_mm;
+  // 32-bit shadow (pw_scan.cuh, HotTable::shadow): the first (min, max) pair over one value expression whose two
+  // CTA-shared words form an aligned 16-byte cell.  Shared words are numbered in accumulator order.
+  int shadow_acc = -1;
+  if (!getenv("PW_NO_SHADOW") && (mm_stride_all & 1) == 0) {
+    int mm_i = 0;
+    for (int a = 0; a < P.n_acc && shadow_acc < 0; ++a) {
+      if (is_count(a) || is_add(a)) continue;
+      if (a + 1 < P.acc_gbase && (mm_i & 1) == 0 && P.accs[a].vexpr == P.accs[a + 1].vexpr && P.accs[a].src == P.accs[a + 1].src &&
+          (P.accs[a].src == SRC_BITS || P.accs[a].src == SRC_F64_ORD) &&
+          ((P.accs[a].op == OP_MIN_I64 && P.accs[a + 1].op == OP_MAX_I64) || (P.accs[a].op == OP_MIN_U64 && P.accs[a + 1].op == OP_MAX_U64)))
+        shadow_acc = a;
+      ++mm_i;
+    }
+  }
   for (bool first = true;; gcap = gcap * 3 / 4, first = false) {
     if (gcap < 4 || ((dense || exact) && !first)) return false;  // a dense range is all or nothing
     // key index: buckets of four tags.  At 4 slots per id (25 % load) a row finds its key in the HOME bucket with
@@ -545,7 +559,7 @@ static bool plan_hot_threads(ScanPlan& P, int64_t groups_hint, int requested_gca
     auto per_warp = [&](int R, int mmp) { return (((size_t)gcap * R * cell_bytes(mmp)) + 15) & ~(size_t)15; };
     auto total = [&](int S, int R, int mmp) {
       const size_t shared = (size_t)S * 4 + (dense ? 0 : (size_t)gcap * 8 * kw) + 48;
-      return shared + (size_t)(mmp ? 0 : mm_stride_all) * gcap * 8 + per_warp(R, mmp) * warps;
+      return shared + (size_t)(mmp ? 0 : mm_stride_all) * gcap * 8 + ((mmp == 0 && shadow_acc >= 0) ? (size_t)gcap * 8 : 0) + per_warp(R, mmp) * warps;
     };
     // Preference order: every word warp-private (plain read-modify-write; first/last words improve on almost every
     // row, so CTA-shared atomics for them are very slow) with two CTAs per SM, then with one CTA per SM, then
@@ -568,7 +582,10 @@ static bool plan_hot_threads(ScanPlan& P, int64_t groups_hint, int requested_gca
     size_t off = (size_t)S * 4;
     off = (off + 15) & ~(size_t)15; g.keys_off = (int32_t)off; off += dense ? 0 : (size_t)gcap * 8 * kw;
     off = (off + 15) & ~(size_t)15; g.mm_off = (int32_t)off; off += (size_t)g.mm_stride * gcap * 8;
-    g.count_off = (int32_t)off; off += 32;  // [count, full flag, -, -][guard scratch: lo, hi]
+    g.count_off = (int32_t)off; off += 32;  // [count, full flag, -, -]
+    g.guard_acc = (mmp == 0) ? shadow_acc : -1;
+    g.shadow_off = (int32_t)off;
+    if (g.guard_acc >= 0) off += (((size_t)gcap * 8) + 15) & ~(size_t)15;
     g.warp_off = (int32_t)off;
     size_t woff = 0;
     int mm_idx = 0;
@@ -586,18 +603,6 @@ static bool plan_hot_threads(ScanPlan& P, int64_t groups_hint, int requested_gca
       }
     }
     if (g.claim_acc < 0) { g.claim_off = (int32_t)woff; woff += (size_t)gcap * R * 4; }
-    // extremum guard: the first CTA-shared (min, max) pair over one value expression that sits in an aligned 16-byte cell
-    g.guard_acc = -1;
-    // measured on C2 (1e3 groups): the guard over ALL groups stays too loose (max over groups of the minima) to pay for
-    // its divergent exact path: 0.715 vs 0.674 ms.  Opt-in for experiments.
-    if (getenv("PW_GUARD"))
-      for (int a = 0; a + 1 < P.n_acc && g.guard_acc < 0; ++a) {
-        const bool pair = (P.accs[a].op == OP_MIN_I64 && P.accs[a + 1].op == OP_MAX_I64) || (P.accs[a].op == OP_MIN_U64 && P.accs[a + 1].op == OP_MAX_U64);
-        if (pair && P.accs[a].vexpr == P.accs[a + 1].vexpr && P.accs[a].src == P.accs[a + 1].src && P.accs[a].src != SRC_ROWIDX && P.accs[a].src != SRC_ROW &&
-            g.acc_kind[a] == HOT_SHARED_MM && g.acc_kind[a + 1] == HOT_SHARED_MM && (g.acc_off[a] & 1) == 0 && g.acc_off[a + 1] == g.acc_off[a] + 1 &&
-            (g.mm_stride & 1) == 0 && a < P.acc_gbase)
-          g.guard_acc = a;
-      }
     woff = (woff + 15) & ~(size_t)15;
     g.warp_bytes = (int32_t)woff;
     g.total_bytes = (int32_t)(off + woff * warps);

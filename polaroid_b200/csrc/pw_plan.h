@@ -139,7 +139,9 @@ struct HotGeom {
   int32_t dense;       // != 0: single integer key with a small value range -> dense id = key - ScanPlan::dense_min
                        // (no key index, no key compare; the per-group row counter marks the ids that exist);
                        // 2 = the range contains -1 / -2, whose bit patterns are the table's key sentinels
-  int32_t guard_acc;   // min word of the CTA-shared (min, max) pair covered by the extremum guard, -1 = none
+  int32_t guard_acc;   // min word of the CTA-shared (min, max) pair that has a 32-bit shadow, -1 = none
+  int32_t shadow_off;  // byte offset of the shadow array (int2 per id)
+  int32_t pad4;
   int32_t threads;     // CTA size the geometry was planned for (warp-private regions = threads / 32)
   int32_t acc_kind[MAX_ACC];
   int32_t acc_off[MAX_ACC];  // HOT_SHARED_MM: word inside the group's min/max block; private kinds: byte offset inside the warp region

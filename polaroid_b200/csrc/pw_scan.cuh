@@ -229,43 +229,12 @@ struct HotTable {
   uint32_t* count;       // [0] dense ids handed out, [1] "a row found the table full"
   unsigned char* wbase;  // this warp's private region
   unsigned char* wall;   // warp 0's private region
-  // Extremum guard (registers, refreshed at the periodic CTA barrier): every dense id < g_cov already holds a minimum
-  // <= G_lo and a maximum >= G_hi, so a row whose value lies strictly inside (G_lo, G_hi) cannot improve any of them
-  // and skips the min/max words altogether.  Only the high 32 bits of the 64-bit images are kept (conservative).
-  int32_t g_lo_h, g_hi_h, g_cov;
-  __device__ __forceinline__ void guard_off() { g_lo_h = 0x7FFFFFFF; g_hi_h = (int32_t)0x80000000; g_cov = 0; }
-  __device__ __forceinline__ uint64_t* guard_words() const { return (uint64_t*)(count + 4); }
-  // CTA-wide, between two barriers placed by the caller: reset scratch (before), reduce (here), read back (after)
-  __device__ __forceinline__ void guard_reduce(const ScanPlan& P, int n_ids) {
-    const int a = CT::h_guard_acc(P);
-    const bool uns = CT::acc_op(P, a) == OP_MIN_U64;
-    const uint64_t flip = uns ? 0x8000000000000000ull : 0ull;  // reduce in the signed domain
-    long long lo = (long long)0x8000000000000000ull, hi = 0x7FFFFFFFFFFFFFFFll;  // max of minima, min of maxima
-    for (int id = threadIdx.x; id < n_ids; id += blockDim.x) {
-      const uint64_t* q = &mm[(size_t)id * CT::h_mm_stride(P) + CT::h_off(P, a)];
-      const long long mn = (long long)(q[0] ^ flip), mx = (long long)(q[1] ^ flip);
-      lo = mn > lo ? mn : lo;  // an id without a value yet holds (+inf, -inf): the guard closes
-      hi = mx < hi ? mx : hi;
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      const long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
-      lo = l2 > lo ? l2 : lo;
-      hi = h2 < hi ? h2 : hi;
-    }
-    if ((threadIdx.x & 31) == 0) {
-      atomicMax((long long*)guard_words(), lo);
-      atomicMin((long long*)guard_words() + 1, hi);
-    }
-  }
-  __device__ __forceinline__ void guard_read(const ScanPlan& P, int n_ids) {
-    const volatile uint64_t* g = guard_words();  // signed-domain images (unsigned words are compared after the same flip)
-    g_lo_h = (int32_t)(uint32_t)(g[0] >> 32);
-    g_hi_h = (int32_t)(uint32_t)(g[1] >> 32);
-    g_cov = n_ids;
-    if (g_lo_h >= g_hi_h) guard_off();  // empty interval (an id without a value yet, or a single-valued column)
-  }
-
+  // 32-bit SHADOW of one CTA-shared (min, max) pair: per id the high words of the two 64-bit images, always on the
+  // safe side of the truth (shadow min >= true min, shadow max <= true max in the high word), so
+  // `hi(x) <= shadow.min || hi(x) >= shadow.max` catches every row that could improve an extremum.  The common row
+  // reads 8 bytes and does two 32-bit compares instead of 16 bytes and two 64-bit compares; the rare row takes the
+  // exact path and tightens the shadow with native 32-bit shared-memory atomics.
+  int2* shadow;
   __device__ __forceinline__ void bind(unsigned char* smem, const ScanPlan& P, int warp) {
     tag = (uint32_t*)smem;
     keys = (uint64_t*)(smem + CT::h_keys_off(P));
@@ -273,7 +242,7 @@ struct HotTable {
     count = (uint32_t*)(smem + CT::h_count_off(P));
     wall = smem + CT::h_warp_off(P);
     wbase = wall + (size_t)warp * CT::h_warp_bytes(P);
-    guard_off();
+    shadow = (int2*)(smem + CT::h_shadow_off(P));
   }
   // reset everything (CTA-wide; caller syncs)
   __device__ __forceinline__ void clear(const ScanPlan& P) {
@@ -296,6 +265,8 @@ struct HotTable {
         }
       }
     }
+    if (CT::h_guard_acc(P) >= 0)
+      for (int i = threadIdx.x; i < G; i += blockDim.x) shadow[i] = make_int2(0x7FFFFFFF, (int)0x80000000);
     if (threadIdx.x == 0) { count[0] = 0u; count[1] = 0u; }
   }
   __device__ __forceinline__ bool key_equals(const ScanPlan& P, int id, const uint64_t (&k)[KW]) const {
@@ -807,31 +778,20 @@ struct HotSinkB {
   template <int OPMIN>
   __device__ __forceinline__ void minmax_pair(const ScanPlan& P, int a, const uint64_t (&x)[B], const bool (&ok)[B], bool is_f64, part_tag<true>) const {
     bool en[B];
-    const bool guarded = a == CT::h_guard_acc(P) && B > 1 && hot.g_cov > 0;  // CTA-uniform
-    if (guarded) {
-      // extremum guard: two 32-bit compares per row decide whether the row can matter at all.  NaN images lie outside
-      // every guard interval, so they reach the exact filter below.
-      bool any = false;
+    if (a == CT::h_guard_acc(P) && B > 1) {
+      int2 sh[B];
 #pragma unroll
       for (int i = 0; i < B; ++i) {
-        const uint32_t xh = (uint32_t)(x[i] >> 32);
-        const bool outside = OPMIN == OP_MIN_I64 ? ((int32_t)xh <= hot.g_lo_h || (int32_t)xh >= hot.g_hi_h)
-                                                 : ((int32_t)(xh ^ 0x80000000u) <= hot.g_lo_h || (int32_t)(xh ^ 0x80000000u) >= hot.g_hi_h);
-        en[i] = ok[i] && (outside || id[i] >= hot.g_cov);
-        any = any || en[i];
+        asm volatile("ld.volatile.shared.v2.s32 {%0,%1}, [%2];" : "=r"(sh[i].x), "=r"(sh[i].y)
+                     : "r"((uint32_t)__cvta_generic_to_shared(&hot.shadow[ok[i] ? id[i] : 0])));
       }
-      if (!any) return;
-    } else {
-#pragma unroll
-      for (int i = 0; i < B; ++i) en[i] = ok[i];
-    }
-#pragma unroll
-    for (int i = 0; i < B; ++i) en[i] = en[i] && !(is_f64 && image_is_nan(x[i]));
-    if (guarded) {
-      // few rows get here once the guard has tightened: one row per lane per round through a single-row body
       uint32_t m = 0;
 #pragma unroll
-      for (int i = 0; i < B; ++i) m |= (en[i] ? 1u : 0u) << i;
+      for (int i = 0; i < B; ++i) {
+        const int32_t xh = (int32_t)((uint32_t)(x[i] >> 32) ^ (OPMIN == OP_MIN_I64 ? 0u : 0x80000000u));  // signed domain
+        m |= ((ok[i] && (xh <= sh[i].x || xh >= sh[i].y)) ? 1u : 0u) << i;  // NaN images lie outside every interval
+      }
+      // few rows get here once a group has seen some rows: one row per lane per round through a single-row body
       while (m) {
         const int j = __ffs((int)m) - 1;
         m &= m - 1u;
@@ -839,19 +799,23 @@ struct HotSinkB {
         int idv = id[0];
 #pragma unroll
         for (int i = 1; i < B; ++i) if (j == i) { xv = x[i]; idv = id[i]; }
+        if (is_f64 && image_is_nan(xv)) continue;
         uint64_t* q = &hot.mm[(size_t)idv * CT::h_mm_stride(P) + CT::h_off(P, a)];
         const uint4 cur = lds128_volatile((const uint32_t*)q);
         const uint64_t lo = (uint64_t)cur.y << 32 | cur.x, hi = (uint64_t)cur.w << 32 | cur.z;
+        const int32_t xh = (int32_t)((uint32_t)(xv >> 32) ^ (OPMIN == OP_MIN_I64 ? 0u : 0x80000000u));
         if (OPMIN == OP_MIN_I64) {
-          if ((long long)xv < (long long)lo) atomicMin((long long*)q, (long long)xv);
-          if ((long long)xv > (long long)hi) atomicMax((long long*)(q + 1), (long long)xv);
+          if ((long long)xv < (long long)lo) { atomicMin((long long*)q, (long long)xv); atomicMin(&hot.shadow[idv].x, xh); }
+          if ((long long)xv > (long long)hi) { atomicMax((long long*)(q + 1), (long long)xv); atomicMax(&hot.shadow[idv].y, xh); }
         } else {
-          if (xv < lo) atomicMin((unsigned long long*)q, (unsigned long long)xv);
-          if (xv > hi) atomicMax((unsigned long long*)(q + 1), (unsigned long long)xv);
+          if (xv < lo) { atomicMin((unsigned long long*)q, (unsigned long long)xv); atomicMin(&hot.shadow[idv].x, xh); }
+          if (xv > hi) { atomicMax((unsigned long long*)(q + 1), (unsigned long long)xv); atomicMax(&hot.shadow[idv].y, xh); }
         }
       }
       return;
     }
+#pragma unroll
+    for (int i = 0; i < B; ++i) en[i] = ok[i] && !(is_f64 && image_is_nan(x[i]));
     {
       uint4 cur[B];
 #pragma unroll
@@ -1314,14 +1278,9 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
       const bool full = *(volatile uint32_t*)(hot.count + 1) != 0u;
       const uint32_t G = (uint32_t)CT::h_gcap(P);
       const bool nearly = CT::rowid_slot(P) >= 0 ? cnt >= (G >> 1) : (cnt >= G - (G >> 3) && !stable_set);
-      if (CT::h_guard_acc(P) >= 0 && threadIdx.x == 0) {  // guard scratch: (max of minima, min of maxima), signed domain
-        hot.guard_words()[0] = 0x8000000000000000ull;
-        hot.guard_words()[1] = 0x7FFFFFFFFFFFFFFFull;
-      }
       __syncthreads();
       ++tiles_since_flush;
       const bool wrap = tiles_since_flush >= 30000;  // private counters share their word with the claim byte: 24 bits
-      bool flushed = false;
       if ((full || nearly || wrap) && tile + 1 < tile_hi) {
         if (!full && !wrap && flushed_once && tiles_since_flush <= 2 && CT::rowid_slot(P) < 0) stable_set = true;  // refilled at once: same groups again
         else {
@@ -1331,18 +1290,7 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
           __syncthreads();
           flushed_once = true;
           tiles_since_flush = 0;
-          flushed = true;
-          hot.guard_off();
         }
-      }
-      // refresh the extremum guard every 16th check, from the 32nd after a flush on: the interval tightens like 1/rows
-      // seen per group, and a loose guard (most warps still find a row that needs the exact test) costs more than the
-      // branch-free exact path it replaces
-      if (CT::h_guard_acc(P) >= 0 && !flushed && tiles_since_flush >= 32 && (tiles_since_flush & 15) == 0) {
-        const int n_ids = CT::h_dense(P) ? (int)G : (int)min(cnt, G);
-        hot.guard_reduce(P, n_ids);
-        __syncthreads();
-        hot.guard_read(P, n_ids);
       }
     }
   }
