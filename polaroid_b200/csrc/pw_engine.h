@@ -85,6 +85,8 @@ int launch_scan_jit(const ScanPlan& P, int nc, int kw, bool hot, int threads, in
 int launch_seg_jit(const ScanPlan& P, const SegParams& sp, int nc, int threads, size_t smem, int sm_count, cudaStream_t st);
 int launch_part_jit(const ScanPlan& P, const PartParams& pp, int nc, int kw, int sm_count, cudaStream_t st);
 bool jit_available();
+struct PilotParams;
+int launch_pilot_jit(const ScanPlan& P, const PilotParams& pp, int nc, int kw, cudaStream_t st);
 int jit_selftest_compile(const ScanPlan& P, int nc, int kw, bool hot, int threads, std::string* err);
 int launch_scan_aot(ScanPlan P, int sm, cudaStream_t st);
 int ensure_device();

@@ -19,6 +19,7 @@
 
 #include "pw_engine.h"
 #include "pw_partition.cuh"
+#include "pw_pilot.cuh"
 #include "pw_scan.cuh"
 
 namespace pw {
@@ -193,10 +194,17 @@ std::string part_entry(int nc, int kw, int threads) {
   return src.str();
 }
 
+std::string pilot_entry(int nc, int kw, int threads) {
+  std::ostringstream src;
+  src << "extern \"C\" __global__ void __launch_bounds__(" << threads << ") pw_pilot_jit(const __grid_constant__ pw::ScanPlan P, const pw::PilotParams pp) {\n"
+      << "  pw::pilot_body<pw::JitCtl, " << nc << ", " << kw << ">(P, pp);\n}\n";
+  return src.str();
+}
+
 Compiled compile(const std::string& ctl, const std::string& entry, const char* entry_name) {
   Api& a = api();
   Compiled c;
-  const std::string text = "#include \"pw_segmented.cuh\"\n#include \"pw_partition.cuh\"\nnamespace pw {\n" + ctl + "}\n" + entry;
+  const std::string text = "#include \"pw_segmented.cuh\"\n#include \"pw_partition.cuh\"\n#include \"pw_pilot.cuh\"\nnamespace pw {\n" + ctl + "}\n" + entry;
   nvrtcProgram prog = nullptr;
   if (a.nvrtcCreateProgram(&prog, text.c_str(), "pw_scan_jit.cu", 0, nullptr, nullptr) != 0) { c.failed = true; return c; }
   const std::string inc = "--include-path=" + csrc_dir();
@@ -247,7 +255,7 @@ int jit_selftest_compile(const ScanPlan& P, int nc, int kw, bool hot, int thread
     *(void**)(&a.nvrtcGetCUBIN) = dlsym(rtc, "nvrtcGetCUBIN");
     *(void**)(&a.nvrtcDestroyProgram) = dlsym(rtc, "nvrtcDestroyProgram");
   }
-  const std::string text = "#include \"pw_segmented.cuh\"\n#include \"pw_partition.cuh\"\nnamespace pw {\n" + jit_ctl(P) + "}\n" + scan_entry(nc, kw, hot, threads) + seg_entry(nc, 256) + part_entry(nc, kw, 256);
+  const std::string text = "#include \"pw_segmented.cuh\"\n#include \"pw_partition.cuh\"\n#include \"pw_pilot.cuh\"\nnamespace pw {\n" + jit_ctl(P) + "}\n" + scan_entry(nc, kw, hot, threads) + seg_entry(nc, 256) + part_entry(nc, kw, 256) + pilot_entry(nc, kw, 256);
   nvrtcProgram prog = nullptr;
   if (a.nvrtcCreateProgram(&prog, text.c_str(), "pw_scan_jit.cu", 0, nullptr, nullptr) != 0) { *err = "nvrtcCreateProgram failed"; return 2; }
   const std::string inc = "--include-path=" + csrc_dir();
@@ -372,6 +380,36 @@ int launch_part_jit(const ScanPlan& P, const PartParams& pp, int nc, int kw, int
   void* params[] = {&copy, &ppc};
   const CUresult rc = a.cuLaunchKernel(c.fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, 0, (CUstream)st, params, nullptr);
   if (rc != 0) return fail(PW_ERR_CUDA, "cuLaunchKernel(pw_part_jit) failed with %d", rc);
+  ctx().timings.kernel_launches++;
+  return 0;
+}
+// the fused key-sample pilot; returns 0 launched, 1 unavailable
+int launch_pilot_jit(const ScanPlan& P, const PilotParams& pp, int nc, int kw, cudaStream_t st) {
+  static const bool disabled = getenv("PW_NO_JIT") != nullptr;
+  if (disabled) return 1;
+  Api& a = api();
+  if (!a.ok) return 1;
+  const int threads = 256;
+  std::string key = plan_key(P);
+  const int32_t tail[3] = {-3 /* pilot */, nc, kw};
+  key.append((const char*)tail, sizeof tail);
+  Compiled c;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_cache.find(key);
+    if (it == g_cache.end()) {
+      c = compile(jit_ctl(P), pilot_entry(nc, kw, threads), "pw_pilot_jit");
+      g_cache[key] = c;
+    } else c = it->second;
+  }
+  if (c.failed || !c.fn) return 1;
+  const int64_t n_max = std::max(pp.n[0], pp.n[1]);
+  int64_t grid = std::max<int64_t>(1, (n_max / 2 + threads - 1) / threads);
+  ScanPlan copy = P;
+  PilotParams ppc = pp;
+  void* params[] = {&copy, &ppc};
+  const CUresult rc = a.cuLaunchKernel(c.fn, (unsigned)grid, 2, 1, (unsigned)threads, 1, 1, 0, (CUstream)st, params, nullptr);
+  if (rc != 0) return fail(PW_ERR_CUDA, "cuLaunchKernel(pw_pilot_jit) failed with %d", rc);
   ctx().timings.kernel_launches++;
   return 0;
 }
