@@ -220,6 +220,7 @@ int lower_query(const PwQuery* q, const PwFrame* f, Lowered* L) {
     P.dyn.every = dyn->every; P.dyn.period = dyn->period;
     // window starts lie on the grid offset + k*every: truncate(t0, every) + offset (window.rs:115-170)
     P.dyn.origin = dyn->offset;
+    div_prepare((uint64_t)dyn->every, &P.dyn.div_magic, &P.dyn.div_more);
     P.check_sorted = q->n_keys == 0;
   }
 

@@ -100,9 +100,42 @@ struct VExpr {
 struct Acc { int32_t op, src, vexpr, pad; };
 
 struct Dyn {
-  int32_t enabled, slot, closed, pad;
+  int32_t enabled, slot, closed;
+  int32_t div_more;               // division by `every` as multiply + shift: shift | 0x40 (add step) | 0x80 (power of two)
   int64_t every, period, origin;  // window k = [origin + k*every, origin + k*every + period)
+  uint64_t div_magic;             // 0 = not prepared (plain 64-bit division)
 };
+// floor(n / d) for unsigned n through the precomputed (magic, more) of d — the round-up method of Granlund & Montgomery
+// ("Division by invariant integers using multiplication"), as libdivide's u64 branch-free variant lays it out.  A
+// 64-bit division is ~70 instructions per row on the GPU; this is 4-6.
+#ifndef __CUDACC_RTC__
+__host__ inline void div_prepare(uint64_t d, uint64_t* magic, int32_t* more) {
+  if ((d & (d - 1)) == 0) { int sh = 0; while ((1ull << sh) < d) ++sh; *magic = 0; *more = sh | 0x80; return; }
+  int fl = 63; while (!((d >> fl) & 1)) --fl;            // floor(log2 d)
+  const unsigned __int128 num = (unsigned __int128)1 << (64 + fl);
+  uint64_t m = (uint64_t)(num / d);
+  const uint64_t rem = (uint64_t)(num % d);
+  const uint64_t e = d - rem;
+  if (e < (1ull << fl)) { *more = fl; }
+  else {
+    m += m;
+    const uint64_t twice = rem + rem;
+    if (twice >= d || twice < rem) m += 1;
+    *more = fl | 0x40;
+  }
+  *magic = m + 1;
+}
+#endif
+__host__ __device__ inline uint64_t div_apply(uint64_t n, uint64_t magic, int32_t more) {
+  if (more & 0x80) return n >> (more & 0x3F);
+#ifdef __CUDA_ARCH__
+  const uint64_t q = __umul64hi(magic, n);
+#else
+  const uint64_t q = (uint64_t)(((unsigned __int128)magic * n) >> 64);
+#endif
+  if (more & 0x40) return (((n - q) >> 1) + q) >> (more & 0x3F);
+  return q >> (more & 0x3F);
+}
 
 // HBM open-addressing table (also the partial-aggregate state exchanged between GPUs)
 // Layout: hash tables are ARRAY OF STRUCTS — one row [key words | accumulator words | pad] of 4/8/16/32 words per

@@ -619,13 +619,18 @@ __device__ __forceinline__ void row_vexprs(const ScanPlan& P, const Row<NC>& r, 
 }
 
 // tumbling window index of t and membership (each row belongs to at most one window on this path)
+// floor(a / every) with the host-prepared multiplier when there is one (every > 0)
+__device__ __forceinline__ int64_t floor_div_every(const Dyn& d, int64_t a) {
+  if (d.div_magic == 0 && !(d.div_more & 0x80)) return floor_div(a, d.every);
+  return a >= 0 ? (int64_t)div_apply((uint64_t)a, d.div_magic, d.div_more) : ~(int64_t)div_apply(~(uint64_t)a, d.div_magic, d.div_more);
+}
 __device__ __forceinline__ bool window_of(const Dyn& d, int closed, int64_t t, int64_t& kk) {
   const int64_t rel = t - d.origin;
   if (closed == 1) {  // right: (s, s+period]
-    kk = floor_div(rel - 1, d.every);
+    kk = floor_div_every(d, rel - 1);
     return rel - kk * d.every <= d.period;
   }
-  kk = floor_div(rel, d.every);
+  kk = floor_div_every(d, rel);
   const int64_t off = rel - kk * d.every;
   if (closed == 0) return off < d.period;               // left  [s, s+period)
   if (closed == 3) return off > 0 && off < d.period;    // none  (s, s+period)
