@@ -55,9 +55,12 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 template <int KW>
 __device__ __forceinline__ uint64_t hash_words(const uint64_t (&k)[KW]) {
   if (KW == 1) return k[0] * 0x55fbfd6bfc5458e9ull;
-  uint64_t h = mix64(k[0]);
+  // several words: one multiply per word (xor-fold, add the next word, multiply) and one finishing round — the first
+  // version ran a full two-multiply mixer per word (8 64-bit multiplies per row for Q1's two string keys)
+  uint64_t h = k[0] * 0x9E3779B97F4A7C15ull;
 #pragma unroll
-  for (int w = 1; w < KW; ++w) h = mix64(h ^ (k[w] + 0x9E3779B97F4A7C15ull * (uint64_t)w));
+  for (int w = 1; w < KW; ++w) h = ((h ^ (h >> 32)) + k[w]) * 0xd6e8feb86659fd93ull;
+  h ^= h >> 32; h *= 0x55fbfd6bfc5458e9ull;
   return h;
 }
 
