@@ -635,6 +635,34 @@ extern "C" __attribute__((visibility("default"))) int pw_b200_jit_selftest(char*
   if (log && log_len) { strncpy(log, err.c_str(), log_len - 1); log[log_len - 1] = 0; }
   return rc;
 }
+// Diagnostics without a GPU (tests/test_abi_cpu.py): the multiply-shift window division against native division, and
+// the result-buffer pool's fall-back to pageable memory when nothing can be pinned.  Returns the number of mismatches.
+extern "C" __attribute__((visibility("default"))) int64_t pw_b200_host_selftest(void) {
+  using namespace pw;
+  int64_t bad = 0;
+  const uint64_t ds[] = {1, 2, 3, 7, 10, 60, 1000, 60000000ull, 86400000000ull, 3600000000000ull, (1ull << 40) + 1, (1ull << 62) + 12345,
+                         0x7FFFFFFFFFFFFFFFull, 999999937ull, 641, 4294967297ull};
+  uint64_t x = 0x9E3779B97F4A7C15ull;
+  for (uint64_t d : ds) {
+    uint64_t magic; int32_t more;
+    div_prepare(d, &magic, &more);
+    for (int i = 0; i < 200000; ++i) {
+      x ^= x << 13; x ^= x >> 7; x ^= x << 17;   // xorshift64
+      uint64_t n = x >> (i % 61);
+      if (i % 7 == 0) n = d * (n % 1000) + (uint64_t)(i % 3) - 1;   // around multiples of d
+      if (i == 0) n = ~0ull;
+      if (i == 1) n = 0;
+      if (div_apply(n, magic, more) != n / d) ++bad;
+    }
+  }
+  void* p = host_alloc(3u << 20);
+  if (!p) ++bad; else { memset(p, 0x5A, 3u << 20); host_free(p); }
+  void* q2 = host_alloc(3u << 20);   // a pinned block would come back from the pool; a pageable one is simply fresh
+  if (!q2) ++bad; else host_free(q2);
+  void* small = host_alloc(100);
+  if (!small) ++bad; else host_free(small);
+  return bad;
+}
 namespace pw {
 
 struct Control {  // device control block (zeroed per run)

@@ -79,3 +79,11 @@ def test_jit_specialisation_compiles_without_a_gpu():
     if rc == 1:
         pytest.skip("libnvrtc is not installed on this machine")
     assert rc == 0, buf.value.decode()
+
+
+def test_host_side_arithmetic_and_result_pool_without_a_gpu():
+    # window index by multiply-shift == native 64-bit division (pw_plan.h: div_prepare / div_apply); large result
+    # buffers fall back to pageable memory when nothing can be pinned
+    L = engine.lib()
+    L.pw_b200_host_selftest.restype = C.c_int64
+    assert L.pw_b200_host_selftest() == 0
