@@ -108,7 +108,7 @@ std::string hexdouble(double d) {
 
 std::string jit_ctl(const ScanPlan& P) {
   Gen g;
-  g.o << "struct JitCtl {\n";
+  g.o << "struct JitCtl {\n  static constexpr bool kJit = true;\n";
   g.scalar("int", "n_slots", P.n_slots);
   g.table1("int", "slot_dtype", P.n_slots, [&](int i) { return P.slots[i].dtype; });
   g.table1("bool", "slot_nullable", P.n_slots, [&](int i) { return P.slots[i].validity != nullptr ? 1 : 0; });

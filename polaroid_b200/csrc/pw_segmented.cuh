@@ -27,6 +27,18 @@ struct CellSink {  // lane-private cells of the current window
     *q = acc_combine(OP, *q, x);
   }
 };
+// The same cells in REGISTERS: under the query-shape specialised build every accumulator index is a compile-time
+// constant after unrolling, so the array never leaves the register file and a row costs one ALU op per word instead of a
+// shared-memory load and store (the ahead-of-time kernels index at run time and keep the shared-memory cells).
+struct RegSink {
+  uint64_t (&acc)[MAX_ACC];
+  template <int OP>
+  __device__ __forceinline__ void add(const ScanPlan&, int a, uint64_t x) const {
+#pragma unroll
+    for (int i = 0; i < MAX_ACC; ++i)
+      if (i == a) acc[i] = acc_combine(OP, acc[i], x);
+  }
+};
 struct DenseSink {  // straight into the dense window table (boundary rows)
   const Table& T;
   uint64_t slot;
@@ -35,15 +47,29 @@ struct DenseSink {  // straight into the dense window table (boundary rows)
 };
 
 template <class CT>
-__device__ __forceinline__ void seg_flush(const ScanPlan& P, const SegParams& sp, uint64_t* cells, int lane, int64_t k, bool any) {
+__device__ __forceinline__ void seg_flush(const ScanPlan& P, const SegParams& sp, uint64_t* cells, uint64_t (&regs)[MAX_ACC], int lane, int64_t k, bool any) {
   if (!any) return;
-  for (int a = 0; a < CT::n_acc(P); ++a) {
-    const int op = CT::acc_op(P, a);
-    uint64_t v = cells[a * 32 + lane];
-    cells[a * 32 + lane] = acc_init(op);
+  if constexpr (CT::kJit) {
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v = acc_combine(op, v, __shfl_xor_sync(0xffffffffu, v, d));
-    if (lane == 0 && v != acc_init(op)) acc_apply_global(&tacc(P.table, a, (uint64_t)(k - sp.k0)), op, v);
+    for (int a = 0; a < MAX_ACC; ++a) {
+      if (a < CT::n_acc(P)) {
+        const int op = CT::acc_op(P, a);
+        uint64_t v = regs[a];
+        regs[a] = acc_init(op);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v = acc_combine(op, v, __shfl_xor_sync(0xffffffffu, v, d));
+        if (lane == 0 && v != acc_init(op)) acc_apply_global(&tacc(P.table, a, (uint64_t)(k - sp.k0)), op, v);
+      }
+    }
+  } else {
+    for (int a = 0; a < CT::n_acc(P); ++a) {
+      const int op = CT::acc_op(P, a);
+      uint64_t v = cells[a * 32 + lane];
+      cells[a * 32 + lane] = acc_init(op);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v = acc_combine(op, v, __shfl_xor_sync(0xffffffffu, v, d));
+      if (lane == 0 && v != acc_init(op)) acc_apply_global(&tacc(P.table, a, (uint64_t)(k - sp.k0)), op, v);
+    }
   }
 }
 
@@ -58,8 +84,8 @@ __device__ __forceinline__ bool in_window(int closed, int64_t t, int64_t s, int6
 
 template <class CT, int NC, int HF>
 __device__ __forceinline__ void seg_rows(const ScanPlan& P, const SegParams& sp, const uint4 (&raw)[2][NC], const uint32_t (&vbits)[2][NC],
-                                         int64_t base, int lane, int64_t n_rows, uint64_t* cells, int64_t& cur_k, int64_t& cur_s,
-                                         int64_t& cur_e, bool& dirty) {
+                                         int64_t base, int lane, int64_t n_rows, uint64_t* cells, uint64_t (&regs)[MAX_ACC], int64_t& cur_k,
+                                         int64_t& cur_s, int64_t& cur_e, bool& dirty) {
   constexpr int NV = NVof<NC>::value;
 #pragma unroll 1
   for (int j = 0; j < 2; ++j) {
@@ -75,11 +101,15 @@ __device__ __forceinline__ void seg_rows(const ScanPlan& P, const SegParams& sp,
     row_vexprs<CT, NC, NV>(P, r, o.v, o.v_valid);
     const uint64_t grow = (uint64_t)(row + P.row_offset);
     if (__all_sync(0xffffffffu, !alive || k == cur_k)) {
-      if (alive) { const CellSink s{cells, lane}; accumulate_row<CT, NV, 1>(P, o, grow, s); dirty = true; }
+      if (alive) {
+        if constexpr (CT::kJit) { const RegSink s{regs}; accumulate_row<CT, NV, 1>(P, o, grow, s); }
+        else { const CellSink s{cells, lane}; accumulate_row<CT, NV, 1>(P, o, grow, s); }
+        dirty = true;
+      }
     } else {
       // a window boundary inside this row slot: publish the current window, send these rows straight to the table,
       // continue with the latest window seen
-      seg_flush<CT>(P, sp, cells, lane, cur_k, __any_sync(0xffffffffu, dirty));
+      seg_flush<CT>(P, sp, cells, regs, lane, cur_k, __any_sync(0xffffffffu, dirty));
       dirty = false;
       if (alive) { const DenseSink s{P.table, (uint64_t)(k - sp.k0)}; accumulate_row<CT, NV, 1>(P, o, grow, s); }
       const int64_t kmax = alive ? k : INT64_MIN;
@@ -99,6 +129,9 @@ __device__ __forceinline__ void seg_body(const ScanPlan& P, const SegParams& sp)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   uint64_t* cells = (uint64_t*)smem_raw + (size_t)warp * CT::n_acc(P) * 32;
   for (int a = 0; a < CT::n_acc(P); ++a) cells[a * 32 + lane] = acc_init(CT::acc_op(P, a));
+  uint64_t regs[MAX_ACC];
+#pragma unroll
+  for (int a = 0; a < MAX_ACC; ++a) regs[a] = a < CT::n_acc(P) ? acc_init(CT::acc_op(P, a)) : 0ull;
   __syncwarp();
   const int64_t n_rows = P.n_rows;
   const int64_t n_steps = (n_rows + ROWS_PER_STEP - 1) / ROWS_PER_STEP;
@@ -115,10 +148,10 @@ __device__ __forceinline__ void seg_body(const ScanPlan& P, const SegParams& sp)
     uint32_t vbits[2][NC];
     load_step<CT, NC>(P, base, lane, n_rows, raw, vbits);
     check_sorted_step<CT, NC>(P, raw, base, lane, n_rows);
-    seg_rows<CT, NC, 0>(P, sp, raw, vbits, base, lane, n_rows, cells, cur_k, cur_s, cur_e, dirty);
-    seg_rows<CT, NC, 1>(P, sp, raw, vbits, base, lane, n_rows, cells, cur_k, cur_s, cur_e, dirty);
+    seg_rows<CT, NC, 0>(P, sp, raw, vbits, base, lane, n_rows, cells, regs, cur_k, cur_s, cur_e, dirty);
+    seg_rows<CT, NC, 1>(P, sp, raw, vbits, base, lane, n_rows, cells, regs, cur_k, cur_s, cur_e, dirty);
   }
-  seg_flush<CT>(P, sp, cells, lane, cur_k, __any_sync(0xffffffffu, dirty));
+  seg_flush<CT>(P, sp, cells, regs, lane, cur_k, __any_sync(0xffffffffu, dirty));
 }
 
 #ifndef __CUDACC_RTC__
