@@ -83,12 +83,29 @@ __device__ __forceinline__ bool in_window(int closed, int64_t t, int64_t s, int6
 }
 
 template <class CT, int NC, int HF>
+__device__ __forceinline__ void seg_row(const ScanPlan& P, const SegParams& sp, const uint4 (&raw)[2][NC], const uint32_t (&vbits)[2][NC], int j,
+                                        int64_t base, int lane, int64_t n_rows, uint64_t* cells, uint64_t (&regs)[MAX_ACC], int64_t& cur_k,
+                                        int64_t& cur_s, int64_t& cur_e, bool& dirty);
+
+template <class CT, int NC, int HF>
 __device__ __forceinline__ void seg_rows(const ScanPlan& P, const SegParams& sp, const uint4 (&raw)[2][NC], const uint32_t (&vbits)[2][NC],
                                          int64_t base, int lane, int64_t n_rows, uint64_t* cells, uint64_t (&regs)[MAX_ACC], int64_t& cur_k,
                                          int64_t& cur_s, int64_t& cur_e, bool& dirty) {
-  constexpr int NV = NVof<NC>::value;
+  if constexpr (CT::kJit) {  // specialised build: both pair elements inline (compile-time j: no selects on the raw words)
+    seg_row<CT, NC, HF>(P, sp, raw, vbits, 0, base, lane, n_rows, cells, regs, cur_k, cur_s, cur_e, dirty);
+    seg_row<CT, NC, HF>(P, sp, raw, vbits, 1, base, lane, n_rows, cells, regs, cur_k, cur_s, cur_e, dirty);
+  } else {
 #pragma unroll 1
-  for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < 2; ++j) seg_row<CT, NC, HF>(P, sp, raw, vbits, j, base, lane, n_rows, cells, regs, cur_k, cur_s, cur_e, dirty);
+  }
+}
+
+template <class CT, int NC, int HF>
+__device__ __forceinline__ void seg_row(const ScanPlan& P, const SegParams& sp, const uint4 (&raw)[2][NC], const uint32_t (&vbits)[2][NC], int j,
+                                        int64_t base, int lane, int64_t n_rows, uint64_t* cells, uint64_t (&regs)[MAX_ACC], int64_t& cur_k,
+                                        int64_t& cur_s, int64_t& cur_e, bool& dirty) {
+  constexpr int NV = NVof<NC>::value;
+  {
     const int64_t row = base + HF * 64 + 2 * lane + j;
     Row<NC> r;
     row_decode<CT, NC>(P, raw[HF], vbits[HF], j, r);
