@@ -50,14 +50,18 @@ GATHER_CAP_ROWS = int(os.environ.get("PW_MGPU_GATHER_ROWS", "8192"))  # 0 disabl
 _gather_bufs = {}
 
 
-def _gathered_exchange(L, engine, bq, frame, plan, rank: int, world: int):
+def _gathered_exchange(L, engine, bq, frame, plan, rank: int, world: int, memo=None):
     """Small results (<= GATHER_CAP_ROWS groups per rank): ONE all-gather of fixed-size buffers, row counts stay on the
     device, no host synchronisation between the local aggregation and the merge.  Returns the result table, or None when
     some rank had too many groups (every rank sees the same headers, so every rank falls back together)."""
     import pyarrow as pa
-    rw = L.pw_b200_partial_row_words(C.byref(bq.q), frame.handle)
-    if rw <= 0:
-        engine._check(int(rw))
+    rw = memo.get("row_words") if memo is not None else None
+    if rw is None:
+        rw = L.pw_b200_partial_row_words(C.byref(bq.q), frame.handle)
+        if rw <= 0:
+            engine._check(int(rw))
+        if memo is not None:
+            memo["row_words"] = rw
     words = 1 + GATHER_CAP_ROWS * (rw + 1)
     dev = torch.device("cuda", torch.cuda.current_device())
     key = (dev.index, world, words)
@@ -89,9 +93,18 @@ def group_by_sharded(frame, plan, rank: int, world: int, row_offset: int = 0, **
     import pyarrow as pa
     from . import engine
     L = engine.lib()
-    bq = engine._BuiltQuery(frame.table_schema, plan, row_offset=row_offset, **opts)
+    # the lowered PwQuery of a plan object is reused across calls on the same frame (as DeviceFrame.group_by does)
+    ck = (id(plan), row_offset, tuple(sorted(opts.items())))
+    cache = frame.__dict__.setdefault("_queries_sharded", {})
+    hit = cache.get(ck)
+    if hit is None or hit[0] is not plan:
+        if len(cache) > 64:
+            cache.clear()
+        hit = (plan, engine._BuiltQuery(frame.table_schema, plan, row_offset=row_offset, **opts), {})
+        cache[ck] = hit
+    bq, memo = hit[1], hit[2]
     if GATHER_CAP_ROWS > 0 and dist.is_initialized() and dist.get_backend() == "nccl":
-        got = _gathered_exchange(L, engine, bq, frame, plan, rank, world)
+        got = _gathered_exchange(L, engine, bq, frame, plan, rank, world, memo)
         if got is not None:
             return got
     part = C.c_void_p()
