@@ -846,6 +846,7 @@ static void part_free(PartTemp& t) { dev_free(t.words); dev_free(t.hist); dev_fr
 static bool part_eligible(const PwQuery* q, const ScanPlan& P) {
   if ((q->flags & PW_FLAG_NO_PARTITION) || getenv("PW_NO_PARTITION") || !jit_available()) return false;
   if (P.dyn.enabled || P.row_group_out || P.n_slots + 1 > 4 || !narrow_class(P) || P.n_slots > 8) return false;
+  if (P.n_rows >= ((int64_t)1 << 32) - 64) return false;  // 32-bit partition cursors: larger inputs keep the plain HBM-table path
   for (int s = 0; s < P.n_slots; ++s)
     if (P.slots[s].dtype == DT_VIEW || P.slots[s].dtype == DT_VIEW_HI || P.slots[s].dtype == DT_BOOL) return false;
   return true;
