@@ -176,6 +176,8 @@ typedef struct PwTimings {
   float reserved;         /* 1 = the query-shape specialised (NVRTC) kernel ran, 0 = the ahead-of-time kernel */
   float host_ms;          /* wall-clock time spent inside the last pw_b200_frame_groupby call (host + device) */
   float partition_ms;     /* strategy 5: histogram + scatter passes (part of scan_ms) */
+  int32_t jit_compiles;   /* NVRTC compilations during the last call */
+  int32_t jit_cache_hits; /* specialised kernels loaded from the on-disk cubin cache during the last call */
 } PwTimings;
 int pw_b200_last_timings(PwTimings* out);
 

@@ -136,14 +136,27 @@ int pw_b200_frame_groupby(const PwQuery* q, const PwFrame* frame, struct ArrowAr
   PW_TRY(lower_query(q, frame, &L));
   if (q->dynamic && !L.tumbling)
     return fail(PW_ERR_UNSUPPORTED, "overlapping windows (period > every) together with group_by keys (SURVEY 8f rank 4)");
-  Table T{};
-  uint32_t* slots = nullptr;
-  uint64_t G = 0;
-  PW_TRY(run_groupby(q, frame, L, &T, &slots, &G));
-  int rc = emit_results(L, T, slots, G, out_cols, out_schemas, n_out);
-  dev_free(slots);
-  free_table(T);
-  if (rc) return rc;
+  RunOpts ro;
+  ro.allow_deferred = true;
+  for (;;) {
+    Table T{};
+    uint32_t* slots = nullptr;
+    uint64_t G = 0;
+    RunState rs;
+    PW_TRY(run_groupby(q, frame, L, &T, &slots, &G, &ro, &rs));
+    int rc = emit_results(L, T, slots, G, out_cols, out_schemas, n_out, &rs);
+    dev_free(slots);
+    free_table(T);
+    if (rc == PW_RETRY) {
+      // the table was sized from a sample and overflowed, which the deferred path only learns here: go again with a
+      // larger table, synchronously (the classic path grows on its own)
+      ro.min_cap = rs.cap * 4; ro.allow_deferred = false;
+      c.timings.retries++;
+      continue;
+    }
+    if (rc) return rc;
+    break;
+  }
   float ms;
   if (cudaEventElapsedTime(&ms, c.ev[1], c.ev[2]) == cudaSuccess) c.timings.estimate_ms = ms;
   if (cudaEventElapsedTime(&ms, c.ev[2], c.ev[3]) == cudaSuccess) c.timings.scan_ms = ms;

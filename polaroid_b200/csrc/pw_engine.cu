@@ -208,7 +208,12 @@ int lower_query(const PwQuery* q, const PwFrame* f, Lowered* L) {
   if (dyn) {
     if (!col_ok(dyn->index_column)) return fail(PW_ERR_INVALID, "index column out of range");
     const FrameColumn& c = f->cols[dyn->index_column];
-    if (dtype_class(c.dtype) != CLS_I64 || c.dtype == DT_VIEW) return fail(PW_ERR_INVALID, "group_by_dynamic index column '%s' must be a signed integer / temporal column", c.name.c_str());
+    // polars-time/src/group_by/dynamic.rs:210-258 accepts Date, Datetime, Int32 and Int64 only (physical i32 / i64)
+    {
+      const bool fmt_ok = c.format == "i" || c.format == "l" || c.format == "tdD" || c.format.rfind("ts", 0) == 0;
+      if (!fmt_ok || (c.dtype != DT_I32 && c.dtype != DT_I64))
+        return fail(PW_ERR_INVALID, "expected any of the following dtypes: { Date, Datetime, Int32, Int64 }, got column '%s' of format %s", c.name.c_str(), c.format.c_str());
+    }
     if (c.null_count) return fail(PW_ERR_INVALID, "null values in `group_by_dynamic` index column are not supported");
     if (dyn->every <= 0) return fail(PW_ERR_INVALID, "'every' argument must be positive");
     if (dyn->period <= 0) return fail(PW_ERR_INVALID, "'period' argument must be positive");
@@ -665,17 +670,6 @@ extern "C" __attribute__((visibility("default"))) int64_t pw_b200_host_selftest(
 }
 namespace pw {
 
-struct Control {  // device control block (zeroed per run)
-  int32_t overflow;
-  int32_t not_sorted;
-  unsigned long long spilled;
-  unsigned long long counter;
-  unsigned long long null_counts[64];
-  // key range of the pilot samples, as maxima of order-preserving unsigned images (zero-initialised = empty):
-  // kmax_u = max(key ^ 2^63), kmin_n = max(~(key ^ 2^63))
-  unsigned long long kmax_u, kmin_n;
-};
-
 // value range of a single integer key column over a row sample (row = begin + i * stride): decides whether
 // dense ids apply (the analogue of a perfect-hash / direct-address aggregate over a small key domain)
 __global__ void key_range_kernel(RawSlot key, int64_t begin, int64_t stride, int64_t n, unsigned long long* kmax_u, unsigned long long* kmin_n) {
@@ -742,13 +736,13 @@ void free_table(Table& T) {
   if (!aos) dev_free(T.accs);
   T.keys = nullptr; T.state = nullptr; T.accs = nullptr;
 }
-static int init_table(const Table& T, const ScanPlan& P, cudaStream_t st) {
+static int init_table(const Table& T, const ScanPlan& P, cudaStream_t st, Control* zero = nullptr) {
   AccOps ops{};
   ops.n = P.n_acc;
   for (int a = 0; a < P.n_acc; ++a) ops.op[a] = P.accs[a].op;
   const uint64_t n = T.cap + 2;
   int grid = (int)std::min<uint64_t>((n + 255) / 256, 148 * 8);
-  table_init_kernel<<<grid, 256, 0, st>>>(T, padded_kw(P.n_kw), ops);
+  table_init_kernel<<<grid, 256, 0, st>>>(T, padded_kw(P.n_kw), ops, zero);
   PW_CUDA(cudaGetLastError());
   ctx().timings.kernel_launches++;
   return 0;
@@ -806,7 +800,7 @@ static double solve_groups(double d, double n) {
 }
 
 // order the compacted group list by the plan's sort words (LSD radix passes, least significant first)
-int order_groups(const Lowered& L, const Table& T, int kw, uint32_t** slots_io, uint64_t G) {
+int order_groups(const Lowered& L, const Table& T, int kw, uint32_t** slots_io, uint64_t G, const unsigned long long* g_dev) {
   ThreadCtx& c = ctx();
   PwTimings& tm = c.timings;
   uint32_t* slots = *slots_io;
@@ -823,7 +817,7 @@ int order_groups(const Lowered& L, const Table& T, int kw, uint32_t** slots_io, 
     PW_TRY(dev_alloc(&tmp, tmp_bytes));
     const int grid = (int)((G + 255) / 256);
     for (const SortSpec& sp : L.sort) {  // LSD: least significant word first, every pass stable
-      sort_key_kernel<<<grid, 256, 0, c.stream>>>(T, kw, L.null_word, sp, slots, G, k_in);
+      sort_key_kernel<<<grid, 256, 0, c.stream>>>(T, kw, L.null_word, sp, slots, G, k_in, g_dev);
       PW_CUDA(cudaGetLastError());
       PW_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, slots, v_out, (int64_t)G, 0, 64, c.stream));
       std::swap(slots, v_out);
@@ -911,15 +905,45 @@ static int partition_input(const ScanPlan& P, double g_hint, ScanPlan* P2out, Pa
   return 0;
 }
 
-int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out, uint32_t** slot_list_out, uint64_t* n_groups_out) {
+// ---- result block layout: [header][values 0][validity 0][values 1] ... every piece 256-byte aligned
+struct BlockLayout {
+  std::vector<size_t> val_bytes, valid_bytes, val_off, valid_off;
+  size_t total = 0;
+};
+static void plan_block(const Lowered& L, uint64_t G, size_t header_bytes, BlockLayout* b) {
+  const size_t ncol = L.outs.size();
+  b->val_bytes.resize(ncol); b->valid_bytes.resize(ncol); b->val_off.resize(ncol); b->valid_off.resize(ncol);
+  size_t total = (header_bytes + 255) / 256 * 256;
+  auto place = [&](size_t bytes) { size_t o = total; total += (bytes + 255) / 256 * 256; return o; };
+  for (size_t i = 0; i < ncol; ++i) {
+    b->val_bytes[i] = (size_t)G * dtype_bytes(L.outs[i].out_dtype);
+    b->valid_bytes[i] = ((G + 31) / 32) * 4;
+    b->val_off[i] = place(b->val_bytes[i]);
+    b->valid_off[i] = place(b->valid_bytes[i]);
+  }
+  b->total = total;
+}
+
+// cache key of the pilot statistics: the key columns (and the window grid) are all the pilot looks at
+static std::string pilot_key(const PwQuery* q) {
+  std::string k;
+  auto put = [&](const void* p, size_t n) { k.append((const char*)p, n); };
+  put(&q->n_keys, 4);
+  for (int i = 0; i < q->n_keys; ++i) put(&q->key_columns[i], 4);
+  if (q->dynamic) { const PwDynamic& d = *q->dynamic; put(&d.index_column, 4); put(&d.closed, 4); put(&d.every, 8); put(&d.period, 8); put(&d.offset, 8); }
+  return k;
+}
+
+int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out, uint32_t** slot_list_out, uint64_t* n_groups_out,
+                const RunOpts* opts, RunState* state) {
   ThreadCtx& c = ctx();
   ScanPlan& P = L.plan;
   const int64_t N = f->n_rows;
   PwTimings& tm = c.timings;
   tm.n_rows = N;
+  if (state) *state = RunState{};
 
-  Control* dctl = nullptr;
-  { void* p = nullptr; PW_TRY(dev_alloc(&p, sizeof(Control))); dctl = (Control*)p; }
+  Control* dctl = nullptr;  // allocated once the table size is known (deferred mode: header of the result block)
   Control hctl{};
 
   // ---- strategy + table size -------------------------------------------------------------------
@@ -948,100 +972,124 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     if (!cap) cap = (uint64_t)std::max<int64_t>(2 * N, 64);
     if ((q->flags & PW_FLAG_FORCE_HOT_TABLE) && q->hot_table_slots == 0 && N > 0 && dense_eligible(q, P)) {
       // unit-sized inputs reach the dense-id path through the force flag: range of ALL keys, one extra sync
-      PW_CUDA(cudaMemsetAsync(dctl, 0, sizeof(Control), c.stream));
-      key_range_kernel<<<64, 256, 0, c.stream>>>(P.slots[P.keys[0].slot], 0, 1, N, &dctl->kmax_u, &dctl->kmin_n);
+      Control* kctl = nullptr;
+      { void* p = nullptr; PW_TRY(dev_alloc(&p, sizeof(Control))); kctl = (Control*)p; }
+      PW_CUDA(cudaMemsetAsync(kctl, 0, sizeof(Control), c.stream));
+      key_range_kernel<<<64, 256, 0, c.stream>>>(P.slots[P.keys[0].slot], 0, 1, N, &kctl->kmax_u, &kctl->kmin_n);
       tm.kernel_launches++;
-      PW_CUDA(cudaMemcpyAsync(&hctl, dctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream));
+      PW_CUDA(cudaMemcpyAsync(&hctl, kctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream));
       PW_CUDA(cudaStreamSynchronize(c.stream));
+      dev_free(kctl);
       take_range(hctl.kmax_u, hctl.kmin_n, 1024);
     }
   } else if (!cap || !(q->flags & (PW_FLAG_FORCE_HOT_TABLE | PW_FLAG_FORCE_GLOBAL_TABLE))) {
     // (1) strided sample over the whole input -> table size; (2) a contiguous block from the middle -> do
     // consecutive rows share few groups (then the hot table pays)?  Both pilots are queued, then one sync.
+    // A frame remembers what the pilot found per key set (PwFrame::pilot): resident frames pay this phase once.
     const int64_t n_s = N >= (32ll << 20) ? (1 << 17) : (1 << 16);
     const int64_t n_b = 1 << 16;
     int64_t mid = ((N / 2) / ROWS_PER_STEP) * ROWS_PER_STEP;
     if (mid + n_b > N) mid = 0;
-    Pilot p1, p2;
-    Control h1{}, h2{};
-    // fused pilot (one launch, pw_pilot.cuh); the two-scan form below is the fallback without NVRTC
-    int frc = 1;
-    if (jit_available() && !getenv("PW_NO_FUSED_PILOT")) {
-      ScanPlan PP = L.plan;
-      PP.row_begin = 0; PP.row_stride = 2; PP.vec_ok = 0;  // shape: strided scalar loads
-      PP.hot_slots = 0; memset(&PP.hot, 0, sizeof PP.hot); PP.check_sorted = 0; PP.n_preds = 0;
-      PP.n_acc = 1; PP.accs[0].op = OP_ADD_I64; PP.accs[0].src = SRC_ONE; PP.accs[0].vexpr = 0; PP.n_vexpr = 0;
-      PP.gflags = GF_LEN; PP.acc_gbase = 0;
-      const int kw = padded_kw(PP.n_kw);
-      PP.n_kw = kw;
-      int row = 4;
-      while (row < kw + 1) row <<= 1;
-      const uint64_t cap1 = (uint64_t)n_s * 2 + 64, cap2 = (uint64_t)n_b * 2 + 64;
-      const size_t rows_bytes = ((cap1 + 2) + (cap2 + 2)) * 8 * (size_t)row;
-      const size_t ctl_bytes = (sizeof(Control) + 15) & ~(size_t)15;
-      const size_t zero_bytes = ctl_bytes + ((cap1 + 2) + (cap2 + 2)) * 4;
-      char* arena = nullptr;
-      { void* p = nullptr; PW_TRY(dev_alloc(&p, rows_bytes + zero_bytes)); arena = (char*)p; }
-      PW_CUDA(cudaMemsetAsync(arena, 0xFF, rows_bytes, c.stream));
-      PW_CUDA(cudaMemsetAsync(arena + rows_bytes, 0, zero_bytes, c.stream));
-      Control* pctl = (Control*)(arena + rows_bytes);
-      PilotParams pp{};
-      pp.begin[0] = 0; pp.stride[0] = N / n_s; pp.n[0] = n_s;
-      pp.begin[1] = mid; pp.stride[1] = 1; pp.n[1] = n_b;
-      uint64_t* rows0 = (uint64_t*)arena;
-      uint32_t* state0 = (uint32_t*)(arena + rows_bytes + ctl_bytes);
-      for (int t = 0; t < 2; ++t) {
-        Table& T = pp.table[t];
-        T.keys = t == 0 ? rows0 : rows0 + (cap1 + 2) * (uint64_t)row;
-        T.accs = T.keys + kw;
-        T.state = t == 0 ? state0 : state0 + (cap1 + 2);
-        T.cap = t == 0 ? cap1 : cap2;
-        T.key_sw = T.acc_sw = 1; T.key_ss = T.acc_ss = (uint64_t)row;
-        T.overflow = &pctl->overflow; T.spilled = &pctl->spilled;
-      }
-      pp.distinct[0] = &pctl->counter; pp.distinct[1] = &pctl->null_counts[0];
-      if (dense_eligible(q, P)) { pp.kmax_u = &pctl->kmax_u; pp.kmin_n = &pctl->kmin_n; }
-      PP.table = pp.table[0]; PP.not_sorted = &pctl->not_sorted;
-      const int kwc = kw <= 1 ? 1 : (kw <= 2 ? 2 : (kw <= 4 ? 4 : 6));
-      frc = launch_pilot_jit(PP, pp, narrow_class(PP) ? 4 : 12, kwc, c.stream);
-      if (frc == 0) {
-        cudaMemcpyAsync(&h1, pctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream);
-        if (cudaStreamSynchronize(c.stream) != cudaSuccess) frc = fail(PW_ERR_CUDA, "pilot failed: %s", cudaGetErrorString(cudaGetLastError()));
-        h2.counter = h1.null_counts[0];
-        h2.overflow = h1.overflow;
-      }
-      dev_free(arena);
-      if (frc < 0) { dev_free(dctl); return frc; }
+    PilotStats ps;
+    bool cached = false;
+    const std::string pkey = pilot_key(q);
+    static const bool no_pilot_cache = getenv("PW_NO_PILOT_CACHE") != nullptr;
+    if (!no_pilot_cache) {
+      std::lock_guard<std::mutex> lk(f->mu);
+      auto it = f->pilot.find(pkey);
+      if (it != f->pilot.end()) { ps = it->second; cached = true; }
     }
-    int prc = 0;
-    if (frc != 0) {
-      prc = pilot_launch(L, 0, N / n_s, n_s, &p1);
-      if (!prc && dense_eligible(q, P)) {
-        const RawSlot& ks = P.slots[P.keys[0].slot];
-        key_range_kernel<<<64, 256, 0, c.stream>>>(ks, 0, N / n_s, n_s, &p1.dctl->kmax_u, &p1.dctl->kmin_n);
-        key_range_kernel<<<64, 256, 0, c.stream>>>(ks, mid, 1, n_b, &p1.dctl->kmax_u, &p1.dctl->kmin_n);
-        tm.kernel_launches += 2;
+    if (!cached) {
+      Pilot p1, p2;
+      Control h1{}, h2{};
+      // fused pilot (one launch, pw_pilot.cuh); the two-scan form below is the fallback without NVRTC
+      int frc = 1;
+      if (jit_available() && !getenv("PW_NO_FUSED_PILOT")) {
+        ScanPlan PP = L.plan;
+        PP.row_begin = 0; PP.row_stride = 2; PP.vec_ok = 0;  // shape: strided scalar loads
+        PP.hot_slots = 0; memset(&PP.hot, 0, sizeof PP.hot); PP.check_sorted = 0; PP.n_preds = 0;
+        PP.n_acc = 1; PP.accs[0].op = OP_ADD_I64; PP.accs[0].src = SRC_ONE; PP.accs[0].vexpr = 0; PP.n_vexpr = 0;
+        PP.gflags = GF_LEN; PP.acc_gbase = 0;
+        const int kw = padded_kw(PP.n_kw);
+        PP.n_kw = kw;
+        int row = 4;
+        while (row < kw + 1) row <<= 1;
+        const uint64_t cap1 = (uint64_t)n_s * 2 + 64, cap2 = (uint64_t)n_b * 2 + 64;
+        const size_t rows_bytes = ((cap1 + 2) + (cap2 + 2)) * 8 * (size_t)row;
+        const size_t ctl_bytes = (sizeof(Control) + 15) & ~(size_t)15;
+        const size_t zero_bytes = ctl_bytes + ((cap1 + 2) + (cap2 + 2)) * 4;
+        char* arena = nullptr;
+        { void* p = nullptr; PW_TRY(dev_alloc(&p, rows_bytes + zero_bytes)); arena = (char*)p; }
+        PW_CUDA(cudaMemsetAsync(arena, 0xFF, rows_bytes, c.stream));
+        PW_CUDA(cudaMemsetAsync(arena + rows_bytes, 0, zero_bytes, c.stream));
+        Control* pctl = (Control*)(arena + rows_bytes);
+        PilotParams pp{};
+        pp.begin[0] = 0; pp.stride[0] = N / n_s; pp.n[0] = n_s;
+        pp.begin[1] = mid; pp.stride[1] = 1; pp.n[1] = n_b;
+        uint64_t* rows0 = (uint64_t*)arena;
+        uint32_t* state0 = (uint32_t*)(arena + rows_bytes + ctl_bytes);
+        for (int t = 0; t < 2; ++t) {
+          Table& T = pp.table[t];
+          T.keys = t == 0 ? rows0 : rows0 + (cap1 + 2) * (uint64_t)row;
+          T.accs = T.keys + kw;
+          T.state = t == 0 ? state0 : state0 + (cap1 + 2);
+          T.cap = t == 0 ? cap1 : cap2;
+          T.key_sw = T.acc_sw = 1; T.key_ss = T.acc_ss = (uint64_t)row;
+          T.overflow = &pctl->overflow; T.spilled = &pctl->spilled;
+        }
+        pp.distinct[0] = &pctl->counter; pp.distinct[1] = &pctl->null_counts[0];
+        if (dense_eligible(q, P)) { pp.kmax_u = &pctl->kmax_u; pp.kmin_n = &pctl->kmin_n; }
+        PP.table = pp.table[0]; PP.not_sorted = &pctl->not_sorted;
+        const int kwc = kw <= 1 ? 1 : (kw <= 2 ? 2 : (kw <= 4 ? 4 : 6));
+        frc = launch_pilot_jit(PP, pp, narrow_class(PP) ? 4 : 12, kwc, c.stream);
+        if (frc == 0) {
+          cudaMemcpyAsync(&h1, pctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream);
+          if (cudaStreamSynchronize(c.stream) != cudaSuccess) frc = fail(PW_ERR_CUDA, "pilot failed: %s", cudaGetErrorString(cudaGetLastError()));
+          h2.counter = h1.null_counts[0];
+          h2.overflow = h1.overflow;
+        }
+        dev_free(arena);
+        if (frc < 0) return frc;
       }
-      if (!prc) {
-        cudaMemcpyAsync(&h1, p1.dctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream);
-        prc = pilot_launch(L, mid, 1, n_b, &p2);
+      int prc = 0;
+      if (frc != 0) {
+        prc = pilot_launch(L, 0, N / n_s, n_s, &p1);
+        if (!prc && dense_eligible(q, P)) {
+          const RawSlot& ks = P.slots[P.keys[0].slot];
+          key_range_kernel<<<64, 256, 0, c.stream>>>(ks, 0, N / n_s, n_s, &p1.dctl->kmax_u, &p1.dctl->kmin_n);
+          key_range_kernel<<<64, 256, 0, c.stream>>>(ks, mid, 1, n_b, &p1.dctl->kmax_u, &p1.dctl->kmin_n);
+          tm.kernel_launches += 2;
+        }
+        if (!prc) {
+          cudaMemcpyAsync(&h1, p1.dctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream);
+          prc = pilot_launch(L, mid, 1, n_b, &p2);
+        }
+        if (!prc) {
+          cudaMemcpyAsync(&h2, p2.dctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream);
+          if (cudaStreamSynchronize(c.stream) != cudaSuccess) prc = fail(PW_ERR_CUDA, "pilot failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
       }
-      if (!prc) {
-        cudaMemcpyAsync(&h2, p2.dctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream);
-        if (cudaStreamSynchronize(c.stream) != cudaSuccess) prc = fail(PW_ERR_CUDA, "pilot failed: %s", cudaGetErrorString(cudaGetLastError()));
+      pilot_free(&p1); pilot_free(&p2);
+      if (prc) return prc;
+      ps.distinct_strided = h1.counter; ps.distinct_block = h2.counter;
+      ps.kmax_u = h1.kmax_u; ps.kmin_n = h1.kmin_n;
+      ps.overflow = (h1.overflow == 2 || h2.overflow == 2) ? 2 : 0;
+      if (!no_pilot_cache) {
+        std::lock_guard<std::mutex> lk(f->mu);
+        if (f->pilot.size() > 256) f->pilot.clear();
+        f->pilot[pkey] = ps;
       }
     }
-    pilot_free(&p1); pilot_free(&p2);
-    if (prc) { dev_free(dctl); return prc; }
-    if (h1.overflow == 2 || h2.overflow == 2) { dev_free(dctl); return fail(PW_ERR_UNSUPPORTED, "string key longer than 12 bytes (long views need the data buffers: SURVEY 8f rank 1)"); }
-    double g = solve_groups((double)h1.counter, (double)n_s);
+    if (ps.overflow == 2) return fail(PW_ERR_UNSUPPORTED, "string key longer than 12 bytes (long views need the data buffers: SURVEY 8f rank 1)");
+    double g = solve_groups((double)ps.distinct_strided, (double)n_s);
     g = std::min(g, (double)N);
     g_est = g;
     if (!cap) cap = (uint64_t)std::max(1024.0, std::min(2.0 * (double)N + 64.0, 2.5 * g + 1024.0));
-    live_groups = (int64_t)h2.counter;
-    use_hot = h2.counter <= 2048;
-    if (use_hot) take_range(h1.kmax_u, h1.kmin_n, live_groups);
+    live_groups = (int64_t)ps.distinct_block;
+    use_hot = ps.distinct_block <= 2048;
+    if (use_hot) take_range(ps.kmax_u, ps.kmin_n, live_groups);
   }
+  if (opts && opts->min_cap > cap) cap = opts->min_cap;
   if (q->flags & PW_FLAG_FORCE_HOT_TABLE) use_hot = true;
   if (q->flags & PW_FLAG_FORCE_GLOBAL_TABLE) use_hot = false;
   if (live_groups == 0) live_groups = std::min<int64_t>(std::max<int64_t>(N, 4), 1024);
@@ -1067,63 +1115,95 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
       PW_CUDA(cudaEventRecord(c.ev[10], c.stream));
       const int prc = partition_input(P, g_est > 0 ? g_est : std::max<double>((double)N / 4.0, 64.0), &PP, &ptmp);
       PW_CUDA(cudaEventRecord(c.ev[11], c.stream));
-      if (prc < 0) { part_free(ptmp); dev_free(dctl); return prc; }
+      if (prc < 0) { part_free(ptmp); return prc; }
       partitioned = prc == 0;
       if (!partitioned) part_free(ptmp);
     }
   }
 
+  // ---- small table: leave the group count on the device (one host synchronisation per query, in emit_results)
+  static const bool no_deferred = getenv("PW_NO_DEFERRED") != nullptr;
+  BlockLayout bl;
+  bool deferred = false;
+  if (opts && opts->allow_deferred && state && !no_deferred && cap + 2 <= (1u << 16)) {
+    plan_block(L, cap + 2, sizeof(Control), &bl);
+    deferred = bl.total <= STAGING_BYTES;
+  }
+  char* block = nullptr;
+  if (deferred) { void* p = nullptr; PW_TRY(dev_alloc(&p, bl.total)); block = (char*)p; dctl = (Control*)block; }
+  else { void* p = nullptr; PW_TRY(dev_alloc(&p, sizeof(Control))); dctl = (Control*)p; }
+
   // ---- scan (with growth retries) ------------------------------------------------------------------
   Table T{};
   uint32_t* slots = nullptr;
-  tm.retries = 0;
+  if (!(opts && opts->min_cap)) tm.retries = 0;
+  auto drop = [&]() { part_free(ptmp); if (T.keys) free_table(T); dev_free(slots); dev_free(deferred ? (void*)block : (void*)dctl); };
   for (;;) {
-    PW_TRY(alloc_table(&T, padded_kw(P.n_kw), P.n_acc, cap, dctl));
-    PW_TRY(init_table(T, P, c.stream));
-    PW_CUDA(cudaMemsetAsync(dctl, 0, sizeof(Control), c.stream));
+    int rc = alloc_table(&T, padded_kw(P.n_kw), P.n_acc, cap, dctl);
+    if (!rc) rc = init_table(T, P, c.stream, dctl);  // also clears the control block
+    if (rc) { drop(); return rc; }
     P.table = T;
     P.not_sorted = &dctl->not_sorted;
     P.hot_slots = use_hot ? P.hot.idx_slots : 0;
-    PW_CUDA(cudaEventRecord(c.ev[8], c.stream));
+    cudaEventRecord(c.ev[8], c.stream);
     if (partitioned) {
       PP.table = T; PP.not_sorted = &dctl->not_sorted; PP.hot_slots = PP.hot.idx_slots;
-      if (PP.n_rows > 0) PW_TRY(launch_scan(PP, c.sm_count, c.stream));
-    } else if (N > 0) PW_TRY(launch_scan(P, c.sm_count, c.stream));
-    PW_CUDA(cudaEventRecord(c.ev[9], c.stream));
+      if (PP.n_rows > 0) rc = launch_scan(PP, c.sm_count, c.stream);
+    } else if (N > 0) rc = launch_scan(P, c.sm_count, c.stream);
+    if (rc) { drop(); return rc; }
+    cudaEventRecord(c.ev[9], c.stream);
     // queue the compaction right behind the scan: its result is simply discarded when the scan overflowed
-    { void* p = nullptr; PW_TRY(dev_alloc(&p, (cap + 2) * 4)); slots = (uint32_t*)p; }
+    { void* p = nullptr; rc = dev_alloc(&p, (cap + 2) * 4); if (rc) { drop(); return rc; } slots = (uint32_t*)p; }
     {
       int grid = (int)std::min<uint64_t>((cap + 2 + 255) / 256, 148 * 8);
       compact_kernel<<<grid, 256, 0, c.stream>>>(T, padded_kw(P.n_kw), slots, &dctl->counter);
-      PW_CUDA(cudaGetLastError());
+      if (cudaGetLastError() != cudaSuccess) { drop(); return fail(PW_ERR_CUDA, "compact_kernel launch failed"); }
       tm.kernel_launches++;
     }
-    PW_CUDA(cudaMemcpyAsync(&hctl, dctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream));
-    PW_CUDA(cudaStreamSynchronize(c.stream));
-    if (hctl.overflow == 2) { part_free(ptmp); free_table(T); dev_free(slots); dev_free(dctl); return fail(PW_ERR_UNSUPPORTED, "string key longer than 12 bytes (long views need the data buffers: SURVEY 8f rank 1)"); }
+    if (deferred) break;
+    if (cudaMemcpyAsync(&hctl, dctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream) != cudaSuccess ||
+        cudaStreamSynchronize(c.stream) != cudaSuccess) {
+      drop();
+      return fail(PW_ERR_CUDA, "scan failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (hctl.overflow == 2) { drop(); return fail(PW_ERR_UNSUPPORTED, "string key longer than 12 bytes (long views need the data buffers: SURVEY 8f rank 1)"); }
     if (hctl.overflow == 1) {
       free_table(T); dev_free(slots); slots = nullptr;
-      if (cap >= (uint64_t)2 * (uint64_t)N + 64) { part_free(ptmp); dev_free(dctl); return fail(PW_ERR_INTERNAL, "hash table overflow at maximum size"); }
+      if (cap >= (uint64_t)2 * (uint64_t)N + 64) { drop(); return fail(PW_ERR_INTERNAL, "hash table overflow at maximum size"); }
       cap = std::min<uint64_t>(cap * 4, (uint64_t)2 * (uint64_t)N + 64);
       tm.retries++;
       continue;
     }
     break;
   }
+  tm.strategy = partitioned ? 5 : (use_hot ? (P.hot.dense ? 4 : 1) : 2);
+  tm.table_slots = (int64_t)cap;
+  tm.partition_ms = 0.0f;
+  if (deferred) {
+    // count, overflow and sortedness are looked at by emit_results, after the single synchronisation
+    part_free(ptmp);
+    cudaEventRecord(c.ev[3], c.stream);
+    const uint64_t bound = cap + 2;
+    int rc = order_groups(L, T, padded_kw(P.n_kw), &slots, bound, &dctl->counter);
+    if (rc) { ptmp = PartTemp{}; drop(); return rc; }
+    state->deferred = true; state->dctl = dctl; state->block = block; state->cap = cap;
+    *table_out = T;
+    *slot_list_out = slots;
+    *n_groups_out = bound;
+    return 0;
+  }
   if (hctl.not_sorted) {
-    part_free(ptmp); free_table(T); dev_free(slots); dev_free(dctl);
+    drop();
     return fail(PW_ERR_NOT_SORTED, "argument in operation 'group_by_dynamic' is not sorted, please sort the 'expr/series/column' first");
   }
   part_free(ptmp);
-  tm.partition_ms = 0.0f;
   if (partitioned) { float ms = 0; if (cudaEventElapsedTime(&ms, c.ev[10], c.ev[11]) == cudaSuccess) tm.partition_ms = ms; }
-  tm.strategy = partitioned ? 5 : (use_hot ? (P.hot.dense ? 4 : 1) : 2);
   tm.spilled_rows = (int64_t)hctl.spilled;
-  tm.table_slots = (int64_t)cap;
   PW_CUDA(cudaEventRecord(c.ev[3], c.stream));
   const uint64_t G = hctl.counter;
   tm.n_groups = (int64_t)G;
-  PW_TRY(order_groups(L, T, padded_kw(P.n_kw), &slots, G));
+  if (state) state->cap = cap;
+  { int rc = order_groups(L, T, padded_kw(P.n_kw), &slots, G); if (rc) { ptmp = PartTemp{}; drop(); return rc; } }
   dev_free(dctl);
   *table_out = T;
   *slot_list_out = slots;
@@ -1135,77 +1215,105 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
 // result emission: one kernel per output column, then D2H into malloc'd Arrow buffers
 // ------------------------------------------------------------------------------------------------------
 int emit_results(const Lowered& L, const Table& T, const uint32_t* slot_list, uint64_t G,
-                 struct ArrowArray* out_cols, struct ArrowSchema* out_schemas, size_t* n_out) {
+                 struct ArrowArray* out_cols, struct ArrowSchema* out_schemas, size_t* n_out, RunState* state) {
   ThreadCtx& c = ctx();
   const size_t ncol = L.outs.size();
-  if (*n_out < ncol) return fail(PW_ERR_INVALID, "output capacity %zu < %zu result columns", *n_out, ncol);
-  if (ncol > 64) return fail(PW_ERR_UNSUPPORTED, "more than 64 result columns");
+  const bool deferred = state && state->deferred;  // G is a bound; the count is in the block's header (device)
+  auto bail = [&](int rc) { if (deferred) { dev_free(state->block); state->block = nullptr; } return rc; };
+  if (*n_out < ncol) return bail(fail(PW_ERR_INVALID, "output capacity %zu < %zu result columns", *n_out, ncol));
+  if (ncol > 64) return bail(fail(PW_ERR_UNSUPPORTED, "more than 64 result columns"));
   const int kw = padded_kw(L.plan.n_kw);
   const int grid = (int)std::max<uint64_t>(1, (G + 255) / 256);
-  std::vector<size_t> val_bytes(ncol), valid_bytes(ncol), val_off(ncol), valid_off(ncol);
-  // one device block: [null counts: 64 x u64][values 0][validity 0][values 1] ... every piece 256-byte aligned
-  size_t total = 64 * 8;
-  auto place = [&](size_t bytes) { size_t o = total; total += (bytes + 255) / 256 * 256; return o; };
-  for (size_t i = 0; i < ncol; ++i) {
-    val_bytes[i] = (size_t)G * dtype_bytes(L.outs[i].out_dtype);
-    valid_bytes[i] = ((G + 31) / 32) * 4;
-    val_off[i] = place(val_bytes[i]);
-    valid_off[i] = place(valid_bytes[i]);
-  }
+  BlockLayout bl;
+  plan_block(L, G, deferred ? sizeof(Control) : 64 * 8, &bl);
+  const size_t total = bl.total;
   char* d_block = nullptr;
-  { void* p = nullptr; PW_TRY(dev_alloc(&p, total)); d_block = (char*)p; }
-  unsigned long long* d_nulls = (unsigned long long*)d_block;
-  PW_CUDA(cudaMemsetAsync(d_nulls, 0, 64 * 8, c.stream));
+  unsigned long long* d_nulls = nullptr;
+  if (deferred) { d_block = state->block; d_nulls = state->dctl->null_counts; }
+  else {
+    void* p = nullptr;
+    PW_TRY(dev_alloc(&p, total));
+    d_block = (char*)p;
+    d_nulls = (unsigned long long*)d_block;
+    if (cudaMemsetAsync(d_nulls, 0, 64 * 8, c.stream) != cudaSuccess) { dev_free(d_block); return fail(PW_ERR_CUDA, "memset failed"); }
+  }
   for (size_t i0 = 0; i0 < ncol && G; i0 += EMIT_BATCH) {
     EmitBatch batch;
     const size_t nb = std::min<size_t>(EMIT_BATCH, ncol - i0);
     for (size_t j = 0; j < nb; ++j) {
       EmitDesc d = L.outs[i0 + j].emit;
-      d.out_values = d_block + val_off[i0 + j];
-      d.out_validity = (uint32_t*)(d_block + valid_off[i0 + j]);
+      d.out_values = d_block + bl.val_off[i0 + j];
+      d.out_validity = (uint32_t*)(d_block + bl.valid_off[i0 + j]);
       d.null_count = d_nulls + i0 + j;
       batch.d[j] = d;
     }
-    emit_kernel<<<dim3((unsigned)grid, (unsigned)nb), 256, 0, c.stream>>>(T, kw, batch, slot_list, G);
-    PW_CUDA(cudaGetLastError());
+    emit_kernel<<<dim3((unsigned)grid, (unsigned)nb), 256, 0, c.stream>>>(T, kw, batch, slot_list, G, deferred ? state->dctl : nullptr);
+    if (cudaGetLastError() != cudaSuccess) { dev_free(d_block); if (deferred) state->block = nullptr; return fail(PW_ERR_CUDA, "emit_kernel launch failed"); }
     c.timings.kernel_launches++;
   }
-  PW_CUDA(cudaEventRecord(c.ev[4], c.stream));
+  cudaEventRecord(c.ev[4], c.stream);
+  auto cuda_fail = [&](const char* what) {
+    dev_free(d_block);
+    if (deferred) state->block = nullptr;
+    return fail(PW_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(cudaGetLastError()));
+  };
   unsigned long long h_nulls[64] = {0};
-  std::vector<void*> h_vals(ncol, nullptr), h_valid(ncol, nullptr);
-  for (size_t i = 0; i < ncol; ++i) {
-    h_vals[i] = host_alloc(val_bytes[i]);
-    h_valid[i] = host_alloc(valid_bytes[i]);
-    if (!h_vals[i] || !h_valid[i]) return fail(PW_ERR_INTERNAL, "out of host memory");
-  }
+  const char* h = nullptr;  // staged copy of the block (small results)
   if (total <= STAGING_BYTES) {
     // small result: ONE copy into this thread's pinned staging block, then split on the host.  Copies into
     // pageable memory cost a driver round trip each (~10 us x 2 x columns: most of a Q1-sized query).
-    if (!c.staging) PW_CUDA(cudaHostAlloc(&c.staging, STAGING_BYTES, cudaHostAllocPortable));
-    PW_CUDA(cudaMemcpyAsync(c.staging, d_block, total, cudaMemcpyDeviceToHost, c.stream));
-    PW_CUDA(cudaEventRecord(c.ev[5], c.stream));
-    PW_CUDA(cudaStreamSynchronize(c.stream));
-    const char* h = (const char*)c.staging;
-    memcpy(h_nulls, h, 64 * 8);
+    if (!c.staging && cudaHostAlloc(&c.staging, STAGING_BYTES, cudaHostAllocPortable) != cudaSuccess) return cuda_fail("cudaHostAlloc");
+    if (cudaMemcpyAsync(c.staging, d_block, total, cudaMemcpyDeviceToHost, c.stream) != cudaSuccess) return cuda_fail("cudaMemcpyAsync");
+    cudaEventRecord(c.ev[5], c.stream);
+    if (cudaStreamSynchronize(c.stream) != cudaSuccess) return cuda_fail("cudaStreamSynchronize");
+    h = (const char*)c.staging;
+  }
+  uint64_t n_final = G;
+  if (deferred) {
+    const Control* hc = (const Control*)h;
+    c.timings.spilled_rows = (int64_t)hc->spilled;
+    if (hc->overflow == 2) return bail(fail(PW_ERR_UNSUPPORTED, "string key longer than 12 bytes (long views need the data buffers: SURVEY 8f rank 1)"));
+    if (hc->overflow == 1) { dev_free(d_block); state->block = nullptr; return PW_RETRY; }
+    if (hc->not_sorted) return bail(fail(PW_ERR_NOT_SORTED, "argument in operation 'group_by_dynamic' is not sorted, please sort the 'expr/series/column' first"));
+    n_final = hc->counter;
+    c.timings.n_groups = (int64_t)n_final;
+    memcpy(h_nulls, hc->null_counts, 64 * 8);
+  }
+  const uint64_t Gf = n_final;
+  std::vector<size_t> vb(ncol), qb(ncol);
+  std::vector<void*> h_vals(ncol, nullptr), h_valid(ncol, nullptr);
+  for (size_t i = 0; i < ncol; ++i) {
+    vb[i] = (size_t)Gf * dtype_bytes(L.outs[i].out_dtype);
+    qb[i] = ((Gf + 31) / 32) * 4;
+    h_vals[i] = host_alloc(vb[i]);
+    h_valid[i] = host_alloc(qb[i]);
+    if (!h_vals[i] || !h_valid[i]) { dev_free(d_block); if (deferred) state->block = nullptr; return fail(PW_ERR_INTERNAL, "out of host memory"); }
+  }
+  if (h) {
+    if (!deferred) memcpy(h_nulls, h, 64 * 8);
     for (size_t i = 0; i < ncol; ++i) {
-      memcpy(h_vals[i], h + val_off[i], val_bytes[i]);
-      memcpy(h_valid[i], h + valid_off[i], valid_bytes[i]);
+      memcpy(h_vals[i], h + bl.val_off[i], vb[i]);
+      memcpy(h_valid[i], h + bl.valid_off[i], qb[i]);
     }
   } else {
-    PW_CUDA(cudaMemcpyAsync(h_nulls, d_nulls, 64 * 8, cudaMemcpyDeviceToHost, c.stream));
+    if (cudaMemcpyAsync(h_nulls, d_nulls, 64 * 8, cudaMemcpyDeviceToHost, c.stream) != cudaSuccess) return cuda_fail("cudaMemcpyAsync");
     for (size_t i = 0; i < ncol; ++i) {
-      PW_CUDA(cudaMemcpyAsync(h_vals[i], d_block + val_off[i], val_bytes[i], cudaMemcpyDeviceToHost, c.stream));
-      PW_CUDA(cudaMemcpyAsync(h_valid[i], d_block + valid_off[i], valid_bytes[i], cudaMemcpyDeviceToHost, c.stream));
+      if (cudaMemcpyAsync(h_vals[i], d_block + bl.val_off[i], vb[i], cudaMemcpyDeviceToHost, c.stream) != cudaSuccess ||
+          cudaMemcpyAsync(h_valid[i], d_block + bl.valid_off[i], qb[i], cudaMemcpyDeviceToHost, c.stream) != cudaSuccess)
+        return cuda_fail("cudaMemcpyAsync");
     }
-    PW_CUDA(cudaEventRecord(c.ev[5], c.stream));
-    PW_CUDA(cudaStreamSynchronize(c.stream));
-  }
-  for (size_t i = 0; i < ncol; ++i) {
-    const OutCol& o = L.outs[i];
-    PW_TRY(make_host_array((int64_t)G, (int64_t)h_nulls[i], h_valid[i], h_vals[i], o.out_dtype == DT_VIEW ? 1 : 0, &out_cols[i]));
-    PW_TRY(make_schema(o.format.c_str(), o.name.c_str(), true, &out_schemas[i]));
+    cudaEventRecord(c.ev[5], c.stream);
+    if (cudaStreamSynchronize(c.stream) != cudaSuccess) return cuda_fail("cudaStreamSynchronize");
   }
   dev_free(d_block);
+  if (deferred) state->block = nullptr;
+  for (size_t i = 0; i < ncol; ++i) {
+    const OutCol& o = L.outs[i];
+    // a validity bitmap shorter than the bound's may carry bits past the count in its last word: harmless (Arrow readers
+    // look at `length` bits)
+    PW_TRY(make_host_array((int64_t)Gf, (int64_t)h_nulls[i], h_valid[i], h_vals[i], o.out_dtype == DT_VIEW ? 1 : 0, &out_cols[i]));
+    PW_TRY(make_schema(o.format.c_str(), o.name.c_str(), true, &out_schemas[i]));
+  }
   *n_out = ncol;
   return 0;
 }

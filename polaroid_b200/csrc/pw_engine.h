@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -53,10 +55,24 @@ struct FrameColumn {
 
 }  // namespace pw
 
+namespace pw {
+// What the key-sample pilot of a query learnt about a frame's key columns (run_groupby).  Cached on the frame per key
+// set: a resident frame pays the pilot launch and its host synchronisation once.  The statistics are hints only — a
+// stale entry (zero-copy frames can change under us) costs speed, never correctness: the table grows on overflow and
+// keys outside a dense range take the HBM table.
+struct PilotStats {
+  unsigned long long distinct_strided = 0, distinct_block = 0;
+  unsigned long long kmax_u = 0, kmin_n = 0;
+  int32_t overflow = 0;
+};
+}  // namespace pw
+
 struct PwFrame {
   int device = 0;
   int64_t n_rows = 0;
   std::vector<pw::FrameColumn> cols;
+  mutable std::mutex mu;
+  mutable std::map<std::string, pw::PilotStats> pilot;
 };
 
 namespace pw {
@@ -94,12 +110,28 @@ int dev_alloc(void** p, size_t bytes);
 void dev_free(void* p);
 
 int lower_query(const PwQuery* q, const PwFrame* f, Lowered* out);
-int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out, uint32_t** slot_list_out, uint64_t* n_groups_out);
+// Small results ("count on the device" mode): when the table is small, run_groupby does not wait for the group count.
+// It allocates the result block up front — [Control | every result column sized for the table's capacity] — uses the
+// block's header as the scan's control block, and leaves the count on the device; ordering and emission are launched
+// for the capacity and read the count on the device; emit_results copies the block to the host and synchronises ONCE.
+struct RunOpts {
+  uint64_t min_cap = 0;      // lower bound of the HBM table size (retry after an overflow seen late)
+  bool allow_deferred = false;
+};
+struct RunState {
+  bool deferred = false;     // *n_groups_out is the capacity bound, the count is dctl->counter (device)
+  Control* dctl = nullptr;   // deferred: header of `block`
+  char* block = nullptr;     // deferred: result block (freed by emit_results)
+  uint64_t cap = 0;          // table slots used
+};
+constexpr int PW_RETRY = 1;  // emit_results (deferred): the scan overflowed its table — run again with a larger one
+int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out, uint32_t** slot_list_out, uint64_t* n_groups_out,
+                const RunOpts* opts = nullptr, RunState* state = nullptr);
 int emit_results(const Lowered& L, const Table& T, const uint32_t* slot_list, uint64_t n_groups,
-                 struct ArrowArray* out_cols, struct ArrowSchema* out_schemas, size_t* n_out);
+                 struct ArrowArray* out_cols, struct ArrowSchema* out_schemas, size_t* n_out, RunState* state = nullptr);
 void free_table(Table& T);
 int alloc_table_raw(Table* T, int n_kw, int n_acc, uint64_t cap, int32_t* overflow, unsigned long long* spilled);
-int order_groups(const Lowered& L, const Table& T, int kw, uint32_t** slots_io, uint64_t G);
+int order_groups(const Lowered& L, const Table& T, int kw, uint32_t** slots_io, uint64_t G, const unsigned long long* g_dev = nullptr);
 
 // segmented (sorted-run) dynamic path, pw_segmented.cu
 int run_dynamic_segmented(const PwQuery* q, const PwFrame* f, struct ArrowArray* out_cols, struct ArrowSchema* out_schemas,

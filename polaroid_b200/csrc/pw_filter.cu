@@ -142,6 +142,8 @@ static int build_pred_plan(const PwPredicate* preds, int32_t n_preds, const PwFr
 // device selection vector; caller frees *ids_out
 static int select_rows(const PredPlan& pp, int64_t n, uint32_t** ids_out, int64_t* n_sel) {
   ThreadCtx& c = ctx();
+  // row ids are IdxSize = u32 (polars-utils/src/index.rs:9-11)
+  if (n > 0xFFFFFFF0ll) return fail(PW_ERR_UNSUPPORTED, "IdxSize is u32: more than 2^32 rows in a filter selection");
   const int64_t tile = (int64_t)SEL_THREADS * SEL_ROWS;
   const int64_t n_tiles = std::max<int64_t>(1, (n + tile - 1) / tile);
   unsigned long long *counts = nullptr, *base = nullptr;

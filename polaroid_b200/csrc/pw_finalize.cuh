@@ -12,8 +12,24 @@ namespace pw {
 
 struct AccOps { int32_t n; int32_t op[MAX_ACC]; };
 
-static __global__ void table_init_kernel(Table T, int n_kw, AccOps ops) {
+// device control block of one query (zeroed per run).  Its scalar fields travel back to the host in front of the
+// result block, so a query whose result is small needs ONE device->host copy and ONE synchronisation.
+struct Control {
+  int32_t overflow;
+  int32_t not_sorted;
+  unsigned long long spilled;
+  unsigned long long counter;          // number of groups (compact_kernel)
+  unsigned long long null_counts[64];  // per result column (emit_kernel)
+  // key range of the pilot samples, as maxima of order-preserving unsigned images (zero-initialised = empty):
+  // kmax_u = max(key ^ 2^63), kmin_n = max(~(key ^ 2^63))
+  unsigned long long kmax_u, kmin_n;
+};
+
+// `zero` (optional): control block cleared by the same launch (saves a memset per query)
+static __global__ void table_init_kernel(Table T, int n_kw, AccOps ops, Control* zero = nullptr) {
   const uint64_t n = T.cap + 2;
+  if (zero && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < (int)(sizeof(Control) / 4); i += blockDim.x) ((uint32_t*)zero)[i] = 0u;
   for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (uint64_t)gridDim.x * blockDim.x) {
     if (n_kw == 1) tkey(T, 0, s) = KEY_EMPTY;
     T.state[s] = 0u;
@@ -64,9 +80,13 @@ __device__ __forceinline__ bool key_is_null(const Table& T, int n_kw, uint64_t s
   return false;
 }
 
-static __global__ void sort_key_kernel(Table T, int n_kw, int null_word, SortSpec sp, const uint32_t* slot_list, uint64_t n, uint64_t* out) {
+// n_dev (optional): the group count is still on the device and `n` is only an upper bound — entries past the count get
+// the largest key, which a STABLE sort leaves behind every real entry
+static __global__ void sort_key_kernel(Table T, int n_kw, int null_word, SortSpec sp, const uint32_t* slot_list, uint64_t n, uint64_t* out,
+                                       const unsigned long long* n_dev = nullptr) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (n_dev && i >= *n_dev) { out[i] = ~0ull; return; }
   const uint64_t slot = slot_list[i];
   uint64_t v = 0;
   const bool isnull = key_is_null(T, n_kw, slot, null_word, sp.nullbit, sp.single_key_null);
@@ -138,9 +158,17 @@ __device__ __forceinline__ void store_typed(void* base, uint64_t i, int dt, uint
 // One launch emits up to EMIT_BATCH result columns: blockIdx.y selects the column.
 constexpr int EMIT_BATCH = 16;
 struct EmitBatch { EmitDesc d[EMIT_BATCH]; };
-static __global__ void emit_kernel(Table T, int n_kw, const __grid_constant__ EmitBatch batch, const uint32_t* slot_list, uint64_t n) {
+// ctl (optional, "count on the device" mode): n is an upper bound, the real count is ctl->counter.  In that mode the
+// control block is the header of the result block itself, so the null counts this kernel accumulates, the group count
+// and the overflow / not-sorted flags reach the host with the same copy as the columns.
+static __global__ void emit_kernel(Table T, int n_kw, const __grid_constant__ EmitBatch batch, const uint32_t* slot_list, uint64_t n,
+                                   const Control* ctl = nullptr) {
   const EmitDesc& d = batch.d[blockIdx.y];
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ctl) {
+    const uint64_t cnt = ctl->counter;
+    n = cnt < n ? cnt : n;
+  }
   bool valid = true;
   if (i < n) {
     const uint64_t slot = slot_list[i];

@@ -10,6 +10,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <map>
 #include <mutex>
@@ -201,10 +203,103 @@ std::string pilot_entry(int nc, int kw, int threads) {
   return src.str();
 }
 
+// ---- persistent cubin cache -----------------------------------------------------------------------------------
+// A fresh process used to pay ~0.7 s of NVRTC for the first query of every shape (a one-shot collect() pays it every
+// time).  Compiled cubins are kept on disk under a name derived from the generated source text, the contents of the
+// kernel headers it includes and the target architecture; PW_JIT_CACHE_DIR chooses the directory ("off" disables it).
+uint64_t fnv1a(const void* p, size_t n, uint64_t h) {
+  const unsigned char* b = (const unsigned char*)p;
+  for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 0x100000001b3ull; }
+  return h;
+}
+// hash of every header the generated translation unit includes (computed once per process)
+void sources_hash(uint64_t* h0, uint64_t* h1) {
+  static uint64_t a0 = 0, a1 = 0;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    a0 = 0xcbf29ce484222325ull; a1 = 0x84222325cbf29ce4ull;
+    for (const char* name : {"pw_plan.h", "pw_ctl.h", "pw_scan.cuh", "pw_segmented.cuh", "pw_partition.cuh", "pw_pilot.cuh", "pw_dense.cuh"}) {
+      const std::string path = csrc_dir() + "/" + name;
+      FILE* f = fopen(path.c_str(), "rb");
+      if (!f) continue;
+      char buf[1 << 16];
+      size_t n;
+      while ((n = fread(buf, 1, sizeof buf, f)) > 0) { a0 = fnv1a(buf, n, a0); a1 = fnv1a(buf, n, a1 ^ 0x9E3779B97F4A7C15ull); }
+      fclose(f);
+    }
+  });
+  *h0 = a0; *h1 = a1;
+}
+std::string cache_dir() {
+  static std::string dir;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* e = getenv("PW_JIT_CACHE_DIR");
+    if (e && !strcmp(e, "off")) return;
+    std::vector<std::string> cands;
+    if (e && *e) cands.push_back(e);
+    else {
+      if (const char* x = getenv("XDG_CACHE_HOME")) cands.push_back(std::string(x) + "/polarway_b200");
+      if (const char* hm = getenv("HOME")) cands.push_back(std::string(hm) + "/.cache/polarway_b200");
+      cands.push_back("/tmp/polarway_b200_jit_" + std::to_string((long)getuid()));
+    }
+    for (const std::string& d : cands) {
+      std::string acc;
+      for (size_t i = 0; i <= d.size(); ++i)   // mkdir -p
+        if (i == d.size() || (d[i] == '/' && i > 0)) { acc = d.substr(0, i); mkdir(acc.c_str(), 0700); }
+      if (access(d.c_str(), W_OK | X_OK) == 0) { dir = d; return; }
+    }
+  });
+  return dir;
+}
+std::string cache_path(const std::string& text) {
+  const std::string d = cache_dir();
+  if (d.empty()) return "";
+  uint64_t h0, h1;
+  sources_hash(&h0, &h1);
+  h0 = fnv1a(text.data(), text.size(), h0);
+  h1 = fnv1a(text.data(), text.size(), h1 ^ 0x9E3779B97F4A7C15ull);
+  char name[96];
+  snprintf(name, sizeof name, "/sm_100a_%016llx%016llx.cubin", (unsigned long long)h0, (unsigned long long)h1);
+  return d + name;
+}
+bool cache_read(const std::string& path, std::vector<char>* out) {
+  if (path.empty()) return false;
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  fseek(f, 0, SEEK_END);
+  const long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  bool ok = n > 64;
+  if (ok) { out->resize((size_t)n); ok = fread(out->data(), 1, (size_t)n, f) == (size_t)n; }
+  fclose(f);
+  return ok && !memcmp(out->data(), "\x7f" "ELF", 4);
+}
+void cache_write(const std::string& path, const std::vector<char>& cubin) {
+  if (path.empty()) return;
+  char tmp[64];
+  snprintf(tmp, sizeof tmp, ".tmp.%ld.%p", (long)getpid(), (void*)&cubin);
+  const std::string t = path + tmp;
+  FILE* f = fopen(t.c_str(), "wb");
+  if (!f) return;
+  const bool ok = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+  fclose(f);
+  if (ok) rename(t.c_str(), path.c_str()); else unlink(t.c_str());   // atomic publish: concurrent processes race benignly
+}
+
 Compiled compile(const std::string& ctl, const std::string& entry, const char* entry_name) {
   Api& a = api();
   Compiled c;
   const std::string text = "#include \"pw_segmented.cuh\"\n#include \"pw_partition.cuh\"\n#include \"pw_pilot.cuh\"\nnamespace pw {\n" + ctl + "}\n" + entry;
+  const std::string cpath = getenv("PW_JIT_DUMP") || getenv("PW_DEBUG") ? std::string() : cache_path(text);
+  {
+    std::vector<char> cached;
+    if (cache_read(cpath, &cached)) {
+      CUmodule mod = nullptr;
+      if (a.cuModuleLoadData(&mod, cached.data()) == 0 && a.cuModuleGetFunction(&c.fn, mod, entry_name) == 0) { ctx().timings.jit_cache_hits++; return c; }
+      c.fn = nullptr;  // stale or damaged file: compile again (and overwrite it)
+    }
+  }
   nvrtcProgram prog = nullptr;
   if (a.nvrtcCreateProgram(&prog, text.c_str(), "pw_scan_jit.cu", 0, nullptr, nullptr) != 0) { c.failed = true; return c; }
   const std::string inc = "--include-path=" + csrc_dir();
@@ -233,6 +328,8 @@ Compiled compile(const std::string& ctl, const std::string& entry, const char* e
   CUmodule mod = nullptr;
   if (a.cuModuleLoadData(&mod, cubin.data()) != 0) { c.failed = true; return c; }
   if (a.cuModuleGetFunction(&c.fn, mod, entry_name) != 0) { c.failed = true; c.fn = nullptr; }
+  else cache_write(cpath, cubin);
+  ctx().timings.jit_compiles++;
   return c;
 }
 
@@ -288,6 +385,10 @@ static std::string plan_key(const ScanPlan& P) {
   k.reserve(1024);
   auto put = [&](const void* p, size_t n) { k.append((const char*)p, n); };
   auto i32 = [&](int32_t v) { put(&v, 4); };
+  // a CUfunction belongs to the context it was loaded in (one primary context per device): the calling thread's
+  // device is part of the key, so pw_b200_set_device(other) compiles/loads its own copy instead of launching a
+  // handle from a foreign context
+  i32(ctx().device);
   i32(P.n_slots);
   for (int i = 0; i < P.n_slots; ++i) { i32(P.slots[i].dtype); i32(P.slots[i].validity != nullptr); }
   i32(P.n_preds);

@@ -47,11 +47,14 @@ struct Unpickler {
   std::string err;
   bool need(size_t n) { if ((size_t)(end - p) < n) { err = "truncated pickle"; return false; } return true; }
   uint64_t le(int n) { uint64_t v = 0; for (int k = 0; k < n; ++k) v |= (uint64_t)p[k] << (8 * k); p += n; return v; }
-  std::vector<PV> pop_mark() {
-    size_t m = marks.back(); marks.pop_back();
-    std::vector<PV> out(stack.begin() + m, stack.end());
+  // false (err set) when there is no pending MARK or the mark lies above the stack: malformed bytes must not index
+  // out of the vectors (these bytes cross the C ABI from the host process)
+  bool pop_mark(std::vector<PV>* out) {
+    if (marks.empty() || marks.back() > stack.size()) { err = "stack underflow"; return false; }
+    const size_t m = marks.back(); marks.pop_back();
+    out->assign(stack.begin() + m, stack.end());
     stack.resize(m);
-    return out;
+    return true;
   }
   bool run(PV* out) {
     while (p < end) {
@@ -61,7 +64,7 @@ struct Unpickler {
         case 0x95: if (!need(8)) return false; p += 8; break;                 // FRAME
         case '}': { PV v; v.kind = PV::DICT; stack.push_back(v); break; }
         case ']': case ')': { PV v; v.kind = PV::LIST; stack.push_back(v); break; }
-        case 0x94: memo.push_back(stack.back()); break;                       // MEMOIZE
+        case 0x94: if (stack.empty()) { err = "stack underflow"; return false; } memo.push_back(stack.back()); break;  // MEMOIZE
         case 'h': { if (!need(1)) return false; size_t k = *p++; if (k >= memo.size()) { err = "bad memo"; return false; } stack.push_back(memo[k]); break; }
         case 'j': { if (!need(4)) return false; size_t k = (size_t)le(4); if (k >= memo.size()) { err = "bad memo"; return false; } stack.push_back(memo[k]); break; }
         case 0x8c: { if (!need(1)) return false; size_t n = *p++; if (!need(n)) return false; PV v; v.kind = PV::STR; v.s.assign((const char*)p, n); p += n; stack.push_back(v); break; }
@@ -79,16 +82,18 @@ struct Unpickler {
         case 0x88: case 0x89: { PV v; v.kind = PV::BOOL; v.i = op == 0x88; stack.push_back(v); break; }
         case 'N': stack.push_back(PV()); break;
         case '(': marks.push_back(stack.size()); break;
-        case 't': { PV v; v.kind = PV::LIST; v.items = pop_mark(); stack.push_back(v); break; }
+        case 't': { PV v; v.kind = PV::LIST; if (!pop_mark(&v.items)) return false; stack.push_back(v); break; }
         case 0x85: case 0x86: case 0x87: {
           const size_t n = op - 0x84; if (stack.size() < n) { err = "stack underflow"; return false; }
           PV v; v.kind = PV::LIST; v.items.assign(stack.end() - n, stack.end()); stack.resize(stack.size() - n); stack.push_back(v); break; }
-        case 'a': { if (stack.size() < 2) { err = "stack underflow"; return false; } PV x = stack.back(); stack.pop_back(); stack.back().items.push_back(x); break; }
-        case 'e': { std::vector<PV> xs = pop_mark(); if (stack.empty()) { err = "stack underflow"; return false; } for (auto& x : xs) stack.back().items.push_back(x); break; }
+        case 'a': { if (stack.size() < 2) { err = "stack underflow"; return false; } PV x = stack.back(); stack.pop_back();
+                    if (stack.back().kind != PV::LIST) { err = "APPEND to a non-list"; return false; } stack.back().items.push_back(x); break; }
+        case 'e': { std::vector<PV> xs; if (!pop_mark(&xs)) return false; if (stack.empty()) { err = "stack underflow"; return false; }
+                    if (stack.back().kind != PV::LIST) { err = "APPENDS to a non-list"; return false; } for (auto& x : xs) stack.back().items.push_back(x); break; }
         case 's': { if (stack.size() < 3) { err = "stack underflow"; return false; } PV v = stack.back(); stack.pop_back(); PV k = stack.back(); stack.pop_back();
-                    stack.back().kv.emplace_back(k.s, v); break; }
-        case 'u': { std::vector<PV> xs = pop_mark(); if (stack.empty() || xs.size() % 2) { err = "bad SETITEMS"; return false; }
-                    for (size_t k = 0; k < xs.size(); k += 2) stack.back().kv.emplace_back(xs[k].s, xs[k + 1]); break; }
+                    if (stack.back().kind != PV::DICT || k.kind != PV::STR) { err = "bad SETITEM"; return false; } stack.back().kv.emplace_back(k.s, v); break; }
+        case 'u': { std::vector<PV> xs; if (!pop_mark(&xs)) return false; if (stack.empty() || xs.size() % 2 || stack.back().kind != PV::DICT) { err = "bad SETITEMS"; return false; }
+                    for (size_t k = 0; k < xs.size(); k += 2) { if (xs[k].kind != PV::STR) { err = "bad SETITEMS"; return false; } stack.back().kv.emplace_back(xs[k].s, xs[k + 1]); } break; }
         case '.': if (stack.empty()) { err = "empty pickle"; return false; } *out = stack.back(); return true;
         default: { char b[64]; snprintf(b, sizeof b, "unsupported pickle opcode 0x%02x", op); err = b; return false; }
       }

@@ -49,6 +49,10 @@ struct DenseSink {  // straight into the dense window table (boundary rows)
 template <class CT>
 __device__ __forceinline__ void seg_flush(const ScanPlan& P, const SegParams& sp, uint64_t* cells, uint64_t (&regs)[MAX_ACC], int lane, int64_t k, bool any) {
   if (!any) return;
+  // The host sizes the dense table from the first and last index value only.  A window outside it can only come from
+  // an unsorted index (an interior value beyond both ends): report it instead of writing out of bounds.
+  const bool inside = (uint64_t)(k - sp.k0) < (uint64_t)sp.n_dense;
+  if (!inside && lane == 0) *P.not_sorted = 1;
   if constexpr (CT::kJit) {
 #pragma unroll
     for (int a = 0; a < MAX_ACC; ++a) {
@@ -58,7 +62,7 @@ __device__ __forceinline__ void seg_flush(const ScanPlan& P, const SegParams& sp
         regs[a] = acc_init(op);
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) v = acc_combine(op, v, __shfl_xor_sync(0xffffffffu, v, d));
-        if (lane == 0 && v != acc_init(op)) acc_apply_global(&tacc(P.table, a, (uint64_t)(k - sp.k0)), op, v);
+        if (lane == 0 && inside && v != acc_init(op)) acc_apply_global(&tacc(P.table, a, (uint64_t)(k - sp.k0)), op, v);
       }
     }
   } else {
@@ -68,7 +72,7 @@ __device__ __forceinline__ void seg_flush(const ScanPlan& P, const SegParams& sp
       cells[a * 32 + lane] = acc_init(op);
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) v = acc_combine(op, v, __shfl_xor_sync(0xffffffffu, v, d));
-      if (lane == 0 && v != acc_init(op)) acc_apply_global(&tacc(P.table, a, (uint64_t)(k - sp.k0)), op, v);
+      if (lane == 0 && inside && v != acc_init(op)) acc_apply_global(&tacc(P.table, a, (uint64_t)(k - sp.k0)), op, v);
     }
   }
 }
@@ -128,7 +132,10 @@ __device__ __forceinline__ void seg_row(const ScanPlan& P, const SegParams& sp, 
       // continue with the latest window seen
       seg_flush<CT>(P, sp, cells, regs, lane, cur_k, __any_sync(0xffffffffu, dirty));
       dirty = false;
-      if (alive) { const DenseSink s{P.table, (uint64_t)(k - sp.k0)}; accumulate_row<CT, NV, 1>(P, o, grow, s); }
+      if (alive) {
+        if ((uint64_t)(k - sp.k0) < (uint64_t)sp.n_dense) { const DenseSink s{P.table, (uint64_t)(k - sp.k0)}; accumulate_row<CT, NV, 1>(P, o, grow, s); }
+        else *P.not_sorted = 1;  // outside [first, last]: the index is not sorted (see seg_flush)
+      }
       const int64_t kmax = alive ? k : INT64_MIN;
       int64_t km = kmax;
 #pragma unroll

@@ -70,7 +70,8 @@ class PwTimings(C.Structure):
                 ("d2h_ms", C.c_float), ("total_device_ms", C.c_float), ("n_rows", C.c_int64), ("n_groups", C.c_int64),
                 ("table_slots", C.c_int64), ("strategy", C.c_int32), ("retries", C.c_int32),
                 ("kernel_launches", C.c_int64), ("spilled_rows", C.c_int64), ("scan_kernel_ms", C.c_float),
-                ("reserved", C.c_float), ("host_ms", C.c_float), ("partition_ms", C.c_float)]
+                ("reserved", C.c_float), ("host_ms", C.c_float), ("partition_ms", C.c_float),
+                ("jit_compiles", C.c_int32), ("jit_cache_hits", C.c_int32)]
 
 
 class ArrowSchema(C.Structure):

@@ -59,3 +59,43 @@ def test_filter_fused_into_sorted_windows():
          .agg(c("price").first().alias("open"), c("price").last().alias("close"), c("volume").sum().alias("v"), pw.len().alias("n")))
     got = engine.run_group_by(q.table, q.plan)
     G.assert_tables_equal(got, oracle.collect(q), rtol=1e-12)
+
+
+@pytest.mark.parametrize("spike", [10**12, -10**12])
+@pytest.mark.parametrize("n", [3, 50_000])
+def test_unsorted_interior_value_outside_first_last_is_a_clean_error(spike, n):
+    """First and last index value are in order, an interior value lies far outside [first, last]: the sorted fast path
+    sizes its dense window table from the two ends, so this used to write out of bounds before `not_sorted` was seen
+    (round-1 advisor finding).  The reference raises (polars-time/src/group_by/dynamic.rs:77-80)."""
+    ts = np.arange(5, 5 + n, dtype=np.int64)
+    ts[n // 2] = spike
+    t = pa.table({"ts": pa.array(ts), "v": pa.array(np.ones(n, dtype=np.int64))})
+    q = pw.LazyFrame(t).group_by_dynamic("ts", every="2i").agg(pw.col("v").sum())
+    for opts in ({}, {"flags": engine.FLAG_FORCE_SEGMENTED}):
+        with pytest.raises(engine.PolarwayError) as e:
+            engine.run_group_by(q.table, q.plan, **opts)
+        assert e.value.code == -4
+    # the library (and the GPU) are still healthy afterwards
+    ok = pa.table({"ts": pa.array(np.arange(n, dtype=np.int64)), "v": pa.array(np.ones(n, dtype=np.int64))})
+    q2 = pw.LazyFrame(ok).group_by_dynamic("ts", every="2i").agg(pw.col("v").sum())
+    G.assert_tables_equal(engine.run_group_by(q2.table, q2.plan), oracle.collect(q2))
+
+
+@pytest.mark.parametrize("typ", [pa.int8(), pa.int16(), pa.uint32(), pa.duration("us"), pa.float64()])
+def test_index_dtype_must_be_date_datetime_int32_int64(typ):
+    """polars-time/src/group_by/dynamic.rs:210-258: anything but Date, Datetime, Int32, Int64 is rejected."""
+    base = pa.array([1, 2, 3, 4], type=pa.int64())
+    t = pa.table({"ts": base.cast(typ), "v": pa.array([1, 2, 3, 4])})
+    q = pw.LazyFrame(t).group_by_dynamic("ts", every="2i").agg(pw.col("v").sum())
+    with pytest.raises(engine.PolarwayError) as e:
+        engine.run_group_by(q.table, q.plan)
+    assert e.value.code == -1 and "Date, Datetime, Int32, Int64" in str(e.value)
+
+
+@pytest.mark.parametrize("typ", [pa.int32(), pa.date32(), pa.timestamp("ms")])
+def test_index_dtypes_the_reference_accepts(typ):
+    base = pa.array([0, 1, 2, 5, 9, 9, 12], type=pa.int32() if typ in (pa.int32(), pa.date32()) else pa.int64())
+    t = pa.table({"ts": base.cast(typ), "v": pa.array([1, 2, 3, 4, 5, 6, 7])})
+    every = "2i" if typ == pa.int32() else ("2d" if typ == pa.date32() else "2ms")
+    q = pw.LazyFrame(t).group_by_dynamic("ts", every=every).agg(pw.col("v").sum(), pw.len().alias("n"))
+    G.assert_tables_equal(engine.run_group_by(q.table, q.plan), oracle.collect(q))
