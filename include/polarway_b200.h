@@ -138,6 +138,7 @@ typedef struct PwDynamic {
 #define PW_FLAG_NO_SEGMENTED (1ull << 3)       /* dynamic without keys through the hash path */
 #define PW_FLAG_FORCE_PARTITION (1ull << 4)    /* radix-partition the rows by key hash first (high-cardinality tier) */
 #define PW_FLAG_NO_PARTITION (1ull << 5)       /* never partition (POLARS_NO_PARTITION) */
+#define PW_FLAG_NO_DENSE_IDS (1ull << 6)       /* never map a small integer key range to dense ids: always the hash index */
 
 #define PW_ABI_VERSION 1u
 typedef struct PwQuery {

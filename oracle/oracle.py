@@ -114,10 +114,11 @@ def widen(arr: pa.Array):
         return np.ascontiguousarray(v, dtype=np.float64), F64, valid
     if pa.types.is_float32(t):
         return np.ascontiguousarray(v, dtype=np.float32), F32, valid
+    # widening is exact; a column that already has the 8-byte class type is used in place (no copy)
     if pa.types.is_unsigned_integer(t):
-        return np.ascontiguousarray(v.astype(np.uint64)), U64, valid
+        return np.ascontiguousarray(v, dtype=np.uint64), U64, valid
     if pa.types.is_signed_integer(t):
-        return np.ascontiguousarray(v.astype(np.int64)), I64, valid
+        return np.ascontiguousarray(v, dtype=np.int64), I64, valid
     raise NotImplementedError(f"value dtype {t}")
 
 
@@ -248,11 +249,16 @@ def _make_aggs(table, aggs):
     n = table.num_rows
     c_aggs = (OrcAgg * max(1, len(aggs)))()
     keep, meta = [], []
+    memo = {}   # every value expression is widened / evaluated once, however many aggregates read it
     for i, a in enumerate(aggs):
         if a.expr is None:
-            v, vc, valid, st = np.zeros(n, dtype=np.int64), I64, None, None
+            if None not in memo:
+                memo[None] = (np.zeros(1, dtype=np.int64), I64, None, None)   # len() reads no values
+            v, vc, valid, st = memo[None]
         else:
-            v, vc, valid, st = eval_value_expr(table, a.expr)
+            if a.expr not in memo:
+                memo[a.expr] = eval_value_expr(table, a.expr)
+            v, vc, valid, st = memo[a.expr]
         keep.append((v, valid))
         c_aggs[i].kind = _KIND[a.kind]
         c_aggs[i].vclass = vc

@@ -332,25 +332,77 @@ typedef struct {
     const uint8_t *sel; const OrcAgg *aggs; int n_aggs; int64_t lo, hi; OrcTable *tb;
 } ShardJob;
 
-/* one pipeline of the sink phase (nodes/group_by.rs:116-214): a thread-local
- * table over a contiguous row shard */
+/* Morsel-wise update of one aggregate: the shape of GroupedReduction::update_groups_subset
+ * (polars-expr/src/reduce/mod.rs:292-312) — group indices first, then ONE typed loop per
+ * aggregate with the dispatch outside of it.  Same arithmetic as state_update (which stays the
+ * reference for every other kind / class and for the slice path). */
+static void update_morsel(OrcState *st, int n_aggs, int a, const OrcAgg *g,
+                          const int32_t *gid, const int64_t *rows, int m) {
+    const uint8_t *valid = g->valid;
+    if (g->kind == ORC_LEN) {
+        for (int k = 0; k < m; k++) st[(int64_t)gid[k] * n_aggs + a].cnt++;
+    } else if (g->kind == ORC_COUNT) {
+        for (int k = 0; k < m; k++) st[(int64_t)gid[k] * n_aggs + a].cnt += !valid || valid[rows[k]];
+    } else if (g->vclass == ORC_F64 && (g->kind == ORC_SUM || g->kind == ORC_MEAN)) {
+        const double *v = (const double *)g->values;
+        const int mean = g->kind == ORC_MEAN;
+        for (int k = 0; k < m; k++) {
+            if (valid && !valid[rows[k]]) continue;
+            OrcState *s = &st[(int64_t)gid[k] * n_aggs + a];
+            kahan_add(s, v[rows[k]]);
+            s->cnt += mean;
+        }
+    } else if (g->vclass == ORC_F64 && (g->kind == ORC_MIN || g->kind == ORC_MAX)) {
+        const double *v = (const double *)g->values;
+        const int is_min = g->kind == ORC_MIN;
+        for (int k = 0; k < m; k++) {
+            if (valid && !valid[rows[k]]) continue;
+            OrcState *s = &st[(int64_t)gid[k] * n_aggs + a];
+            const double x = v[rows[k]];
+            s->cnt++;
+            if (isnan(x)) continue;
+            if (s->aux == 0) s->w0 = d2u(x);
+            else {
+                const double c = u2d(s->w0);
+                const int lt = (x < c) || (x == c && signbit(x) && !signbit(c));
+                const int gt = (x > c) || (x == c && !signbit(x) && signbit(c));
+                if (is_min ? lt : gt) s->w0 = d2u(x);
+            }
+            s->aux++;
+        }
+    } else {
+        for (int k = 0; k < m; k++) state_update(&st[(int64_t)gid[k] * n_aggs + a], g, rows[k]);
+    }
+}
+
+/* one pipeline of the sink phase (nodes/group_by.rs:116-214): a thread-local table over a
+ * contiguous row shard, fed morsel by morsel: probe -> group index per row, then one pass per
+ * aggregate (update_morsel) */
+#define ORC_MORSEL 2048
 static void *shard_main(void *arg) {
     ShardJob *j = (ShardJob *)arg;
     OrcTable *tb = j->tb;
     int n_words = j->n_words, n_aggs = j->n_aggs;
     table_init(tb, n_words, n_aggs, 1024);
     uint64_t kw[16];
-    for (int64_t i = j->lo; i < j->hi; i++) {
-        if (j->sel && !j->sel[i]) continue;
-        uint32_t nm = 0;
-        for (int w = 0; w < n_words; w++) {
-            int ok = !j->key_valid || !j->key_valid[w] || j->key_valid[w][i];
-            kw[w] = ok ? j->keys[w][i] : 0;
-            nm |= (uint32_t)(!ok) << w;
+    int32_t gid[ORC_MORSEL];
+    int64_t rows[ORC_MORSEL];
+    for (int64_t lo = j->lo; lo < j->hi; lo += ORC_MORSEL) {
+        const int64_t hi = lo + ORC_MORSEL < j->hi ? lo + ORC_MORSEL : j->hi;
+        int m = 0;
+        for (int64_t i = lo; i < hi; i++) {
+            if (j->sel && !j->sel[i]) continue;
+            uint32_t nm = 0;
+            for (int w = 0; w < n_words; w++) {
+                int ok = !j->key_valid || !j->key_valid[w] || j->key_valid[w][i];
+                kw[w] = ok ? j->keys[w][i] : 0;
+                nm |= (uint32_t)(!ok) << w;
+            }
+            gid[m] = (int32_t)table_find_or_insert(tb, kw, nm, n_words, n_aggs, i);
+            rows[m++] = i;
         }
-        int64_t g = table_find_or_insert(tb, kw, nm, n_words, n_aggs, i);
-        OrcState *st = &tb->st[g * n_aggs];
-        for (int a = 0; a < n_aggs; a++) state_update(&st[a], &j->aggs[a], i);
+        /* the table may have grown (realloc) while probing: take the state pointer afterwards */
+        for (int a = 0; a < n_aggs; a++) update_morsel(tb->st, n_aggs, a, &j->aggs[a], gid, rows, m);
     }
     return NULL;
 }

@@ -29,11 +29,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIB_DIR, exist_ok=True)
     objs = []
     procs = []
+    # an object is rebuilt when its own source or any header (everything that is not one of SOURCES) is newer
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f not in SOURCES] + [os.path.join(HERE, "..", "include", "polarway_b200.h")]
+    t_hdr = max(os.path.getmtime(h) for h in headers)
     for src in SOURCES:
         obj = os.path.join(LIB_DIR, src.rsplit(".", 1)[0] + ".o")
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(t_hdr, os.path.getmtime(os.path.join(CSRC, src))):
+            continue
         cmd = ["nvcc", *NVCC_FLAGS, "-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(obj)
     for src, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0:

@@ -593,6 +593,16 @@ static bool plan_hot_threads(ScanPlan& P, int64_t groups_hint, int requested_gca
     off = (off + 15) & ~(size_t)15; g.mm_off = (int32_t)off; off += (size_t)g.mm_stride * gcap * 8;
     g.count_off = (int32_t)off; off += 32;  // [count, full flag, -, -]
     g.guard_acc = (mmp == 0) ? shadow_acc : -1;
+    // value guard in front of the shadow: needs the counter of non-null values of the shadowed expression (or the row
+    // counter when the expression has no nulls) as a warp-private word
+    g.guard_on = 0; g.guard_cnt = -1;
+    if (g.guard_acc >= 0 && !getenv("PW_NO_GUARD")) {
+      const VExpr& V = P.vexprs[P.accs[g.guard_acc].vexpr];
+      int cnt = -1;
+      if (V.flags & VF_COUNT) { cnt = V.acc_base; for (int b2 = 1; b2 < VF_COUNT; b2 <<= 1) if (V.flags & b2) ++cnt; }
+      else if (P.gflags & GF_LEN) cnt = P.acc_gbase;
+      if (cnt >= 0 && is_count(cnt)) { g.guard_on = 1; g.guard_cnt = cnt; }
+    }
     g.shadow_off = (int32_t)off;
     if (g.guard_acc >= 0) off += (((size_t)gcap * 8) + 15) & ~(size_t)15;
     g.warp_off = (int32_t)off;
@@ -611,7 +621,11 @@ static bool plan_hot_threads(ScanPlan& P, int64_t groups_hint, int requested_gca
         }
       }
     }
-    if (g.claim_acc < 0) { g.claim_off = (int32_t)woff; woff += (size_t)gcap * R * 4; }
+    // duplicate rows of a warp instruction: combined in registers through warp votes (no claim byte) unless switched off
+    static const bool no_dedup = getenv("PW_NO_DEDUP") != nullptr;
+    g.dedup = (!no_dedup && R < 32) ? 1 : 0;
+    if (g.dedup) { g.claim_acc = -1; g.claim_off = 0; }
+    else if (g.claim_acc < 0) { g.claim_off = (int32_t)woff; woff += (size_t)gcap * R * 4; }
     woff = (woff + 15) & ~(size_t)15;
     g.warp_bytes = (int32_t)woff;
     g.total_bytes = (int32_t)(off + woff * warps);
@@ -636,7 +650,11 @@ extern "C" __attribute__((visibility("default"))) int pw_b200_jit_selftest(char*
   if (!plan_hot(P, 1000, 0, getenv("PW_SELFTEST_DENSE") ? 1000 : 0)) return -1;
   P.hot_slots = P.hot.idx_slots;
   std::string err;
-  const int rc = jit_selftest_compile(P, 4, 1, true, ScanCfg<4>::THREADS, &err);
+  if (getenv("PW_SELFTEST_THREADS")) {  // the geometry a 16-warp CTA would get
+    if (!plan_hot_threads(P, 1000, P.hot.gcap, getenv("PW_SELFTEST_DENSE") ? 1000 : 0, atoi(getenv("PW_SELFTEST_THREADS")), true)) return -2;
+    P.hot_slots = P.hot.idx_slots;
+  }
+  const int rc = jit_selftest_compile(P, 4, 1, true, P.hot.threads, &err);
   if (log && log_len) { strncpy(log, err.c_str(), log_len - 1); log[log_len - 1] = 0; }
   return rc;
 }
@@ -703,7 +721,7 @@ __global__ void key_range_kernel(RawSlot key, int64_t begin, int64_t stride, int
 }
 // may this query use dense ids at all?  One plain signed (or narrow unsigned) integer key, a per-group row counter
 static bool dense_eligible(const PwQuery* q, const ScanPlan& P) {
-  if (getenv("PW_NO_DENSE")) return false;
+  if (getenv("PW_NO_DENSE") || (q->flags & PW_FLAG_NO_DENSE_IDS)) return false;
   if (q->n_keys != 1 || P.dyn.enabled || P.n_kw != 1 || !(P.gflags & GF_LEN) || P.row_group_out) return false;
   switch (P.keys[0].dtype) {
     case DT_I8: case DT_U8: case DT_I16: case DT_U16: case DT_I32: case DT_U32: case DT_I64: return true;

@@ -174,8 +174,12 @@ struct HotGeom {
                        // 2 = the range contains -1 / -2, whose bit patterns are the table's key sentinels
   int32_t guard_acc;   // min word of the CTA-shared (min, max) pair that has a 32-bit shadow, -1 = none
   int32_t shadow_off;  // byte offset of the shadow array (int2 per id)
-  int32_t pad4;
+  int32_t dedup;       // != 0: rows of one warp instruction that hit the same private cell are found with warp votes over the
+                       // bits of the dense id and COMBINED in registers (the lowest lane does one plain read-modify-write):
+                       // no claim byte, no retry rounds (pw_scan.cuh, VoteSink)
   int32_t threads;     // CTA size the geometry was planned for (warp-private regions = threads / 32)
+  int32_t guard_on;    // != 0: per-warp value guard in front of the shadow (HotTable::guard_snapshot)
+  int32_t guard_cnt;   // private 32-bit counter that tells whether a warp has fed a value of the shadowed expression into an id
   int32_t acc_kind[MAX_ACC];
   int32_t acc_off[MAX_ACC];  // HOT_SHARED_MM: word inside the group's min/max block; private kinds: byte offset inside the warp region
 };

@@ -238,7 +238,77 @@ struct HotTable {
   // reads 8 bytes and does two 32-bit compares instead of 16 bytes and two 64-bit compares; the rare row takes the
   // exact path and tightens the shadow with native 32-bit shared-memory atomics.
   int2* shadow;
+  // VALUE GUARD in front of the shadow (registers, per warp).  Most rows of a steady-state group set lie strictly
+  // between the largest group minimum and the smallest group maximum; for those even the 8-byte shadow read (a random
+  // shared-memory access: ~6 wavefronts per warp instruction, 18 % of this kernel's shared-memory traffic on C2) is
+  // wasted.  A single CTA-wide interval was tried in round 1 and lost because every row paid for ids that had not
+  // settled yet; here the interval only speaks for ids this warp has itself fed before the last snapshot:
+  //   snapshot (between the two CTA barriers of an eviction check, every warp for itself): g_lo / g_hi = max of the
+  //     shadow minima / min of the shadow maxima over every id that has a shadow, and a bitmap of the ids whose
+  //     shadow exists AND whose private value counter of this warp is non-zero ("covered").
+  //   row: covered id and g_lo < hi(x) < g_hi  ->  the row cannot improve an extremum, skip the shadow read.
+  // Shadows only tighten between snapshots and a covered id was part of the snapshot, so the test stays on the safe
+  // side; ids that appear later, NaN-only ids and ids this warp has not fed are not covered and read their shadow.
+  int g_lo, g_hi;
+  uint32_t cov[4];  // bit (id & 31) of word (id >> 5): lane (id >> 5) & 31 holds it in cov[id >> 10]
+  __device__ __forceinline__ void guard_reset() {
+    g_lo = 0x7FFFFFFF; g_hi = (int)0x80000000;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cov[k] = 0u;
+  }
+  __device__ __forceinline__ void guard_snapshot(const ScanPlan& P, int lane) {
+    const int G = CT::h_gcap(P), R = CT::h_rep(P);
+    const uint32_t* cnt = (const uint32_t*)(wbase + CT::h_off(P, CT::h_guard_cnt(P)));
+    int lo = (int)0x80000000, hi = 0x7FFFFFFF;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t mine = 0u;
+      if (k * 1024 < G) {
+        for (int j = 0; j < 32; ++j) {
+          const int idx = (k * 32 + j) * 32 + lane;
+          bool c = false;
+          if (idx < G) {
+            int2 sh;
+            sh.x = *(volatile int*)&shadow[idx].x;
+            sh.y = *(volatile int*)&shadow[idx].y;
+            if (sh.x != 0x7FFFFFFF) {   // the id has a shadow
+              lo = sh.x > lo ? sh.x : lo;
+              hi = sh.y < hi ? sh.y : hi;
+              uint32_t fed = 0u;
+              for (int r = 0; r < R; ++r) fed |= cnt[(size_t)idx * R + r];
+              c = (fed & (CT::h_guard_cnt(P) == CT::h_claim_acc(P) ? 0x00FFFFFFu : 0xFFFFFFFFu)) != 0u;  // claim byte on top
+            }
+          }
+          const uint32_t b = __ballot_sync(0xffffffffu, c);
+          if (lane == j) mine = b;
+          if ((k * 32 + j + 1) * 32 >= G) break;
+        }
+      }
+      cov[k] = mine;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const int l2 = __shfl_xor_sync(0xffffffffu, lo, d), h2 = __shfl_xor_sync(0xffffffffu, hi, d);
+      lo = l2 > lo ? l2 : lo;
+      hi = h2 < hi ? h2 : hi;
+    }
+    g_lo = lo; g_hi = hi;
+  }
+  // may the row (id, high word xh of its value image in the shadow's signed domain) skip the shadow?  Convergent.
+  __device__ __forceinline__ bool guard_skips(const ScanPlan& P, int id, int32_t xh) const {
+    const int wi = id >> 5;
+    uint32_t w = __shfl_sync(0xffffffffu, cov[0], wi & 31);
+    if (CT::h_gcap(P) > 1024) {
+#pragma unroll
+      for (int k = 1; k < 4; ++k) {
+        const uint32_t wk = __shfl_sync(0xffffffffu, cov[k], wi & 31);
+        if (k * 1024 < CT::h_gcap(P) && (wi >> 5) == k) w = wk;
+      }
+    }
+    return id >= 0 && ((w >> (id & 31)) & 1u) && xh > g_lo && xh < g_hi;
+  }
   __device__ __forceinline__ void bind(unsigned char* smem, const ScanPlan& P, int warp) {
+    guard_reset();
     tag = (uint32_t*)smem;
     keys = (uint64_t*)(smem + CT::h_keys_off(P));
     mm = (uint64_t*)(smem + CT::h_mm_off(P));
@@ -788,16 +858,27 @@ struct HotSinkB {
     bool en[B];
     if (a == CT::h_guard_acc(P) && B > 1) {
       int2 sh[B];
+      bool look[B];
 #pragma unroll
       for (int i = 0; i < B; ++i) {
-        asm volatile("ld.volatile.shared.v2.s32 {%0,%1}, [%2];" : "=r"(sh[i].x), "=r"(sh[i].y)
-                     : "r"((uint32_t)__cvta_generic_to_shared(&hot.shadow[ok[i] ? id[i] : 0])));
+        look[i] = ok[i];
+        if (CT::h_guard_on(P)) {
+          const int32_t xh = (int32_t)((uint32_t)(x[i] >> 32) ^ (OPMIN == OP_MIN_I64 ? 0u : 0x80000000u));
+          look[i] = ok[i] && !hot.guard_skips(P, id[i], xh);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < B; ++i) {
+        sh[i] = make_int2((int)0x80000000, 0x7FFFFFFF);   // not looked at: inside every interval
+        if (look[i])
+          asm volatile("ld.volatile.shared.v2.s32 {%0,%1}, [%2];" : "=r"(sh[i].x), "=r"(sh[i].y)
+                       : "r"((uint32_t)__cvta_generic_to_shared(&hot.shadow[id[i]])));
       }
       uint32_t m = 0;
 #pragma unroll
       for (int i = 0; i < B; ++i) {
         const int32_t xh = (int32_t)((uint32_t)(x[i] >> 32) ^ (OPMIN == OP_MIN_I64 ? 0u : 0x80000000u));  // signed domain
-        m |= ((ok[i] && (xh <= sh[i].x || xh >= sh[i].y)) ? 1u : 0u) << i;  // NaN images lie outside every interval
+        m |= ((look[i] && (xh <= sh[i].x || xh >= sh[i].y)) ? 1u : 0u) << i;  // NaN images lie outside every interval
       }
       // few rows get here once a group has seen some rows: one row per lane per round through a single-row body
       while (m) {
@@ -856,6 +937,84 @@ struct HotSinkB {
     }
   }
 };
+
+// Shared-memory hot table, ONE row slot of the warp (32 rows, one per lane), duplicates combined in registers.
+// `peers` = lanes of this slot whose row targets the same private cell as this lane's (found by the caller with warp
+// votes over the id bits); the lowest lane of every peer set is its LEADER: it pulls its peers' contributions with
+// shuffles, combines them with the accumulator's own op and does one plain read-modify-write.  Nothing else touches the
+// cell in this instruction, so there is no claim and no retry; rows of LATER slots see the stores (same warp, program
+// order, __syncwarp between slots).  Why: in the claim protocol (HotSinkB) a third of the shared-memory wavefronts were
+// claim bytes, claim checks and retry rounds (profiles/r02_c2_scan.md); votes and shuffles use issue slots instead,
+// of which this kernel has 55 % to spare.
+template <class CT, int KW>
+struct VoteSink {
+  const HotTable<CT, KW>& hot;
+  int id, cell, lane;
+  uint32_t peers;   // lanes sharing this lane's cell (own bit included); 0 for a lane without a row
+  bool leader;      // lowest lane of its peer set
+  bool any_dup;     // warp-uniform: some peer set has more than one lane
+  template <int OP>
+  __device__ __forceinline__ uint64_t gather(uint64_t v) const {
+    // leaders walk their peers (lowest first); everybody executes the shuffles (warp-uniform trip count)
+    uint32_t rest = leader ? (peers & ~(1u << lane)) : 0u;
+    while (__any_sync(0xffffffffu, rest != 0u)) {
+      const int src = rest ? (__ffs((int)rest) - 1) : lane;
+      const uint64_t o = __shfl_sync(0xffffffffu, v, src);
+      if (rest) v = acc_combine(OP, v, o);
+      rest &= rest - 1u;
+    }
+    return v;
+  }
+  template <int OP>
+  __device__ __forceinline__ void add(const ScanPlan& P, int a, const uint64_t (&x)[1], const bool (&en)[1]) const {
+    const int kind = CT::h_kind(P, a);
+    if (kind == HOT_PRIV64) {
+      uint64_t v = en[0] ? x[0] : acc_init(OP);   // the op's identity: a row that does not take part changes nothing
+      if (any_dup) v = gather<OP>(v);
+      if (leader) {
+        uint64_t* q = (uint64_t*)(hot.wbase + CT::h_off(P, a)) + cell;
+        *q = acc_combine(OP, *q, v);
+      }
+    } else if (kind == HOT_PRIV32) {
+      // counters: the combined contribution is a population count, no shuffles
+      const uint32_t votes = __ballot_sync(0xffffffffu, en[0] && x[0] != 0ull);
+      if (leader) {
+        uint32_t* q = (uint32_t*)(hot.wbase + CT::h_off(P, a)) + cell;
+        *q = *q + (uint32_t)__popc(votes & peers);
+      }
+    }
+    // CTA-shared min/max words need no ownership: the caller updates them for all of a lane's rows at once (HotSinkB)
+  }
+  template <int OPMIN, int OPMAX>
+  __device__ __forceinline__ void minmax(const ScanPlan& P, int a, const uint64_t (&x)[1], const bool (&ok)[1], bool is_f64) const {
+    bool en[1] = {ok[0] && !(is_f64 && HotSinkB<CT, KW, 1, PART_ALL>::image_is_nan(x[0]))};
+    add<OPMIN>(P, a, x, en);
+    add<OPMAX>(P, a + 1, x, en);
+  }
+};
+
+// lanes of the warp whose (alive) row has the same dense id and the same replica as this lane's: one vote per id bit.
+// nbits covers every id below the table's capacity.
+template <class CT>
+__device__ __forceinline__ uint32_t vote_peers(const ScanPlan& P, int id, bool pend, int lane) {
+  const int R = CT::h_rep(P);
+  int nbits = 1;
+  while ((1 << nbits) < CT::h_gcap(P)) ++nbits;
+  uint32_t peers = __ballot_sync(0xffffffffu, pend);
+  if (R > 1) {   // replica = lane % R: only lanes of the same residue share cells
+    const uint32_t every = R == 2 ? 0x55555555u : (R == 4 ? 0x11111111u : (R == 8 ? 0x01010101u : 0x00010001u));
+    peers &= every << (lane & (R - 1));
+  }
+#pragma unroll
+  for (int b = 0; b < 12; ++b) {
+    if (b < nbits) {
+      const bool bit = (id >> b) & 1;
+      const uint32_t m = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? m : ~m;
+    }
+  }
+  return pend ? peers : 0u;
+}
 
 // B-row form of accumulate_row (same walk over the aggregate flags; `en` = rows that take part)
 template <class CT, int NV, int KW, int B, class Sink>
@@ -1032,7 +1191,23 @@ __device__ __forceinline__ void rows_accumulate(const ScanPlan& P, HotTable<CT, 
     const HotSinkB<CT, KW, B, PART_ALL> sink{hot, id, cell, cw};
     const HotSinkB<CT, KW, B, PART_PRIVATE> sink_private{hot, id, cell, cw};
     const HotSinkB<CT, KW, B, PART_SHARED> sink_shared{hot, id, cell, cw};
-    if (R == 32) {
+    if (R < 32 && CT::h_dedup(P)) {
+      // duplicates combined in registers (VoteSink): the CTA-shared min/max words first, for all B rows at once (they
+      // need no ownership), then the private words slot by slot
+      if (CT::h_n_mm(P) > 0) accumulate_rows<CT, NV, KW, B>(P, o, grow, pend, sink_shared);
+#pragma unroll
+      for (int i = 0; i < B; ++i) {
+        const uint32_t peers = vote_peers<CT>(P, id[i], pend[i], lane);
+        const bool dup = (peers & (peers - 1u)) != 0u;
+        const VoteSink<CT, KW> vs{hot, id[i], cell[i], lane, peers, pend[i] && (peers & ((1u << lane) - 1u)) == 0u, __any_sync(0xffffffffu, dup) != 0};
+        RowOut<KW, NV> so[1];
+        uint64_t sgrow[1];
+        bool sen[1];
+        so[0] = o[i]; sgrow[0] = grow[i]; sen[0] = pend[i];
+        accumulate_rows<CT, NV, KW, 1>(P, so, sgrow, sen, vs);
+        __syncwarp();   // the next slot's loads see this slot's stores
+      }
+    } else if (R == 32) {
       // every lane owns its replica: no claims.  Two rows of one lane may share a cell -> one row at a time.
 #pragma unroll
       for (int i = 0; i < B; ++i) {
@@ -1228,39 +1403,103 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
   unsigned long long spilled = 0;
   bool stable_set = false, flushed_once = false;  // eviction heuristics (CTA-uniform)
   int tiles_since_flush = 0;
+  int n_checks = 0;  // eviction checks since the last clear (value-guard snapshots)
 
-  // narrow class: the loads of the NEXT tile are issued before the current tile is processed (software pipeline;
-  // 12 warps per SM cannot hide an HBM round trip per tile otherwise).  The wide class has no registers to spare.
-  constexpr bool PREFETCH = NC <= 4;
-  uint4 raw[2][NC], nraw[2][NC];
-  uint32_t vbits[2][NC], nvbits[2][NC];
-  if (PREFETCH && tile_lo < tile_hi) load_step<CT, NC>(P, (tile_lo * warps + warp) * ROWS_PER_STEP, lane, n_rows, raw, vbits);
+  // eviction check after a tile (CTA-wide: every warp calls it for the same tiles).  Every 4 tiles (8192 rows at 16
+  // warps): two CTA barriers.  Partitioned input walks through disjoint group sets (one per partition, a tile or two
+  // long): check every tile and evict at half full, so that the next partitions always find room
+  auto evict_check = [&](int64_t tile) {
+    if (!(HOT && (CT::rowid_slot(P) >= 0 || ((tile - tile_lo) & 3) == 3))) return;
+    __syncthreads();
+    // Evict everything (FixedIndexTable evicts per slot; a wholesale flush keeps the per-row path free of
+    // eviction logic) when a row found the table full, or — for group sets that drift (time-sorted input) —
+    // before that happens: at 7/8 full, unless the table refilled right after the previous eviction (a stable
+    // group set that simply needs most of the table: then only a full table evicts).
+    const uint32_t cnt = *(volatile uint32_t*)hot.count;
+    const bool full = *(volatile uint32_t*)(hot.count + 1) != 0u;
+    const uint32_t G = (uint32_t)CT::h_gcap(P);
+    const bool nearly = CT::rowid_slot(P) >= 0 ? cnt >= (G >> 1) : (cnt >= G - (G >> 3) && !stable_set);
+    // value guard: a fresh snapshot at the first checks (the group set settles quickly), then at every eighth one
+    if (CT::h_guard_on(P) && CT::h_guard_acc(P) >= 0 && CT::rowid_slot(P) < 0 && (n_checks < 4 || (n_checks & 7) == 0)) hot.guard_snapshot(P, lane);
+    ++n_checks;
+    __syncthreads();
+    ++tiles_since_flush;
+    const bool wrap = tiles_since_flush >= 30000;  // private counters share their word with the claim byte: 24 bits
+    if ((full || nearly || wrap) && tile + 1 < tile_hi) {
+      if (!full && !wrap && flushed_once && tiles_since_flush <= 2 && CT::rowid_slot(P) < 0) stable_set = true;  // refilled at once: same groups again
+      else {
+        hot.flush(P);
+        __syncthreads();
+        hot.clear(P);
+        hot.guard_reset();
+        n_checks = 0;
+        __syncthreads();
+        flushed_once = true;
+        tiles_since_flush = 0;
+      }
+    }
+  };
 
-  for (int64_t tile = tile_lo; tile < tile_hi; ++tile) {
-    const int64_t step = tile * warps + warp;
-    const int64_t base = step * ROWS_PER_STEP;
-    if (PREFETCH) load_step<CT, NC>(P, base + (int64_t)warps * ROWS_PER_STEP, lane, tile + 1 < tile_hi ? n_rows : 0, nraw, nvbits);
-    if (step < n_steps) {
-      const int64_t left = n_rows - base;
-      const int rem = left >= ROWS_PER_STEP ? ROWS_PER_STEP : (int)left;
-      if (!PREFETCH) load_step<CT, NC>(P, base, lane, n_rows, raw, vbits);
+  if constexpr (NC <= 4) {
+    // Narrow class: evaluate, PROBE and AGGREGATE the lane's four rows together (independent chains -> instruction-
+    // level parallelism; one claim round for all four), with the loads of the NEXT tile in flight while the current
+    // one is processed (software pipeline: 12-16 warps per SM cannot hide an HBM round trip per tile otherwise).  The
+    // tile loop is unrolled by two so that the two register buffers alternate in place (the first version rotated
+    // them with ~20 register moves per step), and the row index advances by a constant stride.
+    auto rows4 = [&](const uint4 (&raw)[2][NC], const uint32_t (&vbits)[2][NC], int64_t base, int rem) {
       if (CT::check_sorted(P)) check_sorted_step<CT, NC>(P, raw, base, lane, n_rows);
-      if (NC <= 4) {
-        // narrow class: evaluate, PROBE and AGGREGATE the lane's four rows together (independent chains ->
-        // instruction-level parallelism; one claim round for all four)
-        RowOut<KW, NV> o[4];
-        uint64_t h[4];
-        int id[4];
-        row_front<CT, NC, KW, NV, 0>(P, raw, vbits, 0, base, lane, rem, o[0]);
-        row_front<CT, NC, KW, NV, 0>(P, raw, vbits, 1, base, lane, rem, o[1]);
-        row_front<CT, NC, KW, NV, 1>(P, raw, vbits, 0, base, lane, rem, o[2]);
-        row_front<CT, NC, KW, NV, 1>(P, raw, vbits, 1, base, lane, rem, o[3]);
-        rows_probe<CT, KW, NV, HOT, 4>(P, hot, o, h, id);
-        rows_accumulate<CT, KW, NV, HOT, 4>(P, hot, o, h, id, lane, spilled);
-      } else {
-        // wide class (register-bound): one row at a time; the half is unrolled.  The pair element is a real loop in the
-        // ahead-of-time kernels (code size); the specialised build inlines both (compile-time j: no selects on the raw
-        // words — the same change took the sorted-window kernel from 75 % to 87 % of the HBM roofline)
+      RowOut<KW, NV> o[4];
+      uint64_t h[4];
+      int id[4];
+      row_front<CT, NC, KW, NV, 0>(P, raw, vbits, 0, base, lane, rem, o[0]);
+      row_front<CT, NC, KW, NV, 0>(P, raw, vbits, 1, base, lane, rem, o[1]);
+      row_front<CT, NC, KW, NV, 1>(P, raw, vbits, 0, base, lane, rem, o[2]);
+      row_front<CT, NC, KW, NV, 1>(P, raw, vbits, 1, base, lane, rem, o[3]);
+      rows_probe<CT, KW, NV, HOT, 4>(P, hot, o, h, id);
+      rows_accumulate<CT, KW, NV, HOT, 4>(P, hot, o, h, id, lane, spilled);
+    };
+    const int64_t stride = (int64_t)warps * ROWS_PER_STEP;
+    int64_t base = (tile_lo * warps + warp) * ROWS_PER_STEP;
+    int64_t partial_base = -1;  // the input's last, incomplete step (one warp of one CTA): handled after the loop
+    // a step that lies completely inside the input (all but the last) runs with a compile-time row count: no
+    // per-row bounds checks
+    auto step = [&](const uint4 (&raw)[2][NC], const uint32_t (&vbits)[2][NC], int64_t b) {
+      const int64_t left = n_rows - b;
+      if (left >= ROWS_PER_STEP) rows4(raw, vbits, b, ROWS_PER_STEP);
+      else if (left > 0) partial_base = b;
+    };
+    uint4 rawA[2][NC], rawB[2][NC];
+    uint32_t vbA[2][NC], vbB[2][NC];
+    if (tile_lo < tile_hi) load_step<CT, NC>(P, base, lane, n_rows, rawA, vbA);
+    for (int64_t tile = tile_lo; tile < tile_hi; tile += 2) {
+      load_step<CT, NC>(P, base + stride, lane, tile + 1 < tile_hi ? n_rows : 0, rawB, vbB);
+      step(rawA, vbA, base);
+      evict_check(tile);
+      if (tile + 1 < tile_hi) {
+        load_step<CT, NC>(P, base + 2 * stride, lane, tile + 2 < tile_hi ? n_rows : 0, rawA, vbA);
+        step(rawB, vbB, base + stride);
+        evict_check(tile + 1);
+      }
+      base += 2 * stride;
+    }
+    if (partial_base >= 0) {
+      load_step<CT, NC>(P, partial_base, lane, n_rows, rawA, vbA);
+      rows4(rawA, vbA, partial_base, (int)(n_rows - partial_base));
+    }
+  } else {
+    // wide class (register-bound, no prefetch): one row at a time; the half is unrolled.  The pair element is a real
+    // loop in the ahead-of-time kernels (code size); the specialised build inlines both (compile-time j: no selects
+    // on the raw words — the same change took the sorted-window kernel from 75 % to 87 % of the HBM roofline)
+    uint4 raw[2][NC];
+    uint32_t vbits[2][NC];
+    for (int64_t tile = tile_lo; tile < tile_hi; ++tile) {
+      const int64_t step = tile * warps + warp;
+      const int64_t base = step * ROWS_PER_STEP;
+      if (step < n_steps) {
+        const int64_t left = n_rows - base;
+        const int rem = left >= ROWS_PER_STEP ? ROWS_PER_STEP : (int)left;
+        load_step<CT, NC>(P, base, lane, n_rows, raw, vbits);
+        if (CT::check_sorted(P)) check_sorted_step<CT, NC>(P, raw, base, lane, n_rows);
         if constexpr (CT::kJit) {
           wide_row<CT, NC, KW, NV, HOT, 0>(P, hot, raw, vbits, 0, base, lane, rem, spilled);
           wide_row<CT, NC, KW, NV, HOT, 0>(P, hot, raw, vbits, 1, base, lane, rem, spilled);
@@ -1273,40 +1512,7 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
           for (int j = 0; j < 2; ++j) wide_row<CT, NC, KW, NV, HOT, 1>(P, hot, raw, vbits, j, base, lane, rem, spilled);
         }
       }
-    }
-    if (PREFETCH) {
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf)
-#pragma unroll
-        for (int c = 0; c < NC; ++c) { raw[hf][c] = nraw[hf][c]; vbits[hf][c] = nvbits[hf][c]; }
-    }
-    // every 4 tiles (6144 rows at 12 warps): two CTA barriers.  Partitioned input walks through disjoint group sets
-    // (one per partition, a tile or two long): check every tile and evict at half full, so that the next partitions
-    // always find room
-    if (HOT && (CT::rowid_slot(P) >= 0 || ((tile - tile_lo) & 3) == 3)) {
-      __syncthreads();
-      // Evict everything (FixedIndexTable evicts per slot; a wholesale flush keeps the per-row path free of
-      // eviction logic) when a row found the table full, or — for group sets that drift (time-sorted input) —
-      // before that happens: at 7/8 full, unless the table refilled right after the previous eviction (a stable
-      // group set that simply needs most of the table: then only a full table evicts).
-      const uint32_t cnt = *(volatile uint32_t*)hot.count;
-      const bool full = *(volatile uint32_t*)(hot.count + 1) != 0u;
-      const uint32_t G = (uint32_t)CT::h_gcap(P);
-      const bool nearly = CT::rowid_slot(P) >= 0 ? cnt >= (G >> 1) : (cnt >= G - (G >> 3) && !stable_set);
-      __syncthreads();
-      ++tiles_since_flush;
-      const bool wrap = tiles_since_flush >= 30000;  // private counters share their word with the claim byte: 24 bits
-      if ((full || nearly || wrap) && tile + 1 < tile_hi) {
-        if (!full && !wrap && flushed_once && tiles_since_flush <= 2 && CT::rowid_slot(P) < 0) stable_set = true;  // refilled at once: same groups again
-        else {
-          hot.flush(P);
-          __syncthreads();
-          hot.clear(P);
-          __syncthreads();
-          flushed_once = true;
-          tiles_since_flush = 0;
-        }
-      }
+      evict_check(tile);
     }
   }
   if (HOT) {

@@ -26,6 +26,7 @@ FLAG_FORCE_SEGMENTED = 1 << 2
 FLAG_NO_SEGMENTED = 1 << 3
 FLAG_FORCE_PARTITION = 1 << 4
 FLAG_NO_PARTITION = 1 << 5
+FLAG_NO_DENSE_IDS = 1 << 6
 
 
 class PolarwayError(RuntimeError):
@@ -295,16 +296,19 @@ def _import_columns(out_arrays, out_schemas, n) -> tuple:
     return names, cols
 
 
-def _restore_types(names, cols, table: pa.Table, key_names) -> list:
-    """Result string keys come back as Utf8View; hand them back in the caller's string type."""
-    out = []
-    for n, c in zip(names, cols):
-        if n in key_names and n in table.column_names:
-            t = table.schema.field(n).type
-            if c.type != t and (pa.types.is_string(t) or pa.types.is_large_string(t) or pa.types.is_binary(t) or pa.types.is_large_binary(t)):
-                c = c.cast(t)
-        out.append(c)
-    return out
+def _arrow_format(t: pa.DataType) -> bytes:
+    """Arrow C Data Interface format string of the column types this path reads."""
+    simple = {pa.int8(): b"c", pa.uint8(): b"C", pa.int16(): b"s", pa.uint16(): b"S", pa.int32(): b"i", pa.uint32(): b"I",
+              pa.int64(): b"l", pa.uint64(): b"L", pa.float32(): b"f", pa.float64(): b"g", pa.date32(): b"tdD",
+              pa.string_view(): b"vu", pa.binary_view(): b"vz", pa.bool_(): b"b"}
+    if t in simple:
+        return simple[t]
+    unit = {"s": b"s", "ms": b"m", "us": b"u", "ns": b"n"}
+    if pa.types.is_timestamp(t):
+        return b"ts" + unit[t.unit] + b":" + (t.tz.encode() if t.tz else b"")
+    if pa.types.is_duration(t):
+        return b"tD" + unit[t.unit]
+    raise NotImplementedError(f"device frame column of type {t}")
 
 
 # ---- plan -> PwQuery -----------------------------------------------------------------------------------
@@ -432,6 +436,46 @@ class DeviceFrame:
         self.num_rows = table.num_rows
         self._queries = {}
 
+    @classmethod
+    def from_device(cls, columns) -> "DeviceFrame":
+        """Zero-copy frame over buffers that already live in HBM (``pw_b200_frame_from_device``).
+
+        columns: list of ``(name, arrow_type, length, values_ptr, validity_ptr_or_0, null_count, extra)`` where the
+        pointers are DEVICE addresses laid out as the Arrow spec prescribes (values: element 0 = row 0; validity:
+        LSB-first bitmap) and ``extra`` keeps the owners (e.g. torch tensors) alive as long as the frame."""
+        L = lib()
+        n = len(columns)
+        self = cls.__new__(cls)
+        c_arrays = (ArrowArray * n)()
+        c_schemas = (ArrowSchema * n)()
+        keep = []
+        fields = []
+        for i, (name, typ, length, vptr, nptr, nulls, extra) in enumerate(columns):
+            fmt = _arrow_format(typ)
+            nbuf = 4 if fmt in (b"vu", b"vz") else 2
+            bufs = (C.c_void_p * nbuf)(nptr or None, vptr, None, None) if nbuf == 4 else (C.c_void_p * 2)(nptr or None, vptr)
+            nm = name.encode()
+            keep.append((bufs, nm, extra))
+            c_arrays[i].length = length
+            c_arrays[i].null_count = nulls
+            c_arrays[i].offset = 0
+            c_arrays[i].n_buffers = nbuf
+            c_arrays[i].buffers = C.cast(bufs, C.POINTER(C.c_void_p))
+            c_schemas[i].format = fmt
+            c_schemas[i].name = nm
+            c_schemas[i].flags = 2
+            fields.append(pa.field(name, typ))
+        arr_ptrs = (C.c_void_p * n)(*[C.addressof(c_arrays[i]) for i in range(n)])
+        sch_ptrs = (C.c_void_p * n)(*[C.addressof(c_schemas[i]) for i in range(n)])
+        h = C.c_void_p()
+        _check(L.pw_b200_frame_from_device(arr_ptrs, sch_ptrs, n, C.byref(h)))
+        self.handle = h
+        self.table_schema = pa.schema(fields)
+        self.num_rows = columns[0][2] if columns else 0
+        self._queries = {}
+        self._keep = keep
+        return self
+
     def free(self):
         if self.handle:
             lib().pw_b200_frame_free(self.handle)
@@ -470,7 +514,7 @@ def _restore_string_types(names, cols, schema: pa.Schema, key_names) -> list:
     for n, c in zip(names, cols):
         if n in key_names and n in schema.names:
             t = schema.field(n).type
-            if c.type != t and _is_stringlike(t):
+            if c.type != t and _is_stringlike(t) and not (pa.types.is_string_view(t) or pa.types.is_binary_view(t)):
                 c = c.cast(t)
         out.append(c)
     return out
