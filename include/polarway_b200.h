@@ -86,7 +86,13 @@ typedef enum PwCmpOp { PW_EQ = 0, PW_NE = 1, PW_LT = 2, PW_LE = 3, PW_GT = 4, PW
 /* aggregations: the pre-aggregatable reductions of polars-expr/src/reduce/convert.rs:23-168 that this
  * path covers (sum.rs, mean.rs, min_max.rs, count.rs, len.rs, first_last.rs). */
 typedef enum PwAggKind {
-  PW_SUM = 0, PW_MEAN = 1, PW_MIN = 2, PW_MAX = 3, PW_COUNT = 4, PW_LEN = 5, PW_FIRST = 6, PW_LAST = 7
+  PW_SUM = 0, PW_MEAN = 1, PW_MIN = 2, PW_MAX = 3, PW_COUNT = 4, PW_LEN = 5, PW_FIRST = 6, PW_LAST = 7,
+  /* the rest of the pre-aggregatable reductions (convert.rs:46-150): */
+  PW_VAR = 8, PW_STD = 9,                       /* reduce/var_std.rs; PwAgg.ddof */
+  PW_FIRST_NON_NULL = 10, PW_LAST_NON_NULL = 11,/* first/last(ignore_nulls=True): reduce/first_last_nonnull.rs */
+  PW_NULL_COUNT = 12,                           /* reduce/count.rs NullCountReduce */
+  PW_BIT_AND = 13, PW_BIT_OR = 14, PW_BIT_XOR = 15, /* reduce/bitwise.rs (integers and booleans) */
+  PW_ANY = 16, PW_ALL = 17                      /* reduce/any_all.rs, ignore_nulls = true (boolean input) */
 } PwAggKind;
 
 /* polars-time/src/windows/group_by.rs:24-44 */
@@ -114,7 +120,7 @@ typedef struct PwAgg {
   int32_t kind;      /* PwAggKind */
   int32_t column;    /* plain input column, or -1 when `factors` is used / for PW_LEN */
   int32_t n_factors; /* 0: plain column; >0: product of factors[0..n) (f64) */
-  int32_t reserved;
+  int32_t ddof;      /* PW_VAR / PW_STD: delta degrees of freedom (Polars default 1); 0 for every other kind */
   PwFactor factors[PW_MAX_FACTORS];
   const char* name;  /* output column name (borrowed) */
 } PwAgg;
@@ -186,7 +192,7 @@ int pw_b200_last_timings(PwTimings* out);
 typedef struct PwFrame PwFrame; /* opaque: columns resident on one device */
 
 /* Copy `n_cols` host Arrow arrays to the device.  Arrays are borrowed for the duration of the call
- * (not released).  All columns must have the same length.  Supported formats: c C s S i I l L f g,
+ * (not released).  All columns must have the same length.  Supported formats: b c C s S i I l L f g,
  * tdD, ts{s,m,u,n}:*, tD{s,m,u,n}, vu, vz (inline views). */
 int pw_b200_frame_upload(const struct ArrowArray* const* cols, const struct ArrowSchema* const* schemas,
                          size_t n_cols, PwFrame** out);

@@ -16,8 +16,38 @@ int upload_column(const struct ArrowArray* a, const struct ArrowSchema* s, bool 
   out->format = s->format ? s->format : "";
   out->name = s->name ? s->name : "";
   PW_TRY(parse_format(s->format, &out->dtype));
-  if (out->dtype == DT_BOOL) return fail(PW_ERR_UNSUPPORTED, "boolean column '%s' (SURVEY 8f)", out->name.c_str());
   if (a->n_buffers < 2) return fail(PW_ERR_INVALID, "column '%s': expected at least 2 buffers", out->name.c_str());
+  if (out->dtype == DT_BOOL) {
+    // Boolean values are a bitmap like validity: both are taken from the byte that holds bit `offset`, so that one
+    // residual bit offset serves both
+    const int64_t n = a->length;
+    const unsigned char* vals = (const unsigned char*)a->buffers[1];
+    const unsigned char* valid = (const unsigned char*)a->buffers[0];
+    int64_t nulls = a->null_count;
+    if (!valid) nulls = 0;
+    else if (nulls < 0) nulls = 1;
+    out->null_count = nulls;
+    out->bit_offset = (int32_t)(a->offset & 7);
+    const size_t first = (size_t)(a->offset >> 3);
+    const size_t bytes = (size_t)(((a->offset & 7) + n + 7) >> 3);
+    if (zero_copy) {
+      out->values = vals + first;
+      out->validity = nulls ? valid + first : nullptr;
+      return 0;
+    }
+    cudaStream_t st = ctx().stream;
+    void* d = nullptr;
+    PW_TRY(dev_alloc(&d, bytes + 32));
+    if (bytes) PW_CUDA(cudaMemcpyAsync(d, vals + first, bytes, cudaMemcpyHostToDevice, st));
+    out->values = d; out->owned_values = d;
+    if (nulls) {
+      void* dv = nullptr;
+      PW_TRY(dev_alloc(&dv, bytes + 32));
+      PW_CUDA(cudaMemcpyAsync(dv, valid + first, bytes, cudaMemcpyHostToDevice, st));
+      out->validity = (const uint8_t*)dv; out->owned_validity = dv;
+    }
+    return 0;
+  }
   const int w = out->dtype == DT_VIEW ? 16 : (out->dtype == DT_I8 || out->dtype == DT_U8 ? 1 : (out->dtype == DT_I16 || out->dtype == DT_U16 ? 2 : (out->dtype == DT_I32 || out->dtype == DT_U32 || out->dtype == DT_F32 ? 4 : 8)));
   const int64_t n = a->length;
   const unsigned char* vals = (const unsigned char*)a->buffers[1] + (size_t)a->offset * w;

@@ -135,7 +135,7 @@ static __global__ void __launch_bounds__(256) slice_agg_kernel(const __grid_cons
       for (int c = 0; c < NC; ++c) {
         r.in[c] = 0;
         if (c < P.n_slots) {
-          const uint4 raw = load_pair(P.slots[c].values, P.slots[c].dtype, row, row + 1, false);
+          const uint4 raw = load_row(P.slots[c], row);
           r.in[c] = decode(raw, P.slots[c].dtype, 0);
           r.in_valid |= (load_valid_pair(P.slots[c], row, row + 1) & 1u) << c;
         }

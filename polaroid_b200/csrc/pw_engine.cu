@@ -86,9 +86,13 @@ static inline int dtype_bytes(int dt) {
     default: return 8;
   }
 }
+// bytes of a result column of G rows (Boolean columns are bit-packed in 32-bit words)
+static inline size_t out_col_bytes(int dt, uint64_t G) {
+  return dt == DT_BOOL ? (size_t)((G + 31) / 32) * 4 : (size_t)G * dtype_bytes(dt);
+}
 static inline int dtype_class(int dt) {
   switch (dt) {
-    case DT_U8: case DT_U16: case DT_U32: case DT_U64: return CLS_U64;
+    case DT_U8: case DT_U16: case DT_U32: case DT_U64: case DT_BOOL: return CLS_U64;
     case DT_F32: case DT_F64: return CLS_F64;
     default: return CLS_I64;
   }
@@ -168,6 +172,44 @@ struct Lowerer {
 
 }  // namespace
 
+// mean of a strided sample (<= 4096 non-null rows) of a numeric column: the shift of its var/std words
+static __global__ void shift_sample_kernel(RawSlot s, int64_t n, int64_t stride, double* sum, unsigned long long* cnt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = i * stride;
+  double v = 0.0;
+  bool ok = row < n;
+  if (ok && s.validity) { const int64_t b = (int64_t)s.bit_offset + row; ok = (s.validity[b >> 3] >> (b & 7)) & 1; }
+  if (ok) {
+    v = bits_to_f64(decode(load_row(s, row), s.dtype, 0), slot_class(s.dtype));
+    ok = v == v && fabs(v) < 1.0e300;
+  }
+  if (ok) { atomicAdd(sum, v); atomicAdd(cnt, 1ull); }
+}
+static int column_shift(const PwFrame* f, int col, const RawSlot& slot, double* out) {
+  const FrameColumn& c = f->cols[col];
+  std::lock_guard<std::mutex> lk(f->mu);
+  if (!c.shift_known) {
+    struct { double sum; unsigned long long cnt; } h{0.0, 0ull};
+    if (f->n_rows > 0) {   // (schema-only frames — output dtype inference — never touch the device)
+      PW_TRY(ensure_device());
+      ThreadCtx& t = ctx();
+      void* d = nullptr;
+      PW_TRY(dev_alloc(&d, 16));
+      PW_CUDA(cudaMemsetAsync(d, 0, 16, t.stream));
+      const int64_t stride = std::max<int64_t>(1, f->n_rows / 4096);
+      const int64_t m = (f->n_rows + stride - 1) / stride;
+      shift_sample_kernel<<<(unsigned)((m + 255) / 256), 256, 0, t.stream>>>(slot, f->n_rows, stride, (double*)d, (unsigned long long*)d + 1);
+      PW_CUDA(cudaMemcpyAsync(&h, d, 16, cudaMemcpyDeviceToHost, t.stream));
+      PW_CUDA(cudaStreamSynchronize(t.stream));
+      dev_free(d);
+    }
+    c.var_shift = h.cnt ? h.sum / (double)h.cnt : 0.0;
+    c.shift_known = true;
+  }
+  *out = c.var_shift;
+  return 0;
+}
+
 int lower_query(const PwQuery* q, const PwFrame* f, Lowered* L) {
   if (!q || !f) return fail(PW_ERR_INVALID, "null query or frame");
   if (q->abi_version != PW_ABI_VERSION) return fail(PW_ERR_INVALID, "PwQuery.abi_version %u != %u", q->abi_version, PW_ABI_VERSION);
@@ -188,7 +230,7 @@ int lower_query(const PwQuery* q, const PwFrame* f, Lowered* L) {
     const PwPredicate& p = q->predicates[i];
     if (!col_ok(p.column)) return fail(PW_ERR_INVALID, "predicate column %d out of range", p.column);
     const FrameColumn& c = f->cols[p.column];
-    if (c.dtype == DT_VIEW || c.dtype == DT_BOOL) return fail(PW_ERR_UNSUPPORTED, "predicate on column '%s' of format %s", c.name.c_str(), c.format.c_str());
+    if (c.dtype == DT_VIEW) return fail(PW_ERR_UNSUPPORTED, "predicate on column '%s' of format %s", c.name.c_str(), c.format.c_str());
     const int s = lw.slot_for(p.column);
     if (s < 0) return fail(PW_ERR_UNSUPPORTED, "query touches more than %d column slots", MAX_SLOTS);
     Pred& d = P.preds[P.n_preds++];
@@ -237,8 +279,7 @@ int lower_query(const PwQuery* q, const PwFrame* f, Lowered* L) {
     const int kcol = q->key_columns[i];
     if (!col_ok(kcol)) return fail(PW_ERR_INVALID, "key column %d out of range", kcol);
     const FrameColumn& c = f->cols[kcol];
-    if (c.dtype == DT_BOOL) return fail(PW_ERR_UNSUPPORTED, "boolean key column '%s'", c.name.c_str());
-    const int s = lw.slot_for(kcol);
+    const int s = lw.slot_for(kcol);   // Boolean keys: the key word is 0 / 1 (the reference row-encodes them, hash_keys.rs:37,114-141)
     if (s < 0) return fail(PW_ERR_UNSUPPORTED, "too many column slots");
     KeyCol& k = P.keys[P.n_keys++];
     k.slot = s; k.dtype = c.dtype; k.n_words = c.dtype == DT_VIEW ? 2 : 1; k.nullable = c.null_count != 0;
@@ -314,14 +355,14 @@ int lower_query(const PwQuery* q, const PwFrame* f, Lowered* L) {
       for (int k = 0; k < a.n_factors; ++k) {
         if (!col_ok(a.factors[k].column)) return fail(PW_ERR_INVALID, "factor column out of range");
         const int dt = f->cols[a.factors[k].column].dtype;
-        if (dt == DT_VIEW || dt == DT_BOOL) return fail(PW_ERR_UNSUPPORTED, "arithmetic on a non-numeric column");
+        if (dt == DT_VIEW) return fail(PW_ERR_UNSUPPORTED, "arithmetic on a non-numeric column");
       }
       ve = lw.vexpr_product(a);
     } else {
       if (!col_ok(a.column)) return fail(PW_ERR_INVALID, "aggregation column %d out of range", a.column);
       const FrameColumn& c = f->cols[a.column];
-      if ((c.dtype == DT_VIEW || c.dtype == DT_BOOL) && a.kind != PW_COUNT)
-        return fail(PW_ERR_UNSUPPORTED, "aggregation over column '%s' of format %s (strings/booleans are SURVEY 8f)", c.name.c_str(), c.format.c_str());
+      if (c.dtype == DT_VIEW && a.kind != PW_COUNT && a.kind != PW_NULL_COUNT)
+        return fail(PW_ERR_UNSUPPORTED, "aggregation over column '%s' of format %s (string aggregations are SURVEY 8f)", c.name.c_str(), c.format.c_str());
       in_dtype = c.dtype; in_format = c.format;
       ve = lw.vexpr_plain(a.column);
     }
@@ -336,10 +377,14 @@ int lower_query(const PwQuery* q, const PwFrame* f, Lowered* L) {
     else for (int k = 0; k < V.n_factors; ++k) ve_nullable = ve_nullable || P.slots[V.f[k].slot].validity != nullptr;
     auto need_count = [&]() { if (ve_nullable) V.flags |= VF_COUNT; else gflags |= GF_LEN; };
     t.ve = ve; t.ve_nullable = ve_nullable; t.is_float = is_float; t.cls = cls;
+    const bool is_bool = in_dtype == DT_BOOL;
     switch (a.kind) {
       case PW_SUM:
         if (temporal && in_format[1] != 'D') return fail(PW_ERR_UNSUPPORTED, "`sum` operation not supported for dtype %s", in_format.c_str());
-        if (is_float) {
+        if (is_bool) {   // Boolean -> IDX_DTYPE (sum.rs:43)
+          V.flags |= VF_SUM_I;
+          o.emit.kind = EMIT_SUM_INT; o.out_dtype = DT_U32; o.format = "I";
+        } else if (is_float) {
           V.flags |= VF_SUM_F;
           o.emit.kind = EMIT_SUM_F64; o.out_dtype = in_dtype == DT_F32 ? DT_F32 : DT_F64; o.format = in_dtype == DT_F32 ? "f" : "g";
         } else {
@@ -373,9 +418,42 @@ int lower_query(const PwQuery* q, const PwFrame* f, Lowered* L) {
         o.emit.kind = EMIT_FIRSTLAST; o.out_dtype = in_dtype; o.format = in_format; o.nullable = true;
         o.emit.src = P.slots[V.slot];
         break;
+      case PW_FIRST_NON_NULL: case PW_LAST_NON_NULL:   // reduce/first_last_nonnull.rs: nulls never replace a value
+        if (a.n_factors > 0) return fail(PW_ERR_UNSUPPORTED, "first/last of a computed expression");
+        V.flags |= (a.kind == PW_FIRST_NON_NULL ? VF_FIRST_NN : VF_LAST_NN);
+        o.emit.kind = EMIT_FIRSTLAST; o.out_dtype = in_dtype; o.format = in_format; o.nullable = true;
+        o.emit.src = P.slots[V.slot];
+        o.emit.period = 1;   // "still at init" means no non-null row: null
+        o.emit.every = (int64_t)acc_init(a.kind == PW_FIRST_NON_NULL ? OP_MIN_U64 : OP_MAX_U64);
+        break;
+      case PW_VAR: case PW_STD:
+        // reduce/var_std.rs:9-48: numeric and Boolean inputs; the result is Float64 (Float32 stays Float32)
+        if (temporal) return fail(PW_ERR_UNSUPPORTED, "`%s` operation not supported for dtype %s", a.kind == PW_STD ? "std" : "var", in_format.c_str());
+        if (a.ddof < 0 || a.ddof > 255) return fail(PW_ERR_INVALID, "ddof must be in [0, 255]");
+        V.flags |= VF_SUMD | VF_SUMD2; need_count();
+        o.emit.kind = EMIT_VAR; o.nullable = true; o.emit.pad = a.ddof; o.emit.src_cls = a.kind == PW_STD ? 1 : 0;
+        if (in_dtype == DT_F32) { o.emit.mean_out = MEAN_F32; o.out_dtype = DT_F32; o.format = "f"; }
+        else { o.emit.mean_out = MEAN_F64; o.out_dtype = DT_F64; o.format = "g"; }
+        break;
+      case PW_NULL_COUNT:
+        gflags |= GF_LEN;
+        if (ve_nullable) V.flags |= VF_COUNT;
+        o.emit.kind = EMIT_NULL_COUNT; o.out_dtype = DT_U32; o.format = "I";
+        break;
+      case PW_BIT_AND: case PW_BIT_OR: case PW_BIT_XOR:
+        if (is_float || temporal || a.n_factors > 0) return fail(PW_ERR_UNSUPPORTED, "bitwise aggregation of a non-integer column");
+        V.flags |= (a.kind == PW_BIT_AND ? VF_AND : (a.kind == PW_BIT_OR ? VF_OR : VF_XOR)); need_count();
+        o.emit.kind = EMIT_BITWISE; o.out_dtype = in_dtype; o.format = in_format; o.nullable = true;
+        break;
+      case PW_ANY: case PW_ALL:
+        if (!is_bool) return fail(PW_ERR_INVALID, "any/all need a Boolean column, got %s", in_format.c_str());
+        V.flags |= (a.kind == PW_ANY ? VF_MAX : VF_MIN);
+        o.emit.kind = EMIT_ANYALL; o.out_dtype = DT_BOOL; o.format = "b"; o.nullable = false;
+        break;
       default: return fail(PW_ERR_INVALID, "unknown aggregation kind %d", a.kind);
     }
-    o.emit.out_dtype = o.out_dtype; o.emit.src_cls = cls;
+    o.emit.out_dtype = o.out_dtype;
+    if (o.emit.kind != EMIT_VAR) o.emit.src_cls = cls;   // EMIT_VAR keeps its var/std switch there
     tmp.push_back(t);
   }
   if (dyn) gflags |= GF_LEN;  // the sorted fast path finds the non-empty windows through the row counter
@@ -403,6 +481,21 @@ int lower_query(const PwQuery* q, const PwFrame* f, Lowered* L) {
     if (V.flags & VF_MAX) push_acc(u ? OP_MAX_U64 : OP_MAX_I64, fl ? SRC_F64_ORD : SRC_BITS, e);
     if (V.flags & VF_FIRST) push_acc(OP_MIN_U64, SRC_ROWIDX, e);
     if (V.flags & VF_LAST) push_acc(OP_MAX_U64, SRC_ROWIDX, e);
+    if (V.flags & VF_SUMD) push_acc(OP_ADD_F64, SRC_F64_D, e);
+    if (V.flags & VF_SUMD2) push_acc(OP_ADD_F64, SRC_F64_D2, e);
+    if (V.flags & VF_FIRST_NN) push_acc(OP_MIN_U64, SRC_ROWIDX_NN, e);
+    if (V.flags & VF_LAST_NN) push_acc(OP_MAX_U64, SRC_ROWIDX_NN, e);
+    if (V.flags & VF_AND) push_acc(OP_AND_U64, SRC_BITS, e);
+    if (V.flags & VF_OR) push_acc(OP_OR_U64, SRC_BITS, e);
+    if (V.flags & VF_XOR) push_acc(OP_XOR_U64, SRC_BITS, e);
+  }
+  for (int e = 0; e < P.n_vexpr; ++e) {
+    P.var_shift[e] = 0.0;
+    if ((P.vexprs[e].flags & VF_SUMD) && P.vexprs[e].n_factors == 0) {
+      int col = -1;
+      for (int c2 = 0; c2 < ncols; ++c2) if (lw.slot_of_col[c2] == P.vexprs[e].slot) col = c2;
+      if (col >= 0) PW_TRY(column_shift(f, col, P.slots[P.vexprs[e].slot], &P.var_shift[e]));
+    }
   }
   if (P.n_acc == 0 && gflags == 0) gflags |= GF_LEN;  // a table needs at least one word per group
   P.gflags = gflags;
@@ -429,7 +522,18 @@ int lower_query(const PwQuery* q, const PwFrame* f, Lowered* L) {
         o.emit.every = (int64_t)acc_init(P.accs[o.emit.acc].op);  // "no non-NaN value seen" marker for floats
         break;
       case PW_COUNT: o.emit.acc = cnt(); break;
-      default: o.emit.acc = acc_of(t.ve, t.kind == PW_FIRST ? VF_FIRST : VF_LAST); break;
+      case PW_FIRST: o.emit.acc = acc_of(t.ve, VF_FIRST); break;
+      case PW_LAST: o.emit.acc = acc_of(t.ve, VF_LAST); break;
+      case PW_FIRST_NON_NULL: o.emit.acc = acc_of(t.ve, VF_FIRST_NN); break;
+      case PW_LAST_NON_NULL: o.emit.acc = acc_of(t.ve, VF_LAST_NN); break;
+      case PW_VAR: case PW_STD: o.emit.acc = acc_of(t.ve, VF_SUMD); o.emit.acc_nn = acc_of(t.ve, VF_SUMD2); o.emit.acc_cnt = cnt(); break;
+      case PW_NULL_COUNT: o.emit.acc = acc_len; o.emit.acc_cnt = t.ve_nullable ? acc_of(t.ve, VF_COUNT) : -1; break;
+      case PW_BIT_AND: o.emit.acc = acc_of(t.ve, VF_AND); o.emit.acc_cnt = cnt(); break;
+      case PW_BIT_OR: o.emit.acc = acc_of(t.ve, VF_OR); o.emit.acc_cnt = cnt(); break;
+      case PW_BIT_XOR: o.emit.acc = acc_of(t.ve, VF_XOR); o.emit.acc_cnt = cnt(); break;
+      case PW_ANY: o.emit.acc = acc_of(t.ve, VF_MAX); break;
+      case PW_ALL: o.emit.acc = acc_of(t.ve, VF_MIN); break;
+      default: return fail(PW_ERR_INVALID, "unknown aggregation kind %d", t.kind);
     }
     L->outs.push_back(o);
   }
@@ -531,7 +635,8 @@ static bool plan_hot_threads(ScanPlan& P, int64_t groups_hint, int requested_gca
   const int kw = padded_kw(P.n_kw);
   const int warps = threads / 32;
   int n_priv64 = 0, n_priv32 = 0, n_mm = 0;
-  auto is_add = [&](int a) { return P.accs[a].op == OP_ADD_F64 || P.accs[a].op == OP_ADD_I64; };
+  // words updated by a plain read-modify-write under exclusive ownership: sums and the bitwise folds
+  auto is_add = [&](int a) { const int op = P.accs[a].op; return op == OP_ADD_F64 || op == OP_ADD_I64 || op == OP_AND_U64 || op == OP_OR_U64 || op == OP_XOR_U64; };
   auto is_count = [&](int a) { return P.accs[a].op == OP_ADD_I64 && (P.accs[a].src == SRC_ONE || P.accs[a].src == SRC_VALID); };
   for (int a = 0; a < P.n_acc; ++a) { if (is_count(a)) n_priv32++; else if (is_add(a)) n_priv64++; else n_mm++; }
   // dense ids: a little head-room over the live-group estimate
@@ -593,16 +698,6 @@ static bool plan_hot_threads(ScanPlan& P, int64_t groups_hint, int requested_gca
     off = (off + 15) & ~(size_t)15; g.mm_off = (int32_t)off; off += (size_t)g.mm_stride * gcap * 8;
     g.count_off = (int32_t)off; off += 32;  // [count, full flag, -, -]
     g.guard_acc = (mmp == 0) ? shadow_acc : -1;
-    // value guard in front of the shadow: needs the counter of non-null values of the shadowed expression (or the row
-    // counter when the expression has no nulls) as a warp-private word
-    g.guard_on = 0; g.guard_cnt = -1;
-    if (g.guard_acc >= 0 && !getenv("PW_NO_GUARD")) {
-      const VExpr& V = P.vexprs[P.accs[g.guard_acc].vexpr];
-      int cnt = -1;
-      if (V.flags & VF_COUNT) { cnt = V.acc_base; for (int b2 = 1; b2 < VF_COUNT; b2 <<= 1) if (V.flags & b2) ++cnt; }
-      else if (P.gflags & GF_LEN) cnt = P.acc_gbase;
-      if (cnt >= 0 && is_count(cnt)) { g.guard_on = 1; g.guard_cnt = cnt; }
-    }
     g.shadow_off = (int32_t)off;
     if (g.guard_acc >= 0) off += (((size_t)gcap * 8) + 15) & ~(size_t)15;
     g.warp_off = (int32_t)off;
@@ -622,10 +717,7 @@ static bool plan_hot_threads(ScanPlan& P, int64_t groups_hint, int requested_gca
       }
     }
     // duplicate rows of a warp instruction: combined in registers through warp votes (no claim byte) unless switched off
-    static const bool no_dedup = getenv("PW_NO_DEDUP") != nullptr;
-    g.dedup = (!no_dedup && R < 32) ? 1 : 0;
-    if (g.dedup) { g.claim_acc = -1; g.claim_off = 0; }
-    else if (g.claim_acc < 0) { g.claim_off = (int32_t)woff; woff += (size_t)gcap * R * 4; }
+    if (g.claim_acc < 0) { g.claim_off = (int32_t)woff; woff += (size_t)gcap * R * 4; }
     woff = (woff + 15) & ~(size_t)15;
     g.warp_bytes = (int32_t)woff;
     g.total_bytes = (int32_t)(off + woff * warps);
@@ -934,12 +1026,24 @@ static void plan_block(const Lowered& L, uint64_t G, size_t header_bytes, BlockL
   size_t total = (header_bytes + 255) / 256 * 256;
   auto place = [&](size_t bytes) { size_t o = total; total += (bytes + 255) / 256 * 256; return o; };
   for (size_t i = 0; i < ncol; ++i) {
-    b->val_bytes[i] = (size_t)G * dtype_bytes(L.outs[i].out_dtype);
+    b->val_bytes[i] = out_col_bytes(L.outs[i].out_dtype, G);
     b->valid_bytes[i] = ((G + 31) / 32) * 4;
     b->val_off[i] = place(b->val_bytes[i]);
     b->valid_off[i] = place(b->valid_bytes[i]);
   }
   b->total = total;
+}
+
+int alloc_result_block(const Lowered& L, uint64_t bound, char** block, bool* fits) {
+  BlockLayout bl;
+  plan_block(L, bound, sizeof(Control), &bl);
+  *fits = bl.total <= STAGING_BYTES && getenv("PW_NO_DEFERRED") == nullptr;
+  *block = nullptr;
+  if (!*fits) return 0;
+  void* p = nullptr;
+  PW_TRY(dev_alloc(&p, bl.total));
+  *block = (char*)p;
+  return 0;
 }
 
 // cache key of the pilot statistics: the key columns (and the window grid) are all the pilot looks at
@@ -1144,8 +1248,11 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
   BlockLayout bl;
   bool deferred = false;
   if (opts && opts->allow_deferred && state && !no_deferred && cap + 2 <= (1u << 16)) {
-    plan_block(L, cap + 2, sizeof(Control), &bl);
-    deferred = bl.total <= STAGING_BYTES;
+    if (opts->control_only) { bl.total = sizeof(Control); deferred = true; }
+    else {
+      plan_block(L, cap + 2, sizeof(Control), &bl);
+      deferred = bl.total <= STAGING_BYTES;
+    }
   }
   char* block = nullptr;
   if (deferred) { void* p = nullptr; PW_TRY(dev_alloc(&p, bl.total)); block = (char*)p; dctl = (Control*)block; }
@@ -1291,7 +1398,7 @@ int emit_results(const Lowered& L, const Table& T, const uint32_t* slot_list, ui
     const Control* hc = (const Control*)h;
     c.timings.spilled_rows = (int64_t)hc->spilled;
     if (hc->overflow == 2) return bail(fail(PW_ERR_UNSUPPORTED, "string key longer than 12 bytes (long views need the data buffers: SURVEY 8f rank 1)"));
-    if (hc->overflow == 1) { dev_free(d_block); state->block = nullptr; return PW_RETRY; }
+    if (hc->overflow == 1 || hc->overflow == 3) { dev_free(d_block); state->block = nullptr; return PW_RETRY; }  // 3: a gathered segment overflowed (pw_partial.cu)
     if (hc->not_sorted) return bail(fail(PW_ERR_NOT_SORTED, "argument in operation 'group_by_dynamic' is not sorted, please sort the 'expr/series/column' first"));
     n_final = hc->counter;
     c.timings.n_groups = (int64_t)n_final;
@@ -1301,7 +1408,7 @@ int emit_results(const Lowered& L, const Table& T, const uint32_t* slot_list, ui
   std::vector<size_t> vb(ncol), qb(ncol);
   std::vector<void*> h_vals(ncol, nullptr), h_valid(ncol, nullptr);
   for (size_t i = 0; i < ncol; ++i) {
-    vb[i] = (size_t)Gf * dtype_bytes(L.outs[i].out_dtype);
+    vb[i] = out_col_bytes(L.outs[i].out_dtype, Gf);
     qb[i] = ((Gf + 31) / 32) * 4;
     h_vals[i] = host_alloc(vb[i]);
     h_valid[i] = host_alloc(qb[i]);

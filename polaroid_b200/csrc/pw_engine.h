@@ -51,6 +51,9 @@ struct FrameColumn {
   int32_t bit_offset = 0;
   void* owned_values = nullptr; // freed with the frame
   void* owned_validity = nullptr;
+  // var/std shift (a sample mean of the column), computed the first time a query needs it (guarded by PwFrame::mu)
+  mutable bool shift_known = false;
+  mutable double var_shift = 0.0;
 };
 
 }  // namespace pw
@@ -117,6 +120,7 @@ int lower_query(const PwQuery* q, const PwFrame* f, Lowered* out);
 struct RunOpts {
   uint64_t min_cap = 0;      // lower bound of the HBM table size (retry after an overflow seen late)
   bool allow_deferred = false;
+  bool control_only = false; // deferred, but the caller does not emit columns: the block is just the control header
 };
 struct RunState {
   bool deferred = false;     // *n_groups_out is the capacity bound, the count is dctl->counter (device)
@@ -131,6 +135,8 @@ int emit_results(const Lowered& L, const Table& T, const uint32_t* slot_list, ui
                  struct ArrowArray* out_cols, struct ArrowSchema* out_schemas, size_t* n_out, RunState* state = nullptr);
 void free_table(Table& T);
 int alloc_table_raw(Table* T, int n_kw, int n_acc, uint64_t cap, int32_t* overflow, unsigned long long* spilled);
+// deferred result block for `bound` result rows: [Control | columns]; *fits = false when it would not fit the staging copy
+int alloc_result_block(const Lowered& L, uint64_t bound, char** block, bool* fits);
 int order_groups(const Lowered& L, const Table& T, int kw, uint32_t** slots_io, uint64_t G, const unsigned long long* g_dev = nullptr);
 
 // segmented (sorted-run) dynamic path, pw_segmented.cu

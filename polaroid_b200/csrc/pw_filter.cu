@@ -33,7 +33,7 @@ __device__ __forceinline__ bool eval_preds(const PredPlan& pp, int64_t row) {
   for (int q = 0; q < pp.n_preds; ++q) {
     const RawSlot& s = pp.slot[q];
     const bool ok = load_valid_pair(s, row, row + 1) & 1u;
-    const uint64_t v = decode(load_pair(s.values, s.dtype, row, row + 1, false), s.dtype, 0);
+    const uint64_t v = decode(load_row(s, row), s.dtype, 0);
     alive = alive && ok && compare(v, pp.pred[q].scalar, pp.pred[q].cls, pp.pred[q].op);
   }
   return alive;

@@ -123,7 +123,11 @@ static __global__ void gather_u32_kernel(const uint32_t* src, const uint32_t* id
 // ---- emission -----------------------------------------------------------------------------------------
 enum EmitKind : int32_t {
   EMIT_KEY_INT = 0, EMIT_KEY_VIEW, EMIT_SUM_INT, EMIT_SUM_F64, EMIT_MEAN, EMIT_MINMAX_INT, EMIT_MINMAX_F64,
-  EMIT_COUNT, EMIT_FIRSTLAST, EMIT_DYN_LOWER, EMIT_DYN_UPPER, EMIT_ACC_I64
+  EMIT_COUNT, EMIT_FIRSTLAST, EMIT_DYN_LOWER, EMIT_DYN_UPPER, EMIT_ACC_I64,
+  EMIT_VAR,         // acc = sum of d, acc_nn = sum of d*d, acc_cnt = count; pad = ddof, mean_out = MEAN_F64/MEAN_F32, src_cls = 1 -> std
+  EMIT_NULL_COUNT,  // acc = row counter, acc_cnt = non-null counter (-1: the column has no nulls)
+  EMIT_BITWISE,     // acc = and/or/xor word, acc_cnt = non-null counter: all-null group -> null (reduce/bitwise.rs)
+  EMIT_ANYALL       // acc = max / min word over 0/1: never null (reduce/any_all.rs, ignore_nulls)
 };
 enum MeanOut : int32_t { MEAN_F64 = 0, MEAN_F32, MEAN_DATE_US, MEAN_I64 };
 
@@ -145,8 +149,10 @@ struct EmitDesc {
   unsigned long long* null_count;
 };
 
+// DT_BOOL results are bit-packed by the caller (emit_kernel: one ballot per warp), not stored here
 __device__ __forceinline__ void store_typed(void* base, uint64_t i, int dt, uint64_t bits) {
   switch (dt) {
+    case DT_BOOL: break;
     case DT_I8: case DT_U8: ((uint8_t*)base)[i] = (uint8_t)bits; break;
     case DT_I16: case DT_U16: ((uint16_t*)base)[i] = (uint16_t)bits; break;
     case DT_I32: case DT_U32: ((uint32_t*)base)[i] = (uint32_t)bits; break;
@@ -170,6 +176,7 @@ static __global__ void emit_kernel(Table T, int n_kw, const __grid_constant__ Em
     n = cnt < n ? cnt : n;
   }
   bool valid = true;
+  uint64_t bval = 0;  // the value when the output column is Boolean (bit-packed below)
   if (i < n) {
     const uint64_t slot = slot_list[i];
     uint64_t bits = 0;
@@ -177,6 +184,7 @@ static __global__ void emit_kernel(Table T, int n_kw, const __grid_constant__ Em
       case EMIT_KEY_INT:
         valid = !key_is_null(T, n_kw, slot, d.null_word, d.nullbit, d.single_key_null);
         bits = valid ? tkey(T, d.word, slot) : 0;
+        bval = bits;
         store_typed(d.out_values, i, d.out_dtype, bits);
         break;
       case EMIT_KEY_VIEW: {
@@ -207,10 +215,30 @@ static __global__ void emit_kernel(Table T, int n_kw, const __grid_constant__ Em
           default: ((int64_t*)d.out_values)[i] = (int64_t)m; break;
         }
         break; }
-      case EMIT_MINMAX_INT:
+      case EMIT_MINMAX_INT: case EMIT_BITWISE:
         valid = tacc(T, d.acc_cnt, slot) != 0;
-        store_typed(d.out_values, i, d.out_dtype, valid ? tacc(T, d.acc, slot) : 0);
+        bval = valid ? tacc(T, d.acc, slot) : 0;
+        store_typed(d.out_values, i, d.out_dtype, bval);
         break;
+      case EMIT_ANYALL:
+        bval = tacc(T, d.acc, slot) & 1ull;   // all: the MIN word's init (all ones) reads as true; any: MAX's init 0 as false
+        break;
+      case EMIT_NULL_COUNT:
+        ((uint32_t*)d.out_values)[i] = d.acc_cnt >= 0 ? (uint32_t)(tacc(T, d.acc, slot) - tacc(T, d.acc_cnt, slot)) : 0u;
+        break;
+      case EMIT_VAR: {
+        // var = (sum d^2 - (sum d)^2 / n) / (n - ddof) over d = x - shift; n <= ddof -> null (moment.rs:126-133)
+        const double cnt = (double)tacc(T, d.acc_cnt, slot);
+        valid = cnt > (double)d.pad;
+        double out = 0.0;
+        if (valid) {
+          const double s1 = __longlong_as_double((long long)tacc(T, d.acc, slot)), s2 = __longlong_as_double((long long)tacc(T, d.acc_nn, slot));
+          double var = (s2 - s1 * s1 / cnt) / (cnt - (double)d.pad);
+          if (var < 0.0) var = 0.0;   // rounding can leave a tiny negative residue for constant groups
+          out = d.src_cls == 1 ? sqrt(var) : var;
+        }
+        if (d.mean_out == MEAN_F32) ((float*)d.out_values)[i] = (float)out; else ((double*)d.out_values)[i] = out;
+        break; }
       case EMIT_MINMAX_F64: {
         valid = tacc(T, d.acc_cnt, slot) != 0;
         // the ordered image of a real value never equals the init sentinel (INT64_MAX/MIN map to NaN payloads)
@@ -225,15 +253,17 @@ static __global__ void emit_kernel(Table T, int n_kw, const __grid_constant__ Em
       case EMIT_FIRSTLAST: {
         const uint64_t packed = tacc(T, d.acc, slot);
         valid = packed & 1ull;
+        if (d.period == 1 && packed == (uint64_t)d.every) valid = false;  // ignore_nulls form: the word never left its init value
         const int64_t row = (int64_t)(packed >> 1) - d.row_offset;
         uint64_t b = 0;
         if (valid) {
           if (d.fl_values) b = d.fl_values[slot];
           else {
-            uint4 r = load_pair(d.src, row, row + 1, false);  // scalar path, row only
+            uint4 r = load_row(d.src, row);  // scalar path, row only
             b = decode(r, d.src.dtype, 0);
           }
         }
+        bval = b;
         store_typed(d.out_values, i, d.out_dtype, b);
         break; }
       case EMIT_DYN_LOWER: case EMIT_DYN_UPPER: {
@@ -242,6 +272,10 @@ static __global__ void emit_kernel(Table T, int n_kw, const __grid_constant__ Em
         store_typed(d.out_values, i, d.out_dtype, (uint64_t)t);
         break; }
     }
+  }
+  if (d.out_dtype == DT_BOOL) {   // Boolean column: LSB-first bitmap, one word per warp
+    const uint32_t bm = __ballot_sync(0xffffffffu, i < n && valid && (bval & 1ull));
+    if ((threadIdx.x & 31) == 0 && i < n) ((uint32_t*)d.out_values)[i >> 5] = bm;
   }
   if (d.out_validity) {
     const uint32_t m = __ballot_sync(0xffffffffu, valid && i < n);

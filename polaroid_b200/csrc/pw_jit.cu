@@ -163,9 +163,6 @@ std::string jit_ctl(const ScanPlan& P) {
   g.scalar("bool", "h_dense", P.hot.dense != 0);
   g.scalar("bool", "h_dense_sentinels", P.hot.dense == 2);
   g.scalar("int", "h_guard_acc", P.hot.guard_acc);
-  g.scalar("bool", "h_dedup", P.hot.dedup != 0);
-  g.scalar("bool", "h_guard_on", P.hot.guard_on != 0);
-  g.scalar("int", "h_guard_cnt", P.hot.guard_cnt);
   g.scalar("int", "h_shadow_off", P.hot.shadow_off);
   g.scalar("int", "h_mm_stride", P.hot.mm_stride > 0 ? P.hot.mm_stride : 1);
   g.scalar("bool", "group_out", P.row_group_out != nullptr);

@@ -74,16 +74,23 @@ static __global__ void export_kernel(Table T, PackLayout pl, const uint32_t* slo
     uint64_t bits = 0;
     if (packed & 1ull) {
       const int64_t row = (int64_t)(packed >> 1) - row_offset;
-      bits = decode(load_pair(pl.fl_src[f].values, pl.fl_src[f].dtype, row, row + 1, false), pl.fl_src[f].dtype, 0);
+      bits = decode(load_row(pl.fl_src[f], row), pl.fl_src[f].dtype, 0);
     }
     r[1 + pl.kw + pl.n_acc + f] = bits;
   }
 }
 
 // small-result exchange: rows go straight into the caller's send buffer, unsorted, each tagged with its owner
+// ctl (optional): the group count is still on the device (deferred run): n is the capacity of the send buffer, the count
+// comes from ctl->counter; a count beyond the capacity — or a scan that overflowed its table — writes the overflow header
 static __global__ void export_gather_kernel(Table T, PackLayout pl, const uint32_t* slot_list, uint64_t n, int n_parts, int64_t row_offset,
-                                            uint64_t* buf, uint64_t header) {
+                                            uint64_t* buf, uint64_t header, const Control* ctl = nullptr) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ctl) {
+    const uint64_t cnt = ctl->counter;
+    header = (cnt > n || ctl->overflow != 0 || ctl->not_sorted != 0) ? ~0ull : cnt;
+    n = cnt < n ? cnt : n;
+  }
   if (i == 0) buf[0] = header;
   if (i >= n || header == ~0ull) return;
   const uint64_t slot = slot_list[i];
@@ -99,7 +106,7 @@ static __global__ void export_gather_kernel(Table T, PackLayout pl, const uint32
     uint64_t bits = 0;
     if (packed & 1ull) {
       const int64_t row = (int64_t)(packed >> 1) - row_offset;
-      bits = decode(load_pair(pl.fl_src[f].values, pl.fl_src[f].dtype, row, row + 1, false), pl.fl_src[f].dtype, 0);
+      bits = decode(load_row(pl.fl_src[f], row), pl.fl_src[f].dtype, 0);
     }
     r[2 + pl.kw + pl.n_acc + f] = bits;
   }
@@ -273,16 +280,28 @@ int pw_b200_frame_groupby_partial_into(const PwQuery* q, const PwFrame* frame, i
   Table T{};
   uint32_t* slots = nullptr;
   uint64_t G = 0;
-  PW_TRY(run_groupby(q, frame, L, &T, &slots, &G));
+  RunOpts ro;
+  ro.allow_deferred = true; ro.control_only = true;   // small tables: the count never visits the host
+  RunState rs;
+  PW_TRY(run_groupby(q, frame, L, &T, &slots, &G, &ro, &rs));
   PackLayout pl = make_layout(L, kw_class(L.plan.n_kw));
-  const bool fits = G <= (uint64_t)cap_rows;
-  const uint64_t n = fits ? G : 0;
-  export_gather_kernel<<<(int)std::max<uint64_t>(1, (n + 255) / 256), 256, 0, c.stream>>>(T, pl, slots, n, n_parts, q->row_offset, (uint64_t*)send_device,
-                                                                                          fits ? G : GATHER_OVERFLOW);
-  PW_CUDA(cudaGetLastError());
+  bool fits = true;
+  if (rs.deferred) {
+    const uint64_t n = std::min<uint64_t>(G, (uint64_t)cap_rows);   // G = the table's capacity bound
+    export_gather_kernel<<<(int)std::max<uint64_t>(1, (n + 255) / 256), 256, 0, c.stream>>>(T, pl, slots, (uint64_t)cap_rows, n_parts, q->row_offset,
+                                                                                            (uint64_t*)send_device, 0, rs.dctl);
+    PW_CUDA(cudaGetLastError());
+    dev_free(rs.block);
+  } else {
+    fits = G <= (uint64_t)cap_rows;
+    const uint64_t n = fits ? G : 0;
+    export_gather_kernel<<<(int)std::max<uint64_t>(1, (n + 255) / 256), 256, 0, c.stream>>>(T, pl, slots, n, n_parts, q->row_offset, (uint64_t*)send_device,
+                                                                                            fits ? G : GATHER_OVERFLOW);
+    PW_CUDA(cudaGetLastError());
+    float ms;
+    if (cudaEventElapsedTime(&ms, c.ev[8], c.ev[9]) == cudaSuccess) c.timings.scan_kernel_ms = ms;
+  }
   c.timings.kernel_launches++;
-  float ms;
-  if (cudaEventElapsedTime(&ms, c.ev[8], c.ev[9]) == cudaSuccess) c.timings.scan_kernel_ms = ms;
   dev_free(slots);
   free_table(T);
   return fits ? 0 : 1;
@@ -300,7 +319,12 @@ int pw_b200_merge_gathered(const PwQuery* q, const PwFrame* schema_from, const v
   src.seg_words = 1 + (uint64_t)cap_rows * (uint64_t)(rw + 1);
   src.cap_rows = (uint64_t)cap_rows;
   src.gathered = 1; src.my_rank = my_rank;
-  return merge_impl(q, schema_from, src, (int64_t)world * cap_rows, (uint64_t)std::max<int64_t>(4 * cap_rows, 64), out_cols, out_schemas, n_out);
+  const int rc = merge_impl(q, schema_from, src, (int64_t)world * cap_rows, (uint64_t)std::max<int64_t>(4 * cap_rows, 64), out_cols, out_schemas, n_out);
+  // the local scan of this exchange (pw_b200_frame_groupby_partial_into, deferred) has finished by now: its kernel time
+  ThreadCtx& c = ctx();
+  float ms;
+  if (cudaEventElapsedTime(&ms, c.ev[8], c.ev[9]) == cudaSuccess) c.timings.scan_kernel_ms = ms;
+  return rc;
 }
 
 // returns 0, an error, or 1 = "repeat through the general exchange" (gathered input only: a rank overflowed its
@@ -312,24 +336,31 @@ static int merge_impl(const PwQuery* q, const PwFrame* schema_from, RowSrc src, 
   PW_TRY(lower_query(q, schema_from, &L));
   const int kw = kw_class(L.plan.n_kw);
   PackLayout pl = make_layout(L, kw);
-  struct Ctl { int32_t overflow; int32_t pad; unsigned long long spilled; unsigned long long counter; } hctl{};
-  Ctl* dctl = nullptr;
-  void* v = nullptr;
-  PW_TRY(dev_alloc(&v, sizeof(Ctl))); dctl = (Ctl*)v;
-  PW_CUDA(cudaMemsetAsync(dctl, 0, sizeof(Ctl), c.stream));
-  Table T{};
   const uint64_t nn = cap + 2;
-  PW_TRY(alloc_table_raw(&T, kw, L.plan.n_acc, cap, &dctl->overflow, &dctl->spilled));
+  // Small merge tables keep the group count on the device: the control block is the header of the result block and
+  // the whole merge (upsert, compaction, ordering, emission, copy) needs ONE host synchronisation (emit_results).
+  char* block = nullptr;
+  bool deferred = false;
+  PW_TRY(alloc_result_block(L, nn, &block, &deferred));
+  Control* dctl = nullptr;
+  void* v = nullptr;
+  if (deferred) dctl = (Control*)block;
+  else { PW_TRY(dev_alloc(&v, sizeof(Control))); dctl = (Control*)v; }
+  Table T{};
+  uint32_t *row_slot = nullptr, *slots = nullptr;
+  uint64_t* fl_values = nullptr;
+  auto drop = [&]() { dev_free(slots); dev_free(row_slot); dev_free(fl_values); if (T.keys) free_table(T); };
+  int rc = alloc_table_raw(&T, kw, L.plan.n_acc, cap, &dctl->overflow, &dctl->spilled);
+  if (rc) { dev_free(deferred ? (void*)block : (void*)dctl); return rc; }
   AccOps ops{};
   AccOpsK opsk{};
   ops.n = opsk.n = L.plan.n_acc;
   for (int a = 0; a < L.plan.n_acc; ++a) ops.op[a] = opsk.op[a] = L.plan.accs[a].op;
-  table_init_kernel<<<(int)std::min<uint64_t>((nn + 255) / 256, 148 * 8), 256, 0, c.stream>>>(T, kw, ops);
-  PW_CUDA(cudaGetLastError());
-  uint32_t* row_slot = nullptr;
-  uint64_t* fl_values = nullptr;
-  PW_TRY(dev_alloc(&v, (size_t)std::max<int64_t>(n_rows, 1) * 4)); row_slot = (uint32_t*)v;
-  PW_TRY(dev_alloc(&v, nn * 8 * (uint64_t)std::max(1, pl.n_fl))); fl_values = (uint64_t*)v;
+  table_init_kernel<<<(int)std::min<uint64_t>((nn + 255) / 256, 148 * 8), 256, 0, c.stream>>>(T, kw, ops, dctl);  // clears the control block too
+  if ((rc = dev_alloc(&v, (size_t)std::max<int64_t>(n_rows, 1) * 4)) == 0) row_slot = (uint32_t*)v;
+  if (!rc && (rc = dev_alloc(&v, nn * 8 * (uint64_t)std::max(1, pl.n_fl))) == 0) fl_values = (uint64_t*)v;
+  if (!rc && (rc = dev_alloc(&v, nn * 4)) == 0) slots = (uint32_t*)v;
+  if (rc) { drop(); dev_free(deferred ? (void*)block : (void*)dctl); return rc; }
   if (n_rows) {
     const int grid = (int)((n_rows + 255) / 256);
     switch (kw) {
@@ -338,37 +369,43 @@ static int merge_impl(const PwQuery* q, const PwFrame* schema_from, RowSrc src, 
       case 4: merge_kernel<4><<<grid, 256, 0, c.stream>>>(T, pl, opsk, src, (uint64_t)n_rows, row_slot); break;
       default: merge_kernel<6><<<grid, 256, 0, c.stream>>>(T, pl, opsk, src, (uint64_t)n_rows, row_slot); break;
     }
-    PW_CUDA(cudaGetLastError());
-    if (pl.n_fl) {
-      merge_values_kernel<<<grid, 256, 0, c.stream>>>(T, pl, src, (uint64_t)n_rows, row_slot, fl_values);
-      PW_CUDA(cudaGetLastError());
-    }
+    if (pl.n_fl) merge_values_kernel<<<grid, 256, 0, c.stream>>>(T, pl, src, (uint64_t)n_rows, row_slot, fl_values);
     c.timings.kernel_launches += 3;
   }
   // compact + order + emit (first/last values come from fl_values instead of a column gather)
-  uint32_t* slots = nullptr;
-  PW_TRY(dev_alloc(&v, nn * 4)); slots = (uint32_t*)v;
   compact_kernel<<<(int)std::min<uint64_t>((nn + 255) / 256, 148 * 8), 256, 0, c.stream>>>(T, kw, slots, &dctl->counter);
-  PW_CUDA(cudaGetLastError());
-  PW_CUDA(cudaMemcpyAsync(&hctl, dctl, sizeof(Ctl), cudaMemcpyDeviceToHost, c.stream));
-  PW_CUDA(cudaStreamSynchronize(c.stream));
-  if (hctl.overflow) {
-    dev_free(slots); dev_free(row_slot); dev_free(fl_values); dev_free(dctl);
-    free_table(T);
-    if (src.gathered) return 1;
-    return fail(PW_ERR_INTERNAL, "merge table overflow");
-  }
-  const uint64_t G = hctl.counter;
-  PW_TRY(order_groups(L, T, kw, &slots, G));
+  if (cudaGetLastError() != cudaSuccess) { drop(); dev_free(deferred ? (void*)block : (void*)dctl); return fail(PW_ERR_CUDA, "merge launch failed"); }
   int f_idx = 0;
   for (OutCol& o : L.outs)
     if (o.emit.kind == EMIT_FIRSTLAST) {
       for (int f = 0; f < pl.n_fl; ++f) if (pl.fl_acc[f] == o.emit.acc) f_idx = f;
       o.emit.fl_values = fl_values + (uint64_t)f_idx * nn;
     }
-  int rc = emit_results(L, T, slots, G, out_cols, out_schemas, n_out);
-  dev_free(slots); dev_free(row_slot); dev_free(fl_values); dev_free(dctl);
-  free_table(T);
+  if (deferred) {
+    RunState rs;
+    rs.deferred = true; rs.dctl = dctl; rs.block = block; rs.cap = cap;
+    rc = order_groups(L, T, kw, &slots, nn, &dctl->counter);
+    if (rc) { drop(); dev_free(block); return rc; }
+    rc = emit_results(L, T, slots, nn, out_cols, out_schemas, n_out, &rs);   // frees the block; PW_RETRY on overflow
+    drop();
+    if (rc == PW_RETRY) return src.gathered ? 1 : fail(PW_ERR_INTERNAL, "merge table overflow");
+    return rc;
+  }
+  Control hctl{};
+  if (cudaMemcpyAsync(&hctl, dctl, sizeof(Control), cudaMemcpyDeviceToHost, c.stream) != cudaSuccess || cudaStreamSynchronize(c.stream) != cudaSuccess) {
+    drop(); dev_free(dctl);
+    return fail(PW_ERR_CUDA, "merge failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  dev_free(dctl);
+  if (hctl.overflow) {
+    drop();
+    if (src.gathered) return 1;
+    return fail(PW_ERR_INTERNAL, "merge table overflow");
+  }
+  const uint64_t G = hctl.counter;
+  rc = order_groups(L, T, kw, &slots, G);
+  if (!rc) rc = emit_results(L, T, slots, G, out_cols, out_schemas, n_out);
+  drop();
   return rc;
 }
 

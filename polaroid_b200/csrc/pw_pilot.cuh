@@ -76,7 +76,7 @@ __device__ __forceinline__ void pilot_body(const ScanPlan& P, const PilotParams&
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       if (c < CT::n_slots(P)) {
-        raw[c] = load_pair(P.slots[c].values, CT::slot_dtype(P, c), p, n, false, rb, rs);
+        raw[c] = CT::slot_dtype(P, c) == DT_BOOL ? load_bool_pair(P.slots[c], p, n, rb, rs) : load_pair(P.slots[c].values, CT::slot_dtype(P, c), p, n, false, rb, rs);
         vbits[c] = CT::slot_nullable(P, c) ? load_valid_pair(P.slots[c], p, n, rb, rs) : 3u;
       } else { raw[c] = make_uint4(0u, 0u, 0u, 0u); vbits[c] = 0u; }
     }

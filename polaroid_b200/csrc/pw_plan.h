@@ -35,7 +35,7 @@ enum ValClass : int32_t { CLS_I64 = 0, CLS_U64 = 1, CLS_F64 = 2 };
 
 // accumulator ops: every one is a native 64-bit atomic on sm_100a (global) and an associative,
 // commutative merge, which is what makes partial aggregates exchangeable.
-enum AccOp : int32_t { OP_ADD_F64 = 0, OP_ADD_I64, OP_MIN_I64, OP_MAX_I64, OP_MIN_U64, OP_MAX_U64 };
+enum AccOp : int32_t { OP_ADD_F64 = 0, OP_ADD_I64, OP_MIN_I64, OP_MAX_I64, OP_MIN_U64, OP_MAX_U64, OP_AND_U64, OP_OR_U64, OP_XOR_U64 };
 // what a row contributes to an accumulator
 enum AccSrc : int32_t {
   SRC_BITS = 0,   // raw 64-bit value (int sum / int min / int max); skipped when null
@@ -46,7 +46,10 @@ enum AccSrc : int32_t {
   SRC_ONE,        // 1 per row (len)
   SRC_ROWIDX,     // (global_row << 1) | valid   (first = MIN, last = MAX; nulls included)
   SRC_ROW,        // global row index (group first occurrence for maintain_order / key gather)
-  SRC_INDEX_T     // the dynamic index value itself (label = datapoint -> MIN_I64)
+  SRC_INDEX_T,    // the dynamic index value itself (label = datapoint -> MIN_I64)
+  SRC_F64_D,      // value - shift as f64 (var/std: shifted sum)
+  SRC_F64_D2,     // (value - shift)^2 (var/std: shifted sum of squares)
+  SRC_ROWIDX_NN   // (global_row << 1) | 1, non-null rows only (first/last with ignore_nulls)
 };
 
 constexpr int MAX_SLOTS = 12;  // raw column slots
@@ -84,7 +87,14 @@ enum VFlag : int32_t {
   VF_SUM_F = 2,   // ADD_F64 of the value as f64 (f64 sum, mean numerator)
   VF_COUNT = 4,   // ADD_I64 of "non-null" (only when the expression is nullable; otherwise GF_LEN is shared)
   VF_MIN = 8, VF_MAX = 16,      // class-dependent: ordered-f64 / i64 / u64
-  VF_FIRST = 32, VF_LAST = 64   // MIN/MAX_U64 over (global_row << 1 | valid)
+  VF_FIRST = 32, VF_LAST = 64,  // MIN/MAX_U64 over (global_row << 1 | valid)
+  // var / std (reduce/var_std.rs keeps Welford's (weight, mean, dp); here, so that the state stays a set of words with
+  // a commutative atomic op: count + sum of d + sum of d*d with d = value - shift, shift = a sample mean of the
+  // column (ScanPlan::var_shift) — the textbook shifted-data algorithm, which removes the cancellation of the plain
+  // sum-of-squares form as long as the shift is within a few standard deviations of the group means)
+  VF_SUMD = 128, VF_SUMD2 = 256,
+  VF_FIRST_NN = 512, VF_LAST_NN = 1024,   // MIN/MAX_U64 over (global_row << 1 | 1), non-null rows only
+  VF_AND = 2048, VF_OR = 4096, VF_XOR = 8192
 };
 enum GFlag : int32_t { GF_LEN = 1, GF_ROW = 2, GF_TMIN = 4 };  // per-group words not tied to a value expression
 struct VExpr {
@@ -174,12 +184,8 @@ struct HotGeom {
                        // 2 = the range contains -1 / -2, whose bit patterns are the table's key sentinels
   int32_t guard_acc;   // min word of the CTA-shared (min, max) pair that has a 32-bit shadow, -1 = none
   int32_t shadow_off;  // byte offset of the shadow array (int2 per id)
-  int32_t dedup;       // != 0: rows of one warp instruction that hit the same private cell are found with warp votes over the
-                       // bits of the dense id and COMBINED in registers (the lowest lane does one plain read-modify-write):
-                       // no claim byte, no retry rounds (pw_scan.cuh, VoteSink)
+  int32_t pad4;
   int32_t threads;     // CTA size the geometry was planned for (warp-private regions = threads / 32)
-  int32_t guard_on;    // != 0: per-warp value guard in front of the shadow (HotTable::guard_snapshot)
-  int32_t guard_cnt;   // private 32-bit counter that tells whether a warp has fed a value of the shadowed expression into an id
   int32_t acc_kind[MAX_ACC];
   int32_t acc_off[MAX_ACC];  // HOT_SHARED_MM: word inside the group's min/max block; private kinds: byte offset inside the warp region
 };
@@ -208,6 +214,7 @@ struct ScanPlan {
   uint32_t* row_group_out; // [n_rows] or nullptr
   const uint32_t* slot_rank; // [cap + 2] rank of every occupied slot in the ordered group list
   int64_t dense_min;       // hot.dense: key value of dense id 0 (data, not part of the JIT shape)
+  double var_shift[MAX_VEXPR];  // per value expression: the shift of its var/std words (data, not part of the JIT shape)
   // Partitioned input (high-cardinality path, pw_partition.cuh): the scan runs over a temporary frame whose rows were
   // scattered into key-hash partitions.  Every slot of that frame is a 64-bit word column; the extra slot
   // `rowid_slot_p1 - 1` holds (original row << 8) | validity bit of every slot.  0 = plain input.
@@ -233,8 +240,8 @@ __host__ __device__ inline uint64_t acc_init(int32_t op) {
   switch (op) {
     case OP_MIN_I64: return 0x7FFFFFFFFFFFFFFFull;
     case OP_MAX_I64: return 0x8000000000000000ull;
-    case OP_MIN_U64: return 0xFFFFFFFFFFFFFFFFull;
-    default: return 0ull;  // ADD_*, MAX_U64
+    case OP_MIN_U64: case OP_AND_U64: return 0xFFFFFFFFFFFFFFFFull;
+    default: return 0ull;  // ADD_*, MAX_U64, OR, XOR
   }
 }
 

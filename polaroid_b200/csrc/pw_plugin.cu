@@ -133,7 +133,7 @@ int query_from_kwargs(const uint8_t* kw, size_t n, QueryHolder* h) {
   if (const PV* v = root.get("keys")) for (const PV& k : v->items) h->keys.push_back((int)k.i);
   if (const PV* v = root.get("aggs")) {
     h->names.reserve(v->items.size());
-    for (const PV& a : v->items) {  // (name, kind, column | None, [(a, b, column), ...] | None)
+    for (const PV& a : v->items) {  // (name, kind, column | None, [(a, b, column), ...] | None[, ddof])
       if (a.items.size() < 3) return fail(PW_ERR_INVALID, "kwargs.aggs: expected (name, kind, column[, factors])");
       PwAgg g{};
       h->names.push_back(a.items[0].s);
@@ -148,6 +148,7 @@ int query_from_kwargs(const uint8_t* kw, size_t n, QueryHolder* h) {
         }
         if (g.n_factors) g.column = -1;
       }
+      if (a.items.size() > 4 && a.items[4].kind == PV::INT) g.ddof = (int)a.items[4].i;   // var / std
       h->aggs.push_back(g);
     }
     for (size_t i = 0; i < h->aggs.size(); ++i) h->aggs[i].name = h->names[i].c_str();

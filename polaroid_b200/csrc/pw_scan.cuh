@@ -127,6 +127,9 @@ __device__ __forceinline__ uint64_t acc_combine(int op, uint64_t a, uint64_t b) 
     case OP_MIN_I64: return (int64_t)b < (int64_t)a ? b : a;
     case OP_MAX_I64: return (int64_t)b > (int64_t)a ? b : a;
     case OP_MIN_U64: return b < a ? b : a;
+    case OP_AND_U64: return a & b;
+    case OP_OR_U64: return a | b;
+    case OP_XOR_U64: return a ^ b;
     default: return b > a ? b : a;
   }
 }
@@ -137,6 +140,9 @@ __device__ __forceinline__ void acc_apply_global(uint64_t* p, int op, uint64_t x
     case OP_MIN_I64: if ((long long)x < (long long)__ldcg((const unsigned long long*)p)) atomicMin((long long*)p, (long long)x); break;
     case OP_MAX_I64: if ((long long)x > (long long)__ldcg((const unsigned long long*)p)) atomicMax((long long*)p, (long long)x); break;
     case OP_MIN_U64: if (x < __ldcg((const unsigned long long*)p)) atomicMin((unsigned long long*)p, (unsigned long long)x); break;
+    case OP_AND_U64: atomicAnd((unsigned long long*)p, (unsigned long long)x); break;
+    case OP_OR_U64: atomicOr((unsigned long long*)p, (unsigned long long)x); break;
+    case OP_XOR_U64: atomicXor((unsigned long long*)p, (unsigned long long)x); break;
     default: if (x > __ldcg((const unsigned long long*)p)) atomicMax((unsigned long long*)p, (unsigned long long)x); break;
   }
 }
@@ -238,77 +244,7 @@ struct HotTable {
   // reads 8 bytes and does two 32-bit compares instead of 16 bytes and two 64-bit compares; the rare row takes the
   // exact path and tightens the shadow with native 32-bit shared-memory atomics.
   int2* shadow;
-  // VALUE GUARD in front of the shadow (registers, per warp).  Most rows of a steady-state group set lie strictly
-  // between the largest group minimum and the smallest group maximum; for those even the 8-byte shadow read (a random
-  // shared-memory access: ~6 wavefronts per warp instruction, 18 % of this kernel's shared-memory traffic on C2) is
-  // wasted.  A single CTA-wide interval was tried in round 1 and lost because every row paid for ids that had not
-  // settled yet; here the interval only speaks for ids this warp has itself fed before the last snapshot:
-  //   snapshot (between the two CTA barriers of an eviction check, every warp for itself): g_lo / g_hi = max of the
-  //     shadow minima / min of the shadow maxima over every id that has a shadow, and a bitmap of the ids whose
-  //     shadow exists AND whose private value counter of this warp is non-zero ("covered").
-  //   row: covered id and g_lo < hi(x) < g_hi  ->  the row cannot improve an extremum, skip the shadow read.
-  // Shadows only tighten between snapshots and a covered id was part of the snapshot, so the test stays on the safe
-  // side; ids that appear later, NaN-only ids and ids this warp has not fed are not covered and read their shadow.
-  int g_lo, g_hi;
-  uint32_t cov[4];  // bit (id & 31) of word (id >> 5): lane (id >> 5) & 31 holds it in cov[id >> 10]
-  __device__ __forceinline__ void guard_reset() {
-    g_lo = 0x7FFFFFFF; g_hi = (int)0x80000000;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) cov[k] = 0u;
-  }
-  __device__ __forceinline__ void guard_snapshot(const ScanPlan& P, int lane) {
-    const int G = CT::h_gcap(P), R = CT::h_rep(P);
-    const uint32_t* cnt = (const uint32_t*)(wbase + CT::h_off(P, CT::h_guard_cnt(P)));
-    int lo = (int)0x80000000, hi = 0x7FFFFFFF;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      uint32_t mine = 0u;
-      if (k * 1024 < G) {
-        for (int j = 0; j < 32; ++j) {
-          const int idx = (k * 32 + j) * 32 + lane;
-          bool c = false;
-          if (idx < G) {
-            int2 sh;
-            sh.x = *(volatile int*)&shadow[idx].x;
-            sh.y = *(volatile int*)&shadow[idx].y;
-            if (sh.x != 0x7FFFFFFF) {   // the id has a shadow
-              lo = sh.x > lo ? sh.x : lo;
-              hi = sh.y < hi ? sh.y : hi;
-              uint32_t fed = 0u;
-              for (int r = 0; r < R; ++r) fed |= cnt[(size_t)idx * R + r];
-              c = (fed & (CT::h_guard_cnt(P) == CT::h_claim_acc(P) ? 0x00FFFFFFu : 0xFFFFFFFFu)) != 0u;  // claim byte on top
-            }
-          }
-          const uint32_t b = __ballot_sync(0xffffffffu, c);
-          if (lane == j) mine = b;
-          if ((k * 32 + j + 1) * 32 >= G) break;
-        }
-      }
-      cov[k] = mine;
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      const int l2 = __shfl_xor_sync(0xffffffffu, lo, d), h2 = __shfl_xor_sync(0xffffffffu, hi, d);
-      lo = l2 > lo ? l2 : lo;
-      hi = h2 < hi ? h2 : hi;
-    }
-    g_lo = lo; g_hi = hi;
-  }
-  // may the row (id, high word xh of its value image in the shadow's signed domain) skip the shadow?  Convergent.
-  __device__ __forceinline__ bool guard_skips(const ScanPlan& P, int id, int32_t xh) const {
-    const int wi = id >> 5;
-    uint32_t w = __shfl_sync(0xffffffffu, cov[0], wi & 31);
-    if (CT::h_gcap(P) > 1024) {
-#pragma unroll
-      for (int k = 1; k < 4; ++k) {
-        const uint32_t wk = __shfl_sync(0xffffffffu, cov[k], wi & 31);
-        if (k * 1024 < CT::h_gcap(P) && (wi >> 5) == k) w = wk;
-      }
-    }
-    return id >= 0 && ((w >> (id & 31)) & 1u) && xh > g_lo && xh < g_hi;
-  }
   __device__ __forceinline__ void bind(unsigned char* smem, const ScanPlan& P, int warp) {
-    guard_reset();
     tag = (uint32_t*)smem;
     keys = (uint64_t*)(smem + CT::h_keys_off(P));
     mm = (uint64_t*)(smem + CT::h_mm_off(P));
@@ -488,6 +424,7 @@ __device__ __forceinline__ int dtype_width(int dt) {
     case DT_I16: case DT_U16: return 2;
     case DT_I32: case DT_U32: case DT_F32: return 4;
     case DT_VIEW: case DT_VIEW_HI: return 16;
+    case DT_BOOL: return 0;  // bit-packed: see load_bool_pair
     default: return 8;
   }
 }
@@ -542,6 +479,23 @@ __device__ __forceinline__ uint4 load_pair(const RawSlot& s, int64_t p, int64_t 
   return load_pair(s.values, s.dtype, p, n_rows, full, rb, rs);
 }
 
+// boolean VALUES are bit-packed like validity (LSB first, same bit offset as the column's validity): rows p, p+1 -> bit0, bit1
+__device__ __forceinline__ uint4 load_bool_pair(const RawSlot& s, int64_t p, int64_t n_rows, int64_t rb = 0, int64_t rs = 1) {
+  uint4 r = make_uint4(0u, 0u, 0u, 0u);
+  const uint8_t* bits = (const uint8_t*)s.values;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int64_t b = (int64_t)s.bit_offset + rb + (p + j) * rs;
+    if (p + j < n_rows) r.x |= ((uint32_t)(__ldg(bits + (b >> 3)) >> (b & 7)) & 1u) << j;
+  }
+  return r;
+}
+
+// one row of any column type (scalar path)
+__device__ __forceinline__ uint4 load_row(const RawSlot& s, int64_t row) {
+  return s.dtype == DT_BOOL ? load_bool_pair(s, row, row + 1) : load_pair(s.values, s.dtype, row, row + 1, false);
+}
+
 // validity bits of logical rows p, p+1 -> bit0, bit1
 __device__ __forceinline__ uint32_t load_valid_pair(const RawSlot& s, int64_t p, int64_t n_rows, int64_t rb = 0, int64_t rs = 1) {
   if (s.validity == nullptr) return 3u;
@@ -565,6 +519,7 @@ __device__ __forceinline__ uint64_t decode(const uint4& r, int dt, int j) {
     case DT_U16: return (uint64_t)((r.x >> (16 * j)) & 0xFFFFu);
     case DT_I8: return (uint64_t)(int64_t)(int8_t)(r.x >> (8 * j));
     case DT_U8: return (uint64_t)((r.x >> (8 * j)) & 0xFFu);
+    case DT_BOOL: return (uint64_t)((r.x >> j) & 1u);
     default: return 0;
   }
 }
@@ -591,7 +546,7 @@ __device__ __forceinline__ bool compare(uint64_t a, uint64_t b, int cls, int op)
 
 __device__ __forceinline__ int slot_class(int dt) {
   switch (dt) {
-    case DT_U8: case DT_U16: case DT_U32: case DT_U64: return CLS_U64;
+    case DT_U8: case DT_U16: case DT_U32: case DT_U64: case DT_BOOL: return CLS_U64;
     case DT_F32: case DT_F64: return CLS_F64;
     default: return CLS_I64;
   }
@@ -858,27 +813,16 @@ struct HotSinkB {
     bool en[B];
     if (a == CT::h_guard_acc(P) && B > 1) {
       int2 sh[B];
-      bool look[B];
 #pragma unroll
       for (int i = 0; i < B; ++i) {
-        look[i] = ok[i];
-        if (CT::h_guard_on(P)) {
-          const int32_t xh = (int32_t)((uint32_t)(x[i] >> 32) ^ (OPMIN == OP_MIN_I64 ? 0u : 0x80000000u));
-          look[i] = ok[i] && !hot.guard_skips(P, id[i], xh);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < B; ++i) {
-        sh[i] = make_int2((int)0x80000000, 0x7FFFFFFF);   // not looked at: inside every interval
-        if (look[i])
-          asm volatile("ld.volatile.shared.v2.s32 {%0,%1}, [%2];" : "=r"(sh[i].x), "=r"(sh[i].y)
-                       : "r"((uint32_t)__cvta_generic_to_shared(&hot.shadow[id[i]])));
+        asm volatile("ld.volatile.shared.v2.s32 {%0,%1}, [%2];" : "=r"(sh[i].x), "=r"(sh[i].y)
+                     : "r"((uint32_t)__cvta_generic_to_shared(&hot.shadow[ok[i] ? id[i] : 0])));
       }
       uint32_t m = 0;
 #pragma unroll
       for (int i = 0; i < B; ++i) {
         const int32_t xh = (int32_t)((uint32_t)(x[i] >> 32) ^ (OPMIN == OP_MIN_I64 ? 0u : 0x80000000u));  // signed domain
-        m |= ((look[i] && (xh <= sh[i].x || xh >= sh[i].y)) ? 1u : 0u) << i;  // NaN images lie outside every interval
+        m |= ((ok[i] && (xh <= sh[i].x || xh >= sh[i].y)) ? 1u : 0u) << i;  // NaN images lie outside every interval
       }
       // few rows get here once a group has seen some rows: one row per lane per round through a single-row body
       while (m) {
@@ -938,84 +882,6 @@ struct HotSinkB {
   }
 };
 
-// Shared-memory hot table, ONE row slot of the warp (32 rows, one per lane), duplicates combined in registers.
-// `peers` = lanes of this slot whose row targets the same private cell as this lane's (found by the caller with warp
-// votes over the id bits); the lowest lane of every peer set is its LEADER: it pulls its peers' contributions with
-// shuffles, combines them with the accumulator's own op and does one plain read-modify-write.  Nothing else touches the
-// cell in this instruction, so there is no claim and no retry; rows of LATER slots see the stores (same warp, program
-// order, __syncwarp between slots).  Why: in the claim protocol (HotSinkB) a third of the shared-memory wavefronts were
-// claim bytes, claim checks and retry rounds (profiles/r02_c2_scan.md); votes and shuffles use issue slots instead,
-// of which this kernel has 55 % to spare.
-template <class CT, int KW>
-struct VoteSink {
-  const HotTable<CT, KW>& hot;
-  int id, cell, lane;
-  uint32_t peers;   // lanes sharing this lane's cell (own bit included); 0 for a lane without a row
-  bool leader;      // lowest lane of its peer set
-  bool any_dup;     // warp-uniform: some peer set has more than one lane
-  template <int OP>
-  __device__ __forceinline__ uint64_t gather(uint64_t v) const {
-    // leaders walk their peers (lowest first); everybody executes the shuffles (warp-uniform trip count)
-    uint32_t rest = leader ? (peers & ~(1u << lane)) : 0u;
-    while (__any_sync(0xffffffffu, rest != 0u)) {
-      const int src = rest ? (__ffs((int)rest) - 1) : lane;
-      const uint64_t o = __shfl_sync(0xffffffffu, v, src);
-      if (rest) v = acc_combine(OP, v, o);
-      rest &= rest - 1u;
-    }
-    return v;
-  }
-  template <int OP>
-  __device__ __forceinline__ void add(const ScanPlan& P, int a, const uint64_t (&x)[1], const bool (&en)[1]) const {
-    const int kind = CT::h_kind(P, a);
-    if (kind == HOT_PRIV64) {
-      uint64_t v = en[0] ? x[0] : acc_init(OP);   // the op's identity: a row that does not take part changes nothing
-      if (any_dup) v = gather<OP>(v);
-      if (leader) {
-        uint64_t* q = (uint64_t*)(hot.wbase + CT::h_off(P, a)) + cell;
-        *q = acc_combine(OP, *q, v);
-      }
-    } else if (kind == HOT_PRIV32) {
-      // counters: the combined contribution is a population count, no shuffles
-      const uint32_t votes = __ballot_sync(0xffffffffu, en[0] && x[0] != 0ull);
-      if (leader) {
-        uint32_t* q = (uint32_t*)(hot.wbase + CT::h_off(P, a)) + cell;
-        *q = *q + (uint32_t)__popc(votes & peers);
-      }
-    }
-    // CTA-shared min/max words need no ownership: the caller updates them for all of a lane's rows at once (HotSinkB)
-  }
-  template <int OPMIN, int OPMAX>
-  __device__ __forceinline__ void minmax(const ScanPlan& P, int a, const uint64_t (&x)[1], const bool (&ok)[1], bool is_f64) const {
-    bool en[1] = {ok[0] && !(is_f64 && HotSinkB<CT, KW, 1, PART_ALL>::image_is_nan(x[0]))};
-    add<OPMIN>(P, a, x, en);
-    add<OPMAX>(P, a + 1, x, en);
-  }
-};
-
-// lanes of the warp whose (alive) row has the same dense id and the same replica as this lane's: one vote per id bit.
-// nbits covers every id below the table's capacity.
-template <class CT>
-__device__ __forceinline__ uint32_t vote_peers(const ScanPlan& P, int id, bool pend, int lane) {
-  const int R = CT::h_rep(P);
-  int nbits = 1;
-  while ((1 << nbits) < CT::h_gcap(P)) ++nbits;
-  uint32_t peers = __ballot_sync(0xffffffffu, pend);
-  if (R > 1) {   // replica = lane % R: only lanes of the same residue share cells
-    const uint32_t every = R == 2 ? 0x55555555u : (R == 4 ? 0x11111111u : (R == 8 ? 0x01010101u : 0x00010001u));
-    peers &= every << (lane & (R - 1));
-  }
-#pragma unroll
-  for (int b = 0; b < 12; ++b) {
-    if (b < nbits) {
-      const bool bit = (id >> b) & 1;
-      const uint32_t m = __ballot_sync(0xffffffffu, bit);
-      peers &= bit ? m : ~m;
-    }
-  }
-  return pend ? peers : 0u;
-}
-
 // B-row form of accumulate_row (same walk over the aggregate flags; `en` = rows that take part)
 template <class CT, int NV, int KW, int B, class Sink>
 __device__ __forceinline__ void accumulate_rows(const ScanPlan& P, const RowOut<KW, NV> (&o)[B], const uint64_t (&grow)[B],
@@ -1074,6 +940,28 @@ __device__ __forceinline__ void accumulate_rows(const ScanPlan& P, const RowOut<
       if (fl & VF_FIRST) { s.template add<OP_MIN_U64>(P, a, x, en); ++a; }
       if (fl & VF_LAST) { s.template add<OP_MAX_U64>(P, a, x, en); ++a; }
     }
+    if (fl & (VF_SUMD | VF_SUMD2)) {
+      // var / std: shifted sums, one rounding per operation (see VFlag)
+      uint64_t d1[B], d2[B];
+#pragma unroll
+      for (int i = 0; i < B; ++i) {
+        const double d = __dsub_rn(bits_to_f64(bits[i], cls), P.var_shift[e]);
+        d1[i] = (uint64_t)__double_as_longlong(d);
+        d2[i] = (uint64_t)__double_as_longlong(__dmul_rn(d, d));
+      }
+      if (fl & VF_SUMD) { s.template add<OP_ADD_F64>(P, a, d1, ok); ++a; }
+      if (fl & VF_SUMD2) { s.template add<OP_ADD_F64>(P, a, d2, ok); ++a; }
+    }
+    if (fl & (VF_FIRST_NN | VF_LAST_NN)) {
+      uint64_t x[B];
+#pragma unroll
+      for (int i = 0; i < B; ++i) x[i] = (grow[i] << 1) | 1ull;
+      if (fl & VF_FIRST_NN) { s.template add<OP_MIN_U64>(P, a, x, ok); ++a; }
+      if (fl & VF_LAST_NN) { s.template add<OP_MAX_U64>(P, a, x, ok); ++a; }
+    }
+    if (fl & VF_AND) { s.template add<OP_AND_U64>(P, a, bits, ok); ++a; }
+    if (fl & VF_OR) { s.template add<OP_OR_U64>(P, a, bits, ok); ++a; }
+    if (fl & VF_XOR) { s.template add<OP_XOR_U64>(P, a, bits, ok); ++a; }
   }
   int a = CT::acc_gbase(P);
   const int gf = CT::gflags(P);
@@ -1114,6 +1002,16 @@ __device__ __forceinline__ void accumulate_row(const ScanPlan& P, const RowOut<K
     }
     if (fl & VF_FIRST) { s.template add<OP_MIN_U64>(P, a, (grow << 1) | (ok ? 1ull : 0ull)); ++a; }
     if (fl & VF_LAST) { s.template add<OP_MAX_U64>(P, a, (grow << 1) | (ok ? 1ull : 0ull)); ++a; }
+    if (fl & (VF_SUMD | VF_SUMD2)) {
+      const double d = __dsub_rn(bits_to_f64(bits, cls), P.var_shift[e]);
+      if (fl & VF_SUMD) { if (ok) s.template add<OP_ADD_F64>(P, a, (uint64_t)__double_as_longlong(d)); ++a; }
+      if (fl & VF_SUMD2) { if (ok) s.template add<OP_ADD_F64>(P, a, (uint64_t)__double_as_longlong(__dmul_rn(d, d))); ++a; }
+    }
+    if (fl & VF_FIRST_NN) { if (ok) s.template add<OP_MIN_U64>(P, a, (grow << 1) | 1ull); ++a; }
+    if (fl & VF_LAST_NN) { if (ok) s.template add<OP_MAX_U64>(P, a, (grow << 1) | 1ull); ++a; }
+    if (fl & VF_AND) { if (ok) s.template add<OP_AND_U64>(P, a, bits); ++a; }
+    if (fl & VF_OR) { if (ok) s.template add<OP_OR_U64>(P, a, bits); ++a; }
+    if (fl & VF_XOR) { if (ok) s.template add<OP_XOR_U64>(P, a, bits); ++a; }
   }
   int a = CT::acc_gbase(P);
   const int gf = CT::gflags(P);
@@ -1191,23 +1089,7 @@ __device__ __forceinline__ void rows_accumulate(const ScanPlan& P, HotTable<CT, 
     const HotSinkB<CT, KW, B, PART_ALL> sink{hot, id, cell, cw};
     const HotSinkB<CT, KW, B, PART_PRIVATE> sink_private{hot, id, cell, cw};
     const HotSinkB<CT, KW, B, PART_SHARED> sink_shared{hot, id, cell, cw};
-    if (R < 32 && CT::h_dedup(P)) {
-      // duplicates combined in registers (VoteSink): the CTA-shared min/max words first, for all B rows at once (they
-      // need no ownership), then the private words slot by slot
-      if (CT::h_n_mm(P) > 0) accumulate_rows<CT, NV, KW, B>(P, o, grow, pend, sink_shared);
-#pragma unroll
-      for (int i = 0; i < B; ++i) {
-        const uint32_t peers = vote_peers<CT>(P, id[i], pend[i], lane);
-        const bool dup = (peers & (peers - 1u)) != 0u;
-        const VoteSink<CT, KW> vs{hot, id[i], cell[i], lane, peers, pend[i] && (peers & ((1u << lane) - 1u)) == 0u, __any_sync(0xffffffffu, dup) != 0};
-        RowOut<KW, NV> so[1];
-        uint64_t sgrow[1];
-        bool sen[1];
-        so[0] = o[i]; sgrow[0] = grow[i]; sen[0] = pend[i];
-        accumulate_rows<CT, NV, KW, 1>(P, so, sgrow, sen, vs);
-        __syncwarp();   // the next slot's loads see this slot's stores
-      }
-    } else if (R == 32) {
+    if (R == 32) {
       // every lane owns its replica: no claims.  Two rows of one lane may share a cell -> one row at a time.
 #pragma unroll
       for (int i = 0; i < B; ++i) {
@@ -1335,7 +1217,8 @@ __device__ __forceinline__ void load_step(const ScanPlan& P, int64_t base, int l
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         if (c < CT::n_slots(P)) {
-          raw[hf][c] = load_pair(P.slots[c].values, CT::slot_dtype(P, c), p, n_rows, true, 0, 1);
+          raw[hf][c] = CT::slot_dtype(P, c) == DT_BOOL ? load_bool_pair(P.slots[c], p, n_rows, 0, 1)
+                                                        : load_pair(P.slots[c].values, CT::slot_dtype(P, c), p, n_rows, true, 0, 1);
           vbits[hf][c] = CT::slot_nullable(P, c) ? load_valid_pair(P.slots[c], p, n_rows, 0, 1) : 3u;
         } else {
           raw[hf][c] = make_uint4(0u, 0u, 0u, 0u);
@@ -1353,10 +1236,12 @@ __device__ __forceinline__ void load_step(const ScanPlan& P, int64_t base, int l
     for (int c = 0; c < NC; ++c) {
       if (c < CT::n_slots(P) && p < n_rows) {
         if (CT::unit_stride(P)) {
-          raw[hf][c] = load_pair(P.slots[c].values, CT::slot_dtype(P, c), p, n_rows, full, 0, 1);
+          raw[hf][c] = CT::slot_dtype(P, c) == DT_BOOL ? load_bool_pair(P.slots[c], p, n_rows, 0, 1)
+                                                        : load_pair(P.slots[c].values, CT::slot_dtype(P, c), p, n_rows, full, 0, 1);
           vbits[hf][c] = CT::slot_nullable(P, c) ? load_valid_pair(P.slots[c], p, n_rows, 0, 1) : 3u;
         } else {
-          raw[hf][c] = load_pair(P.slots[c].values, CT::slot_dtype(P, c), p, n_rows, full, P.row_begin, P.row_stride);
+          raw[hf][c] = CT::slot_dtype(P, c) == DT_BOOL ? load_bool_pair(P.slots[c], p, n_rows, P.row_begin, P.row_stride)
+                                                        : load_pair(P.slots[c].values, CT::slot_dtype(P, c), p, n_rows, full, P.row_begin, P.row_stride);
           vbits[hf][c] = CT::slot_nullable(P, c) ? load_valid_pair(P.slots[c], p, n_rows, P.row_begin, P.row_stride) : 3u;
         }
       } else {
@@ -1403,7 +1288,6 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
   unsigned long long spilled = 0;
   bool stable_set = false, flushed_once = false;  // eviction heuristics (CTA-uniform)
   int tiles_since_flush = 0;
-  int n_checks = 0;  // eviction checks since the last clear (value-guard snapshots)
 
   // eviction check after a tile (CTA-wide: every warp calls it for the same tiles).  Every 4 tiles (8192 rows at 16
   // warps): two CTA barriers.  Partitioned input walks through disjoint group sets (one per partition, a tile or two
@@ -1419,9 +1303,6 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
     const bool full = *(volatile uint32_t*)(hot.count + 1) != 0u;
     const uint32_t G = (uint32_t)CT::h_gcap(P);
     const bool nearly = CT::rowid_slot(P) >= 0 ? cnt >= (G >> 1) : (cnt >= G - (G >> 3) && !stable_set);
-    // value guard: a fresh snapshot at the first checks (the group set settles quickly), then at every eighth one
-    if (CT::h_guard_on(P) && CT::h_guard_acc(P) >= 0 && CT::rowid_slot(P) < 0 && (n_checks < 4 || (n_checks & 7) == 0)) hot.guard_snapshot(P, lane);
-    ++n_checks;
     __syncthreads();
     ++tiles_since_flush;
     const bool wrap = tiles_since_flush >= 30000;  // private counters share their word with the claim byte: 24 bits
@@ -1431,8 +1312,6 @@ __device__ __forceinline__ void scan_body(const ScanPlan& P) {
         hot.flush(P);
         __syncthreads();
         hot.clear(P);
-        hot.guard_reset();
-        n_checks = 0;
         __syncthreads();
         flushed_once = true;
         tiles_since_flush = 0;

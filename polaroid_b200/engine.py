@@ -49,7 +49,7 @@ class PwFactor(C.Structure):
 
 
 class PwAgg(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("column", C.c_int32), ("n_factors", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("kind", C.c_int32), ("column", C.c_int32), ("n_factors", C.c_int32), ("ddof", C.c_int32),
                 ("factors", PwFactor * PW_MAX_FACTORS), ("name", C.c_char_p)]
 
 
@@ -371,6 +371,7 @@ class _BuiltQuery:
         self._names = []
         for i, a in enumerate(plan.aggs):
             self.aggs[i].kind = P.AGG_KINDS[a.kind]
+            self.aggs[i].ddof = int(getattr(a, "ddof", 0) or 0)
             nm = a.name.encode()
             self._names.append(nm)
             self.aggs[i].name = nm

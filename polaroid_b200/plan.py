@@ -27,7 +27,9 @@ from typing import Any, Optional, Sequence
 
 # ---- small enums shared with include/polarway_b200.h ------------------------------------
 CMP_OPS = {"eq": 0, "ne": 1, "lt": 2, "le": 3, "gt": 4, "ge": 5}
-AGG_KINDS = {"sum": 0, "mean": 1, "min": 2, "max": 3, "count": 4, "len": 5, "first": 6, "last": 7}
+AGG_KINDS = {"sum": 0, "mean": 1, "min": 2, "max": 3, "count": 4, "len": 5, "first": 6, "last": 7,
+             "var": 8, "std": 9, "first_non_null": 10, "last_non_null": 11, "null_count": 12,
+             "bitwise_and": 13, "bitwise_or": 14, "bitwise_xor": 15, "any": 16, "all": 17}
 CLOSED = {"left": 0, "right": 1, "both": 2, "none": 3}
 LABEL = {"left": 0, "right": 1, "datapoint": 2}
 
@@ -63,6 +65,7 @@ class AggSpec:
     name: str
     kind: str            # key of AGG_KINDS
     expr: Optional[ValueExpr]  # None for len()
+    ddof: int = 0        # var / std (py-polars Expr.var/std default: 1)
 
 
 @dataclass(frozen=True)
@@ -183,19 +186,37 @@ class Expr:
     def max(self): return self._agg("max")
     def count(self): return self._agg("count")
     def len(self): return self._agg("len")
-    def first(self): return self._agg("first")
-    def last(self): return self._agg("last")
+    # py-polars Expr.first/last(ignore_nulls=...): expr.py (IRAggExpr::FirstNonNull / LastNonNull)
+    def first(self, *, ignore_nulls: bool = False): return self._agg("first_non_null" if ignore_nulls else "first")
+    def last(self, *, ignore_nulls: bool = False): return self._agg("last_non_null" if ignore_nulls else "last")
+    # the remaining pre-aggregatable reductions (polars-expr/src/reduce/convert.rs:46-150)
+    def var(self, ddof: int = 1): return AggExpr("var", self._value_expr(), self._out_name(), ddof)
+    def std(self, ddof: int = 1): return AggExpr("std", self._value_expr(), self._out_name(), ddof)
+    def null_count(self): return self._agg("null_count")
+    def bitwise_and(self): return self._agg("bitwise_and")
+    def bitwise_or(self): return self._agg("bitwise_or")
+    def bitwise_xor(self): return self._agg("bitwise_xor")
+
+    def any(self, *, ignore_nulls: bool = True):
+        if not ignore_nulls:
+            raise NotImplementedError("any(ignore_nulls=False) (Kleene logic) is outside this path")
+        return self._agg("any")
+
+    def all(self, *, ignore_nulls: bool = True):
+        if not ignore_nulls:
+            raise NotImplementedError("all(ignore_nulls=False) (Kleene logic) is outside this path")
+        return self._agg("all")
 
 
 class AggExpr:
-    def __init__(self, kind: str, expr: Optional[ValueExpr], name: str):
-        self.kind, self.expr, self.name = kind, expr, name
+    def __init__(self, kind: str, expr: Optional[ValueExpr], name: str, ddof: int = 0):
+        self.kind, self.expr, self.name, self.ddof = kind, expr, name, ddof
 
     def alias(self, name: str) -> "AggExpr":
-        return AggExpr(self.kind, self.expr, name)
+        return AggExpr(self.kind, self.expr, name, self.ddof)
 
     def spec(self) -> AggSpec:
-        return AggSpec(self.name, self.kind, self.expr)
+        return AggSpec(self.name, self.kind, self.expr, self.ddof)
 
 
 class PredExpr:

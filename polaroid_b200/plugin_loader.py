@@ -40,7 +40,8 @@ def plan_to_kwargs(schema: pa.Schema, plan: P.GroupByPlan, **extra) -> dict:
                        for i in range(len(plan.predicates))],
         "aggs": [(a.name, P.AGG_KINDS[a.kind],
                   None if a.expr is None or a.expr.factors is not None else idx[a.expr.col],
-                  None if a.expr is None or a.expr.factors is None else [(f.a, f.b, idx[f.col]) for f in a.expr.factors])
+                  None if a.expr is None or a.expr.factors is None else [(f.a, f.b, idx[f.col]) for f in a.expr.factors],
+                  int(getattr(a, "ddof", 0) or 0))
                  for a in plan.aggs],
     }
     if bq.dyn is not None:
