@@ -66,7 +66,8 @@ WORKLOADS = {
                 name="C3-shaped multi-GPU run: 1e8 rows per GPU, 1e7 keys, general key-hash all_to_all exchange"),
 }
 STRATEGY = {1: "hot table + spill tier", 2: "HBM table", 3: "segmented sorted windows", 4: "hot table, dense ids + spill tier",
-            5: "radix partition + hot table", 6: "sorted windows by key (dense ids per window)"}
+            5: "radix partition + hot table", 6: "sorted windows by key (dense ids per window)",
+            7: "dense ids bucketed per tile, accumulators in registers + spill tier"}
 
 
 def measured_peak_gbs():
@@ -554,7 +555,7 @@ def main():
     def roofline(rows, bytes_per_row, out_rows, out_bytes_per_row, k_ms, step_ms, tm):
         algo = rows * bytes_per_row + out_rows * out_bytes_per_row
         ach = algo / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-        return {"kernel": {3: "pw_seg_jit", 6: "pw_wseg_jit"}.get(tm["strategy"], "pw_scan_jit") if tm["reserved"] else "ahead-of-time kernel",
+        return {"kernel": {3: "pw_seg_jit", 6: "pw_wseg_jit", 7: "pw_bucket_jit"}.get(tm["strategy"], "pw_scan_jit") if tm["reserved"] else "ahead-of-time kernel",
                 "kernel_ms": k_ms, "algorithmic_bytes_per_launch": algo, "achieved_gbs": ach,
                 "frac_measured": ach / peak, "frac_nominal_8tbs": ach / NOMINAL_GBS,
                 "whole_step_frac_measured": (algo / (step_ms * 1e-3) / 1e9) / peak}
@@ -661,7 +662,7 @@ def main():
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3},
                 "gpu_launches": int(launches) * args.steps,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "kernel": "pw_scan_jit" if tm["reserved"] else "pw::scan_kernel",
+                             "traffic": traffic, "kernel": {7: "pw_bucket_jit"}.get(tm["strategy"], "pw_scan_jit") if tm["reserved"] else "pw::scan_kernel",
                              "kernel_ms": k_ms, "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
                              "frac_nominal_8tbs": achieved / NOMINAL_GBS,
                              "whole_step_frac": (algo_bytes / (ms * 1e-3) / 1e9) / peak},

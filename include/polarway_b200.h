@@ -145,6 +145,7 @@ typedef struct PwDynamic {
 #define PW_FLAG_FORCE_PARTITION (1ull << 4)    /* radix-partition the rows by key hash first (high-cardinality tier) */
 #define PW_FLAG_NO_PARTITION (1ull << 5)       /* never partition (POLARS_NO_PARTITION) */
 #define PW_FLAG_NO_DENSE_IDS (1ull << 6)       /* never map a small integer key range to dense ids: always the hash index */
+#define PW_FLAG_NO_BUCKETS (1ull << 7)         /* dense ids through the per-cell hot table, never the bucket tier (pw_bucket.cuh) */
 
 #define PW_ABI_VERSION 1u
 typedef struct PwQuery {
@@ -175,7 +176,8 @@ int pw_b200_set_stream(void* cuda_stream);     /* calling thread's cudaStream_t 
 typedef struct PwTimings {
   float h2d_ms, estimate_ms, scan_ms, finalize_ms, d2h_ms, total_device_ms;
   int64_t n_rows, n_groups, table_slots;
-  int32_t strategy;      /* 1 hot table, 2 global table, 3 segmented, 4 hot table with dense ids (small integer key range), 5 partitioned */
+  int32_t strategy;      /* 1 hot table, 2 global table, 3 segmented, 4 hot table with dense ids (small integer key range), 5 partitioned,
+                            7 dense ids bucketed per tile, accumulators in registers (pw_bucket.cuh) */
   int32_t retries;       /* table growth re-runs */
   int64_t kernel_launches; /* launches of this library's kernels in the last call */
   int64_t spilled_rows;  /* rows that bypassed the hot table (spill tier) */

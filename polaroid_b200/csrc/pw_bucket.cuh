@@ -1,0 +1,309 @@
+// pw_bucket.cuh — the BUCKET tier of the hot path: dense group ids, accumulators in the owner thread's registers.
+//
+// Why: on the per-cell hot table (pw_scan.cuh) every row pays five or six random shared-memory accesses — claim byte,
+// claim check, sum load, sum store, counter store, min/max shadow — about 34 shared-memory wavefronts per 32 rows, and
+// the LSU data pipe, not HBM, bounds the kernel (C2: 41 % of the measured HBM peak).  A row's accumulator update is a
+// read-modify-write on a cell that any lane of any warp may touch, which is what forces ownership protocols.
+//
+// Here the read-modify-write never happens in shared memory.  A CTA works tile by tile (64 rows per warp):
+//   SCATTER  every live row takes a RANK inside its group's bucket with one native 32-bit shared-memory atomic
+//            (ATOMS.ADD on cnt[id], 2.7 pipe cycles per warp instruction measured on B200 — the same as a plain
+//            random STS.32) and stores its value words at buf[plane][rank][id] (one random STS.64 per word);
+//   barrier;
+//   FOLD     thread g reads bucket g — buf[plane][j][g] for j < cnt[g]: consecutive threads read consecutive words, no
+//            bank conflicts — and folds the rows into accumulators that live in ITS REGISTERS for the whole kernel
+//            (the query-shape specialised build turns every accumulator index into a constant, as in pw_segmented.cuh).
+// Per 32 rows that is ~13 wavefronts (atomic 2.7 + store 5 per word + ~5 for the fold) instead of ~34, min/max cost
+// nothing extra in shared memory, and nothing is claimed or retried.  Buckets are double-buffered (the scatter of tile
+// t+1 overlaps the fold of tile t: one barrier per tile) when two buffers fit next to ~60 KB of L1 — in-flight global
+// loads land in L1, and a CTA that takes all 227 KB of shared memory starves its own loads (measured: 0.42 ms with
+// 221 KB of buckets, 0.32 ms with 172 KB on the C2 shape).
+// Groups narrower than the CTA get several owner threads each (ranks interleaved), wider ones several groups per thread.
+// Rows the buckets cannot take — a rank beyond the bucket depth J (sized from the Poisson tail of rows-per-group per tile:
+// ~1e-4 of the rows), null / out-of-range / sentinel keys — go to the HBM table with atomics, as in the other tiers.
+// At the end every owner publishes its registers into the HBM table.
+//
+// Reference shape: polars-expr/src/hot_groups/fixed_index_table.rs:63-160 feeding GroupedReduction::update_groups
+// (polars-expr/src/reduce/mod.rs:292-312) — there, too, the rows of a morsel are first turned into (group index, value)
+// pairs and each reduction then sweeps its values by group index.
+#pragma once
+#include "pw_scan.cuh"
+
+namespace pw {
+
+// shared memory through 32-bit window addresses and predicated instructions: no generic-address arithmetic and no
+// branches around the per-row atomics and stores (the kernel is bound by warp-instruction issue, not by a data pipe)
+__device__ __forceinline__ uint32_t sh_rank_if(uint32_t addr, bool p) {   // p ? atomicAdd(cnt, 1) : ~0
+  uint32_t r = 0xFFFFFFFFu;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q atom.shared.add.u32 %0, [%1], 1;\n\t}" : "+r"(r) : "r"(addr), "r"((uint32_t)p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void sh_st64_if(uint32_t addr, uint64_t v, bool p) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.b64 [%0], %1;\n\t}" ::"r"(addr), "l"(v), "r"((uint32_t)p) : "memory");
+}
+__device__ __forceinline__ uint64_t sh_ld64(uint32_t addr) {
+  uint64_t v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t sh_ld32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sh_st32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+// accumulators of ONE group in registers; SKIP = an accumulator handled outside the per-row walk (the row counter);
+// NATIVE = bit per accumulator: an f64 min / max kept as the plain double and compared with DSETP (the rows that need the
+// total order — NaN, -0.0 — never reach the buckets), turned into the ordered image once, when the registers are published
+template <int NACC, int SKIP, uint32_t NATIVE>
+struct BucketRegSink {
+  uint64_t (&acc)[NACC];
+  template <int OP>
+  __device__ __forceinline__ void add(const ScanPlan&, int a, uint64_t x) const {
+#pragma unroll
+    for (int i = 0; i < NACC; ++i)
+      if (i == a && i != SKIP) acc[i] = acc_combine(OP, acc[i], x);
+  }
+  __device__ __forceinline__ void fmin(int a, uint64_t bits) const {
+#pragma unroll
+    for (int i = 0; i < NACC; ++i)
+      if (i == a) asm("{\n\t.reg .pred q;\n\tsetp.lt.f64 q, %1, %0;\n\tselp.b64 %0, %1, %0, q;\n\t}" : "+l"(acc[i]) : "l"(bits));
+  }
+  __device__ __forceinline__ void fmax(int a, uint64_t bits) const {
+#pragma unroll
+    for (int i = 0; i < NACC; ++i)
+      if (i == a) asm("{\n\t.reg .pred q;\n\tsetp.gt.f64 q, %1, %0;\n\tselp.b64 %0, %1, %0, q;\n\t}" : "+l"(acc[i]) : "l"(bits));
+  }
+};
+template <int NACC, int SKIP, uint32_t NATIVE>
+struct SinkNative<BucketRegSink<NACC, SKIP, NATIVE>> {
+  using S = BucketRegSink<NACC, SKIP, NATIVE>;
+  static __device__ __forceinline__ constexpr bool on(int a) { return ((NATIVE >> a) & 1u) != 0; }
+  static __device__ __forceinline__ void fmin(const S& s, int a, uint64_t bits) { s.fmin(a, bits); }
+  static __device__ __forceinline__ void fmax(const S& s, int a, uint64_t bits) { s.fmax(a, bits); }
+};
+
+struct BucketWholeTag { static constexpr bool value = true; };     // a tile without a ragged end: no row bounds anywhere
+struct BucketRaggedTag { static constexpr bool value = false; };
+
+// the two rows of every slot this lane owns in the tile at `base` (lane l: rows base + 2l, base + 2l + 1)
+template <class CT, int NC, bool WHOLE>
+__device__ __forceinline__ void bucket_load(const ScanPlan& P, int64_t base, int lane, int64_t n_rows, uint4 (&raw)[NC], uint32_t (&vbits)[NC]) {
+  const int64_t p = base + 2 * lane;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    raw[c] = make_uint4(0u, 0u, 0u, 0u);
+    vbits[c] = 0u;
+    if (c < CT::n_slots(P) && (WHOLE || p < n_rows)) {
+      const bool full = WHOLE || p + 1 < n_rows;
+      raw[c] = CT::slot_dtype(P, c) == DT_BOOL ? load_bool_pair(P.slots[c], p, n_rows, 0, 1)
+                                                : load_pair(P.slots[c].values, CT::slot_dtype(P, c), p, n_rows, full, 0, 1);
+      vbits[c] = CT::slot_nullable(P, c) ? load_valid_pair(P.slots[c], p, n_rows, 0, 1) : 3u;
+    }
+  }
+}
+
+template <class CT, int NC, int KW, int NV>
+__device__ __forceinline__ void bucket_row_front(const ScanPlan& P, const uint4 (&raw)[NC], const uint32_t (&vbits)[NC], int j, int64_t row,
+                                                 bool in_range, RowOut<KW, NV>& o) {
+  o.row = row;
+  Row<NC> r;
+  row_decode<CT, NC>(P, raw, vbits, j, r);
+  bool alive = in_range && row_predicate<CT, NC>(P, r);
+  alive = row_keys<CT, NC, KW>(P, r, raw, vbits, j, alive, o.k, o.sentinel_free) && alive;
+  o.alive = alive;
+  row_vexprs<CT, NC, NV>(P, r, o.v, o.v_valid);
+  o.tval = 0ull;
+}
+
+// a row the buckets cannot take: straight into the HBM table (kept out of line: it is rare and register-hungry)
+template <class CT, int KW, int NV>
+__device__ __noinline__ void bucket_cold_row(const ScanPlan& P, RowOut<KW, NV> o, uint64_t grow) {
+  const uint64_t gslot = table_upsert<KW>(P.table, o.k, hash_words<KW>(o.k), o.sentinel_free || KW != 1);
+  if (gslot != ~0ull) {
+    const ColdSink sink{P.table, gslot};
+    accumulate_row<CT, NV, KW>(P, o, grow, sink);
+  }
+}
+
+template <class CT, int NC, int KW>
+__device__ __forceinline__ void bucket_body(const ScanPlan& P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NV = NVof<NC>::value;
+  constexpr int THREADS = CT::kBThreads, WARPS = THREADS / 32;
+  constexpr int GCAP = CT::kBGcap;        // power of two >= the dense id range
+  constexpr int J = CT::kBJ;              // bucket depth
+  constexpr int NBUF = CT::kBNbuf;        // 2: one barrier per tile, 1: two
+  constexpr int NVE = CT::kNVexpr;        // value planes
+  constexpr bool META = CT::kBMeta;       // extra plane: (global row << 8) | validity bits of the value expressions
+  constexpr int PLANES = NVE + (META ? 1 : 0);
+  constexpr int NACC = CT::kNAcc;
+  constexpr uint32_t NATIVE = CT::kBNativeAcc;   // accumulators kept as plain doubles
+  constexpr uint32_t ODD = CT::kBOddVexpr;       // value expressions whose NaN / -0.0 rows take the HBM path
+  constexpr int GPT = GCAP > THREADS ? GCAP / THREADS : 1;   // groups per owner thread
+  constexpr int SUB = GCAP < THREADS ? THREADS / GCAP : 1;   // owner threads per group
+  // one owner per group: the owner zeroes its own counter while it folds, one counter array per buffer.  Several owners
+  // per group: none of them may zero it while the others still read, so the arrays rotate one step slower than the
+  // buffers and the previous tile's array is cleared after the barrier.
+  constexpr int NCNT = SUB == 1 ? NBUF : NBUF + 1;
+  constexpr int TILE = WARPS * 64;        // rows per tile: two per lane
+  constexpr int LEN_ACC = CT::kLenAcc;    // the row counter is bumped once per fold, not once per row
+  constexpr uint32_t PLANE_BYTES = (uint32_t)J * GCAP * 8u, BUF_BYTES = PLANE_BYTES * PLANES;
+  static_assert((GCAP & (GCAP - 1)) == 0 && (THREADS % 32) == 0, "bucket geometry");
+
+  const uint32_t sbuf = (uint32_t)__cvta_generic_to_shared(smem_raw);   // [NBUF][PLANES][J][GCAP] x 8 bytes
+  const uint32_t scnt = sbuf + (uint32_t)NBUF * BUF_BYTES;              // [NCNT][GCAP] x 4 bytes
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < NCNT * GCAP; i += THREADS) sh_st32(scnt + 4u * i, 0u);
+  __syncthreads();
+
+  uint64_t acc[GPT][NACC];
+  bool seen[GPT];
+#pragma unroll
+  for (int gi = 0; gi < GPT; ++gi) {
+    seen[gi] = false;
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+      const int op = CT::acc_op(P, a);
+      acc[gi][a] = !((NATIVE >> a) & 1u) ? acc_init(op) : (op == OP_MIN_I64 ? 0x7FF0000000000000ull : 0xFFF0000000000000ull);   // +inf / -inf
+    }
+  }
+  const int my_g0 = GCAP >= THREADS ? tid : (tid & (GCAP - 1));   // first (or only) group of this thread
+  const int my_sub = GCAP >= THREADS ? 0 : tid / GCAP;
+
+  const int64_t n_rows = P.n_rows;
+  const int64_t n_tiles = (n_rows + TILE - 1) / TILE, n_whole = n_rows / TILE;
+  const int64_t tile_lo = n_tiles * blockIdx.x / gridDim.x;
+  const int64_t tile_hi = n_tiles * (blockIdx.x + 1) / gridDim.x;
+  const int64_t whole_hi = tile_hi < n_whole ? tile_hi : n_whole;   // [tile_lo, whole_hi): tiles without a ragged end
+  unsigned long long spilled = 0;
+  const int64_t lane_row = (int64_t)warp * 64 + 2 * lane;
+
+  int b = 0, ci = 0;   // buffer / counter array of the current tile
+  auto process = [&](int64_t t, const uint4 (&raw)[NC], const uint32_t (&vb)[NC], auto whole_tag) {
+    constexpr bool WHOLE = decltype(whole_tag)::value;
+    const uint32_t bb = sbuf + (uint32_t)b * BUF_BYTES;
+    const uint32_t cc = scnt + (uint32_t)ci * (GCAP * 4u);
+    // ---- scatter ----
+    {
+      RowOut<KW, NV> o[2];
+      const int64_t row0 = t * TILE + lane_row;
+      bucket_row_front<CT, NC, KW, NV>(P, raw, vb, 0, row0, WHOLE || row0 < n_rows, o[0]);
+      bucket_row_front<CT, NC, KW, NV>(P, raw, vb, 1, row0 + 1, WHOLE || row0 + 1 < n_rows, o[1]);
+      uint32_t id[2], rk[2];
+      bool take[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint64_t d = o[i].k[0] - (uint64_t)P.dense_min;
+        const bool plain = !CT::h_dense_sentinels(P) || o[i].k[0] < KEY_NULL;   // -1 / -2 inside the range: sentinels go cold
+        bool odd = false;   // a value the plain-double min / max cannot order
+#pragma unroll
+        for (int e = 0; e < NVE; ++e)
+          if ((ODD >> e) & 1u) {
+            const double x = __longlong_as_double((long long)o[i].v[e]);
+            odd = odd || x != x || o[i].v[e] == 0x8000000000000000ull;
+          }
+        take[i] = o[i].alive && plain && !odd && d < (uint64_t)CT::h_gcap(P);
+        id[i] = (uint32_t)d & (uint32_t)(GCAP - 1);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) rk[i] = sh_rank_if(cc + 4u * id[i], take[i]);
+      bool late = false;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const bool fits = rk[i] < (uint32_t)J;
+        const uint32_t q = bb + (rk[i] * GCAP + id[i]) * 8u;
+#pragma unroll
+        for (int e = 0; e < NVE; ++e) sh_st64_if(q + (uint32_t)e * PLANE_BYTES, o[i].v[e], fits);
+        if (META) sh_st64_if(q + (uint32_t)NVE * PLANE_BYTES, (global_row<CT>(P, o[i].row) << 8) | (uint64_t)(o[i].v_valid & 0xFFu), fits);
+        late = late || (o[i].alive && !fits);
+      }
+      if (late) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          if (o[i].alive && rk[i] >= (uint32_t)J) { bucket_cold_row<CT, KW, NV>(P, o[i], global_row<CT>(P, o[i].row)); ++spilled; }
+      }
+    }
+    __syncthreads();
+    // ---- fold ----
+    if (SUB > 1) {
+      // the PREVIOUS tile's counters: every thread finished reading them before it arrived at the barrier above, and
+      // their next scatter comes after the next barrier
+      const uint32_t cprev = scnt + (uint32_t)(ci == 0 ? NCNT - 1 : ci - 1) * (GCAP * 4u);
+      for (int i = tid; i < GCAP; i += THREADS) sh_st32(cprev + 4u * i, 0u);
+    }
+#pragma unroll
+    for (int gi = 0; gi < GPT; ++gi) {
+      const int g = my_g0 + gi * THREADS;
+      uint32_t c = sh_ld32(cc + 4u * g);
+      if (SUB == 1 && c) sh_st32(cc + 4u * g, 0u);
+      c = c < (uint32_t)J ? c : (uint32_t)J;
+      uint32_t q = bb + ((uint32_t)my_sub * GCAP + g) * 8u;
+      uint32_t mine = 0;
+      const BucketRegSink<NACC, LEN_ACC, NATIVE> sink{acc[gi]};
+#pragma unroll 1
+      for (uint32_t j = my_sub; j < c; j += SUB, q += (uint32_t)SUB * GCAP * 8u) {
+        RowOut<KW, NV> o;
+#pragma unroll
+        for (int e = 0; e < NV; ++e) o.v[e] = e < NVE ? sh_ld64(q + (uint32_t)e * PLANE_BYTES) : 0ull;
+        uint64_t grow = 0;
+        o.v_valid = 0xFFFFFFFFu;
+        if (META) { const uint64_t m = sh_ld64(q + (uint32_t)NVE * PLANE_BYTES); grow = m >> 8; o.v_valid = (uint32_t)(m & 0xFFu); }
+        o.tval = 0ull;
+        accumulate_row<CT, NV, KW>(P, o, grow, sink);
+        ++mine;
+      }
+      if (mine) {
+        seen[gi] = true;
+        if (LEN_ACC >= 0) {
+#pragma unroll
+          for (int a = 0; a < NACC; ++a) if (a == LEN_ACC) acc[gi][a] += (uint64_t)mine;
+        }
+      }
+    }
+    if (NBUF == 1) __syncthreads();
+    b = (NBUF == 2) ? (b ^ 1) : 0;
+    ci = ci + 1 == NCNT ? 0 : ci + 1;
+  };
+
+  // software pipeline over the whole tiles: the loads of the next tile are in flight while this one is scattered and
+  // folded; the loop is unrolled by two so that the two register buffers alternate in place
+  uint4 rawA[NC], rawB[NC];
+  uint32_t vbA[NC], vbB[NC];
+  if (tile_lo < whole_hi) bucket_load<CT, NC, true>(P, tile_lo * TILE + warp * 64, lane, n_rows, rawA, vbA);
+  for (int64_t t = tile_lo; t < whole_hi; t += 2) {
+    if (t + 1 < whole_hi) bucket_load<CT, NC, true>(P, (t + 1) * TILE + warp * 64, lane, n_rows, rawB, vbB);
+    process(t, rawA, vbA, BucketWholeTag{});
+    if (t + 1 < whole_hi) {
+      if (t + 2 < whole_hi) bucket_load<CT, NC, true>(P, (t + 2) * TILE + warp * 64, lane, n_rows, rawA, vbA);
+      process(t + 1, rawB, vbB, BucketWholeTag{});
+    }
+  }
+  // the ragged last tile (one CTA at most)
+  if (whole_hi < tile_hi) {
+    bucket_load<CT, NC, false>(P, whole_hi * TILE + warp * 64, lane, n_rows, rawA, vbA);
+    process(whole_hi, rawA, vbA, BucketRaggedTag{});
+  }
+
+  // ---- publish the registers ----
+#pragma unroll
+  for (int gi = 0; gi < GPT; ++gi) {
+    if (!seen[gi]) continue;
+    const int g = my_g0 + gi * THREADS;
+    uint64_t k[KW];
+#pragma unroll
+    for (int w = 0; w < KW; ++w) k[w] = w == 0 ? (uint64_t)P.dense_min + (uint64_t)g : 0ull;
+    const uint64_t gs = table_upsert<KW>(P.table, k, hash_words<KW>(k), true);
+    if (gs == ~0ull) continue;
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+      const int op = CT::acc_op(P, a);
+      if ((NATIVE >> a) & 1u) acc_apply_global(&tacc(P.table, a, gs), op, (uint64_t)f64_to_ordered(__longlong_as_double((long long)acc[gi][a])));
+      else if (acc[gi][a] != acc_init(op)) acc_apply_global(&tacc(P.table, a, gs), op, acc[gi][a]);
+    }
+  }
+  if (spilled) atomicAdd(P.table.spilled, spilled);
+}
+
+}  // namespace pw

@@ -604,6 +604,12 @@ static int launch_scan(ScanPlan P, int sm, cudaStream_t st) {
   const bool narrow = narrow_class(P);
   // query-shape specialised kernel (NVRTC); falls back to the ahead-of-time kernel of the same class
   const int kwc = P.n_kw <= 1 ? 1 : (P.n_kw <= 2 ? 2 : (P.n_kw <= 4 ? 4 : 6));
+  if (P.hot_slots > 0 && P.hot.bucket) {
+    // bucket tier (specialised build only); without NVRTC the per-cell geometry in the same HotGeom takes over
+    const int brc = launch_bucket_jit(P, narrow ? 4 : 12, kwc, sm, st);
+    if (brc <= 0) { if (brc == 0) ctx().timings.reserved = 2.0f; return brc; }
+    P.hot.bucket = 0;
+  }
   const int rc = launch_scan_jit(P, narrow ? 4 : 12, kwc, P.hot_slots > 0, scan_threads(P), sm, st);
   if (rc <= 0) { if (rc == 0) ctx().timings.reserved = 1.0f; return rc; }
   if (narrow) return launch_scan_nc4(P, sm, st);
@@ -615,6 +621,7 @@ static int padded_kw(int n_kw) { return n_kw == 3 ? 4 : (n_kw == 5 ? 6 : n_kw); 
 // useful table fits.
 // dense_range > 0: dense ids (id = key - dense_min) over exactly that many ids, no key index.
 static bool plan_hot_threads(ScanPlan& P, int64_t groups_hint, int requested_gcap, int64_t dense_range, int threads, bool exact);
+static bool plan_bucket(ScanPlan& P, int64_t groups, bool assume_jit = false);
 static bool plan_hot(ScanPlan& P, int64_t groups_hint, int requested_gcap, int64_t dense_range = 0) {
   const int base = narrow_class(P) ? ScanCfg<4>::THREADS : ScanCfg<12>::THREADS;
   if (!plan_hot_threads(P, groups_hint, requested_gcap, dense_range, base, false)) return false;
@@ -725,6 +732,59 @@ static bool plan_hot_threads(ScanPlan& P, int64_t groups_hint, int requested_gca
   }
 }
 
+
+// Bucket tier geometry (pw_bucket.cuh) on top of a dense-id hot plan.  `groups` = populated ids expected per tile.
+// Returns false (P.hot.bucket stays 0) when the shape is not eligible or nothing fits.
+static bool plan_bucket(ScanPlan& P, int64_t groups, bool assume_jit) {
+  HotGeom& g = P.hot;
+  g.bucket = 0;
+  static const bool off = getenv("PW_NO_BUCKET") != nullptr;
+  if (off || (!assume_jit && !jit_available()) || !g.dense || g.gcap < 48 || g.gcap > 2048) return false;
+  if (P.dyn.enabled || P.row_group_out || P.rowid_slot_p1 || P.check_sorted || !P.vec_ok || P.row_begin != 0 || P.row_stride != 1) return false;
+  if (P.n_kw != 1 || P.n_vexpr > 8 || P.n_acc < 1) return false;
+  bool meta = (P.gflags & GF_ROW) != 0;
+  for (int e = 0; e < P.n_vexpr; ++e) {
+    const VExpr& V = P.vexprs[e];
+    if (V.flags & (VF_FIRST | VF_LAST | VF_FIRST_NN | VF_LAST_NN)) meta = true;
+    if (V.n_factors == 0) meta = meta || P.slots[V.slot].validity != nullptr;
+    else for (int k = 0; k < V.n_factors; ++k) meta = meta || P.slots[V.f[k].slot].validity != nullptr;
+  }
+  const int planes = P.n_vexpr + (meta ? 1 : 0);
+  if (planes < 1) return false;   // len-only queries: nothing to bucket, the per-cell counters are already cheap
+  int gcap = 64;
+  while (gcap < g.gcap) gcap <<= 1;
+  // bucket depth from the Poisson tail of rows per id per tile: expected share of rows beyond depth J below 1e-4
+  auto depth = [&](double lambda) {
+    double p = exp(-lambda), cdf = 0.0, mean_le = 0.0;   // P(X = k), running sums over k <= J
+    for (int k = 0; k < 4096; ++k) {
+      if (k > 0) p *= lambda / k;
+      cdf += p; mean_le += k * p;
+      // rows beyond depth k: sum_{x > k} (x - k) p(x) = (lambda - mean_le) - k (1 - cdf)
+      const double beyond = (lambda - mean_le) - k * (1.0 - cdf);
+      if (k >= 2 && beyond <= 1e-4 * lambda) return k;
+    }
+    return 4096;
+  };
+  const size_t budget = 172 * 1024;   // per SM; leaves ~56 KB of L1 for the loads in flight (see pw_bucket.cuh)
+  const int64_t pop = std::max<int64_t>(1, std::min<int64_t>(groups > 0 ? groups : g.gcap, g.gcap));
+  // in order of measured preference on the C2 shape (tools/bucket_probe.cu): one 32-warp CTA with two bucket buffers
+  // (one barrier per tile, 0.32 ms), two 16-warp CTAs with one buffer each (0.35 ms), then whatever fits
+  static const struct { int threads, nbuf, cps; } cand[] = {{1024, 2, 1}, {512, 1, 2}, {512, 2, 1}, {1024, 1, 1}, {512, 1, 1}};
+  static const int only = getenv("PW_BUCKET_CAND") ? atoi(getenv("PW_BUCKET_CAND")) : -1;   // experiments: one geometry only
+  for (const auto& cd : cand) {
+    if (only >= 0 && &cd != &cand[only % 5]) continue;
+    const int tile = cd.threads / 32 * 64;
+    const int J = depth((double)tile / (double)pop) + 1;
+    const int ncnt = gcap < cd.threads ? cd.nbuf + 1 : cd.nbuf;
+    const size_t bytes = (size_t)cd.nbuf * planes * J * gcap * 8 + (size_t)ncnt * gcap * 4;
+    if (bytes * cd.cps > budget) continue;
+    g.bucket = 1; g.b_threads = cd.threads; g.b_gcap = gcap; g.b_j = J; g.b_nbuf = cd.nbuf; g.b_halves = 1; g.b_meta = meta ? 1 : 0;
+    g.b_cps = cd.cps;
+    g.b_bytes = (int32_t)bytes;
+    return true;
+  }
+  return false;
+}
 }  // namespace pw
 // Diagnostics: NVRTC-compiles the specialised scan kernel for a C2-shaped plan (int64 key, f64 value,
 // sum/mean/min/max).  Needs no GPU; used by build() as the "does the JIT path build" check.
@@ -741,6 +801,9 @@ extern "C" __attribute__((visibility("default"))) int pw_b200_jit_selftest(char*
   P.n_acc = 4; P.gflags = GF_LEN; P.acc_gbase = 3;
   if (!plan_hot(P, 1000, 0, getenv("PW_SELFTEST_DENSE") ? 1000 : 0)) return -1;
   P.hot_slots = P.hot.idx_slots;
+  if (getenv("PW_SELFTEST_DENSE")) {   // the bucket tier on top of the dense ids (NVRTC exists whenever this function can succeed)
+    if (!plan_bucket(P, 1000, true) && !getenv("PW_NO_BUCKET")) return -3;
+  }
   std::string err;
   if (getenv("PW_SELFTEST_THREADS")) {  // the geometry a 16-warp CTA would get
     if (!plan_hot_threads(P, 1000, P.hot.gcap, getenv("PW_SELFTEST_DENSE") ? 1000 : 0, atoi(getenv("PW_SELFTEST_THREADS")), true)) return -2;
@@ -1215,13 +1278,19 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
   if (q->flags & PW_FLAG_FORCE_HOT_TABLE) use_hot = true;
   if (q->flags & PW_FLAG_FORCE_GLOBAL_TABLE) use_hot = false;
   if (live_groups == 0) live_groups = std::min<int64_t>(std::max<int64_t>(N, 4), 1024);
-  if (use_hot && dense_range > 0 && q->hot_table_slots == 0 && plan_hot(P, live_groups, 0, dense_range)) { if (dense_sentinels) P.hot.dense = 2; }
+  if (use_hot && dense_range > 0 && q->hot_table_slots == 0 && plan_hot(P, live_groups, 0, dense_range)) {
+    if (dense_sentinels) P.hot.dense = 2;
+    if (!(q->flags & PW_FLAG_NO_BUCKETS)) plan_bucket(P, live_groups);
+  }
   else if (use_hot && !plan_hot(P, live_groups, q->hot_table_slots)) use_hot = false;
   if (cap > 0xFFFFFFF0ull) return fail(PW_ERR_UNSUPPORTED, "table larger than 2^32 slots");
   if (getenv("PW_DEBUG"))
     fprintf(stderr, "[pw] rows=%lld kw=%d slots=%d accs=%d cap=%llu hot=%d live=%lld gcap=%d S=%d R=%d n_mm=%d smem=%d dense=%d min=%lld\n", (long long)N, P.n_kw,
             P.n_slots, P.n_acc, (unsigned long long)cap, (int)use_hot, (long long)live_groups, P.hot.gcap, P.hot.idx_slots, P.hot.replicas,
             P.hot.n_mm, P.hot.total_bytes, P.hot.dense, (long long)P.dense_min);
+  if (getenv("PW_DEBUG") && P.hot.bucket)
+    fprintf(stderr, "[pw] bucket tier: threads=%d gcap=%d J=%d nbuf=%d halves=%d meta=%d smem=%d\n", P.hot.b_threads, P.hot.b_gcap, P.hot.b_j, P.hot.b_nbuf,
+            P.hot.b_halves, P.hot.b_meta, P.hot.b_bytes);
   PW_CUDA(cudaEventRecord(c.ev[2], c.stream));
 
   // ---- high-cardinality tier: many groups, several rows each, no locality -> partition the rows by key hash first
@@ -1301,7 +1370,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     }
     break;
   }
-  tm.strategy = partitioned ? 5 : (use_hot ? (P.hot.dense ? 4 : 1) : 2);
+  tm.strategy = partitioned ? 5 : (use_hot ? (P.hot.dense ? (P.hot.bucket ? 7 : 4) : 1) : 2);
   tm.table_slots = (int64_t)cap;
   tm.partition_ms = 0.0f;
   if (deferred) {

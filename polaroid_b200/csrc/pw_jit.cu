@@ -168,6 +168,31 @@ std::string jit_ctl(const ScanPlan& P) {
   g.scalar("bool", "group_out", P.row_group_out != nullptr);
   g.table1("int", "h_kind", P.n_acc, [&](int i) { return P.hot.acc_kind[i]; });
   g.table1("int", "h_off", P.n_acc, [&](int i) { return P.hot.acc_off[i]; });
+  // array extents and geometry of the bucket tier (pw_bucket.cuh) have to be constant expressions of their own
+  g.o << "  static constexpr int kNAcc = " << (P.n_acc > 0 ? P.n_acc : 1) << ", kNVexpr = " << P.n_vexpr
+      << ", kLenAcc = " << ((P.gflags & GF_LEN) ? P.acc_gbase : -1) << ";\n";
+  g.o << "  static constexpr int kBThreads = " << (P.hot.b_threads > 0 ? P.hot.b_threads : 1024) << ", kBGcap = " << (P.hot.b_gcap > 0 ? P.hot.b_gcap : 1024)
+      << ", kBJ = " << (P.hot.b_j > 0 ? P.hot.b_j : 1) << ", kBNbuf = " << (P.hot.b_nbuf > 0 ? P.hot.b_nbuf : 1)
+      << ", kBHalves = " << (P.hot.b_halves > 0 ? P.hot.b_halves : 1) << ";\n";
+  g.o << "  static constexpr bool kBMeta = " << (P.hot.b_meta ? "true" : "false") << ";\n";
+  {
+    // f64 min / max of a value that cannot be null: kept as plain doubles by the bucket tier (rows holding NaN or -0.0
+    // take the HBM path).  Accumulator order inside an expression: sum_i, sum_f, count, min, max (lower_query).
+    uint32_t native = 0, odd = 0;
+    for (int e = 0; e < P.n_vexpr && P.hot.bucket; ++e) {
+      const VExpr& V = P.vexprs[e];
+      if (V.cls != CLS_F64 || !(V.flags & (VF_MIN | VF_MAX))) continue;
+      bool nullable = false;
+      if (V.n_factors == 0) nullable = P.slots[V.slot].validity != nullptr;
+      else for (int k = 0; k < V.n_factors; ++k) nullable = nullable || P.slots[V.f[k].slot].validity != nullptr;
+      if (nullable || getenv("PW_NO_NATIVE_MINMAX")) continue;
+      int a = V.acc_base + ((V.flags & VF_SUM_I) ? 1 : 0) + ((V.flags & VF_SUM_F) ? 1 : 0) + ((V.flags & VF_COUNT) ? 1 : 0);
+      if (V.flags & VF_MIN) native |= 1u << a++;
+      if (V.flags & VF_MAX) native |= 1u << a++;
+      odd |= 1u << e;
+    }
+    g.o << "  static constexpr unsigned kBNativeAcc = " << native << "u, kBOddVexpr = " << odd << "u;\n";
+  }
   g.o << "};\n";
   return g.o.str();
 }
@@ -180,6 +205,12 @@ std::string scan_entry(int nc, int kw, bool hot, int threads, int min_blocks = 1
   std::ostringstream src;
   src << "extern \"C\" __global__ void __launch_bounds__(" << threads << ", " << min_blocks << ") pw_scan_jit(const __grid_constant__ pw::ScanPlan P) {\n"
       << "  pw::scan_body<pw::JitCtl, " << nc << ", " << kw << ", " << (hot ? "true" : "false") << ">(P);\n}\n";
+  return src.str();
+}
+std::string bucket_entry(int nc, int kw, int threads, int cps) {
+  std::ostringstream src;
+  src << "extern \"C\" __global__ void __launch_bounds__(" << threads << ", " << (cps > 0 ? cps : 1) << ") pw_bucket_jit(const __grid_constant__ pw::ScanPlan P) {\n"
+      << "  pw::bucket_body<pw::JitCtl, " << nc << ", " << kw << ">(P);\n}\n";
   return src.str();
 }
 std::string seg_entry(int nc, int threads) {
@@ -218,7 +249,7 @@ void sources_hash(uint64_t* h0, uint64_t* h1) {
   static std::once_flag once;
   std::call_once(once, [] {
     a0 = 0xcbf29ce484222325ull; a1 = 0x84222325cbf29ce4ull;
-    for (const char* name : {"pw_plan.h", "pw_ctl.h", "pw_scan.cuh", "pw_segmented.cuh", "pw_partition.cuh", "pw_pilot.cuh", "pw_dense.cuh"}) {
+    for (const char* name : {"pw_plan.h", "pw_ctl.h", "pw_scan.cuh", "pw_segmented.cuh", "pw_partition.cuh", "pw_pilot.cuh", "pw_bucket.cuh"}) {
       const std::string path = csrc_dir() + "/" + name;
       FILE* f = fopen(path.c_str(), "rb");
       if (!f) continue;
@@ -290,7 +321,7 @@ void cache_write(const std::string& path, const std::vector<char>& cubin) {
 Compiled compile(const std::string& ctl, const std::string& entry, const char* entry_name) {
   Api& a = api();
   Compiled c;
-  const std::string text = "#include \"pw_segmented.cuh\"\n#include \"pw_partition.cuh\"\n#include \"pw_pilot.cuh\"\nnamespace pw {\n" + ctl + "}\n" + entry;
+  const std::string text = "#include \"pw_segmented.cuh\"\n#include \"pw_partition.cuh\"\n#include \"pw_pilot.cuh\"\n#include \"pw_bucket.cuh\"\nnamespace pw {\n" + ctl + "}\n" + entry;
   const std::string cpath = getenv("PW_JIT_DUMP") || getenv("PW_DEBUG") ? std::string() : cache_path(text);
   {
     std::vector<char> cached;
@@ -352,7 +383,8 @@ int jit_selftest_compile(const ScanPlan& P, int nc, int kw, bool hot, int thread
     *(void**)(&a.nvrtcGetCUBIN) = dlsym(rtc, "nvrtcGetCUBIN");
     *(void**)(&a.nvrtcDestroyProgram) = dlsym(rtc, "nvrtcDestroyProgram");
   }
-  const std::string text = "#include \"pw_segmented.cuh\"\n#include \"pw_partition.cuh\"\n#include \"pw_pilot.cuh\"\nnamespace pw {\n" + jit_ctl(P) + "}\n" + scan_entry(nc, kw, hot, threads) + seg_entry(nc, 256) + part_entry(nc, kw, 256) + pilot_entry(nc, kw, 256);
+  const std::string text = "#include \"pw_segmented.cuh\"\n#include \"pw_partition.cuh\"\n#include \"pw_pilot.cuh\"\n#include \"pw_bucket.cuh\"\nnamespace pw {\n" + jit_ctl(P) + "}\n" + scan_entry(nc, kw, hot, threads) + seg_entry(nc, 256) + part_entry(nc, kw, 256) + pilot_entry(nc, kw, 256) +
+                           (P.hot.bucket ? bucket_entry(nc, kw, P.hot.b_threads, P.hot.b_cps) : std::string());
   nvrtcProgram prog = nullptr;
   if (a.nvrtcCreateProgram(&prog, text.c_str(), "pw_scan_jit.cu", 0, nullptr, nullptr) != 0) { *err = "nvrtcCreateProgram failed"; return 2; }
   const std::string inc = "--include-path=" + csrc_dir();
@@ -446,6 +478,45 @@ int launch_scan_jit(const ScanPlan& P, int nc, int kw, bool hot, int threads, in
   void* params[] = {&copy};
   const CUresult rc = a.cuLaunchKernel(c.fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)smem, (CUstream)st, params, nullptr);
   if (rc != 0) return fail(PW_ERR_CUDA, "cuLaunchKernel(pw_scan_jit) failed with %d", rc);
+  ctx().timings.kernel_launches++;
+  return 0;
+}
+
+// the bucket tier (pw_bucket.cuh): one CTA of P.hot.b_threads threads per SM; returns 0 launched, 1 unavailable
+int launch_bucket_jit(const ScanPlan& P, int nc, int kw, int sm_count, cudaStream_t st) {
+  static const bool disabled = getenv("PW_NO_JIT") != nullptr;
+  if (disabled) return 1;
+  Api& a = api();
+  if (!a.ok) return 1;
+  const int threads = P.hot.b_threads;
+  const size_t smem = (size_t)P.hot.b_bytes;
+  std::string key = plan_key(P);
+  const int32_t tail[3] = {-4 /* bucket */, nc, kw};
+  key.append((const char*)tail, sizeof tail);
+  Compiled c;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_cache.find(key);
+    if (it == g_cache.end()) {
+      c = compile(jit_ctl(P), bucket_entry(nc, kw, threads, P.hot.b_cps), "pw_bucket_jit");
+      if (!c.failed && c.fn) {
+        if (a.cuFuncSetAttribute(c.fn, 8 /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/, (int)smem) != 0 ||
+            a.cuOccupancyMaxActiveBlocksPerMultiprocessor(&c.per_sm, c.fn, threads, smem) != 0 || c.per_sm < 1)
+          c.failed = true;
+      }
+      g_cache[key] = c;
+    } else c = it->second;
+  }
+  if (c.failed || !c.fn) return 1;
+  const int64_t tile = (int64_t)(threads / 32) * 64 * P.hot.b_halves;
+  const int64_t n_tiles = (P.n_rows + tile - 1) / tile;
+  int64_t grid = (int64_t)sm_count * c.per_sm;
+  if (grid > n_tiles) grid = n_tiles;
+  if (grid < 1) grid = 1;
+  ScanPlan copy = P;
+  void* params[] = {&copy};
+  const CUresult rc = a.cuLaunchKernel(c.fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)smem, (CUstream)st, params, nullptr);
+  if (rc != 0) return fail(PW_ERR_CUDA, "cuLaunchKernel(pw_bucket_jit) failed with %d", rc);
   ctx().timings.kernel_launches++;
   return 0;
 }

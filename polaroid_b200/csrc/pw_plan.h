@@ -186,6 +186,18 @@ struct HotGeom {
   int32_t shadow_off;  // byte offset of the shadow array (int2 per id)
   int32_t pad4;
   int32_t threads;     // CTA size the geometry was planned for (warp-private regions = threads / 32)
+  // BUCKET tier (pw_bucket.cuh; dense ids only, specialised build only).  The fields above stay valid: when the
+  // specialised build is not available the scan falls back to the per-cell table they describe.
+  int32_t bucket;      // != 0: rows are bucketed by dense id and folded in the owner threads' registers
+  int32_t b_threads;   // CTA size
+  int32_t b_gcap;      // ids per CTA: power of two >= gcap
+  int32_t b_j;         // bucket depth (rows per id per tile; deeper rows take the HBM path)
+  int32_t b_nbuf;      // bucket buffers (2: one barrier per tile)
+  int32_t b_halves;    // 64-row halves per warp per tile
+  int32_t b_meta;      // != 0: extra plane (global row << 8 | validity bits of the value expressions)
+  int32_t b_bytes;     // dynamic shared memory of the bucket kernel
+  int32_t b_cps;       // CTAs per SM the geometry was planned for (launch bound)
+  int32_t b_pad;
   int32_t acc_kind[MAX_ACC];
   int32_t acc_off[MAX_ACC];  // HOT_SHARED_MM: word inside the group's min/max block; private kinds: byte offset inside the warp region
 };

@@ -975,6 +975,14 @@ __device__ __forceinline__ void accumulate_rows(const ScanPlan& P, const RowOut<
   }
 }
 
+// a sink may keep some f64 min / max accumulators as plain doubles (pw_bucket.cuh); every other sink sees ordered images
+template <class S>
+struct SinkNative {
+  static __device__ __forceinline__ constexpr bool on(int) { return false; }
+  static __device__ __forceinline__ void fmin(const S&, int, uint64_t) {}
+  static __device__ __forceinline__ void fmax(const S&, int, uint64_t) {}
+};
+
 // one pass over the aggregate flags of every value expression; accumulator words are consecutive per
 // expression in VFlag order (host: lower_query), then LEN, ROW, TMIN
 template <class CT, int NV, int KW, class Sink>
@@ -989,7 +997,11 @@ __device__ __forceinline__ void accumulate_row(const ScanPlan& P, const RowOut<K
     if (fl & VF_SUM_I) { if (ok) s.template add<OP_ADD_I64>(P, a, bits); ++a; }
     if (fl & VF_SUM_F) { if (ok) s.template add<OP_ADD_F64>(P, a, (uint64_t)__double_as_longlong(bits_to_f64(bits, cls))); ++a; }
     if (fl & VF_COUNT) { if (ok) s.template add<OP_ADD_I64>(P, a, 1ull); ++a; }
-    if (fl & (VF_MIN | VF_MAX)) {
+    if ((fl & (VF_MIN | VF_MAX)) && SinkNative<Sink>::on(a)) {
+      // plain doubles: the sink's rows are never null, NaN or -0.0 here (they took another path)
+      if (fl & VF_MIN) { SinkNative<Sink>::fmin(s, a, bits); ++a; }
+      if (fl & VF_MAX) { SinkNative<Sink>::fmax(s, a, bits); ++a; }
+    } else if (fl & (VF_MIN | VF_MAX)) {
       uint64_t x = bits;
       bool use = ok;
       if (cls == CLS_F64) {

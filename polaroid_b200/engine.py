@@ -27,6 +27,7 @@ FLAG_NO_SEGMENTED = 1 << 3
 FLAG_FORCE_PARTITION = 1 << 4
 FLAG_NO_PARTITION = 1 << 5
 FLAG_NO_DENSE_IDS = 1 << 6
+FLAG_NO_BUCKETS = 1 << 7
 
 
 class PolarwayError(RuntimeError):

@@ -19,9 +19,19 @@ AGGS = lambda: [pw.col("v").sum().alias("sum"), pw.col("v").mean().alias("mean")
 
 
 def run(q, sort_by, expect_dense=True, **opts):
+    """Dense ids run through the bucket tier (strategy 7: rows bucketed per tile, accumulators in registers) when the
+    shape allows it and through the per-cell hot table (strategy 4) otherwise; both are checked."""
+    want = oracle.collect(q)
     got = engine.run_group_by(q.table, q.plan, **opts)
-    assert (engine.last_timings()["strategy"] == 4) == expect_dense
-    G.assert_tables_equal(got, oracle.collect(q), sort_by=sort_by, rtol=1e-12)
+    first = engine.last_timings()["strategy"]
+    assert (first in (4, 7)) == expect_dense
+    G.assert_tables_equal(got, want, sort_by=sort_by, rtol=1e-12)
+    if first == 7:
+        o2 = dict(opts)
+        o2["flags"] = o2.get("flags", 0) | engine.FLAG_NO_BUCKETS
+        got2 = engine.run_group_by(q.table, q.plan, **o2)
+        assert engine.last_timings()["strategy"] == 4
+        G.assert_tables_equal(got2, want, sort_by=sort_by, rtol=1e-12)
     return got
 
 

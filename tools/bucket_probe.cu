@@ -65,85 +65,114 @@ __global__ void __launch_bounds__(1024, 1) stream_kernel(const int64_t* __restri
 }
 
 // ---- the bucket scheme ------------------------------------------------------------------------------------------------
-// One CTA of 1024 threads per SM.  Tile = 1024 * RPT rows.  Per tile: every row takes a rank inside its id's bucket
-// (shared atomic on cnt[id]) and stores its value at buf[rank][id]; after ONE barrier thread g folds bucket g into its
-// registers (reads buf[j][g]: consecutive threads, consecutive words: conflict-free).  Two buffers: the scatter of tile
-// t+1 may start before every thread has folded tile t.
-template <int J, int RPT>
-__global__ void __launch_bounds__(1024, 1) bucket_kernel(const int64_t* __restrict__ keys, const double* __restrict__ vals, int64_t n,
+// THREADS threads per CTA, GCAP / THREADS groups per thread.  Tile = THREADS * RPT rows.  Per tile: every row takes a rank
+// inside its id's bucket (shared atomic on cnt[id]) and stores its value at buf[rank][id]; after a barrier thread g folds
+// bucket g into its registers (reads buf[j][g]: consecutive threads, consecutive words: conflict-free).  NBUF = 2: the
+// scatter of tile t+1 may start before every thread has folded tile t (one barrier per tile); NBUF = 1: two barriers.
+template <int THREADS, int J, int RPT, int NBUF, int CPS>
+__global__ void __launch_bounds__(THREADS, CPS) bucket_kernel(const int64_t* __restrict__ keys, const double* __restrict__ vals, int64_t n,
                                                           int64_t kmin, Part* parts, double* ov_sum, unsigned long long* ov_cnt,
                                                           long long* ov_mn, long long* ov_mx, unsigned long long* ov_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* buf = (double*)smem_raw;                       // [2][J][GCAP]
-  uint32_t* cnt = (uint32_t*)(buf + 2 * J * GCAP);       // [2][GCAP]
+  constexpr int GPT = GCAP / THREADS;
+  double* buf = (double*)smem_raw;                          // [NBUF][J][GCAP]
+  uint32_t* cnt = (uint32_t*)(buf + NBUF * J * GCAP);       // [NBUF][GCAP]
   const int tid = threadIdx.x;
-  cnt[tid] = 0; cnt[GCAP + tid] = 0;
+  for (int i = tid; i < NBUF * GCAP; i += THREADS) cnt[i] = 0;
   __syncthreads();
-  const int64_t tile_rows = 1024 * RPT;
-  const int64_t n_tiles = (n + tile_rows - 1) / tile_rows;
-  double sum = 0.0, mn = INFINITY, mx = -INFINITY;
-  unsigned long long c_total = 0;
+  constexpr int64_t tile_rows = THREADS * RPT;
+  const int64_t n_tiles = n / tile_rows;   // full tiles; the tail goes through the overflow path below
+  double sum[GPT], mn[GPT], mx[GPT];
+  unsigned long long c_total[GPT];
+#pragma unroll
+  for (int g = 0; g < GPT; ++g) { sum[g] = 0.0; mn[g] = INFINITY; mx[g] = -INFINITY; c_total[g] = 0; }
   unsigned long long ov = 0;
 
-  longlong2 k2[2][RPT / 2];
-  double2 v2[2][RPT / 2];
-  auto load = [&](int set, int64_t t) {
-    const int64_t base = t * tile_rows;
+  auto spill = [&](uint64_t id, double v) {
+    atomicAdd(&ov_sum[id], v); atomicAdd(&ov_cnt[id], 1ull);
+    long long o = __double_as_longlong(v); o ^= (o >> 63) & 0x7FFFFFFFFFFFFFFFll;
+    atomicMin(&ov_mn[id], o); atomicMax(&ov_mx[id], o);
+    ++ov;
+  };
+
+  longlong2 k2[RPT / 2], kn[RPT / 2];
+  double2 v2[RPT / 2], vn[RPT / 2];
+  int64_t t = blockIdx.x;
+  if (t < n_tiles) {
 #pragma unroll
     for (int r = 0; r < RPT / 2; ++r) {
-      const int64_t p = base + (int64_t)r * 2048 + tid * 2;
-      if (p + 1 < n) {
-        k2[set][r] = *(const longlong2*)(keys + p);
-        v2[set][r] = *(const double2*)(vals + p);
-      } else {
-        k2[set][r].x = p < n ? keys[p] : -1; k2[set][r].y = -1;
-        v2[set][r].x = p < n ? vals[p] : 0.0; v2[set][r].y = 0.0;
-      }
+      const int64_t p = t * tile_rows + (int64_t)r * 2 * THREADS + tid * 2;
+      kn[r] = *(const longlong2*)(keys + p);
+      vn[r] = *(const double2*)(vals + p);
     }
-  };
-  int64_t t = blockIdx.x;
+  }
   int b = 0;
-  if (t < n_tiles) load(0, t);
-  int set = 0;
-  for (; t < n_tiles; t += gridDim.x, b ^= 1, set ^= 1) {
+  for (; t < n_tiles; t += gridDim.x) {
+#pragma unroll
+    for (int r = 0; r < RPT / 2; ++r) { k2[r] = kn[r]; v2[r] = vn[r]; }
     if (t + gridDim.x < n_tiles) {
-      if (set == 0) load(1, t + gridDim.x); else load(0, t + gridDim.x);
+#pragma unroll
+      for (int r = 0; r < RPT / 2; ++r) {
+        const int64_t p = (t + gridDim.x) * tile_rows + (int64_t)r * 2 * THREADS + tid * 2;
+        kn[r] = *(const longlong2*)(keys + p);
+        vn[r] = *(const double2*)(vals + p);
+      }
     }
     double* bb = buf + (size_t)b * J * GCAP;
     uint32_t* cc = cnt + b * GCAP;
-    auto put = [&](int64_t k, double v) {
-      const uint64_t id = (uint64_t)(k - kmin);
-      if (id < (uint64_t)GCAP) {
-        const uint32_t rk = atomicAdd(&cc[id], 1u);
-        if (rk < (uint32_t)J) bb[rk * GCAP + id] = v;
-        else {
-          atomicAdd(&ov_sum[id], v); atomicAdd(&ov_cnt[id], 1ull);
-          long long o = __double_as_longlong(v); o ^= (o >> 63) & 0x7FFFFFFFFFFFFFFFll;
-          atomicMin(&ov_mn[id], o); atomicMax(&ov_mx[id], o);
-          ++ov;
-        }
-      }
-    };
+    uint64_t id[RPT];
+    double v[RPT];
+    uint32_t rk[RPT];
 #pragma unroll
     for (int r = 0; r < RPT / 2; ++r) {
-      if (set == 0) { put(k2[0][r].x, v2[0][r].x); put(k2[0][r].y, v2[0][r].y); }
-      else { put(k2[1][r].x, v2[1][r].x); put(k2[1][r].y, v2[1][r].y); }
+      id[2 * r] = (uint64_t)(k2[r].x - kmin); id[2 * r + 1] = (uint64_t)(k2[r].y - kmin);
+      v[2 * r] = v2[r].x; v[2 * r + 1] = v2[r].y;
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) rk[r] = id[r] < (uint64_t)GCAP ? atomicAdd(&cc[id[r]], 1u) : 0xFFFFFFFFu;
+    bool late = false;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      if (rk[r] < (uint32_t)J) bb[rk[r] * GCAP + (uint32_t)id[r]] = v[r];
+      else late = true;
+    }
+    if (late) {
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) if (rk[r] >= (uint32_t)J && rk[r] != 0xFFFFFFFFu) spill(id[r], v[r]);
     }
     __syncthreads();
-    uint32_t c = cc[tid];
-    if (c) cc[tid] = 0;
-    c = c < (uint32_t)J ? c : (uint32_t)J;
-    c_total += c;
-#pragma unroll 2
-    for (uint32_t j = 0; j < c; ++j) {
-      const double x = bb[j * GCAP + tid];
-      sum += x;
-      mn = fmin(mn, x);
-      mx = fmax(mx, x);
+#pragma unroll
+    for (int g = 0; g < GPT; ++g) {
+      const int gid = g * THREADS + tid;
+      uint32_t c = cc[gid];
+      if (c) cc[gid] = 0;
+      c = c < (uint32_t)J ? c : (uint32_t)J;
+      c_total[g] += c;
+      const double* q = bb + gid;
+      double s_ = sum[g], lo_ = mn[g], hi_ = mx[g];
+#pragma unroll 1
+      for (uint32_t j = 0; j < c; ++j, q += GCAP) {
+        const double x = *q;
+        s_ += x;
+        lo_ = x < lo_ ? x : lo_;
+        hi_ = x > hi_ ? x : hi_;
+      }
+      sum[g] = s_; mn[g] = lo_; mx[g] = hi_;
+    }
+    if (NBUF == 2) b ^= 1; else __syncthreads();
+  }
+  // tail rows (less than a tile): CTA 0, through the spill path
+  if (blockIdx.x == 0) {
+    for (int64_t p = n_tiles * tile_rows + tid; p < n; p += THREADS) {
+      const uint64_t idt = (uint64_t)(keys[p] - kmin);
+      if (idt < (uint64_t)GCAP) spill(idt, vals[p]);
     }
   }
-  Part p; p.sum = sum; p.cnt = c_total; p.mn = mn; p.mx = mx;
-  parts[(size_t)blockIdx.x * GCAP + tid] = p;
+#pragma unroll
+  for (int g = 0; g < GPT; ++g) {
+    Part p; p.sum = sum[g]; p.cnt = c_total[g]; p.mn = mn[g]; p.mx = mx[g];
+    parts[(size_t)blockIdx.x * GCAP + g * THREADS + tid] = p;
+  }
   if (ov) atomicAdd(ov_rows, ov);
 }
 
@@ -187,15 +216,16 @@ void run_atoms(const char* name) {
   cudaFree(d);
 }
 
-template <int J, int RPT>
+template <int THREADS, int J, int RPT, int NBUF, int CPS>
 void run_bucket(const int64_t* keys, const double* vals, int64_t n, int groups, const std::vector<double>& rsum, const std::vector<unsigned long long>& rcnt,
                 const std::vector<long long>& rmn, const std::vector<long long>& rmx) {
   Part* parts;
   double* ov_sum; unsigned long long *ov_cnt, *ov_rows; long long *ov_mn, *ov_mx;
-  CK(cudaMalloc(&parts, sizeof(Part) * 148 * GCAP));
+  const int grid = 148 * CPS;
+  CK(cudaMalloc(&parts, sizeof(Part) * grid * GCAP));
   CK(cudaMalloc(&ov_sum, 8 * GCAP)); CK(cudaMalloc(&ov_cnt, 8 * GCAP)); CK(cudaMalloc(&ov_mn, 8 * GCAP)); CK(cudaMalloc(&ov_mx, 8 * GCAP)); CK(cudaMalloc(&ov_rows, 8));
-  const size_t smem = (size_t)2 * J * GCAP * 8 + 2 * GCAP * 4;
-  CK(cudaFuncSetAttribute(bucket_kernel<J, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = (size_t)NBUF * J * GCAP * 8 + NBUF * GCAP * 4;
+  CK(cudaFuncSetAttribute(bucket_kernel<THREADS, J, RPT, NBUF, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   float best = 1e9f, tot = 0;
@@ -204,16 +234,16 @@ void run_bucket(const int64_t* keys, const double* vals, int64_t n, int groups, 
     CK(cudaMemset(ov_sum, 0, 8 * GCAP)); CK(cudaMemset(ov_cnt, 0, 8 * GCAP)); CK(cudaMemset(ov_rows, 0, 8));
     CK(cudaMemset(ov_mn, 0x7f, 8 * GCAP)); CK(cudaMemset(ov_mx, 0x80, 8 * GCAP));
     cudaEventRecord(e0);
-    bucket_kernel<J, RPT><<<148, 1024, smem>>>(keys, vals, n, 0, parts, ov_sum, ov_cnt, ov_mn, ov_mx, ov_rows);
+    bucket_kernel<THREADS, J, RPT, NBUF, CPS><<<grid, THREADS, smem>>>(keys, vals, n, 0, parts, ov_sum, ov_cnt, ov_mn, ov_mx, ov_rows);
     cudaEventRecord(e1);
     CK(cudaEventSynchronize(e1));
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     if (it >= 3) { best = ms < best ? ms : best; tot += ms; }
   }
-  std::vector<Part> hp((size_t)148 * GCAP);
+  std::vector<Part> hp((size_t)grid * GCAP);
   std::vector<double> os(GCAP); std::vector<unsigned long long> oc(GCAP); std::vector<long long> omn(GCAP), omx(GCAP);
   unsigned long long ovr = 0;
-  CK(cudaMemcpy(hp.data(), parts, sizeof(Part) * 148 * GCAP, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hp.data(), parts, sizeof(Part) * grid * GCAP, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(os.data(), ov_sum, 8 * GCAP, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(oc.data(), ov_cnt, 8 * GCAP, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(omn.data(), ov_mn, 8 * GCAP, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(omx.data(), ov_mx, 8 * GCAP, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(&ovr, ov_rows, 8, cudaMemcpyDeviceToHost));
@@ -222,7 +252,7 @@ void run_bucket(const int64_t* keys, const double* vals, int64_t n, int groups, 
     double s = os[g]; unsigned long long c = oc[g];
     auto img = [](double v) { long long o; memcpy(&o, &v, 8); o ^= (o >> 63) & 0x7FFFFFFFFFFFFFFFll; return o; };
     long long mn = omn[g], mx = omx[g];
-    for (int b = 0; b < 148; ++b) {
+    for (int b = 0; b < grid; ++b) {
       const Part& p = hp[(size_t)b * GCAP + g];
       s += p.sum; c += p.cnt;
       if (p.cnt) { mn = std::min(mn, img(p.mn)); mx = std::max(mx, img(p.mx)); }
@@ -233,7 +263,7 @@ void run_bucket(const int64_t* keys, const double* vals, int64_t n, int groups, 
     }
   }
   const double gb = (double)n * 16 / 1e9;
-  printf("bucket J=%2d RPT=%d smem=%6zu B: best %.4f ms avg %.4f ms  -> %.0f GB/s (best), overflow rows %llu, %s\n", J, RPT, smem, best, tot / reps,
+  printf("bucket T=%4d J=%2d RPT=%d NBUF=%d CTAs/SM=%d smem=%6zu B: best %.4f ms avg %.4f ms  -> %.0f GB/s (best), overflow rows %llu, %s\n", THREADS, J, RPT, NBUF, CPS, smem, best, tot / reps,
          gb / (best * 1e-3), ovr, bad ? "WRONG" : "results ok");
   cudaFree(parts); cudaFree(ov_sum); cudaFree(ov_cnt); cudaFree(ov_mn); cudaFree(ov_mx); cudaFree(ov_rows);
 }
@@ -275,9 +305,11 @@ int main(int argc, char** argv) {
     }
     printf("stream (148 x 1024 threads, 64 B per thread per tile): best %.4f ms -> %.0f GB/s\n", best, (double)n * 16 / 1e9 / (best * 1e-3));
   }
-  run_bucket<12, 4>(keys, vals, n, groups, hs, hc, hmn, hmx);
-  run_bucket<13, 4>(keys, vals, n, groups, hs, hc, hmn, hmx);
-  run_bucket<8, 2>(keys, vals, n, groups, hs, hc, hmn, hmx);
-  run_bucket<10, 2>(keys, vals, n, groups, hs, hc, hmn, hmx);
+  run_bucket<512, 10, 4, 1, 2>(keys, vals, n, groups, hs, hc, hmn, hmx);
+  run_bucket<512, 7, 2, 1, 3>(keys, vals, n, groups, hs, hc, hmn, hmx);
+  run_bucket<256, 7, 4, 1, 3>(keys, vals, n, groups, hs, hc, hmn, hmx);
+  run_bucket<1024, 10, 2, 2, 1>(keys, vals, n, groups, hs, hc, hmn, hmx);
+  run_bucket<1024, 13, 4, 2, 1>(keys, vals, n, groups, hs, hc, hmn, hmx);
+  run_bucket<512, 9, 4, 1, 2>(keys, vals, n, groups, hs, hc, hmn, hmx);
   return 0;
 }
