@@ -30,12 +30,15 @@ _LIB = None
 
 I64, U64, F64, F32 = 0, 1, 2, 3
 _CMP = {"eq": 0, "ne": 1, "lt": 2, "le": 3, "gt": 4, "ge": 5}
-_KIND = {"sum": 0, "mean": 1, "min": 2, "max": 3, "count": 4, "len": 5, "first": 6, "last": 7}
+_KIND = {"sum": 0, "mean": 1, "min": 2, "max": 3, "count": 4, "len": 5, "first": 6, "last": 7,
+         "var": 8, "std": 9, "first_non_null": 10, "last_non_null": 11, "null_count": 12,
+         "bitwise_and": 13, "bitwise_or": 14, "bitwise_xor": 15, "any": 16, "all": 17}
 _CLOSED = {"left": 0, "right": 1, "both": 2, "none": 3}
 
 
 class OrcAgg(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("vclass", C.c_int32), ("values", C.c_void_p), ("valid", C.c_void_p)]
+    _fields_ = [("kind", C.c_int32), ("vclass", C.c_int32), ("values", C.c_void_p), ("valid", C.c_void_p),
+                ("ddof", C.c_int32), ("is_bool", C.c_int32)]
 
 
 def build(force: bool = False) -> str:
@@ -105,10 +108,11 @@ def widen(arr: pa.Array):
     arr = _physical(_combine(arr))
     t = arr.type
     valid = _valid_bytes(arr)
-    filled = arr.fill_null(0) if arr.null_count else arr
     if pa.types.is_boolean(t):
+        filled = arr.fill_null(False) if arr.null_count else arr
         v = np.asarray(filled.to_numpy(zero_copy_only=False)).astype(np.uint64)
         return v, U64, valid
+    filled = arr.fill_null(0) if arr.null_count else arr
     v = filled.to_numpy(zero_copy_only=False)
     if pa.types.is_float64(t):
         return np.ascontiguousarray(v, dtype=np.float64), F64, valid
@@ -206,8 +210,17 @@ def eval_value_expr(table: pa.Table, expr):
 # ---- output typing --------------------------------------------------------------------------
 def _out_array(kind: str, bits: np.ndarray, ok: np.ndarray, vclass: int, src_type):
     mask = None if ok.all() else ~ok.astype(bool)
-    if kind in ("count", "len"):
+    if kind in ("count", "len", "null_count"):
         return pa.array(bits.astype(np.uint32), type=pa.uint32())
+    if kind in ("any", "all"):
+        return pa.array(bits.astype(bool), type=pa.bool_())
+    if kind in ("var", "std"):   # reduce/var_std.rs:104-140: Float32 in -> Float32 out, everything else Float64
+        vals = bits.view(np.float64)
+        if src_type is not None and pa.types.is_float32(src_type):
+            return pa.array(vals.astype(np.float32), mask=mask, type=pa.float32())
+        return pa.array(vals, mask=mask, type=pa.float64())
+    if kind.startswith("bitwise_") and src_type is not None and pa.types.is_boolean(src_type):
+        return pa.array(bits.astype(bool), mask=mask, type=pa.bool_())
     if kind == "mean":
         vals = bits.view(np.float64)
         if src_type is not None and pa.types.is_float32(src_type):
@@ -264,6 +277,8 @@ def _make_aggs(table, aggs):
         c_aggs[i].vclass = vc
         c_aggs[i].values = v.ctypes.data
         c_aggs[i].valid = valid.ctypes.data if valid is not None else None
+        c_aggs[i].ddof = int(getattr(a, "ddof", 0) or 0)
+        c_aggs[i].is_bool = 1 if (st is not None and pa.types.is_boolean(st)) else 0
         meta.append((vc, st))
     return c_aggs, keep, meta
 

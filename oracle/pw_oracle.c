@@ -26,7 +26,10 @@
 /* ---- shared small enums (documented in include/polarway_b200.h) ---------- */
 enum { ORC_EQ = 0, ORC_NE = 1, ORC_LT = 2, ORC_LE = 3, ORC_GT = 4, ORC_GE = 5 };
 enum { ORC_SUM = 0, ORC_MEAN = 1, ORC_MIN = 2, ORC_MAX = 3, ORC_COUNT = 4,
-       ORC_LEN = 5, ORC_FIRST = 6, ORC_LAST = 7 };
+       ORC_LEN = 5, ORC_FIRST = 6, ORC_LAST = 7,
+       /* the other reductions the streaming engine pre-aggregates (reduce/convert.rs:46-150) */
+       ORC_VAR = 8, ORC_STD = 9, ORC_FIRST_NN = 10, ORC_LAST_NN = 11, ORC_NULL_COUNT = 12,
+       ORC_BIT_AND = 13, ORC_BIT_OR = 14, ORC_BIT_XOR = 15, ORC_ANY = 16, ORC_ALL = 17 };
 /* value classes the Python wrapper widens to (exact widenings) */
 enum { ORC_I64 = 0, ORC_U64 = 1, ORC_F64 = 2, ORC_F32 = 3 };
 enum { ORC_CLOSED_LEFT = 0, ORC_CLOSED_RIGHT = 1, ORC_CLOSED_BOTH = 2, ORC_CLOSED_NONE = 3 };
@@ -105,6 +108,8 @@ typedef struct {
     int32_t vclass;      /* ORC_I64.. */
     const void *values;  /* widened 8-byte values (or float for F32) */
     const uint8_t *valid;/* byte per row or NULL */
+    int32_t ddof;        /* VAR / STD */
+    int32_t is_bool;     /* the source column is Boolean (values widened to 0 / 1) */
 } OrcAgg;
 
 typedef struct { uint64_t w0, w1; int64_t cnt; int64_t aux; } OrcState;
@@ -113,7 +118,13 @@ typedef struct { uint64_t w0, w1; int64_t cnt; int64_t aux; } OrcState;
  *  MEAN: w0=sum w1=comp cnt=non-null
  *  MIN/MAX: w0=current cnt=non-null aux=non-NaN count
  *  COUNT/LEN: cnt
- *  FIRST/LAST: w0=value bits w1=row index cnt=has aux=valid */
+ *  FIRST/LAST: w0=value bits w1=row index cnt=has aux=valid
+ *  VAR/STD: w0=mean w1=dp cnt=weight (polars-compute/src/moment.rs:40-44 VarState);
+ *           Boolean input: w0=number of true values cnt=non-null (var_std.rs:144-160)
+ *  FIRST_NN/LAST_NN: as FIRST/LAST over the non-null rows only (first_last_nonnull.rs)
+ *  NULL_COUNT: cnt=nulls (count.rs NullCountReduce)
+ *  BIT_AND/OR/XOR: w0=accumulator cnt=non-null (bitwise.rs; masked: no non-null value => null)
+ *  ANY: w0=1 once a true was seen; ALL: w0=number of non-null false values (any_all.rs, ignore_nulls) */
 
 static inline double u2d(uint64_t u) { double d; memcpy(&d, &u, 8); return d; }
 static inline uint64_t d2u(double d) { uint64_t u; memcpy(&u, &d, 8); return u; }
@@ -196,6 +207,37 @@ static inline void state_update(OrcState *s, const OrcAgg *a, int64_t row) {
     case ORC_LAST:
         s->cnt = 1; s->w1 = (uint64_t)row; s->aux = ok; s->w0 = ok ? get_bits(a, row) : 0;
         break;
+    case ORC_VAR: case ORC_STD:
+        if (!ok) break;
+        if (a->is_bool) { s->w0 += ((const uint64_t *)a->values)[row] != 0; s->cnt++; break; }
+        {   /* VarState::insert_one, moment.rs:87-97 */
+            const double x = get_f64(a, row);
+            const double new_weight = (double)s->cnt + 1.0;
+            const double mean = u2d(s->w0), delta_mean = x - mean;
+            const double new_mean = mean + delta_mean / new_weight;
+            s->w1 = d2u(u2d(s->w1) + (x - new_mean) * delta_mean);
+            s->w0 = d2u(new_mean);
+            s->cnt++;
+        }
+        break;
+    case ORC_FIRST_NN:
+        if (ok && !s->cnt) { s->cnt = 1; s->w1 = (uint64_t)row; s->aux = 1; s->w0 = get_bits(a, row); }
+        break;
+    case ORC_LAST_NN:
+        if (ok) { s->cnt = 1; s->w1 = (uint64_t)row; s->aux = 1; s->w0 = get_bits(a, row); }
+        break;
+    case ORC_NULL_COUNT: s->cnt += !ok; break;
+    case ORC_BIT_AND: case ORC_BIT_OR: case ORC_BIT_XOR:
+        if (!ok) break;
+        {
+            const uint64_t v = ((const uint64_t *)a->values)[row];
+            if (!s->cnt) s->w0 = a->kind == ORC_BIT_AND ? ~0ull : 0ull;   /* the identity element (bitwise.rs:68-120) */
+            s->w0 = a->kind == ORC_BIT_AND ? (s->w0 & v) : a->kind == ORC_BIT_OR ? (s->w0 | v) : (s->w0 ^ v);
+            s->cnt++;
+        }
+        break;
+    case ORC_ANY: if (ok && ((const uint64_t *)a->values)[row]) s->w0 = 1; break;
+    case ORC_ALL: if (ok && !((const uint64_t *)a->values)[row]) s->w0++; break;
     }
 }
 
@@ -240,6 +282,34 @@ static inline void state_combine(OrcState *a, const OrcState *b, const OrcAgg *g
     case ORC_LAST:
         if (b->cnt && (!a->cnt || b->w1 >= a->w1)) *a = *b;
         break;
+    case ORC_VAR: case ORC_STD:
+        if (g->is_bool) { a->w0 += b->w0; a->cnt += b->cnt; break; }
+        if (b->cnt == 0) break;
+        {   /* VarState::combine, moment.rs:111-124 */
+            const double bw = (double)b->cnt, new_weight = (double)a->cnt + bw;
+            const double frac = bw / new_weight;
+            const double delta_mean = u2d(b->w0) - u2d(a->w0);
+            const double new_mean = u2d(a->w0) + delta_mean * frac;
+            a->w1 = d2u(u2d(a->w1) + u2d(b->w1) + bw * (u2d(b->w0) - new_mean) * delta_mean);
+            a->w0 = d2u(new_mean);
+            a->cnt += b->cnt;
+        }
+        break;
+    case ORC_FIRST_NN:
+        if (b->cnt && (!a->cnt || b->w1 < a->w1)) *a = *b;
+        break;
+    case ORC_LAST_NN:
+        if (b->cnt && (!a->cnt || b->w1 >= a->w1)) *a = *b;
+        break;
+    case ORC_NULL_COUNT: a->cnt += b->cnt; break;
+    case ORC_BIT_AND: case ORC_BIT_OR: case ORC_BIT_XOR:
+        if (!b->cnt) break;
+        if (!a->cnt) a->w0 = b->w0;
+        else a->w0 = g->kind == ORC_BIT_AND ? (a->w0 & b->w0) : g->kind == ORC_BIT_OR ? (a->w0 | b->w0) : (a->w0 ^ b->w0);
+        a->cnt += b->cnt;
+        break;
+    case ORC_ANY: a->w0 |= b->w0; break;
+    case ORC_ALL: a->w0 += b->w0; break;
     }
 }
 
@@ -499,9 +569,28 @@ void orc_result_agg(const OrcResult *r, const OrcAgg *aggs, int a, uint64_t *out
             else v = s->w0;
             break;
         case ORC_COUNT: case ORC_LEN: v = (uint64_t)s->cnt; break;
-        case ORC_FIRST: case ORC_LAST:
+        case ORC_FIRST: case ORC_LAST: case ORC_FIRST_NN: case ORC_LAST_NN:
             if (!s->cnt || !s->aux) ok = 0; else v = s->w0;
             break;
+        case ORC_VAR: case ORC_STD: {
+            /* VarState::finalize, moment.rs:126-139; Boolean: var_std.rs:144-160 */
+            if (s->cnt <= (int64_t)g->ddof) { ok = 0; break; }
+            double var;
+            if (g->is_bool) {
+                const double sum = (double)s->w0;
+                var = sum * (1.0 - sum / (double)s->cnt) / (double)(s->cnt - g->ddof);
+            } else {
+                var = u2d(s->w1) / ((double)s->cnt - (double)g->ddof);
+                if (var < 0.0) var = 0.0;
+            }
+            v = d2u(g->kind == ORC_STD ? sqrt(var) : var);
+            break; }
+        case ORC_NULL_COUNT: v = (uint64_t)s->cnt; break;
+        case ORC_BIT_AND: case ORC_BIT_OR: case ORC_BIT_XOR:
+            if (!s->cnt) ok = 0; else v = s->w0;
+            break;
+        case ORC_ANY: v = s->w0 != 0; break;
+        case ORC_ALL: v = s->w0 == 0; break;
         }
         out[i] = v; out_valid[i] = ok;
     }

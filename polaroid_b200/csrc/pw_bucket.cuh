@@ -33,10 +33,21 @@ namespace pw {
 
 // shared memory through 32-bit window addresses and predicated instructions: no generic-address arithmetic and no
 // branches around the per-row atomics and stores (the kernel is bound by warp-instruction issue, not by a data pipe)
+__device__ __forceinline__ uint32_t sh_rank(uint32_t addr) {   // atomicAdd(cnt, 1)
+  uint32_t r;
+  asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(r) : "r"(addr) : "memory");
+  return r;
+}
 __device__ __forceinline__ uint32_t sh_rank_if(uint32_t addr, bool p) {   // p ? atomicAdd(cnt, 1) : ~0
   uint32_t r = 0xFFFFFFFFu;
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q atom.shared.add.u32 %0, [%1], 1;\n\t}" : "+r"(r) : "r"(addr), "r"((uint32_t)p) : "memory");
   return r;
+}
+__device__ __forceinline__ uint32_t atomicAdd_shared_u32(uint32_t addr) { return sh_rank(addr); }
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t x) {   // a value the compiler may not recompute (it lives in a register)
+  uint32_t y;
+  asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
 }
 __device__ __forceinline__ void sh_st64_if(uint32_t addr, uint64_t v, bool p) {
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.b64 [%0], %1;\n\t}" ::"r"(addr), "l"(v), "r"((uint32_t)p) : "memory");
@@ -53,10 +64,37 @@ __device__ __forceinline__ uint32_t sh_ld32(uint32_t addr) {
 }
 __device__ __forceinline__ void sh_st32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
+// ---- input staging: bulk async copies (TMA, cp.async.bulk -> UBLKCP) completing on an mbarrier ----
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "PW_MBAR_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra PW_MBAR_DONE;\n\t"
+      "bra PW_MBAR_WAIT;\n\t"
+      "PW_MBAR_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// this lane's two rows of a staged slot, in the register format of load_pair (pw_scan.cuh)
+__device__ __forceinline__ uint4 staged_pair(uint32_t addr, int w) {
+  uint4 r = make_uint4(0u, 0u, 0u, 0u);
+  if (w == 8) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+  else if (w == 4) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr) : "memory");
+  else if (w == 2) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r.x) : "r"(addr) : "memory");
+  else asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r.x) : "r"(addr) : "memory");
+  return r;
+}
+
 // accumulators of ONE group in registers; SKIP = an accumulator handled outside the per-row walk (the row counter);
 // NATIVE = bit per accumulator: an f64 min / max kept as the plain double and compared with DSETP (the rows that need the
 // total order — NaN, -0.0 — never reach the buckets), turned into the ordered image once, when the registers are published
-template <int NACC, int SKIP, uint32_t NATIVE>
+template <int NACC, int SKIP, uint32_t NATIVE, bool SELECT_MM = false>
 struct BucketRegSink {
   uint64_t (&acc)[NACC];
   template <int OP>
@@ -65,20 +103,28 @@ struct BucketRegSink {
     for (int i = 0; i < NACC; ++i)
       if (i == a && i != SKIP) acc[i] = acc_combine(OP, acc[i], x);
   }
+  // SELECT_MM: compare-and-select on both halves (measured faster: 0.419 vs 0.465 ms on C2); otherwise compare and
+  // skip the update (fewer instructions, but the predicated moves wait on the FP64 compare)
   __device__ __forceinline__ void fmin(int a, uint64_t bits) const {
 #pragma unroll
     for (int i = 0; i < NACC; ++i)
-      if (i == a) asm("{\n\t.reg .pred q;\n\tsetp.lt.f64 q, %1, %0;\n\tselp.b64 %0, %1, %0, q;\n\t}" : "+l"(acc[i]) : "l"(bits));
+      if (i == a) {
+        if (SELECT_MM) acc[i] = __longlong_as_double((long long)bits) < __longlong_as_double((long long)acc[i]) ? bits : acc[i];
+        else if (__longlong_as_double((long long)bits) < __longlong_as_double((long long)acc[i])) { asm volatile("" ::: "memory"); acc[i] = bits; }
+      }
   }
   __device__ __forceinline__ void fmax(int a, uint64_t bits) const {
 #pragma unroll
     for (int i = 0; i < NACC; ++i)
-      if (i == a) asm("{\n\t.reg .pred q;\n\tsetp.gt.f64 q, %1, %0;\n\tselp.b64 %0, %1, %0, q;\n\t}" : "+l"(acc[i]) : "l"(bits));
+      if (i == a) {
+        if (SELECT_MM) acc[i] = __longlong_as_double((long long)bits) > __longlong_as_double((long long)acc[i]) ? bits : acc[i];
+        else if (__longlong_as_double((long long)bits) > __longlong_as_double((long long)acc[i])) { asm volatile("" ::: "memory"); acc[i] = bits; }
+      }
   }
 };
-template <int NACC, int SKIP, uint32_t NATIVE>
-struct SinkNative<BucketRegSink<NACC, SKIP, NATIVE>> {
-  using S = BucketRegSink<NACC, SKIP, NATIVE>;
+template <int NACC, int SKIP, uint32_t NATIVE, bool SELECT_MM>
+struct SinkNative<BucketRegSink<NACC, SKIP, NATIVE, SELECT_MM>> {
+  using S = BucketRegSink<NACC, SKIP, NATIVE, SELECT_MM>;
   static __device__ __forceinline__ constexpr bool on(int a) { return ((NATIVE >> a) & 1u) != 0; }
   static __device__ __forceinline__ void fmin(const S& s, int a, uint64_t bits) { s.fmin(a, bits); }
   static __device__ __forceinline__ void fmax(const S& s, int a, uint64_t bits) { s.fmax(a, bits); }
@@ -149,13 +195,41 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
   constexpr int NCNT = SUB == 1 ? NBUF : NBUF + 1;
   constexpr int TILE = WARPS * 64;        // rows per tile: two per lane
   constexpr int LEN_ACC = CT::kLenAcc;    // the row counter is bumped once per fold, not once per row
+  constexpr int STAGES = CT::kBStages;    // > 0: input tiles arrive in shared memory by bulk async copies, this many tiles ahead
+  constexpr uint32_t VAR = CT::kBVar;     // experiment switches (PW_BUCKET_VAR): 1 branch-form min / max, 2 predicated rank atomics
+  // OVERFLOW LIST: a row whose rank is beyond the bucket depth is appended to a short CTA-wide list (id + value words)
+  // that every owner scans after its bucket — a broadcast read per entry.  The HBM path is ~1 us per row (dependent,
+  // contended global atomics; measured: 79 k such rows of 1e8 doubled the kernel time), so it must stay exceptional even
+  // when the host's depth estimate (Poisson tail, 1e-4 of the rows) is off; only a full list falls through to HBM.
+  constexpr int OVF = 32, NOVF = NBUF + 1;
+  constexpr uint32_t OVF_BYTES = (16u + (uint32_t)NBUF * OVF * (4u + 8u * PLANES) + 127u) & ~127u;
   constexpr uint32_t PLANE_BYTES = (uint32_t)J * GCAP * 8u, BUF_BYTES = PLANE_BYTES * PLANES;
   static_assert((GCAP & (GCAP - 1)) == 0 && (THREADS % 32) == 0, "bucket geometry");
 
-  const uint32_t sbuf = (uint32_t)__cvta_generic_to_shared(smem_raw);   // [NBUF][PLANES][J][GCAP] x 8 bytes
-  const uint32_t scnt = sbuf + (uint32_t)NBUF * BUF_BYTES;              // [NCNT][GCAP] x 4 bytes
+  const uint32_t sbuf = opaque_u32((uint32_t)__cvta_generic_to_shared(smem_raw));   // [NBUF][PLANES][J][GCAP] x 8 bytes
+  const uint32_t scnt = sbuf + (uint32_t)NBUF * BUF_BYTES;              // [NCNT][GCAP] x 4 bytes, then 32 dummy cells
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // a row that takes no bucket still runs the rank atomic — on its lane's own dummy cell (one bank each) — so that the
+  // scatter has no branches; the result is ignored
+  const uint32_t dummy = scnt + (uint32_t)NCNT * (GCAP * 4u) + 4u * lane;
+  // staged input: [STAGES][slot][TILE rows], then one mbarrier per stage
+  uint32_t slot_off[NC], stage_bytes = 0;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    slot_off[c] = stage_bytes;
+    if (c < CT::n_slots(P)) stage_bytes += (uint32_t)TILE * (uint32_t)dtype_width(CT::slot_dtype(P, c));
+  }
+  const uint32_t sovf = scnt + (uint32_t)NCNT * (GCAP * 4u) + 128u;     // [NOVF] counters | [NBUF][OVF] ids | [NBUF][PLANES][OVF] words
+  const uint32_t sovf_id = sovf + 16u, sovf_val = sovf_id + (uint32_t)NBUF * OVF * 4u;
+  const uint32_t sstage = sovf + OVF_BYTES;
+  const uint32_t sbar = sstage + (uint32_t)STAGES * stage_bytes;
   for (int i = tid; i < NCNT * GCAP; i += THREADS) sh_st32(scnt + 4u * i, 0u);
+  if (tid < 4) sh_st32(sovf + 4u * tid, 0u);
+  if (STAGES > 0 && tid == 0) {
+    for (int st = 0; st < STAGES; ++st) mbar_init(sbar + 8u * st, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   __syncthreads();
 
   uint64_t acc[GPT][NACC];
@@ -180,7 +254,20 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
   unsigned long long spilled = 0;
   const int64_t lane_row = (int64_t)warp * 64 + 2 * lane;
 
-  int b = 0, ci = 0;   // buffer / counter array of the current tile
+  // one thread starts the copies of tile t into stage `st`: every slot's TILE rows, completing on the stage's mbarrier
+  auto issue = [&](int64_t t, int st) {
+    const uint32_t bar = sbar + 8u * st, dst = sstage + (uint32_t)st * stage_bytes;
+    mbar_expect_tx(bar, stage_bytes);
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      if (c < CT::n_slots(P)) {
+        const uint32_t w = (uint32_t)dtype_width(CT::slot_dtype(P, c));
+        bulk_g2s(dst + slot_off[c], (const unsigned char*)P.slots[c].values + (size_t)t * TILE * w, (uint32_t)TILE * w, bar);
+      }
+  };
+
+  int b = 0, ci = 0, oi = 0;   // buffer / counter array / overflow counter of the current tile
+  int st_cur = 0;      // staged input: stage of the current tile
   auto process = [&](int64_t t, const uint4 (&raw)[NC], const uint32_t (&vb)[NC], auto whole_tag) {
     constexpr bool WHOLE = decltype(whole_tag)::value;
     const uint32_t bb = sbuf + (uint32_t)b * BUF_BYTES;
@@ -192,11 +279,11 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
       bucket_row_front<CT, NC, KW, NV>(P, raw, vb, 0, row0, WHOLE || row0 < n_rows, o[0]);
       bucket_row_front<CT, NC, KW, NV>(P, raw, vb, 1, row0 + 1, WHOLE || row0 + 1 < n_rows, o[1]);
       uint32_t id[2], rk[2];
-      bool take[2];
+      bool take[2], cand[2];
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const uint64_t d = o[i].k[0] - (uint64_t)P.dense_min;
-        const bool plain = !CT::h_dense_sentinels(P) || o[i].k[0] < KEY_NULL;   // -1 / -2 inside the range: sentinels go cold
+        const bool plain = !CT::kBSent || o[i].k[0] < KEY_NULL;   // -1 / -2 inside the range: sentinels go cold
         bool odd = false;   // a value the plain-double min / max cannot order
 #pragma unroll
         for (int e = 0; e < NVE; ++e)
@@ -204,15 +291,17 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
             const double x = __longlong_as_double((long long)o[i].v[e]);
             odd = odd || x != x || o[i].v[e] == 0x8000000000000000ull;
           }
-        take[i] = o[i].alive && plain && !odd && d < (uint64_t)CT::h_gcap(P);
+        take[i] = o[i].alive && plain && !odd && d < (uint64_t)CT::kBRange;
         id[i] = (uint32_t)d & (uint32_t)(GCAP - 1);
       }
 #pragma unroll
-      for (int i = 0; i < 2; ++i) rk[i] = sh_rank_if(cc + 4u * id[i], take[i]);
+      for (int i = 0; i < 2; ++i) rk[i] = (VAR & 2u) ? sh_rank_if(cc + 4u * id[i], take[i]) : sh_rank(take[i] ? cc + 4u * id[i] : dummy);
       bool late = false;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const bool fits = rk[i] < (uint32_t)J;
+        const bool fits = take[i] && rk[i] < (uint32_t)J;
+        cand[i] = take[i];
+        take[i] = fits;
         const uint32_t q = bb + (rk[i] * GCAP + id[i]) * 8u;
 #pragma unroll
         for (int e = 0; e < NVE; ++e) sh_st64_if(q + (uint32_t)e * PLANE_BYTES, o[i].v[e], fits);
@@ -222,10 +311,22 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
       if (late) {
 #pragma unroll
         for (int i = 0; i < 2; ++i)
-          if (o[i].alive && rk[i] >= (uint32_t)J) { bucket_cold_row<CT, KW, NV>(P, o[i], global_row<CT>(P, o[i].row)); ++spilled; }
+          if (o[i].alive && !take[i]) {
+            uint32_t slot = OVF;
+            if (cand[i]) slot = atomicAdd_shared_u32(sovf + 4u * oi);
+            if (slot < (uint32_t)OVF) {
+              sh_st32(sovf_id + ((uint32_t)b * OVF + slot) * 4u, id[i]);
+              const uint32_t q = sovf_val + ((uint32_t)b * PLANES * OVF + slot) * 8u;
+#pragma unroll
+              for (int e = 0; e < NVE; ++e) sh_st64_if(q + (uint32_t)e * OVF * 8u, o[i].v[e], true);
+              if (META) sh_st64_if(q + (uint32_t)NVE * OVF * 8u, (global_row<CT>(P, o[i].row) << 8) | (uint64_t)(o[i].v_valid & 0xFFu), true);
+            } else { bucket_cold_row<CT, KW, NV>(P, o[i], global_row<CT>(P, o[i].row)); ++spilled; }
+          }
       }
     }
     __syncthreads();
+    // every thread has taken its rows out of the stage: the tile STAGES ahead may land there
+    if (STAGES > 0 && WHOLE && tid == 0 && t + STAGES < whole_hi) issue(t + STAGES, st_cur);
     // ---- fold ----
     if (SUB > 1) {
       // the PREVIOUS tile's counters: every thread finished reading them before it arrived at the barrier above, and
@@ -233,6 +334,10 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
       const uint32_t cprev = scnt + (uint32_t)(ci == 0 ? NCNT - 1 : ci - 1) * (GCAP * 4u);
       for (int i = tid; i < GCAP; i += THREADS) sh_st32(cprev + 4u * i, 0u);
     }
+    // the overflow counter two tiles ahead was last read in the fold before the barrier above
+    if (tid == 0) sh_st32(sovf + 4u * (uint32_t)(oi == 0 ? NOVF - 1 : oi - 1), 0u);
+    uint32_t n_ovf = sh_ld32(sovf + 4u * oi);
+    n_ovf = n_ovf < (uint32_t)OVF ? n_ovf : (uint32_t)OVF;
 #pragma unroll
     for (int gi = 0; gi < GPT; ++gi) {
       const int g = my_g0 + gi * THREADS;
@@ -241,7 +346,7 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
       c = c < (uint32_t)J ? c : (uint32_t)J;
       uint32_t q = bb + ((uint32_t)my_sub * GCAP + g) * 8u;
       uint32_t mine = 0;
-      const BucketRegSink<NACC, LEN_ACC, NATIVE> sink{acc[gi]};
+      const BucketRegSink<NACC, LEN_ACC, NATIVE, (VAR & 1u) == 0> sink{acc[gi]};
 #pragma unroll 1
       for (uint32_t j = my_sub; j < c; j += SUB, q += (uint32_t)SUB * GCAP * 8u) {
         RowOut<KW, NV> o;
@@ -250,6 +355,20 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
         uint64_t grow = 0;
         o.v_valid = 0xFFFFFFFFu;
         if (META) { const uint64_t m = sh_ld64(q + (uint32_t)NVE * PLANE_BYTES); grow = m >> 8; o.v_valid = (uint32_t)(m & 0xFFu); }
+        o.tval = 0ull;
+        accumulate_row<CT, NV, KW>(P, o, grow, sink);
+        ++mine;
+      }
+#pragma unroll 1
+      for (uint32_t i = 0; i < n_ovf; ++i) {
+        if (my_sub != 0 || sh_ld32(sovf_id + ((uint32_t)b * OVF + i) * 4u) != (uint32_t)g) continue;
+        const uint32_t qo = sovf_val + ((uint32_t)b * PLANES * OVF + i) * 8u;
+        RowOut<KW, NV> o;
+#pragma unroll
+        for (int e = 0; e < NV; ++e) o.v[e] = e < NVE ? sh_ld64(qo + (uint32_t)e * OVF * 8u) : 0ull;
+        uint64_t grow = 0;
+        o.v_valid = 0xFFFFFFFFu;
+        if (META) { const uint64_t m = sh_ld64(qo + (uint32_t)NVE * OVF * 8u); grow = m >> 8; o.v_valid = (uint32_t)(m & 0xFFu); }
         o.tval = 0ull;
         accumulate_row<CT, NV, KW>(P, o, grow, sink);
         ++mine;
@@ -265,12 +384,36 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
     if (NBUF == 1) __syncthreads();
     b = (NBUF == 2) ? (b ^ 1) : 0;
     ci = ci + 1 == NCNT ? 0 : ci + 1;
+    oi = oi + 1 == NOVF ? 0 : oi + 1;
   };
 
   // software pipeline over the whole tiles: the loads of the next tile are in flight while this one is scattered and
   // folded; the loop is unrolled by two so that the two register buffers alternate in place
   uint4 rawA[NC], rawB[NC];
   uint32_t vbA[NC], vbB[NC];
+  if (STAGES > 0) {
+    // staged pipeline: the copies run STAGES tiles ahead; a tile's rows come out of shared memory (conflict-free
+    // consecutive 16-byte reads) once its mbarrier phase completes
+    if (tid == 0)
+      for (int k = 0; k < STAGES; ++k)
+        if (tile_lo + k < whole_hi) issue(tile_lo + k, k);
+    uint32_t parity = 0;
+    for (int64_t t = tile_lo; t < whole_hi; ++t) {
+      mbar_wait(sbar + 8u * st_cur, parity);
+      const uint32_t base = sstage + (uint32_t)st_cur * stage_bytes;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        rawA[c] = make_uint4(0u, 0u, 0u, 0u);
+        vbA[c] = 3u;
+        if (c < CT::n_slots(P)) {
+          const int w = dtype_width(CT::slot_dtype(P, c));
+          rawA[c] = staged_pair(base + slot_off[c] + (uint32_t)lane_row * (uint32_t)w, w);
+        }
+      }
+      process(t, rawA, vbA, BucketWholeTag{});
+      if (++st_cur == STAGES) { st_cur = 0; parity ^= 1u; }
+    }
+  } else {
   if (tile_lo < whole_hi) bucket_load<CT, NC, true>(P, tile_lo * TILE + warp * 64, lane, n_rows, rawA, vbA);
   for (int64_t t = tile_lo; t < whole_hi; t += 2) {
     if (t + 1 < whole_hi) bucket_load<CT, NC, true>(P, (t + 1) * TILE + warp * 64, lane, n_rows, rawB, vbB);
@@ -279,6 +422,7 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
       if (t + 2 < whole_hi) bucket_load<CT, NC, true>(P, (t + 2) * TILE + warp * 64, lane, n_rows, rawA, vbA);
       process(t + 1, rawB, vbB, BucketWholeTag{});
     }
+  }
   }
   // the ragged last tile (one CTA at most)
   if (whole_hi < tile_hi) {

@@ -621,7 +621,7 @@ static int padded_kw(int n_kw) { return n_kw == 3 ? 4 : (n_kw == 5 ? 6 : n_kw); 
 // useful table fits.
 // dense_range > 0: dense ids (id = key - dense_min) over exactly that many ids, no key index.
 static bool plan_hot_threads(ScanPlan& P, int64_t groups_hint, int requested_gcap, int64_t dense_range, int threads, bool exact);
-static bool plan_bucket(ScanPlan& P, int64_t groups, bool assume_jit = false);
+static bool plan_bucket(ScanPlan& P, int64_t groups, int64_t dense_range, bool sentinels, bool assume_jit = false);
 static bool plan_hot(ScanPlan& P, int64_t groups_hint, int requested_gcap, int64_t dense_range = 0) {
   const int base = narrow_class(P) ? ScanCfg<4>::THREADS : ScanCfg<12>::THREADS;
   if (!plan_hot_threads(P, groups_hint, requested_gcap, dense_range, base, false)) return false;
@@ -735,11 +735,14 @@ static bool plan_hot_threads(ScanPlan& P, int64_t groups_hint, int requested_gca
 
 // Bucket tier geometry (pw_bucket.cuh) on top of a dense-id hot plan.  `groups` = populated ids expected per tile.
 // Returns false (P.hot.bucket stays 0) when the shape is not eligible or nothing fits.
-static bool plan_bucket(ScanPlan& P, int64_t groups, bool assume_jit) {
+// The per-cell geometry already in P.hot (dense ids or the hash index) stays valid: it is what runs when the specialised
+// build is not available.  dense_range = ids [0, dense_range) after subtracting P.dense_min.
+static bool plan_bucket(ScanPlan& P, int64_t groups, int64_t dense_range, bool sentinels, bool assume_jit) {
   HotGeom& g = P.hot;
   g.bucket = 0;
   static const bool off = getenv("PW_NO_BUCKET") != nullptr;
-  if (off || (!assume_jit && !jit_available()) || !g.dense || g.gcap < 48 || g.gcap > 2048) return false;
+  if (off || (!assume_jit && !jit_available()) || dense_range < 48 || dense_range > 2048) return false;
+  g.b_range = (int32_t)dense_range; g.b_sent = sentinels ? 1 : 0;
   if (P.dyn.enabled || P.row_group_out || P.rowid_slot_p1 || P.check_sorted || !P.vec_ok || P.row_begin != 0 || P.row_stride != 1) return false;
   if (P.n_kw != 1 || P.n_vexpr > 8 || P.n_acc < 1) return false;
   bool meta = (P.gflags & GF_ROW) != 0;
@@ -752,34 +755,70 @@ static bool plan_bucket(ScanPlan& P, int64_t groups, bool assume_jit) {
   const int planes = P.n_vexpr + (meta ? 1 : 0);
   if (planes < 1) return false;   // len-only queries: nothing to bucket, the per-cell counters are already cheap
   int gcap = 64;
-  while (gcap < g.gcap) gcap <<= 1;
-  // bucket depth from the Poisson tail of rows per id per tile: expected share of rows beyond depth J below 1e-4
-  auto depth = [&](double lambda) {
+  while (gcap < dense_range) gcap <<= 1;
+  // bucket depth from the Poisson tail of rows per id per tile: expected share of rows beyond depth J below eps
+  auto depth = [&](double lambda, double eps) {
     double p = exp(-lambda), cdf = 0.0, mean_le = 0.0;   // P(X = k), running sums over k <= J
     for (int k = 0; k < 4096; ++k) {
       if (k > 0) p *= lambda / k;
       cdf += p; mean_le += k * p;
       // rows beyond depth k: sum_{x > k} (x - k) p(x) = (lambda - mean_le) - k (1 - cdf)
       const double beyond = (lambda - mean_le) - k * (1.0 - cdf);
-      if (k >= 2 && beyond <= 1e-4 * lambda) return k;
+      if (k >= 2 && beyond <= eps * lambda) return k;
     }
     return 4096;
   };
-  const size_t budget = 172 * 1024;   // per SM; leaves ~56 KB of L1 for the loads in flight (see pw_bucket.cuh)
-  const int64_t pop = std::max<int64_t>(1, std::min<int64_t>(groups > 0 ? groups : g.gcap, g.gcap));
-  // in order of measured preference on the C2 shape (tools/bucket_probe.cu): one 32-warp CTA with two bucket buffers
-  // (one barrier per tile, 0.32 ms), two 16-warp CTAs with one buffer each (0.35 ms), then whatever fits
+  const int64_t pop = std::max<int64_t>(1, std::min<int64_t>(groups > 0 ? groups : dense_range, dense_range));
+  // Input staging by bulk async copies (TMA): every slot a plain 1/2/4/8-byte column without validity, 16-byte aligned.
+  // The copies of the next `stages` tiles are in flight while a tile is scattered and folded — bytes in flight no
+  // longer cost registers or L1 lines (the register pipeline holds one tile = 32 KB per SM in flight on the C2 shape,
+  // about 70 % of what the HBM latency-bandwidth product asks for).
+  static const int stages_env = getenv("PW_BUCKET_STAGES") ? atoi(getenv("PW_BUCKET_STAGES")) : -1;
+  static const int j_env = getenv("PW_BUCKET_J") ? atoi(getenv("PW_BUCKET_J")) : 0;
+  int row_bytes = 0;
+  bool tma_ok = stages_env != 0;
+  for (int c = 0; c < P.n_slots; ++c) {
+    const int dt = P.slots[c].dtype;
+    const int w = (dt == DT_I8 || dt == DT_U8) ? 1 : (dt == DT_I16 || dt == DT_U16) ? 2 : (dt == DT_I32 || dt == DT_U32 || dt == DT_F32) ? 4 :
+                  (dt == DT_I64 || dt == DT_U64 || dt == DT_F64) ? 8 : 0;
+    if (w == 0 || P.slots[c].validity != nullptr || ((uintptr_t)P.slots[c].values & 15u)) tma_ok = false;
+    row_bytes += w;
+  }
+  // in order of measured preference on the C2 shape: one 32-warp CTA with two bucket buffers (one barrier per tile),
+  // two 16-warp CTAs with one buffer each, then whatever fits
   static const struct { int threads, nbuf, cps; } cand[] = {{1024, 2, 1}, {512, 1, 2}, {512, 2, 1}, {1024, 1, 1}, {512, 1, 1}};
   static const int only = getenv("PW_BUCKET_CAND") ? atoi(getenv("PW_BUCKET_CAND")) : -1;   // experiments: one geometry only
   for (const auto& cd : cand) {
     if (only >= 0 && &cd != &cand[only % 5]) continue;
     const int tile = cd.threads / 32 * 64;
-    const int J = depth((double)tile / (double)pop) + 1;
+    const int j_full = depth((double)tile / (double)pop, 1e-4), j_min = depth((double)tile / (double)pop, 1e-3);
     const int ncnt = gcap < cd.threads ? cd.nbuf + 1 : cd.nbuf;
-    const size_t bytes = (size_t)cd.nbuf * planes * J * gcap * 8 + (size_t)ncnt * gcap * 4;
+    const size_t ovf = (16 + (size_t)cd.nbuf * 32 * (4 + 8 * planes) + 127) & ~(size_t)127;   // overflow list (pw_bucket.cuh OVF_BYTES)
+    const size_t fixed = (size_t)ncnt * gcap * 4 + 128 + ovf;   // counters + one dummy counter per lane + overflow list
+    const size_t per_j = (size_t)cd.nbuf * planes * gcap * 8;
+    if (tma_ok && cd.cps == 1) {
+      // staged: shared memory holds the buckets AND the tiles in flight; L1 is not needed for the stream
+      const size_t stage_bytes = (size_t)tile * row_bytes, limit = 226 * 1024;
+      for (int stages = stages_env > 0 ? stages_env : 3; stages >= (stages_env > 0 ? stages_env : 2); --stages) {
+        const size_t tail = (size_t)stages * stage_bytes + (size_t)stages * 8;
+        // full-depth buckets with three tiles in flight if that fits, else two tiles in flight and whatever depth is left
+        const int j_need = stages > 2 && stages_env <= 0 ? j_full : j_min;
+        if (fixed + tail + per_j * j_need > limit) continue;
+        int J = (int)std::min<size_t>((size_t)j_full, (limit - fixed - tail) / per_j);
+        if (j_env > 0) J = j_env;
+        const size_t bytes = per_j * J + fixed + tail;
+        if (bytes > limit) continue;
+        g.bucket = 1; g.b_threads = cd.threads; g.b_gcap = gcap; g.b_j = J; g.b_nbuf = cd.nbuf; g.b_stages = stages; g.b_meta = meta ? 1 : 0;
+        g.b_cps = 1; g.b_stage_bytes = (int32_t)stage_bytes; g.b_bytes = (int32_t)bytes;
+        return true;
+      }
+    }
+    const size_t budget = 172 * 1024;   // per SM; leaves ~56 KB of L1 for the loads in flight (see pw_bucket.cuh)
+    const int J = j_env > 0 ? j_env : j_full;
+    const size_t bytes = per_j * J + fixed;
     if (bytes * cd.cps > budget) continue;
-    g.bucket = 1; g.b_threads = cd.threads; g.b_gcap = gcap; g.b_j = J; g.b_nbuf = cd.nbuf; g.b_halves = 1; g.b_meta = meta ? 1 : 0;
-    g.b_cps = cd.cps;
+    g.bucket = 1; g.b_threads = cd.threads; g.b_gcap = gcap; g.b_j = J; g.b_nbuf = cd.nbuf; g.b_stages = 0; g.b_meta = meta ? 1 : 0;
+    g.b_cps = cd.cps; g.b_stage_bytes = 0;
     g.b_bytes = (int32_t)bytes;
     return true;
   }
@@ -802,7 +841,7 @@ extern "C" __attribute__((visibility("default"))) int pw_b200_jit_selftest(char*
   if (!plan_hot(P, 1000, 0, getenv("PW_SELFTEST_DENSE") ? 1000 : 0)) return -1;
   P.hot_slots = P.hot.idx_slots;
   if (getenv("PW_SELFTEST_DENSE")) {   // the bucket tier on top of the dense ids (NVRTC exists whenever this function can succeed)
-    if (!plan_bucket(P, 1000, true) && !getenv("PW_NO_BUCKET")) return -3;
+    if (!plan_bucket(P, 1000, 1000, false, true) && !getenv("PW_NO_BUCKET")) return -3;
   }
   std::string err;
   if (getenv("PW_SELFTEST_THREADS")) {  // the geometry a 16-warp CTA would get
@@ -1280,17 +1319,20 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
   if (live_groups == 0) live_groups = std::min<int64_t>(std::max<int64_t>(N, 4), 1024);
   if (use_hot && dense_range > 0 && q->hot_table_slots == 0 && plan_hot(P, live_groups, 0, dense_range)) {
     if (dense_sentinels) P.hot.dense = 2;
-    if (!(q->flags & PW_FLAG_NO_BUCKETS)) plan_bucket(P, live_groups);
+    if (!(q->flags & PW_FLAG_NO_BUCKETS)) plan_bucket(P, live_groups, dense_range, dense_sentinels);
   }
   else if (use_hot && !plan_hot(P, live_groups, q->hot_table_slots)) use_hot = false;
+  // the bucket tier does not need the dense per-cell table to fit (many accumulators): it only needs the id range
+  else if (use_hot && dense_range > 0 && q->hot_table_slots == 0 && !(q->flags & (PW_FLAG_NO_BUCKETS | PW_FLAG_NO_DENSE_IDS)))
+    plan_bucket(P, live_groups, dense_range, dense_sentinels);
   if (cap > 0xFFFFFFF0ull) return fail(PW_ERR_UNSUPPORTED, "table larger than 2^32 slots");
   if (getenv("PW_DEBUG"))
     fprintf(stderr, "[pw] rows=%lld kw=%d slots=%d accs=%d cap=%llu hot=%d live=%lld gcap=%d S=%d R=%d n_mm=%d smem=%d dense=%d min=%lld\n", (long long)N, P.n_kw,
             P.n_slots, P.n_acc, (unsigned long long)cap, (int)use_hot, (long long)live_groups, P.hot.gcap, P.hot.idx_slots, P.hot.replicas,
             P.hot.n_mm, P.hot.total_bytes, P.hot.dense, (long long)P.dense_min);
   if (getenv("PW_DEBUG") && P.hot.bucket)
-    fprintf(stderr, "[pw] bucket tier: threads=%d gcap=%d J=%d nbuf=%d halves=%d meta=%d smem=%d\n", P.hot.b_threads, P.hot.b_gcap, P.hot.b_j, P.hot.b_nbuf,
-            P.hot.b_halves, P.hot.b_meta, P.hot.b_bytes);
+    fprintf(stderr, "[pw] bucket tier: threads=%d gcap=%d J=%d nbuf=%d stages=%d meta=%d smem=%d\n", P.hot.b_threads, P.hot.b_gcap, P.hot.b_j, P.hot.b_nbuf,
+            P.hot.b_stages, P.hot.b_meta, P.hot.b_bytes);
   PW_CUDA(cudaEventRecord(c.ev[2], c.stream));
 
   // ---- high-cardinality tier: many groups, several rows each, no locality -> partition the rows by key hash first
@@ -1370,7 +1412,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     }
     break;
   }
-  tm.strategy = partitioned ? 5 : (use_hot ? (P.hot.dense ? (P.hot.bucket ? 7 : 4) : 1) : 2);
+  tm.strategy = partitioned ? 5 : (use_hot ? (P.hot.bucket ? 7 : (P.hot.dense ? 4 : 1)) : 2);
   tm.table_slots = (int64_t)cap;
   tm.partition_ms = 0.0f;
   if (deferred) {

@@ -173,7 +173,9 @@ std::string jit_ctl(const ScanPlan& P) {
       << ", kLenAcc = " << ((P.gflags & GF_LEN) ? P.acc_gbase : -1) << ";\n";
   g.o << "  static constexpr int kBThreads = " << (P.hot.b_threads > 0 ? P.hot.b_threads : 1024) << ", kBGcap = " << (P.hot.b_gcap > 0 ? P.hot.b_gcap : 1024)
       << ", kBJ = " << (P.hot.b_j > 0 ? P.hot.b_j : 1) << ", kBNbuf = " << (P.hot.b_nbuf > 0 ? P.hot.b_nbuf : 1)
-      << ", kBHalves = " << (P.hot.b_halves > 0 ? P.hot.b_halves : 1) << ";\n";
+      << ", kBStages = " << P.hot.b_stages << ";\n";
+  g.o << "  static constexpr int kBRange = " << P.hot.b_range << ";\n  static constexpr bool kBSent = " << (P.hot.b_sent ? "true" : "false") << ";\n";
+  g.o << "  static constexpr unsigned kBVar = " << (getenv("PW_BUCKET_VAR") ? atoi(getenv("PW_BUCKET_VAR")) : 0) << "u;\n";
   g.o << "  static constexpr bool kBMeta = " << (P.hot.b_meta ? "true" : "false") << ";\n";
   {
     // f64 min / max of a value that cannot be null: kept as plain doubles by the bucket tier (rows holding NaN or -0.0
@@ -508,7 +510,7 @@ int launch_bucket_jit(const ScanPlan& P, int nc, int kw, int sm_count, cudaStrea
     } else c = it->second;
   }
   if (c.failed || !c.fn) return 1;
-  const int64_t tile = (int64_t)(threads / 32) * 64 * P.hot.b_halves;
+  const int64_t tile = (int64_t)(threads / 32) * 64;
   const int64_t n_tiles = (P.n_rows + tile - 1) / tile;
   int64_t grid = (int64_t)sm_count * c.per_sm;
   if (grid > n_tiles) grid = n_tiles;

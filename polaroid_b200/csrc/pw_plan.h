@@ -193,11 +193,13 @@ struct HotGeom {
   int32_t b_gcap;      // ids per CTA: power of two >= gcap
   int32_t b_j;         // bucket depth (rows per id per tile; deeper rows take the HBM path)
   int32_t b_nbuf;      // bucket buffers (2: one barrier per tile)
-  int32_t b_halves;    // 64-row halves per warp per tile
+  int32_t b_stages;    // > 0: input tiles staged in shared memory by bulk async copies (TMA), this many tiles ahead; 0: register pipeline
   int32_t b_meta;      // != 0: extra plane (global row << 8 | validity bits of the value expressions)
   int32_t b_bytes;     // dynamic shared memory of the bucket kernel
   int32_t b_cps;       // CTAs per SM the geometry was planned for (launch bound)
-  int32_t b_pad;
+  int32_t b_range;     // dense ids the buckets cover: [0, b_range) after subtracting ScanPlan::dense_min
+  int32_t b_sent;      // the range contains the key images -1 / -2 (table sentinels): those rows take the HBM path
+  int32_t b_stage_bytes;  // bytes of one staged tile (every slot's TILE rows, 16-byte aligned parts)
   int32_t acc_kind[MAX_ACC];
   int32_t acc_off[MAX_ACC];  // HOT_SHARED_MM: word inside the group's min/max block; private kinds: byte offset inside the warp region
 };

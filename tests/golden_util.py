@@ -79,9 +79,13 @@ def build_query(case, tbl, variant=None):
         e = pw.col(c)
         lf = lf.filter({"lt": e < v, "le": e <= v, "gt": e > v, "ge": e >= v, "eq": e == v, "ne": e != v}[op])
     aggs = []
-    for name, kind, colname in q["aggs"]:
+    for name, kind, colname, *extra in q["aggs"]:
         if kind == "len":
             aggs.append(pw.len().alias(name))
+        elif kind in ("first_non_null", "last_non_null"):
+            aggs.append(getattr(pw.col(colname), kind.split("_")[0])(ignore_nulls=True).alias(name))
+        elif kind in ("var", "std"):
+            aggs.append(getattr(pw.col(colname), kind)(*(extra[:1] or [1])).alias(name))   # optional 4th element: ddof
         else:
             aggs.append(getattr(pw.col(colname), kind)().alias(name))
     if "index" in q:
