@@ -558,7 +558,7 @@ def main():
     def roofline(rows, bytes_per_row, out_rows, out_bytes_per_row, k_ms, step_ms, tm):
         algo = rows * bytes_per_row + out_rows * out_bytes_per_row
         ach = algo / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-        return {"kernel": {3: "pw_seg_jit", 6: "pw_wseg_jit", 7: "pw_bucket_jit"}.get(tm["strategy"], "pw_scan_jit") if tm["reserved"] else "ahead-of-time kernel",
+        return {"kernel": {3: "pw_seg_jit", 6: "pw_bucket_jit", 7: "pw_bucket_jit"}.get(tm["strategy"], "pw_scan_jit") if tm["reserved"] else "ahead-of-time kernel",
                 "kernel_ms": k_ms, "algorithmic_bytes_per_launch": algo, "achieved_gbs": ach,
                 "frac_measured": ach / peak, "frac_nominal_8tbs": ach / NOMINAL_GBS,
                 "whole_step_frac_measured": (algo / (step_ms * 1e-3) / 1e9) / peak}

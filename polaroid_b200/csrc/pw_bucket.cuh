@@ -150,6 +150,13 @@ __device__ __forceinline__ void bucket_load(const ScanPlan& P, int64_t base, int
   }
 }
 
+// the plan without its window word: the windowed tier classifies rows against the tile's one or two windows itself
+// (two compares per window instead of a 64-bit division per row); o.k[KW - 1] is filled in only for the HBM path
+template <class CT>
+struct NoDynCtl : CT {
+  static __device__ __forceinline__ constexpr bool dyn_enabled(const ScanPlan&) { return false; }
+};
+
 template <class CT, int NC, int KW, int NV>
 __device__ __forceinline__ void bucket_row_front(const ScanPlan& P, const uint4 (&raw)[NC], const uint32_t (&vbits)[NC], int j, int64_t row,
                                                  bool in_range, RowOut<KW, NV>& o) {
@@ -157,10 +164,10 @@ __device__ __forceinline__ void bucket_row_front(const ScanPlan& P, const uint4 
   Row<NC> r;
   row_decode<CT, NC>(P, raw, vbits, j, r);
   bool alive = in_range && row_predicate<CT, NC>(P, r);
-  alive = row_keys<CT, NC, KW>(P, r, raw, vbits, j, alive, o.k, o.sentinel_free) && alive;
+  alive = row_keys<NoDynCtl<CT>, NC, KW>(P, r, raw, vbits, j, alive, o.k, o.sentinel_free) && alive;
   o.alive = alive;
   row_vexprs<CT, NC, NV>(P, r, o.v, o.v_valid);
-  o.tval = 0ull;
+  o.tval = CT::dyn_enabled(P) ? pick<NC>(r.in, CT::dyn_slot(P)) : 0ull;   // index value (windowed tier)
 }
 
 // a row the buckets cannot take: straight into the HBM table (kept out of line: it is rare and register-hungry)
@@ -196,6 +203,12 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
   constexpr int TILE = WARPS * 64;        // rows per tile: two per lane
   constexpr int LEN_ACC = CT::kLenAcc;    // the row counter is bumped once per fold, not once per row
   constexpr int STAGES = CT::kBStages;    // > 0: input tiles arrive in shared memory by bulk async copies, this many tiles ahead
+  // WINDOWED: group_by_dynamic with ONE dense integer key (OHLCV bars by symbol).  The group is (id, window); the
+  // buckets and the registers hold the ids of ONE window at a time.  A tile of time-ordered rows lies in one window, or
+  // two at a window change: then it is scattered and folded twice, and the registers are published in between.  Rows of
+  // any other window (unsorted input, windows shorter than a tile) take the HBM path — correct, just slow — which is
+  // why the host asks for windows several tiles long before it plans this tier.
+  constexpr bool WIN = CT::kBWin;
   constexpr uint32_t VAR = CT::kBVar;     // experiment switches (PW_BUCKET_VAR): 1 branch-form min / max, 2 predicated rank atomics
   // OVERFLOW LIST: a row whose rank is beyond the bucket depth is appended to a short CTA-wide list (id + value words)
   // that every owner scans after its bucket — a broadcast read per entry.  The HBM path is ~1 us per row (dependent,
@@ -234,15 +247,18 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
 
   uint64_t acc[GPT][NACC];
   bool seen[GPT];
+  auto reset_acc = [&]() {
 #pragma unroll
-  for (int gi = 0; gi < GPT; ++gi) {
-    seen[gi] = false;
+    for (int gi = 0; gi < GPT; ++gi) {
+      seen[gi] = false;
 #pragma unroll
-    for (int a = 0; a < NACC; ++a) {
-      const int op = CT::acc_op(P, a);
-      acc[gi][a] = !((NATIVE >> a) & 1u) ? acc_init(op) : (op == OP_MIN_I64 ? 0x7FF0000000000000ull : 0xFFF0000000000000ull);   // +inf / -inf
+      for (int a = 0; a < NACC; ++a) {
+        const int op = CT::acc_op(P, a);
+        acc[gi][a] = !((NATIVE >> a) & 1u) ? acc_init(op) : (op == OP_MIN_I64 ? 0x7FF0000000000000ull : 0xFFF0000000000000ull);   // +inf / -inf
+      }
     }
-  }
+  };
+  reset_acc();
   const int my_g0 = GCAP >= THREADS ? tid : (tid & (GCAP - 1));   // first (or only) group of this thread
   const int my_sub = GCAP >= THREADS ? 0 : tid / GCAP;
 
@@ -253,6 +269,28 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
   const int64_t whole_hi = tile_hi < n_whole ? tile_hi : n_whole;   // [tile_lo, whole_hi): tiles without a ragged end
   unsigned long long spilled = 0;
   const int64_t lane_row = (int64_t)warp * 64 + 2 * lane;
+  int64_t cur_w = 0;      // WINDOWED: the window the registers belong to
+  bool have_w = false;
+
+  // the registers of this thread's groups go to the HBM table (at the end; WINDOWED: whenever the window changes)
+  auto publish = [&](int64_t w) {
+#pragma unroll
+    for (int gi = 0; gi < GPT; ++gi) {
+      if (!seen[gi]) continue;
+      const int g = my_g0 + gi * THREADS;
+      uint64_t k[KW];
+#pragma unroll
+      for (int x = 0; x < KW; ++x) k[x] = x == 0 ? (uint64_t)P.dense_min + (uint64_t)g : (WIN && x == 1 ? (uint64_t)w : 0ull);
+      const uint64_t gs = table_upsert<KW>(P.table, k, hash_words<KW>(k), true);
+      if (gs == ~0ull) continue;
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) {
+        const int op = CT::acc_op(P, a);
+        if ((NATIVE >> a) & 1u) acc_apply_global(&tacc(P.table, a, gs), op, (uint64_t)f64_to_ordered(__longlong_as_double((long long)acc[gi][a])));
+        else if (acc[gi][a] != acc_init(op)) acc_apply_global(&tacc(P.table, a, gs), op, acc[gi][a]);
+      }
+    }
+  };
 
   // one thread starts the copies of tile t into stage `st`: every slot's TILE rows, completing on the stage's mbarrier
   auto issue = [&](int64_t t, int st) {
@@ -268,8 +306,21 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
 
   int b = 0, ci = 0, oi = 0;   // buffer / counter array / overflow counter of the current tile
   int st_cur = 0;      // staged input: stage of the current tile
-  auto process = [&](int64_t t, const uint4 (&raw)[NC], const uint32_t (&vb)[NC], auto whole_tag) {
+  // WINDOWED: is the row at `rel` (index value - origin) a member of the window that starts at `lo` (= k * every)?
+  // Same membership as window_of (pw_scan.cuh) for each `closed`.
+  constexpr long long EVERY = CT::kDynEvery > 0 ? CT::kDynEvery : 1, PERIOD = CT::kDynPeriod;
+  auto in_window_at = [&](int64_t rel, int64_t lo) -> bool {
+    const int64_t off = rel - lo;
+    const int closed = CT::dyn_closed(P);
+    if (closed == 0) return (uint64_t)off < (uint64_t)PERIOD;                 // left  [s, s+period)
+    if (closed == 1) return (uint64_t)(off - 1) < (uint64_t)PERIOD;           // right (s, s+period]
+    if (closed == 3) return (uint64_t)(off - 1) < (uint64_t)(PERIOD - 1);     // none  (s, s+period)
+    return (uint64_t)off <= (uint64_t)PERIOD;                                 // both  [s, s+period], period < every
+  };
+  // w0 / w1: WINDOWED — the windows of the tile's first and last row; pass 0 handles w0, pass 1 (only when w1 != w0) w1
+  auto process = [&](int64_t t, const uint4 (&raw)[NC], const uint32_t (&vb)[NC], auto whole_tag, int64_t w0, int64_t w1, int pass) {
     constexpr bool WHOLE = decltype(whole_tag)::value;
+    const int64_t wp = pass == 0 ? w0 : w1;
     const uint32_t bb = sbuf + (uint32_t)b * BUF_BYTES;
     const uint32_t cc = scnt + (uint32_t)ci * (GCAP * 4u);
     // ---- scatter ----
@@ -279,7 +330,7 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
       bucket_row_front<CT, NC, KW, NV>(P, raw, vb, 0, row0, WHOLE || row0 < n_rows, o[0]);
       bucket_row_front<CT, NC, KW, NV>(P, raw, vb, 1, row0 + 1, WHOLE || row0 + 1 < n_rows, o[1]);
       uint32_t id[2], rk[2];
-      bool take[2], cand[2];
+      bool take[2], cand[2], cold[2];
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const uint64_t d = o[i].k[0] - (uint64_t)P.dense_min;
@@ -291,7 +342,16 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
             const double x = __longlong_as_double((long long)o[i].v[e]);
             odd = odd || x != x || o[i].v[e] == 0x8000000000000000ull;
           }
-        take[i] = o[i].alive && plain && !odd && d < (uint64_t)CT::kBRange;
+        const bool elig = o[i].alive && plain && !odd && d < (uint64_t)CT::kBRange;
+        if (WIN) {
+          const int64_t rel = (int64_t)o[i].tval - P.dyn.origin;
+          const bool in0 = in_window_at(rel, w0 * EVERY), in1 = w1 != w0 && in_window_at(rel, w1 * EVERY);
+          take[i] = elig && (pass == 0 ? in0 : in1);
+          cold[i] = pass == 0 && o[i].alive && !(elig && (in0 || in1));   // another window, or none: sorted out below
+        } else {
+          take[i] = elig;
+          cold[i] = o[i].alive && !elig;
+        }
         id[i] = (uint32_t)d & (uint32_t)(GCAP - 1);
       }
 #pragma unroll
@@ -306,12 +366,12 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
 #pragma unroll
         for (int e = 0; e < NVE; ++e) sh_st64_if(q + (uint32_t)e * PLANE_BYTES, o[i].v[e], fits);
         if (META) sh_st64_if(q + (uint32_t)NVE * PLANE_BYTES, (global_row<CT>(P, o[i].row) << 8) | (uint64_t)(o[i].v_valid & 0xFFu), fits);
-        late = late || (o[i].alive && !fits);
+        late = late || (cand[i] && !fits) || cold[i];
       }
       if (late) {
 #pragma unroll
         for (int i = 0; i < 2; ++i)
-          if (o[i].alive && !take[i]) {
+          if ((cand[i] && !take[i]) || cold[i]) {
             uint32_t slot = OVF;
             if (cand[i]) slot = atomicAdd_shared_u32(sovf + 4u * oi);
             if (slot < (uint32_t)OVF) {
@@ -320,13 +380,25 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
 #pragma unroll
               for (int e = 0; e < NVE; ++e) sh_st64_if(q + (uint32_t)e * OVF * 8u, o[i].v[e], true);
               if (META) sh_st64_if(q + (uint32_t)NVE * OVF * 8u, (global_row<CT>(P, o[i].row) << 8) | (uint64_t)(o[i].v_valid & 0xFFu), true);
-            } else { bucket_cold_row<CT, KW, NV>(P, o[i], global_row<CT>(P, o[i].row)); ++spilled; }
+            } else {
+              bool member = true;
+              if (WIN) {   // the HBM path needs the row's own window word
+                int64_t kk;
+                member = window_of_ct<CT>(P, (int64_t)o[i].tval, kk);
+                o[i].k[KW - 1] = (uint64_t)kk;
+              }
+              if (member) { bucket_cold_row<CT, KW, NV>(P, o[i], global_row<CT>(P, o[i].row)); ++spilled; }
+            }
           }
       }
     }
     __syncthreads();
     // every thread has taken its rows out of the stage: the tile STAGES ahead may land there
-    if (STAGES > 0 && WHOLE && tid == 0 && t + STAGES < whole_hi) issue(t + STAGES, st_cur);
+    if (STAGES > 0 && WHOLE && tid == 0 && pass == 0 && t + STAGES < whole_hi) issue(t + STAGES, st_cur);
+    if (WIN && (!have_w || wp != cur_w)) {   // a new window: the finished one leaves the registers
+      if (have_w) { publish(cur_w); reset_acc(); }
+      cur_w = wp; have_w = true;
+    }
     // ---- fold ----
     if (SUB > 1) {
       // the PREVIOUS tile's counters: every thread finished reading them before it arrived at the barrier above, and
@@ -387,6 +459,34 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
     oi = oi + 1 == NOVF ? 0 : oi + 1;
   };
 
+  // WINDOWED: window of one row of the time column (scalar read: from the stage when the tile is staged).  The window
+  // of the previous tile's last row, or its successor, is almost always the answer: two range checks before a division.
+  int64_t w_hint = 0;
+  auto window_at = [&](int64_t row, uint32_t stage_base) -> int64_t {
+    const int ts = CT::dyn_slot(P), dt = CT::slot_dtype(P, ts);
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
+    if (STAGES > 0 && stage_base != 0u) {
+      const uint32_t a = stage_base + pick32<NC>(slot_off, ts) + (uint32_t)(row % TILE) * (uint32_t)dtype_width(dt);
+      if (dtype_width(dt) == 8) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a) : "memory");
+      else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r.x) : "r"(a) : "memory");
+    } else r = load_pair(P.slots[ts].values, dt, row, row + 1, false);
+    const int64_t t = (int64_t)decode(r, dt, 0), rel = t - P.dyn.origin;
+    int64_t kk = w_hint;
+    if (!in_window_at(rel, kk * EVERY)) {
+      kk = w_hint + 1;
+      if (!in_window_at(rel, kk * EVERY)) window_of_ct<CT>(P, t, kk);
+    }
+    w_hint = kk;
+    return kk;
+  };
+  auto run_tile = [&](int64_t t, const uint4 (&raw)[NC], const uint32_t (&vb)[NC], auto whole_tag, uint32_t stage_base) {
+    if (!WIN) { process(t, raw, vb, whole_tag, 0, 0, 0); return; }
+    const int64_t last = (t + 1) * TILE <= n_rows ? (t + 1) * TILE - 1 : n_rows - 1;
+    const int64_t w0 = window_at(t * TILE, stage_base), w1 = window_at(last, stage_base);
+    process(t, raw, vb, whole_tag, w0, w1, 0);
+    if (w1 != w0) process(t, raw, vb, whole_tag, w0, w1, 1);
+  };
+
   // software pipeline over the whole tiles: the loads of the next tile are in flight while this one is scattered and
   // folded; the loop is unrolled by two so that the two register buffers alternate in place
   uint4 rawA[NC], rawB[NC];
@@ -410,43 +510,28 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
           rawA[c] = staged_pair(base + slot_off[c] + (uint32_t)lane_row * (uint32_t)w, w);
         }
       }
-      process(t, rawA, vbA, BucketWholeTag{});
+      run_tile(t, rawA, vbA, BucketWholeTag{}, base);
       if (++st_cur == STAGES) { st_cur = 0; parity ^= 1u; }
     }
   } else {
   if (tile_lo < whole_hi) bucket_load<CT, NC, true>(P, tile_lo * TILE + warp * 64, lane, n_rows, rawA, vbA);
   for (int64_t t = tile_lo; t < whole_hi; t += 2) {
     if (t + 1 < whole_hi) bucket_load<CT, NC, true>(P, (t + 1) * TILE + warp * 64, lane, n_rows, rawB, vbB);
-    process(t, rawA, vbA, BucketWholeTag{});
+    run_tile(t, rawA, vbA, BucketWholeTag{}, 0u);
     if (t + 1 < whole_hi) {
       if (t + 2 < whole_hi) bucket_load<CT, NC, true>(P, (t + 2) * TILE + warp * 64, lane, n_rows, rawA, vbA);
-      process(t + 1, rawB, vbB, BucketWholeTag{});
+      run_tile(t + 1, rawB, vbB, BucketWholeTag{}, 0u);
     }
   }
   }
   // the ragged last tile (one CTA at most)
   if (whole_hi < tile_hi) {
     bucket_load<CT, NC, false>(P, whole_hi * TILE + warp * 64, lane, n_rows, rawA, vbA);
-    process(whole_hi, rawA, vbA, BucketRaggedTag{});
+    run_tile(whole_hi, rawA, vbA, BucketRaggedTag{}, 0u);
   }
 
   // ---- publish the registers ----
-#pragma unroll
-  for (int gi = 0; gi < GPT; ++gi) {
-    if (!seen[gi]) continue;
-    const int g = my_g0 + gi * THREADS;
-    uint64_t k[KW];
-#pragma unroll
-    for (int w = 0; w < KW; ++w) k[w] = w == 0 ? (uint64_t)P.dense_min + (uint64_t)g : 0ull;
-    const uint64_t gs = table_upsert<KW>(P.table, k, hash_words<KW>(k), true);
-    if (gs == ~0ull) continue;
-#pragma unroll
-    for (int a = 0; a < NACC; ++a) {
-      const int op = CT::acc_op(P, a);
-      if ((NATIVE >> a) & 1u) acc_apply_global(&tacc(P.table, a, gs), op, (uint64_t)f64_to_ordered(__longlong_as_double((long long)acc[gi][a])));
-      else if (acc[gi][a] != acc_init(op)) acc_apply_global(&tacc(P.table, a, gs), op, acc[gi][a]);
-    }
-  }
+  if (!WIN || have_w) publish(cur_w);
   if (spilled) atomicAdd(P.table.spilled, spilled);
 }
 

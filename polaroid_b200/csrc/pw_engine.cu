@@ -621,7 +621,7 @@ static int padded_kw(int n_kw) { return n_kw == 3 ? 4 : (n_kw == 5 ? 6 : n_kw); 
 // useful table fits.
 // dense_range > 0: dense ids (id = key - dense_min) over exactly that many ids, no key index.
 static bool plan_hot_threads(ScanPlan& P, int64_t groups_hint, int requested_gcap, int64_t dense_range, int threads, bool exact);
-static bool plan_bucket(ScanPlan& P, int64_t groups, int64_t dense_range, bool sentinels, bool assume_jit = false);
+static bool plan_bucket(ScanPlan& P, int64_t groups, int64_t dense_range, bool sentinels, bool windowed, bool assume_jit = false);
 static bool plan_hot(ScanPlan& P, int64_t groups_hint, int requested_gcap, int64_t dense_range = 0) {
   const int base = narrow_class(P) ? ScanCfg<4>::THREADS : ScanCfg<12>::THREADS;
   if (!plan_hot_threads(P, groups_hint, requested_gcap, dense_range, base, false)) return false;
@@ -737,14 +737,14 @@ static bool plan_hot_threads(ScanPlan& P, int64_t groups_hint, int requested_gca
 // Returns false (P.hot.bucket stays 0) when the shape is not eligible or nothing fits.
 // The per-cell geometry already in P.hot (dense ids or the hash index) stays valid: it is what runs when the specialised
 // build is not available.  dense_range = ids [0, dense_range) after subtracting P.dense_min.
-static bool plan_bucket(ScanPlan& P, int64_t groups, int64_t dense_range, bool sentinels, bool assume_jit) {
+static bool plan_bucket(ScanPlan& P, int64_t groups, int64_t dense_range, bool sentinels, bool windowed, bool assume_jit) {
   HotGeom& g = P.hot;
   g.bucket = 0;
   static const bool off = getenv("PW_NO_BUCKET") != nullptr;
-  if (off || (!assume_jit && !jit_available()) || dense_range < 48 || dense_range > 2048) return false;
-  g.b_range = (int32_t)dense_range; g.b_sent = sentinels ? 1 : 0;
-  if (P.dyn.enabled || P.row_group_out || P.rowid_slot_p1 || P.check_sorted || !P.vec_ok || P.row_begin != 0 || P.row_stride != 1) return false;
-  if (P.n_kw != 1 || P.n_vexpr > 8 || P.n_acc < 1) return false;
+  if (off || (!assume_jit && !jit_available()) || dense_range < (windowed ? 16 : 48) || dense_range > 2048) return false;
+  g.b_range = (int32_t)dense_range; g.b_sent = sentinels ? 1 : 0; g.b_win = windowed ? 1 : 0;
+  if ((P.dyn.enabled != 0) != windowed || P.row_group_out || P.rowid_slot_p1 || P.check_sorted || !P.vec_ok || P.row_begin != 0 || P.row_stride != 1) return false;
+  if (P.n_kw != (windowed ? 2 : 1) || P.n_vexpr > 8 || P.n_acc < 1 || (P.gflags & GF_TMIN)) return false;
   bool meta = (P.gflags & GF_ROW) != 0;
   for (int e = 0; e < P.n_vexpr; ++e) {
     const VExpr& V = P.vexprs[e];
@@ -754,7 +754,7 @@ static bool plan_bucket(ScanPlan& P, int64_t groups, int64_t dense_range, bool s
   }
   const int planes = P.n_vexpr + (meta ? 1 : 0);
   if (planes < 1) return false;   // len-only queries: nothing to bucket, the per-cell counters are already cheap
-  int gcap = 64;
+  int gcap = windowed ? 16 : 64;
   while (gcap < dense_range) gcap <<= 1;
   // bucket depth from the Poisson tail of rows per id per tile: expected share of rows beyond depth J below eps
   auto depth = [&](double lambda, double eps) {
@@ -786,10 +786,16 @@ static bool plan_bucket(ScanPlan& P, int64_t groups, int64_t dense_range, bool s
   }
   // in order of measured preference on the C2 shape: one 32-warp CTA with two bucket buffers (one barrier per tile),
   // two 16-warp CTAs with one buffer each, then whatever fits
-  static const struct { int threads, nbuf, cps; } cand[] = {{1024, 2, 1}, {512, 1, 2}, {512, 2, 1}, {1024, 1, 1}, {512, 1, 1}};
+  // (windowed: more live state per thread — two more accumulators, the window bookkeeping — than 64 registers hold:
+  // 16 warps with 128 registers each)
+  struct Cand { int threads, nbuf, cps; };
+  static const Cand cand_plain[5] = {{1024, 2, 1}, {512, 1, 2}, {512, 2, 1}, {1024, 1, 1}, {512, 1, 1}};
+  static const Cand cand_win[5] = {{512, 2, 1}, {512, 1, 1}, {1024, 2, 1}, {1024, 1, 1}, {256, 2, 1}};
+  const Cand* cand = windowed ? cand_win : cand_plain;
   static const int only = getenv("PW_BUCKET_CAND") ? atoi(getenv("PW_BUCKET_CAND")) : -1;   // experiments: one geometry only
-  for (const auto& cd : cand) {
-    if (only >= 0 && &cd != &cand[only % 5]) continue;
+  for (int ci = 0; ci < 5; ++ci) {
+    const Cand& cd = cand[ci];
+    if (only >= 0 && ci != only % 5) continue;
     const int tile = cd.threads / 32 * 64;
     const int j_full = depth((double)tile / (double)pop, 1e-4), j_min = depth((double)tile / (double)pop, 1e-3);
     const int ncnt = gcap < cd.threads ? cd.nbuf + 1 : cd.nbuf;
@@ -838,17 +844,28 @@ extern "C" __attribute__((visibility("default"))) int pw_b200_jit_selftest(char*
   P.accs[0].op = OP_ADD_F64; P.accs[0].src = SRC_F64; P.accs[1].op = OP_MIN_I64; P.accs[1].src = SRC_F64_ORD;
   P.accs[2].op = OP_MAX_I64; P.accs[2].src = SRC_F64_ORD; P.accs[3].op = OP_ADD_I64; P.accs[3].src = SRC_ONE;
   P.n_acc = 4; P.gflags = GF_LEN; P.acc_gbase = 3;
-  if (!plan_hot(P, 1000, 0, getenv("PW_SELFTEST_DENSE") ? 1000 : 0)) return -1;
+  const bool win = getenv("PW_SELFTEST_WIN") != nullptr;   // OHLCV shape: (time, symbol, price) -> windowed bucket tier
+  if (win) {
+    P.n_slots = 3; P.slots[2].dtype = DT_I64;   // slot 2 = time
+    P.dyn.enabled = 1; P.dyn.slot = 2; P.dyn.every = P.dyn.period = 60; P.dyn.closed = 0; P.n_kw = 2;
+    P.keys[0].dtype = DT_I32; P.slots[0].dtype = DT_I32;
+    P.vexprs[0].flags = VF_SUM_F | VF_MIN | VF_MAX | VF_FIRST | VF_LAST;
+    P.accs[3].op = OP_MIN_U64; P.accs[3].src = SRC_ROW; P.accs[4].op = OP_MAX_U64; P.accs[4].src = SRC_ROW;
+    P.accs[5].op = OP_ADD_I64; P.accs[5].src = SRC_ONE; P.n_acc = 6; P.acc_gbase = 5;
+  }
+  if (!plan_hot(P, 1000, 0, getenv("PW_SELFTEST_DENSE") && !win ? 1000 : 0)) return -1;
   P.hot_slots = P.hot.idx_slots;
-  if (getenv("PW_SELFTEST_DENSE")) {   // the bucket tier on top of the dense ids (NVRTC exists whenever this function can succeed)
-    if (!plan_bucket(P, 1000, 1000, false, true) && !getenv("PW_NO_BUCKET")) return -3;
+  if (win) {
+    if (!plan_bucket(P, 100, 100, false, true, true)) return -4;
+  } else if (getenv("PW_SELFTEST_DENSE")) {   // the bucket tier on top of the dense ids (NVRTC exists whenever this function can succeed)
+    if (!plan_bucket(P, 1000, 1000, false, false, true) && !getenv("PW_NO_BUCKET")) return -3;
   }
   std::string err;
   if (getenv("PW_SELFTEST_THREADS")) {  // the geometry a 16-warp CTA would get
     if (!plan_hot_threads(P, 1000, P.hot.gcap, getenv("PW_SELFTEST_DENSE") ? 1000 : 0, atoi(getenv("PW_SELFTEST_THREADS")), true)) return -2;
     P.hot_slots = P.hot.idx_slots;
   }
-  const int rc = jit_selftest_compile(P, 4, 1, true, P.hot.threads, &err);
+  const int rc = jit_selftest_compile(P, 4, win ? 2 : 1, true, P.hot.threads, &err);
   if (log && log_len) { strncpy(log, err.c_str(), log_len - 1); log[log_len - 1] = 0; }
   return rc;
 }
@@ -917,6 +934,18 @@ __global__ void key_range_kernel(RawSlot key, int64_t begin, int64_t stride, int
 static bool dense_eligible(const PwQuery* q, const ScanPlan& P) {
   if (getenv("PW_NO_DENSE") || (q->flags & PW_FLAG_NO_DENSE_IDS)) return false;
   if (q->n_keys != 1 || P.dyn.enabled || P.n_kw != 1 || !(P.gflags & GF_LEN) || P.row_group_out) return false;
+  switch (P.keys[0].dtype) {
+    case DT_I8: case DT_U8: case DT_I16: case DT_U16: case DT_I32: case DT_U32: case DT_I64: return true;
+    default: return false;
+  }
+}
+
+// group_by_dynamic by ONE plain integer key (OHLCV bars by symbol): the windowed form of the bucket tier needs that key's
+// value range from the pilot; the group key is then (id, window)
+static bool wbucket_eligible(const PwQuery* q, const ScanPlan& P) {
+  if (getenv("PW_NO_DENSE") || getenv("PW_NO_WBUCKET") || (q->flags & (PW_FLAG_NO_DENSE_IDS | PW_FLAG_NO_BUCKETS))) return false;
+  if (q->n_keys != 1 || !P.dyn.enabled || P.n_kw != 2 || P.has_null_word || P.row_group_out || (P.gflags & GF_TMIN)) return false;
+  if (P.slots[P.keys[0].slot].validity != nullptr) return false;
   switch (P.keys[0].dtype) {
     case DT_I8: case DT_U8: case DT_I16: case DT_U16: case DT_I32: case DT_U32: case DT_I64: return true;
     default: return false;
@@ -1194,7 +1223,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
   };
   if (N <= SMALL) {
     if (!cap) cap = (uint64_t)std::max<int64_t>(2 * N, 64);
-    if ((q->flags & PW_FLAG_FORCE_HOT_TABLE) && q->hot_table_slots == 0 && N > 0 && dense_eligible(q, P)) {
+    if ((q->flags & PW_FLAG_FORCE_HOT_TABLE) && q->hot_table_slots == 0 && N > 0 && (dense_eligible(q, P) || wbucket_eligible(q, P))) {
       // unit-sized inputs reach the dense-id path through the force flag: range of ALL keys, one extra sync
       Control* kctl = nullptr;
       { void* p = nullptr; PW_TRY(dev_alloc(&p, sizeof(Control))); kctl = (Control*)p; }
@@ -1262,7 +1291,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
           T.overflow = &pctl->overflow; T.spilled = &pctl->spilled;
         }
         pp.distinct[0] = &pctl->counter; pp.distinct[1] = &pctl->null_counts[0];
-        if (dense_eligible(q, P)) { pp.kmax_u = &pctl->kmax_u; pp.kmin_n = &pctl->kmin_n; }
+        if (dense_eligible(q, P) || wbucket_eligible(q, P)) { pp.kmax_u = &pctl->kmax_u; pp.kmin_n = &pctl->kmin_n; }
         PP.table = pp.table[0]; PP.not_sorted = &pctl->not_sorted;
         const int kwc = kw <= 1 ? 1 : (kw <= 2 ? 2 : (kw <= 4 ? 4 : 6));
         frc = launch_pilot_jit(PP, pp, narrow_class(PP) ? 4 : 12, kwc, c.stream);
@@ -1317,14 +1346,17 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
   if (q->flags & PW_FLAG_FORCE_HOT_TABLE) use_hot = true;
   if (q->flags & PW_FLAG_FORCE_GLOBAL_TABLE) use_hot = false;
   if (live_groups == 0) live_groups = std::min<int64_t>(std::max<int64_t>(N, 4), 1024);
-  if (use_hot && dense_range > 0 && q->hot_table_slots == 0 && plan_hot(P, live_groups, 0, dense_range)) {
+  const bool windowed = P.dyn.enabled != 0;
+  // windows several tiles long (the contiguous pilot block of 65 536 rows saw at most ~4 windows), else the hash path
+  if (windowed && dense_range > 0 && N > SMALL && live_groups > 4 * dense_range) dense_range = 0;
+  if (use_hot && dense_range > 0 && !windowed && q->hot_table_slots == 0 && plan_hot(P, live_groups, 0, dense_range)) {
     if (dense_sentinels) P.hot.dense = 2;
-    if (!(q->flags & PW_FLAG_NO_BUCKETS)) plan_bucket(P, live_groups, dense_range, dense_sentinels);
+    if (!(q->flags & PW_FLAG_NO_BUCKETS)) plan_bucket(P, live_groups, dense_range, dense_sentinels, false);
   }
   else if (use_hot && !plan_hot(P, live_groups, q->hot_table_slots)) use_hot = false;
   // the bucket tier does not need the dense per-cell table to fit (many accumulators): it only needs the id range
   else if (use_hot && dense_range > 0 && q->hot_table_slots == 0 && !(q->flags & (PW_FLAG_NO_BUCKETS | PW_FLAG_NO_DENSE_IDS)))
-    plan_bucket(P, live_groups, dense_range, dense_sentinels);
+    plan_bucket(P, windowed ? dense_range : live_groups, dense_range, dense_sentinels, windowed);
   if (cap > 0xFFFFFFF0ull) return fail(PW_ERR_UNSUPPORTED, "table larger than 2^32 slots");
   if (getenv("PW_DEBUG"))
     fprintf(stderr, "[pw] rows=%lld kw=%d slots=%d accs=%d cap=%llu hot=%d live=%lld gcap=%d S=%d R=%d n_mm=%d smem=%d dense=%d min=%lld\n", (long long)N, P.n_kw,
@@ -1412,7 +1444,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     }
     break;
   }
-  tm.strategy = partitioned ? 5 : (use_hot ? (P.hot.bucket ? 7 : (P.hot.dense ? 4 : 1)) : 2);
+  tm.strategy = partitioned ? 5 : (use_hot ? (P.hot.bucket ? (P.hot.b_win ? 6 : 7) : (P.hot.dense ? 4 : 1)) : 2);
   tm.table_slots = (int64_t)cap;
   tm.partition_ms = 0.0f;
   if (deferred) {

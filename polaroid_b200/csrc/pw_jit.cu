@@ -126,6 +126,8 @@ std::string jit_ctl(const ScanPlan& P) {
   g.scalar("bool", "dyn_enabled", P.dyn.enabled);
   g.scalar("int", "dyn_slot", P.dyn.slot);
   g.scalar("int", "dyn_closed", P.dyn.closed);
+  g.o << "  static constexpr long long kDynEvery = " << (P.dyn.enabled && P.dyn.every > 0 ? (long long)P.dyn.every : 0ll) << "ll, kDynPeriod = "
+      << (long long)P.dyn.period << "ll;\n";
   g.scalar("int", "n_vexpr", P.n_vexpr);
   g.table1("int", "ve_nf", P.n_vexpr, [&](int i) { return P.vexprs[i].n_factors; });
   g.table1("int", "ve_slot", P.n_vexpr, [&](int i) { return P.vexprs[i].slot; });
@@ -175,6 +177,7 @@ std::string jit_ctl(const ScanPlan& P) {
       << ", kBJ = " << (P.hot.b_j > 0 ? P.hot.b_j : 1) << ", kBNbuf = " << (P.hot.b_nbuf > 0 ? P.hot.b_nbuf : 1)
       << ", kBStages = " << P.hot.b_stages << ";\n";
   g.o << "  static constexpr int kBRange = " << P.hot.b_range << ";\n  static constexpr bool kBSent = " << (P.hot.b_sent ? "true" : "false") << ";\n";
+  g.o << "  static constexpr bool kBWin = " << (P.hot.b_win ? "true" : "false") << ";\n";
   g.o << "  static constexpr unsigned kBVar = " << (getenv("PW_BUCKET_VAR") ? atoi(getenv("PW_BUCKET_VAR")) : 0) << "u;\n";
   g.o << "  static constexpr bool kBMeta = " << (P.hot.b_meta ? "true" : "false") << ";\n";
   {
@@ -430,6 +433,7 @@ static std::string plan_key(const ScanPlan& P) {
   i32(P.n_keys);
   for (int i = 0; i < P.n_keys; ++i) { i32(P.keys[i].slot); i32(P.keys[i].dtype); i32(P.keys[i].n_words); }
   i32(P.has_null_word); i32(P.dyn.enabled); i32(P.dyn.slot); i32(P.dyn.closed);
+  if (P.dyn.enabled) { put(&P.dyn.every, 8); put(&P.dyn.period, 8); }
   i32(P.n_vexpr);
   for (int e = 0; e < P.n_vexpr; ++e) {
     const VExpr& v = P.vexprs[e];

@@ -89,7 +89,8 @@ __device__ __forceinline__ void pilot_body(const ScanPlan& P, const PilotParams&
       bool sentinel_free;
       if (!row_keys<CT, NC, KW>(P, r, raw, vbits, j, true, k, sentinel_free)) continue;  // row outside every window
       if (pilot_insert<KW>(pp.table[s], k, hash_words<KW>(k), sentinel_free || KW != 1)) ++fresh;
-      if (pp.kmax_u && KW == 1 && !(sentinel_free && k[0] == KEY_NULL)) {  // single integer key, non-null (raw -1 / -2 included)
+      // single integer key, non-null (raw -1 / -2 included); under group_by_dynamic k[0] is that key and k[1] the window
+      if (pp.kmax_u && (KW == 1 ? !(sentinel_free && k[0] == KEY_NULL) : CT::dyn_enabled(P))) {
         const unsigned long long u = k[0] ^ 0x8000000000000000ull;
         hi = u > hi ? u : hi;
         lo = ~u > lo ? ~u : lo;

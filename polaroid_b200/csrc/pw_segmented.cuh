@@ -116,7 +116,7 @@ __device__ __forceinline__ void seg_row(const ScanPlan& P, const SegParams& sp, 
     bool alive = row < n_rows && row_predicate<CT, NC>(P, r);
     const int64_t t = (int64_t)pick<NC>(r.in, CT::dyn_slot(P));
     int64_t k = cur_k;
-    if (alive && !in_window(CT::dyn_closed(P), t, cur_s, cur_e)) alive = window_of(P.dyn, CT::dyn_closed(P), t, k);
+    if (alive && !in_window(CT::dyn_closed(P), t, cur_s, cur_e)) alive = window_of_ct<CT>(P, t, k);
     RowOut<1, NV> o;
     o.k[0] = 0; o.alive = alive; o.sentinel_free = true; o.row = row; o.tval = (uint64_t)t;
     row_vexprs<CT, NC, NV>(P, r, o.v, o.v_valid);
