@@ -1347,6 +1347,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
   if (q->flags & PW_FLAG_FORCE_GLOBAL_TABLE) use_hot = false;
   if (live_groups == 0) live_groups = std::min<int64_t>(std::max<int64_t>(N, 4), 1024);
   const bool windowed = P.dyn.enabled != 0;
+  if (q->flags & PW_FLAG_NO_DENSE_IDS) dense_range = 0;   // (the frame's cached pilot statistics may carry a range)
   // windows several tiles long (the contiguous pilot block of 65 536 rows saw at most ~4 windows), else the hash path
   if (windowed && dense_range > 0 && N > SMALL && live_groups > 4 * dense_range) dense_range = 0;
   if (use_hot && dense_range > 0 && !windowed && q->hot_table_slots == 0 && plan_hot(P, live_groups, 0, dense_range)) {
