@@ -145,6 +145,10 @@ typedef struct PwDynamic {
 #define PW_FLAG_FORCE_PARTITION (1ull << 4)    /* radix-partition the rows by key hash first (high-cardinality tier) */
 #define PW_FLAG_NO_PARTITION (1ull << 5)       /* never partition (POLARS_NO_PARTITION) */
 #define PW_FLAG_NO_DENSE_IDS (1ull << 6)       /* never map a small integer key range to dense ids: always the hash index */
+#define PW_FLAG_KEYS_SORTED (1ull << 8)        /* the key columns are sorted (the IsSorted flag of the reference's Series): groups are
+                                                 contiguous runs -> run-boundary + segmented-reduce scan, pw_runs.cuh
+                                                 (polars-core/src/frame/group_by/into_groups.rs:65-129).  A wrong promise costs time,
+                                                 not correctness: the table still merges by key */
 #define PW_FLAG_NO_BUCKETS (1ull << 7)         /* dense ids through the per-cell hot table, never the bucket tier (pw_bucket.cuh) */
 
 #define PW_ABI_VERSION 1u
@@ -177,7 +181,8 @@ typedef struct PwTimings {
   float h2d_ms, estimate_ms, scan_ms, finalize_ms, d2h_ms, total_device_ms;
   int64_t n_rows, n_groups, table_slots;
   int32_t strategy;      /* 1 hot table, 2 global table, 3 segmented, 4 hot table with dense ids (small integer key range), 5 partitioned,
-                            7 dense ids bucketed per tile, accumulators in registers (pw_bucket.cuh) */
+                            6 the same per (key, window) for group_by_dynamic by one dense key,
+                            7 dense ids bucketed per tile, accumulators in registers (pw_bucket.cuh), 8 sorted-key runs (pw_runs.cuh) */
   int32_t retries;       /* table growth re-runs */
   int64_t kernel_launches; /* launches of this library's kernels in the last call */
   int64_t spilled_rows;  /* rows that bypassed the hot table (spill tier) */
@@ -235,6 +240,13 @@ int pw_b200_frame_filter_select(const PwPredicate* predicates, int32_t n_predica
 int pw_b200_frame_group_tuples(const PwFrame* frame, const int32_t* key_columns, int32_t n_keys,
                                int32_t maintain_order, struct ArrowArray* out_first, struct ArrowArray* out_offsets,
                                struct ArrowArray* out_row_ids, struct ArrowSchema* out_schemas /*[3]*/);
+
+/* GroupsSlice of SORTED key columns: [first, len] per run of equal keys, in row order — partition_to_groups
+ * (polars-arrow/src/legacy/kernels/sort_partition.rs:168) / create_groups_from_sorted
+ * (polars-core/src/frame/group_by/into_groups.rs:65-129).  Null keys form runs like values.  The caller vouches for the
+ * order (as the reference's sorted flag does); a key that reappears later starts another slice.  Both outputs UInt32. */
+int pw_b200_frame_group_slices(const PwFrame* frame, const int32_t* key_columns, int32_t n_keys,
+                               struct ArrowArray* out_first, struct ArrowArray* out_len, struct ArrowSchema* out_schemas /*[2]*/);
 
 /* ---- multi-GPU partial aggregates ------------------------------------------------------ */
 /* Phase 1 on every GPU: build the local partial-aggregate table and export it as fixed-width packed rows

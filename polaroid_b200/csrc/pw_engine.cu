@@ -604,6 +604,12 @@ static int launch_scan(ScanPlan P, int sm, cudaStream_t st) {
   const bool narrow = narrow_class(P);
   // query-shape specialised kernel (NVRTC); falls back to the ahead-of-time kernel of the same class
   const int kwc = P.n_kw <= 1 ? 1 : (P.n_kw <= 2 ? 2 : (P.n_kw <= 4 ? 4 : 6));
+  if (P.runs) {
+    // sorted keys: run-combining scan (specialised build only; otherwise the regular tiers below)
+    const int rrc = launch_runs_jit(P, narrow ? 4 : 12, kwc, sm, st);
+    if (rrc <= 0) { if (rrc == 0) ctx().timings.reserved = 3.0f; return rrc; }
+    P.runs = 0;
+  }
   if (P.hot_slots > 0 && P.hot.bucket) {
     // bucket tier (specialised build only); without NVRTC the per-cell geometry in the same HotGeom takes over
     const int brc = launch_bucket_jit(P, narrow ? 4 : 12, kwc, sm, st);
@@ -1368,6 +1374,10 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
             P.hot.b_stages, P.hot.b_meta, P.hot.b_bytes);
   PW_CUDA(cudaEventRecord(c.ev[2], c.stream));
 
+  // ---- sorted keys (the caller's flag, as the reference's IsSorted): groups are runs of equal keys
+  const bool runs = (q->flags & PW_FLAG_KEYS_SORTED) && !P.dyn.enabled && !P.row_group_out && P.rowid_slot_p1 == 0 && N > 0 && jit_available() &&
+                    !getenv("PW_NO_RUNS") && !(q->flags & (PW_FLAG_FORCE_HOT_TABLE | PW_FLAG_FORCE_GLOBAL_TABLE | PW_FLAG_FORCE_PARTITION));
+  P.runs = runs ? 1 : 0;
   // ---- high-cardinality tier: many groups, several rows each, no locality -> partition the rows by key hash first
   // (the analogue of the reference's partitioned group-by; POLARS_FORCE_PARTITION / POLARS_NO_PARTITION = the flags)
   PartTemp ptmp;
@@ -1377,7 +1387,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     const bool forced = (q->flags & PW_FLAG_FORCE_PARTITION) != 0;
     const bool pays = !use_hot && g_est >= 262144.0 && N >= (4ll << 20) && (double)N >= 3.0 * g_est &&
                       !(q->flags & (PW_FLAG_FORCE_HOT_TABLE | PW_FLAG_FORCE_GLOBAL_TABLE));
-    if ((forced || pays) && N > 0 && part_eligible(q, P)) {
+    if ((forced || pays) && N > 0 && !runs && part_eligible(q, P)) {
       PW_CUDA(cudaEventRecord(c.ev[10], c.stream));
       const int prc = partition_input(P, g_est > 0 ? g_est : std::max<double>((double)N / 4.0, 64.0), &PP, &ptmp);
       PW_CUDA(cudaEventRecord(c.ev[11], c.stream));
@@ -1445,7 +1455,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     }
     break;
   }
-  tm.strategy = partitioned ? 5 : (use_hot ? (P.hot.bucket ? (P.hot.b_win ? 6 : 7) : (P.hot.dense ? 4 : 1)) : 2);
+  tm.strategy = runs ? 8 : partitioned ? 5 : (use_hot ? (P.hot.bucket ? (P.hot.b_win ? 6 : 7) : (P.hot.dense ? 4 : 1)) : 2);
   tm.table_slots = (int64_t)cap;
   tm.partition_ms = 0.0f;
   if (deferred) {

@@ -103,6 +103,7 @@ int launch_scan_nc12(const ScanPlan& P, int sm, cudaStream_t st);
 int launch_scan_jit(const ScanPlan& P, int nc, int kw, bool hot, int threads, int sm_count, cudaStream_t st);
 int launch_seg_jit(const ScanPlan& P, const SegParams& sp, int nc, int threads, size_t smem, int sm_count, cudaStream_t st);
 int launch_bucket_jit(const ScanPlan& P, int nc, int kw, int sm_count, cudaStream_t st);
+int launch_runs_jit(const ScanPlan& P, int nc, int kw, int sm_count, cudaStream_t st);
 int launch_part_jit(const ScanPlan& P, const PartParams& pp, int nc, int kw, int sm_count, cudaStream_t st);
 bool jit_available();
 struct PilotParams;

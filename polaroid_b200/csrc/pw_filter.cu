@@ -7,6 +7,8 @@
 //     offsets and all row ids per group, ascending inside a group.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 #include <stdio.h>
 #include <string.h>
 
@@ -187,6 +189,49 @@ static int device_to_arrow(const void* d_vals, size_t val_bytes, const void* d_v
 
 using namespace pw;
 
+// ---- GroupsSlice of sorted keys: run boundaries (partition_to_groups, sort_partition.rs:168) --------------------------
+// head[i] = row i starts a run: i == 0 or its key (values and null-ness of every key column) differs from row i - 1
+static __device__ __forceinline__ void keys_of_row(const ScanPlan& P, int64_t row, uint64_t (&k)[6], bool& sf) {
+  uint4 raw[12];
+  uint32_t vbits[12];
+  Row<12> r;
+  r.in_valid = 0;
+#pragma unroll
+  for (int c = 0; c < 12; ++c) {
+    raw[c] = make_uint4(0u, 0u, 0u, 0u); vbits[c] = 0u; r.in[c] = 0;
+    if (c < P.n_slots) {
+      raw[c] = load_row(P.slots[c], row);
+      vbits[c] = load_valid_pair(P.slots[c], row, row + 1) & 1u;
+      r.in[c] = decode(raw[c], P.slots[c].dtype, 0);
+      r.in_valid |= vbits[c] << c;
+    }
+  }
+  row_keys<RtCtl, 12, 6>(P, r, raw, vbits, 0, true, k, sf);
+}
+static __global__ void __launch_bounds__(256) run_heads_kernel(const __grid_constant__ ScanPlan P, unsigned char* head) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n_rows; i += (int64_t)gridDim.x * blockDim.x) {
+    bool h = i == 0;
+    if (!h) {
+      uint64_t a[6], b[6];
+      bool sa, sb;
+      keys_of_row(P, i, a, sa);
+      keys_of_row(P, i - 1, b, sb);
+      h = sa != sb;
+#pragma unroll
+      for (int w = 0; w < 6; ++w) h = h || a[w] != b[w];
+    }
+    head[i] = h ? 1 : 0;
+  }
+}
+static __global__ void run_lens_kernel(const int64_t* first64, const unsigned long long* n_runs, int64_t n_rows, uint32_t* first, uint32_t* len, uint64_t cap) {
+  const uint64_t G = *n_runs;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < G && g < cap; g += (uint64_t)gridDim.x * blockDim.x) {
+    const int64_t a = first64[g], b = g + 1 < G ? first64[g + 1] : n_rows;
+    first[g] = (uint32_t)a;
+    len[g] = (uint32_t)(b - a);
+  }
+}
+
 extern "C" {
 
 int pw_b200_frame_filter_select(const PwPredicate* predicates, int32_t n_predicates, const PwFrame* frame,
@@ -323,6 +368,57 @@ int pw_b200_frame_group_tuples(const PwFrame* frame, const int32_t* key_columns,
   dev_free(first); dev_free(row_rank); dev_free(row_rank_sorted); dev_free(row_ids); dev_free(row_ids_sorted);
   dev_free(slot_rank); dev_free(sizes); dev_free(offsets); dev_free(slots);
   free_table(T);
+  return rc;
+}
+
+int pw_b200_frame_group_slices(const PwFrame* frame, const int32_t* key_columns, int32_t n_keys, struct ArrowArray* out_first,
+                               struct ArrowArray* out_len, struct ArrowSchema* out_schemas) {
+  PW_TRY(ensure_device());
+  if (!frame || !key_columns || n_keys < 1 || !out_first || !out_len || !out_schemas) return fail(PW_ERR_INVALID, "null argument");
+  ThreadCtx& c = ctx();
+  const int64_t n = frame->n_rows;
+  if (n > 0xFFFFFFF0ll) return fail(PW_ERR_UNSUPPORTED, "IdxSize is u32: more than 2^32 rows");
+  PwAgg len_agg{};
+  len_agg.kind = PW_LEN; len_agg.column = -1; len_agg.name = "len";
+  PwQuery q{};
+  q.abi_version = PW_ABI_VERSION; q.maintain_order = 1; q.n_keys = n_keys; q.key_columns = key_columns; q.n_aggs = 1; q.aggs = &len_agg;
+  Lowered L;
+  PW_TRY(lower_query(&q, frame, &L));
+  ScanPlan P = L.plan;
+  if (P.n_slots > 12 || P.n_kw > 6) return fail(PW_ERR_UNSUPPORTED, "too many key columns");
+  P.n_rows = n;
+  void* v = nullptr;
+  unsigned char* head = nullptr; int64_t* first64 = nullptr; unsigned long long* d_runs = nullptr; uint32_t *first = nullptr, *len = nullptr;
+  PW_TRY(dev_alloc(&v, (size_t)std::max<int64_t>(n, 1))); head = (unsigned char*)v;
+  PW_TRY(dev_alloc(&v, (size_t)std::max<int64_t>(n, 1) * 8)); first64 = (int64_t*)v;
+  PW_TRY(dev_alloc(&v, 16)); d_runs = (unsigned long long*)v;
+  PW_CUDA(cudaMemsetAsync(d_runs, 0, 16, c.stream));
+  unsigned long long G = 0;
+  if (n > 0) {
+    run_heads_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)c.sm_count * 16), 256, 0, c.stream>>>(P, head);
+    PW_CUDA(cudaGetLastError());
+    cub::CountingInputIterator<int64_t> rows(0);
+    size_t tb = 0;
+    cub::DeviceSelect::Flagged(nullptr, tb, rows, head, first64, d_runs, n, c.stream);
+    void* tmp = nullptr;
+    PW_TRY(dev_alloc(&tmp, tb));
+    PW_CUDA(cub::DeviceSelect::Flagged(tmp, tb, rows, head, first64, d_runs, n, c.stream));
+    PW_CUDA(cudaMemcpyAsync(&G, d_runs, 8, cudaMemcpyDeviceToHost, c.stream));
+    PW_CUDA(cudaStreamSynchronize(c.stream));
+    dev_free(tmp);
+    c.timings.kernel_launches += 2;
+  }
+  PW_TRY(dev_alloc(&v, std::max<uint64_t>(G, 1) * 4)); first = (uint32_t*)v;
+  PW_TRY(dev_alloc(&v, std::max<uint64_t>(G, 1) * 4)); len = (uint32_t*)v;
+  if (G) {
+    run_lens_kernel<<<(unsigned)std::min<uint64_t>((G + 255) / 256, 65535), 256, 0, c.stream>>>(first64, d_runs, n, first, len, G);
+    PW_CUDA(cudaGetLastError());
+    c.timings.kernel_launches++;
+  }
+  int rc = device_to_arrow(first, (size_t)G * 4, nullptr, 0, (int64_t)G, 0, false, "I", "first", out_first, &out_schemas[0]);
+  if (!rc) rc = device_to_arrow(len, (size_t)G * 4, nullptr, 0, (int64_t)G, 0, false, "I", "len", out_len, &out_schemas[1]);
+  dev_free(head); dev_free(first64); dev_free(d_runs); dev_free(first); dev_free(len);
+  c.timings.n_rows = n; c.timings.n_groups = (int64_t)G; c.timings.strategy = 8;
   return rc;
 }
 

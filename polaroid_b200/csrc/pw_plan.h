@@ -235,7 +235,7 @@ struct ScanPlan {
   // scattered into key-hash partitions.  Every slot of that frame is a 64-bit word column; the extra slot
   // `rowid_slot_p1 - 1` holds (original row << 8) | validity bit of every slot.  0 = plain input.
   int32_t rowid_slot_p1;
-  int32_t pad3;
+  int32_t runs;            // != 0: sorted keys — the run-combining scan (pw_runs.cuh) instead of the hot table
   HotGeom hot;
 };
 

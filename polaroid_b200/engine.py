@@ -28,6 +28,7 @@ FLAG_FORCE_PARTITION = 1 << 4
 FLAG_NO_PARTITION = 1 << 5
 FLAG_NO_DENSE_IDS = 1 << 6
 FLAG_NO_BUCKETS = 1 << 7
+FLAG_KEYS_SORTED = 1 << 8
 
 
 class PolarwayError(RuntimeError):
@@ -118,6 +119,7 @@ def lib():
         L.pw_b200_filter.argtypes = [C.POINTER(PwPredicate), C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.pw_b200_frame_filter_select.argtypes = [C.POINTER(PwPredicate), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                                   C.POINTER(C.c_int64)]
+        L.pw_b200_frame_group_slices.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pw_b200_frame_group_tuples.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_void_p,
                                                  C.c_void_p, C.c_void_p, C.c_void_p]
         L.pw_b200_frame_groupby_partial.argtypes = [C.POINTER(PwQuery), C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
@@ -413,7 +415,7 @@ class _BuiltQuery:
         q.key_columns = C.cast(self.keys, C.POINTER(C.c_int32))
         q.aggs = C.cast(self.aggs, C.POINTER(PwAgg))
         q.dynamic = C.pointer(self.dyn) if self.dyn is not None else None
-        q.flags = flags
+        q.flags = flags | (FLAG_KEYS_SORTED if getattr(plan, "keys_sorted", False) and plan.dynamic is None else 0)
         q.row_offset = row_offset
         q.initial_table_slots = initial_table_slots
         self.q = q
@@ -614,5 +616,20 @@ def group_tuples(table: pa.Table, keys, maintain_order: bool = True):
                                             C.byref(oa[2]), os_))
         _, cols = _import_columns(oa, os_, 3)
         return cols[0], cols[1], cols[2]
+    finally:
+        frame.free()
+
+
+def group_slices(table: pa.Table, keys):
+    """GroupsSlice of sorted key columns: (first[g], len[g]) per run of equal keys — ``pw_b200_frame_group_slices``
+    (polars-arrow/src/legacy/kernels/sort_partition.rs:168 partition_to_groups)."""
+    L = lib()
+    frame = DeviceFrame(table)
+    try:
+        kc = (C.c_int32 * max(1, len(keys)))(*[table.column_names.index(k) for k in keys])
+        oa, os_ = (ArrowArray * 2)(), (ArrowSchema * 2)()
+        _check(L.pw_b200_frame_group_slices(frame.handle, kc, len(keys), C.byref(oa[0]), C.byref(oa[1]), os_))
+        _, cols = _import_columns(oa, os_, 2)
+        return cols[0], cols[1]
     finally:
         frame.free()

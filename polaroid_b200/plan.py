@@ -94,6 +94,7 @@ class GroupByPlan:
     aggs: list = field(default_factory=list)
     maintain_order: bool = False
     dynamic: Optional[DynamicOptions] = None
+    keys_sorted: bool = False    # every key column carries the sorted flag (LazyFrame.set_sorted): the GroupsSlice path
 
 
 # ---- expression front-end -----------------------------------------------------------------
@@ -295,10 +296,20 @@ class LazyFrame:
             data = pa.table(data)
         self._table = data
         self._preds: list = []
+        self._sorted: set = set()
 
     def filter(self, pred: PredExpr) -> "LazyFrame":
         out = LazyFrame(self._table)
         out._preds = self._preds + list(pred.preds)
+        out._sorted = set(self._sorted)
+        return out
+
+    def set_sorted(self, column: str) -> "LazyFrame":
+        """Flag a column as sorted (py-polars LazyFrame.set_sorted): a group_by over flagged key columns takes the
+        run-boundary path (polars-core/src/frame/group_by/into_groups.rs:65-129).  The flag is a promise, not a check."""
+        out = LazyFrame(self._table)
+        out._preds = list(self._preds)
+        out._sorted = set(self._sorted) | {column}
         return out
 
     def group_by(self, *keys, maintain_order: bool = False) -> "LazyGroupBy":
@@ -306,7 +317,8 @@ class LazyFrame:
         for k in keys:
             flat.extend(k if isinstance(k, (list, tuple)) else [k])
         names = [k if isinstance(k, str) else k._out_name() for k in flat]
-        return LazyGroupBy(self, GroupByPlan(predicates=list(self._preds), keys=names, maintain_order=maintain_order))
+        return LazyGroupBy(self, GroupByPlan(predicates=list(self._preds), keys=names, maintain_order=maintain_order,
+                                             keys_sorted=bool(names) and all(k in self._sorted for k in names)))
 
     def group_by_dynamic(self, index_column: str, *, every, period=None, offset=None,
                          closed: str = "left", label: str = "left", group_by=None,
