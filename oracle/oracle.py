@@ -131,6 +131,11 @@ def key_words(arr: pa.Array):
     strings <-> equal codes, which is all group identity needs."""
     arr = _combine(arr)
     t = arr.type
+    if pa.types.is_dictionary(t):
+        # Categorical / Enum: the group identity is the physical code (polars-expr/src/hash_keys.rs:32,83-89)
+        idx = arr.indices
+        valid = _valid_bytes(idx)
+        return np.ascontiguousarray(idx.fill_null(0).to_numpy(zero_copy_only=False).astype(np.uint64)), valid
     if pa.types.is_string(t) or pa.types.is_large_string(t) or pa.types.is_string_view(t) or pa.types.is_binary(t):
         if pa.types.is_string_view(t):
             arr = arr.cast(pa.large_string())

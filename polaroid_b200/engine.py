@@ -427,6 +427,7 @@ class DeviceFrame:
 
     def __init__(self, table: pa.Table):
         L = lib()
+        table, self._dicts = _physical_table(table)
         self.table_schema = table.schema
         arrays = [_to_abi_array(table.column(i)) for i in range(table.num_columns)]
         ex = _Exported(arrays)
@@ -509,13 +510,35 @@ class DeviceFrame:
         n_out = C.c_size_t(cap)
         _check(L.pw_b200_frame_groupby(C.byref(bq.q), self.handle, out_arrays, out_schemas, C.byref(n_out)))
         names, cols = _import_columns(out_arrays, out_schemas, n_out.value)
-        cols = _restore_string_types(names, cols, self.table_schema, plan.keys)
+        cols = _restore_string_types(names, cols, self.table_schema, plan.keys, getattr(self, "_dicts", None))
         return pa.Table.from_arrays(cols, names=names)
 
 
-def _restore_string_types(names, cols, schema: pa.Schema, key_names) -> list:
+def _physical_table(table: pa.Table):
+    """Categorical / Enum columns (Arrow dictionary arrays) cross the boundary as their PHYSICAL index column, as the
+    reference's operators see them (polars-expr/src/hash_keys.rs:32,83-89: group identity is the u8/u16/u32 code; the
+    caller reattaches the categories).  -> (table with index columns, {column name: dictionary values})."""
+    dicts = {}
+    if not any(pa.types.is_dictionary(f.type) for f in table.schema):
+        return table, dicts
+    table = table.unify_dictionaries().combine_chunks()
+    for i, f in enumerate(table.schema):
+        if pa.types.is_dictionary(f.type):
+            col = table.column(i)
+            arr = col.chunk(0) if col.num_chunks else pa.DictionaryArray.from_arrays(pa.array([], type=f.type.index_type), pa.array([], type=f.type.value_type))
+            dicts[f.name] = (arr.dictionary, f.type)
+            table = table.set_column(i, f.name, arr.indices)
+    return table, dicts
+
+
+def _restore_string_types(names, cols, schema: pa.Schema, key_names, dicts=None) -> list:
     out = []
     for n, c in zip(names, cols):
+        if dicts and n in key_names and n in dicts:
+            values, typ = dicts[n]
+            c = pa.chunked_array([pa.DictionaryArray.from_arrays(ch.cast(typ.index_type), values) for ch in (c.chunks if isinstance(c, pa.ChunkedArray) else [c])], type=typ)
+            out.append(c)
+            continue
         if n in key_names and n in schema.names:
             t = schema.field(n).type
             if c.type != t and _is_stringlike(t) and not (pa.types.is_string_view(t) or pa.types.is_binary_view(t)):
@@ -548,7 +571,7 @@ def run_group_by(table: pa.Table, plan: P.GroupByPlan, **opts) -> pa.Table:
             used.append(n)
     if not used:
         used = table.column_names[:1]
-    sub = table.select(used)
+    sub, dicts = _physical_table(table.select(used))
     arrays = [_to_abi_array(sub.column(i)) for i in range(sub.num_columns)]
     ex = _Exported(arrays)
     ex.set_names(sub.column_names)
@@ -563,7 +586,7 @@ def run_group_by(table: pa.Table, plan: P.GroupByPlan, **opts) -> pa.Table:
     finally:
         ex.release()
     names, cols = _import_columns(out_arrays, out_schemas, n_out.value)
-    cols = _restore_string_types(names, cols, sub.schema, plan.keys)
+    cols = _restore_string_types(names, cols, sub.schema, plan.keys, dicts)
     return pa.Table.from_arrays(cols, names=names)
 
 
