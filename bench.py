@@ -67,7 +67,8 @@ WORKLOADS = {
 }
 STRATEGY = {1: "hot table + spill tier", 2: "HBM table", 3: "segmented sorted windows", 4: "hot table, dense ids + spill tier",
             5: "radix partition + hot table", 6: "sorted windows by key (dense ids per window)",
-            7: "dense ids bucketed per tile, accumulators in registers + spill tier"}
+            7: "dense ids bucketed per tile, accumulators in registers + spill tier",
+            8: "sorted-key runs in registers", 9: "key-index ids bucketed per tile, accumulators in registers + spill tier"}
 
 
 def measured_peak_gbs():
@@ -558,7 +559,7 @@ def main():
     def roofline(rows, bytes_per_row, out_rows, out_bytes_per_row, k_ms, step_ms, tm):
         algo = rows * bytes_per_row + out_rows * out_bytes_per_row
         ach = algo / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-        return {"kernel": {3: "pw_seg_jit", 6: "pw_bucket_jit", 7: "pw_bucket_jit"}.get(tm["strategy"], "pw_scan_jit") if tm["reserved"] else "ahead-of-time kernel",
+        return {"kernel": {3: "pw_seg_jit", 6: "pw_bucket_jit", 7: "pw_bucket_jit", 8: "pw_runs_jit", 9: "pw_bucket_jit"}.get(tm["strategy"], "pw_scan_jit") if tm["reserved"] else "ahead-of-time kernel",
                 "kernel_ms": k_ms, "algorithmic_bytes_per_launch": algo, "achieved_gbs": ach,
                 "frac_measured": ach / peak, "frac_nominal_8tbs": ach / NOMINAL_GBS,
                 "whole_step_frac_measured": (algo / (step_ms * 1e-3) / 1e9) / peak}
@@ -665,7 +666,7 @@ def main():
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3},
                 "gpu_launches": int(launches) * args.steps,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "kernel": {7: "pw_bucket_jit"}.get(tm["strategy"], "pw_scan_jit") if tm["reserved"] else "pw::scan_kernel",
+                             "traffic": traffic, "kernel": {7: "pw_bucket_jit", 9: "pw_bucket_jit"}.get(tm["strategy"], "pw_scan_jit") if tm["reserved"] else "pw::scan_kernel",
                              "kernel_ms": k_ms, "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
                              "frac_nominal_8tbs": achieved / NOMINAL_GBS,
                              "whole_step_frac": (algo_bytes / (ms * 1e-3) / 1e9) / peak},

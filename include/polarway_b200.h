@@ -182,7 +182,8 @@ typedef struct PwTimings {
   int64_t n_rows, n_groups, table_slots;
   int32_t strategy;      /* 1 hot table, 2 global table, 3 segmented, 4 hot table with dense ids (small integer key range), 5 partitioned,
                             6 the same per (key, window) for group_by_dynamic by one dense key,
-                            7 dense ids bucketed per tile, accumulators in registers (pw_bucket.cuh), 8 sorted-key runs (pw_runs.cuh) */
+                            7 dense ids bucketed per tile, accumulators in registers (pw_bucket.cuh), 8 sorted-key runs (pw_runs.cuh),
+                            9 the bucket tier with ids from a shared-memory key index (sparse integers, strings, several keys) */
   int32_t retries;       /* table growth re-runs */
   int64_t kernel_launches; /* launches of this library's kernels in the last call */
   int64_t spilled_rows;  /* rows that bypassed the hot table (spill tier) */

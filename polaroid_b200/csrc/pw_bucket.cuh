@@ -180,6 +180,81 @@ __device__ __noinline__ void bucket_cold_row(const ScanPlan& P, RowOut<KW, NV> o
   }
 }
 
+// ---- INDEXED ids: keys that do not span a small integer range (sparse integers, short strings, several key columns) ----
+// A CTA-local open-addressing index in shared memory maps the key words to an id in [0, GCAP), assigned in order of
+// first sight; everything after that — ranks, buckets, the owner's registers — is the dense-id tier.  Slot word:
+// 0 empty, 0xFFFFFFFF being written, 0xFFFFFFFE closed (the index was full when this slot was wanted), else id + 1.
+__device__ __forceinline__ uint32_t sh_ld32_volatile(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sh_st32_volatile(uint32_t addr, uint32_t v) { asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t sh_cas32(uint32_t addr, uint32_t cmp, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(addr), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+// -> id of the key, or ~0 when the index is full (the row takes the HBM path).
+// Slot word = (20-bit hash tag << 12) | (id + 1): a probe reads one word and goes to the key words only on a tag match
+// (a foreign key passes the tag test once in 2^20), the index runs at a load factor <= 0.25 so that the first probe
+// almost always ends the search — the warp pays the LONGEST probe sequence among its lanes.
+template <int KW>
+__device__ __forceinline__ uint32_t bucket_index_hash(const uint64_t (&k)[KW]) {
+  uint32_t x = 0x9E3779B1u;
+#pragma unroll
+  for (int w = 0; w < KW; ++w) {
+    x = (x ^ (uint32_t)k[w]) * 0x85EBCA6Bu;
+    x = (x ^ (uint32_t)(k[w] >> 32)) * 0xC2B2AE35u;
+    x ^= x >> 15;
+  }
+  x *= 0x27D4EB2Fu;
+  return x ^ (x >> 16);
+}
+// The index is BUCKETIZED: four slot words per 16-byte bucket, read with one LDS.128.  With <= 0.25 keys per slot word a
+// key sits in its home bucket with probability > 0.99, so the common lookup is: hash, one 16-byte read, four tag
+// compares, one key read — straight-line code, no probe loop (a loop costs the warp its SLOWEST lane).  Everything else
+// — first sight of a key (insert), a full home bucket, a tag collision — goes through this out-of-line routine.
+// -> id, or 0xFFFFFFFF when the index is full.
+template <int KW>
+struct KeyWords { uint64_t w[KW]; };   // by value: the caller's key words stay in registers
+template <int KW, int NB, int GCAP>
+__device__ __noinline__ uint32_t bucket_index_slow(uint32_t sidx, uint32_t skeys, uint32_t scount, KeyWords<KW> k, uint32_t hx) {
+  const uint32_t tag = ((hx & 0x7FFFF000u) | 0x1000u);
+  uint32_t b = hx & (uint32_t)(NB - 1);
+  for (int walked = 0; walked < NB; ++walked, b = (b + 1) & (uint32_t)(NB - 1)) {
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t a = sidx + 16u * b + 4u * (uint32_t)j;
+      uint32_t e = sh_ld32_volatile(a);
+      if (e == 0u) {
+        e = sh_cas32(a, 0u, 0xFFFFFFFFu);
+        if (e == 0u) {   // ours to fill
+          const uint32_t id = sh_rank(scount);
+          if (id >= (uint32_t)GCAP) { sh_st32_volatile(a, 0xFFFFFFFEu); return 0xFFFFFFFFu; }
+#pragma unroll
+          for (int w = 0; w < KW; ++w) sh_st64_if(skeys + ((uint32_t)w * GCAP + id) * 8u, k.w[w], true);
+          __threadfence_block();
+          sh_st32_volatile(a, tag | (id + 1u));
+          return id;
+        }
+      }
+      // another thread is writing this word's key — possibly a lane of this very warp: sleeping hands the scheduler to the
+      // other divergent paths (a bare spin inside an out-of-line function starved the writer: measured as a hang), and
+      // the wait is bounded — a row that gives up takes the HBM path, which is always correct
+      for (int spins = 0; e == 0xFFFFFFFFu && spins < 4096; ++spins) { __nanosleep(64); e = sh_ld32_volatile(a); }
+      if (e >= 0xFFFFFFFEu) return 0xFFFFFFFFu;            // closed: the index was full when this word was wanted (or gave up)
+      if ((e & 0xFFFFF000u) == tag) {
+        const uint32_t id = (e & 0xFFFu) - 1u;
+        bool eq = true;
+#pragma unroll
+        for (int w = 0; w < KW; ++w) eq = eq && sh_ld64(skeys + ((uint32_t)w * GCAP + id) * 8u) == k.w[w];
+        if (eq) return id;
+      }
+    }
+  }
+  return 0xFFFFFFFFu;
+}
+
 template <class CT, int NC, int KW>
 __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -209,6 +284,11 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
   // any other window (unsorted input, windows shorter than a tile) take the HBM path — correct, just slow — which is
   // why the host asks for windows several tiles long before it plans this tier.
   constexpr bool WIN = CT::kBWin;
+  constexpr bool IDX = CT::kBIdx;             // ids from the CTA's key index instead of key - dense_min
+  constexpr int ISLOTS = CT::kBIdxMul * GCAP; // index slot words (8 per id by default: <= 0.125 keys per word)
+  constexpr int INB = ISLOTS / 4;             // buckets of four words
+  constexpr uint32_t IDX_BYTES = IDX ? (uint32_t)(ISLOTS * 4 + GCAP * KW * 8 + 16) : 0u;
+  static_assert(!(IDX && WIN), "indexed ids and the windowed tier are not combined");
   constexpr uint32_t VAR = CT::kBVar;     // experiment switches (PW_BUCKET_VAR): 1 branch-form min / max, 2 predicated rank atomics
   // OVERFLOW LIST: a row whose rank is beyond the bucket depth is appended to a short CTA-wide list (id + value words)
   // that every owner scans after its bucket — a broadcast read per entry.  The HBM path is ~1 us per row (dependent,
@@ -234,10 +314,16 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
   }
   const uint32_t sovf = scnt + (uint32_t)NCNT * (GCAP * 4u) + 128u;     // [NOVF] counters | [NBUF][OVF] ids | [NBUF][PLANES][OVF] words
   const uint32_t sovf_id = sovf + 16u, sovf_val = sovf_id + (uint32_t)NBUF * OVF * 4u;
-  const uint32_t sstage = sovf + OVF_BYTES;
+  const uint32_t sindex = sovf + OVF_BYTES;                 // IDX: [ISLOTS] slot words | [KW][GCAP] key words | id counter
+  const uint32_t sikeys = sindex + (uint32_t)ISLOTS * 4u, sicount = sikeys + (uint32_t)GCAP * KW * 8u;
+  const uint32_t sstage = sindex + IDX_BYTES;
   const uint32_t sbar = sstage + (uint32_t)STAGES * stage_bytes;
   for (int i = tid; i < NCNT * GCAP; i += THREADS) sh_st32(scnt + 4u * i, 0u);
   if (tid < 4) sh_st32(sovf + 4u * tid, 0u);
+  if (IDX) {
+    for (int i = tid; i < ISLOTS; i += THREADS) sh_st32(sindex + 4u * i, 0u);
+    if (tid == 0) sh_st32(sicount, 0u);
+  }
   if (STAGES > 0 && tid == 0) {
     for (int st = 0; st < STAGES; ++st) mbar_init(sbar + 8u * st, 1u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -280,7 +366,10 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
       const int g = my_g0 + gi * THREADS;
       uint64_t k[KW];
 #pragma unroll
-      for (int x = 0; x < KW; ++x) k[x] = x == 0 ? (uint64_t)P.dense_min + (uint64_t)g : (WIN && x == 1 ? (uint64_t)w : 0ull);
+      for (int x = 0; x < KW; ++x) {
+        if (IDX) k[x] = sh_ld64(sikeys + ((uint32_t)x * GCAP + (uint32_t)g) * 8u);
+        else k[x] = x == 0 ? (uint64_t)P.dense_min + (uint64_t)g : (WIN && x == 1 ? (uint64_t)w : 0ull);
+      }
       const uint64_t gs = table_upsert<KW>(P.table, k, hash_words<KW>(k), true);
       if (gs == ~0ull) continue;
 #pragma unroll
@@ -308,7 +397,7 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
   int st_cur = 0;      // staged input: stage of the current tile
   // WINDOWED: is the row at `rel` (index value - origin) a member of the window that starts at `lo` (= k * every)?
   // Same membership as window_of (pw_scan.cuh) for each `closed`.
-  constexpr long long EVERY = CT::kDynEvery > 0 ? CT::kDynEvery : 1, PERIOD = CT::kDynPeriod;
+  constexpr long long EVERY = CT::kDynEvery > 0 ? CT::kDynEvery : 1, PERIOD = CT::kDynPeriod > 0 ? CT::kDynPeriod : 2;
   auto in_window_at = [&](int64_t rel, int64_t lo) -> bool {
     const int64_t off = rel - lo;
     const int closed = CT::dyn_closed(P);
@@ -331,10 +420,63 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
       bucket_row_front<CT, NC, KW, NV>(P, raw, vb, 1, row0 + 1, WHOLE || row0 + 1 < n_rows, o[1]);
       uint32_t id[2], rk[2];
       bool take[2], cand[2], cold[2];
+      // IDX: ids of both rows.  The home-slot probes of the two rows are issued together (slot words, then key words:
+      // two dependent shared-memory round trips for the pair instead of four); only a row whose home slot does not
+      // hold its key walks the probe sequence.
+      uint32_t idx_id[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+      bool idx_plain[2] = {false, false};
+      if (IDX) {
+        uint32_t hx[2], tagw[2];
+        uint4 e[2], f[2];   // home bucket and its successor: a key displaced by a full home bucket sits next door
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          // (a single-word key whose VALUE is one of the table sentinels is told apart by sentinel_free: HBM path)
+          idx_plain[i] = o[i].alive && (KW != 1 || o[i].sentinel_free);
+          hx[i] = bucket_index_hash<KW>(o[i].k);
+          const uint32_t b0 = hx[i] & (uint32_t)(INB - 1), b1 = (b0 + 1u) & (uint32_t)(INB - 1);
+          const uint32_t a = sindex + 16u * b0, a1 = sindex + 16u * b1;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e[i].x), "=r"(e[i].y), "=r"(e[i].z), "=r"(e[i].w) : "r"(a) : "memory");
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(f[i].x), "=r"(f[i].y), "=r"(f[i].z), "=r"(f[i].w) : "r"(a1) : "memory");
+        }
+        uint64_t kw0[2][KW];
+        bool any[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const uint32_t tag = ((hx[i] & 0x7FFFF000u) | 0x1000u);
+          const bool m0 = (e[i].x & 0xFFFFF000u) == tag, m1 = (e[i].y & 0xFFFFF000u) == tag, m2 = (e[i].z & 0xFFFFF000u) == tag,
+                     m3 = (e[i].w & 0xFFFFF000u) == tag, m4 = (f[i].x & 0xFFFFF000u) == tag, m5 = (f[i].y & 0xFFFFF000u) == tag,
+                     m6 = (f[i].z & 0xFFFFF000u) == tag, m7 = (f[i].w & 0xFFFFF000u) == tag;
+          tagw[i] = m0 ? e[i].x : (m1 ? e[i].y : (m2 ? e[i].z : (m3 ? e[i].w : (m4 ? f[i].x : (m5 ? f[i].y : (m6 ? f[i].z : f[i].w))))));
+          any[i] = m0 || m1 || m2 || m3 || m4 || m5 || m6 || m7;
+          const uint32_t cid = ((tagw[i] & 0xFFFu) - 1u) & (uint32_t)(GCAP - 1);   // always a readable key slot
+#pragma unroll
+          for (int w = 0; w < KW; ++w) kw0[i][w] = sh_ld64(sikeys + ((uint32_t)w * GCAP + cid) * 8u);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          bool hit = idx_plain[i] && any[i];
+#pragma unroll
+          for (int w = 0; w < KW; ++w) hit = hit && kw0[i][w] == o[i].k[w];
+          if (hit) idx_id[i] = (tagw[i] & 0xFFFu) - 1u;
+          else if (idx_plain[i]) {
+            KeyWords<KW> kv;
+#pragma unroll
+            for (int w = 0; w < KW; ++w) kv.w[w] = o[i].k[w];
+            idx_id[i] = bucket_index_slow<KW, INB, GCAP>(sindex, sikeys, sicount, kv, hx[i]);
+          }
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const uint64_t d = o[i].k[0] - (uint64_t)P.dense_min;
-        const bool plain = !CT::kBSent || o[i].k[0] < KEY_NULL;   // -1 / -2 inside the range: sentinels go cold
+        uint64_t d;
+        bool plain;
+        if (IDX) {
+          plain = idx_plain[i];
+          d = idx_id[i];
+        } else {
+          d = o[i].k[0] - (uint64_t)P.dense_min;
+          plain = !CT::kBSent || o[i].k[0] < KEY_NULL;   // -1 / -2 inside the range: sentinels go cold
+        }
         bool odd = false;   // a value the plain-double min / max cannot order
 #pragma unroll
         for (int e = 0; e < NVE; ++e)
@@ -342,7 +484,7 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
             const double x = __longlong_as_double((long long)o[i].v[e]);
             odd = odd || x != x || o[i].v[e] == 0x8000000000000000ull;
           }
-        const bool elig = o[i].alive && plain && !odd && d < (uint64_t)CT::kBRange;
+        const bool elig = o[i].alive && plain && !odd && d < (uint64_t)(IDX ? GCAP : CT::kBRange);
         if (WIN) {
           const int64_t rel = (int64_t)o[i].tval - P.dyn.origin;
           const bool in0 = in_window_at(rel, w0 * EVERY), in1 = w1 != w0 && in_window_at(rel, w1 * EVERY);

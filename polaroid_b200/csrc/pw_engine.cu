@@ -747,10 +747,19 @@ static bool plan_bucket(ScanPlan& P, int64_t groups, int64_t dense_range, bool s
   HotGeom& g = P.hot;
   g.bucket = 0;
   static const bool off = getenv("PW_NO_BUCKET") != nullptr;
+  // dense_range == 0: INDEXED ids — the CTA maps the key words to ids through a shared-memory index (any key shape)
+  const bool indexed = dense_range == 0;
+  if (indexed) {
+    if (windowed || groups < 48 || groups > 1600 || getenv("PW_NO_BUCKET_INDEX")) return false;
+    dense_range = 64;
+    while (dense_range < groups + groups / 64 + 8) dense_range <<= 1;   // id capacity: a little head-room over the live-group estimate
+                                                                          // (both pilot samples have seen a low-cardinality key set whole)
+  }
   if (off || (!assume_jit && !jit_available()) || dense_range < (windowed ? 16 : 48) || dense_range > 2048) return false;
-  g.b_range = (int32_t)dense_range; g.b_sent = sentinels ? 1 : 0; g.b_win = windowed ? 1 : 0;
+  g.b_range = (int32_t)dense_range; g.b_sent = sentinels ? 1 : 0; g.b_win = windowed ? 1 : 0; g.b_idx = indexed ? 1 : 0;
   if ((P.dyn.enabled != 0) != windowed || P.row_group_out || P.rowid_slot_p1 || P.check_sorted || !P.vec_ok || P.row_begin != 0 || P.row_stride != 1) return false;
-  if (P.n_kw != (windowed ? 2 : 1) || P.n_vexpr > 8 || P.n_acc < 1 || (P.gflags & GF_TMIN)) return false;
+  if ((!indexed && P.n_kw != (windowed ? 2 : 1)) || P.n_kw > 6 || P.n_vexpr > 8 || P.n_acc < 1 || (P.gflags & GF_TMIN)) return false;
+  const int kw_pad = P.n_kw <= 1 ? 1 : (P.n_kw <= 2 ? 2 : (P.n_kw <= 4 ? 4 : 6));   // the kernel's key-word class (launch_scan)
   bool meta = (P.gflags & GF_ROW) != 0;
   for (int e = 0; e < P.n_vexpr; ++e) {
     const VExpr& V = P.vexprs[e];
@@ -806,7 +815,10 @@ static bool plan_bucket(ScanPlan& P, int64_t groups, int64_t dense_range, bool s
     const int j_full = depth((double)tile / (double)pop, 1e-4), j_min = depth((double)tile / (double)pop, 1e-3);
     const int ncnt = gcap < cd.threads ? cd.nbuf + 1 : cd.nbuf;
     const size_t ovf = (16 + (size_t)cd.nbuf * 32 * (4 + 8 * planes) + 127) & ~(size_t)127;   // overflow list (pw_bucket.cuh OVF_BYTES)
-    const size_t fixed = (size_t)ncnt * gcap * 4 + 128 + ovf;   // counters + one dummy counter per lane + overflow list
+    static const int idx_mul = getenv("PW_BUCKET_IDXMUL") ? atoi(getenv("PW_BUCKET_IDXMUL")) : 8;   // measured on C2 without dense ids: 8 -> 0.73 ms, 4 -> 1.01 ms (old per-cell table 0.91 ms)
+    g.b_idx_mul = idx_mul;
+    const size_t idx_bytes = indexed ? (size_t)idx_mul * gcap * 4 + (size_t)gcap * kw_pad * 8 + 16 : 0;   // key index (pw_bucket.cuh IDX_BYTES)
+    const size_t fixed = (size_t)ncnt * gcap * 4 + 128 + ovf + idx_bytes;   // counters + one dummy counter per lane + overflow list + index
     const size_t per_j = (size_t)cd.nbuf * planes * gcap * 8;
     if (tma_ok && cd.cps == 1) {
       // staged: shared memory holds the buckets AND the tiles in flight; L1 is not needed for the stream
@@ -863,6 +875,8 @@ extern "C" __attribute__((visibility("default"))) int pw_b200_jit_selftest(char*
   P.hot_slots = P.hot.idx_slots;
   if (win) {
     if (!plan_bucket(P, 100, 100, false, true, true)) return -4;
+  } else if (getenv("PW_SELFTEST_INDEX")) {   // ids from the shared-memory key index
+    if (!plan_bucket(P, 1000, 0, false, false, true)) return -5;
   } else if (getenv("PW_SELFTEST_DENSE")) {   // the bucket tier on top of the dense ids (NVRTC exists whenever this function can succeed)
     if (!plan_bucket(P, 1000, 1000, false, false, true) && !getenv("PW_NO_BUCKET")) return -3;
   }
@@ -1364,14 +1378,17 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
   // the bucket tier does not need the dense per-cell table to fit (many accumulators): it only needs the id range
   else if (use_hot && dense_range > 0 && q->hot_table_slots == 0 && !(q->flags & (PW_FLAG_NO_BUCKETS | PW_FLAG_NO_DENSE_IDS)))
     plan_bucket(P, windowed ? dense_range : live_groups, dense_range, dense_sentinels, windowed);
+  // no small dense range (sparse integers, strings, several key columns) but few live groups: ids from a key index
+  else if (use_hot && dense_range == 0 && !windowed && q->hot_table_slots == 0 && !(q->flags & PW_FLAG_NO_BUCKETS) && N > SMALL)
+    plan_bucket(P, live_groups, 0, false, false);
   if (cap > 0xFFFFFFF0ull) return fail(PW_ERR_UNSUPPORTED, "table larger than 2^32 slots");
   if (getenv("PW_DEBUG"))
     fprintf(stderr, "[pw] rows=%lld kw=%d slots=%d accs=%d cap=%llu hot=%d live=%lld gcap=%d S=%d R=%d n_mm=%d smem=%d dense=%d min=%lld\n", (long long)N, P.n_kw,
             P.n_slots, P.n_acc, (unsigned long long)cap, (int)use_hot, (long long)live_groups, P.hot.gcap, P.hot.idx_slots, P.hot.replicas,
             P.hot.n_mm, P.hot.total_bytes, P.hot.dense, (long long)P.dense_min);
   if (getenv("PW_DEBUG") && P.hot.bucket)
-    fprintf(stderr, "[pw] bucket tier: threads=%d gcap=%d J=%d nbuf=%d stages=%d meta=%d smem=%d\n", P.hot.b_threads, P.hot.b_gcap, P.hot.b_j, P.hot.b_nbuf,
-            P.hot.b_stages, P.hot.b_meta, P.hot.b_bytes);
+    fprintf(stderr, "[pw] bucket tier: threads=%d gcap=%d J=%d nbuf=%d stages=%d meta=%d smem=%d idx=%d win=%d range=%d\n", P.hot.b_threads, P.hot.b_gcap, P.hot.b_j, P.hot.b_nbuf,
+            P.hot.b_stages, P.hot.b_meta, P.hot.b_bytes, P.hot.b_idx, P.hot.b_win, P.hot.b_range);
   PW_CUDA(cudaEventRecord(c.ev[2], c.stream));
 
   // ---- sorted keys (the caller's flag, as the reference's IsSorted): groups are runs of equal keys
@@ -1455,7 +1472,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     }
     break;
   }
-  tm.strategy = runs ? 8 : partitioned ? 5 : (use_hot ? (P.hot.bucket ? (P.hot.b_win ? 6 : 7) : (P.hot.dense ? 4 : 1)) : 2);
+  tm.strategy = runs ? 8 : partitioned ? 5 : (use_hot ? (P.hot.bucket ? (P.hot.b_win ? 6 : (P.hot.b_idx ? 9 : 7)) : (P.hot.dense ? 4 : 1)) : 2);
   tm.table_slots = (int64_t)cap;
   tm.partition_ms = 0.0f;
   if (deferred) {

@@ -177,6 +177,8 @@ std::string jit_ctl(const ScanPlan& P) {
       << ", kBJ = " << (P.hot.b_j > 0 ? P.hot.b_j : 1) << ", kBNbuf = " << (P.hot.b_nbuf > 0 ? P.hot.b_nbuf : 1)
       << ", kBStages = " << P.hot.b_stages << ";\n";
   g.o << "  static constexpr int kBRange = " << P.hot.b_range << ";\n  static constexpr bool kBSent = " << (P.hot.b_sent ? "true" : "false") << ";\n";
+  g.o << "  static constexpr int kBIdxMul = " << (P.hot.b_idx_mul > 0 ? P.hot.b_idx_mul : 8) << ";\n";
+  g.o << "  static constexpr bool kBIdx = " << (P.hot.b_idx ? "true" : "false") << ";\n";
   g.o << "  static constexpr bool kBWin = " << (P.hot.b_win ? "true" : "false") << ";\n";
   g.o << "  static constexpr unsigned kBVar = " << (getenv("PW_BUCKET_VAR") ? atoi(getenv("PW_BUCKET_VAR")) : 0) << "u;\n";
   g.o << "  static constexpr bool kBMeta = " << (P.hot.b_meta ? "true" : "false") << ";\n";
