@@ -91,8 +91,11 @@ def plugin_field(schema: pa.Schema, kwargs: dict) -> pa.Schema:
     return res
 
 
-def call_plugin(table: pa.Table, kwargs: dict) -> pa.Table:
-    """`_polars_plugin_<fn>`: every column as a SeriesExport (chunks preserved), result = one Struct series."""
+def call_plugin(table: pa.Table, kwargs: dict, release_log: list | None = None) -> pa.Table:
+    """`_polars_plugin_<fn>`: every column as a SeriesExport (chunks preserved), result = one Struct series.
+    release_log: when given, every input SeriesExport carries a real ``release`` callback (as ``export_column`` gives it,
+    polars-ffi/src/version_0.rs:37-60) that appends the input's position; the callee owns the inputs and must call each
+    exactly once (plugin.rs:127-130: the caller ``mem::forget``s them)."""
     L = E.lib()
     _check_version(L)
     n = table.num_columns
@@ -111,13 +114,25 @@ def call_plugin(table: pa.Table, kwargs: dict) -> pa.Table:
         inputs[i].arrays = ptrs
         inputs[i].len = len(chunks)
         inputs[i].release = None       # the structs are owned by this Python frame; released below
+        if release_log is not None:
+            def _mk(pos, exported):
+                def _release(ptr):
+                    release_log.append(pos)
+                    exported.release()
+                    C.cast(ptr, C.POINTER(SeriesExport)).contents.release = None
+                return C.CFUNCTYPE(None, C.c_void_p)(_release)
+            cb = _mk(i, ex)
+            inputs[i].release = C.cast(cb, C.c_void_p)
+            keep.append((ex, ptrs, cb))
+            continue
         keep.append((ex, ptrs))
     blob = pickle.dumps(kwargs, protocol=5)
     out = SeriesExport()
     ctx = CallerContext(0)
     L._polars_plugin_filter_groupby_agg(inputs, C.c_size_t(n), blob, C.c_size_t(len(blob)), C.byref(out), C.byref(ctx))
-    for ex, _ in keep:
-        ex.release()
+    if release_log is None:
+        for ex, *_ in keep:
+            ex.release()
     if not out.private_data:   # plugin.rs:132-138
         L._polars_plugin_get_last_error_message.restype = C.c_char_p
         raise E.PolarwayError(-1, "the plugin failed with message: " + L._polars_plugin_get_last_error_message().decode())

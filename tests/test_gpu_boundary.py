@@ -120,3 +120,21 @@ def test_result_count_beyond_the_sample_estimate_retries_with_a_larger_table():
     got = engine.run_group_by(q.table, q.plan, initial_table_slots=256)
     G.assert_tables_equal(got, oracle.collect(q), sort_by=["key"], rtol=1e-12)
     assert engine.last_timings()["retries"] >= 1
+
+
+def test_plugin_callee_releases_every_input_exactly_once():
+    # plugin.rs:127-130: the caller forgets the exported inputs; "the inputs get dropped when the ffi side calls the
+    # drop callback" — once per input, on success and on failure alike
+    from polaroid_b200 import plugin_loader
+    rng = np.random.default_rng(81)
+    n = 30_000
+    t = pa.table({"k": pa.array(rng.integers(0, 50, n)), "v": pa.array(rng.random(n)), "w": pa.array(rng.integers(0, 9, n))})
+    q = pw.LazyFrame(t).filter(pw.col("w") < 7).group_by("k").agg(pw.col("v").sum().alias("s"), pw.len().alias("n"))
+    log = []
+    got = plugin_loader.call_plugin(t, plugin_loader.plan_to_kwargs(t.schema, q.plan), release_log=log)
+    assert sorted(log) == [0, 1, 2]
+    G.assert_tables_equal(got, oracle.collect(q), sort_by=["k"], rtol=1e-12)
+    log = []
+    with pytest.raises(engine.PolarwayError):
+        plugin_loader.call_plugin(t, {"keys": [0], "aggs": [("x", 0, 7, None)]}, release_log=log)   # column 7 does not exist
+    assert sorted(log) == [0, 1, 2]
