@@ -91,17 +91,18 @@ __device__ __forceinline__ uint4 staged_pair(uint32_t addr, int w) {
   return r;
 }
 
-// accumulators of ONE group in registers; SKIP = an accumulator handled outside the per-row walk (the row counter);
+// accumulators of ONE group in registers; SKIP = accumulators handled outside the per-row walk (the row counter, and
+// under ROWPOS the row-index words of first / last / maintain_order);
 // NATIVE = bit per accumulator: an f64 min / max kept as the plain double and compared with DSETP (the rows that need the
 // total order — NaN, -0.0 — never reach the buckets), turned into the ordered image once, when the registers are published
-template <int NACC, int SKIP, uint32_t NATIVE, bool SELECT_MM = false>
+template <int NACC, uint32_t SKIP, uint32_t NATIVE, bool SELECT_MM = false>
 struct BucketRegSink {
   uint64_t (&acc)[NACC];
   template <int OP>
   __device__ __forceinline__ void add(const ScanPlan&, int a, uint64_t x) const {
 #pragma unroll
     for (int i = 0; i < NACC; ++i)
-      if (i == a && i != SKIP) acc[i] = acc_combine(OP, acc[i], x);
+      if (i == a && !((SKIP >> i) & 1u)) acc[i] = acc_combine(OP, acc[i], x);
   }
   // SELECT_MM: compare-and-select on both halves (measured faster: 0.419 vs 0.465 ms on C2); otherwise compare and
   // skip the update (fewer instructions, but the predicated moves wait on the FP64 compare)
@@ -122,7 +123,7 @@ struct BucketRegSink {
       }
   }
 };
-template <int NACC, int SKIP, uint32_t NATIVE, bool SELECT_MM>
+template <int NACC, uint32_t SKIP, uint32_t NATIVE, bool SELECT_MM>
 struct SinkNative<BucketRegSink<NACC, SKIP, NATIVE, SELECT_MM>> {
   using S = BucketRegSink<NACC, SKIP, NATIVE, SELECT_MM>;
   static __device__ __forceinline__ constexpr bool on(int a) { return ((NATIVE >> a) & 1u) != 0; }
@@ -284,6 +285,14 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
   // any other window (unsorted input, windows shorter than a tile) take the HBM path — correct, just slow — which is
   // why the host asks for windows several tiles long before it plans this tier.
   constexpr bool WIN = CT::kBWin;
+  // ROWPOS: first / last / first-occurrence words need only the smallest and largest ROW of a group, not a word per
+  // row: when no value can be null (the valid bit is constant) every bucketed row registers its position inside the
+  // tile with a native shared-memory min / max, the meta plane disappears (a third of the bucket memory and of the
+  // fold's loads for OHLCV bars) and the owner turns the two positions into row words once per tile.
+  constexpr bool ROWPOS = CT::kBRowPos;
+  constexpr uint32_t FIRSTW = CT::kBFirstAcc, LASTW = CT::kBLastAcc;   // accumulators: MIN / MAX over a row word
+  constexpr uint32_t ROWTAG = CT::kBRowTagAcc;                         // of those: word = (row << 1) | 1 (else the plain row)
+  constexpr uint32_t POS_BYTES = ROWPOS ? (uint32_t)NBUF * 2u * GCAP * 4u : 0u;
   constexpr bool IDX = CT::kBIdx;             // ids from the CTA's key index instead of key - dense_min
   constexpr int ISLOTS = CT::kBIdxMul * GCAP; // index slot words (8 per id by default: <= 0.125 keys per word)
   constexpr int INB = ISLOTS / 4;             // buckets of four words
@@ -316,10 +325,13 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
   const uint32_t sovf_id = sovf + 16u, sovf_val = sovf_id + (uint32_t)NBUF * OVF * 4u;
   const uint32_t sindex = sovf + OVF_BYTES;                 // IDX: [ISLOTS] slot words | [KW][GCAP] key words | id counter
   const uint32_t sikeys = sindex + (uint32_t)ISLOTS * 4u, sicount = sikeys + (uint32_t)GCAP * KW * 8u;
-  const uint32_t sstage = sindex + IDX_BYTES;
+  const uint32_t spos = sindex + IDX_BYTES;                  // ROWPOS: [NBUF][first | last][GCAP] positions inside the tile
+  const uint32_t sstage = spos + POS_BYTES;
   const uint32_t sbar = sstage + (uint32_t)STAGES * stage_bytes;
   for (int i = tid; i < NCNT * GCAP; i += THREADS) sh_st32(scnt + 4u * i, 0u);
   if (tid < 4) sh_st32(sovf + 4u * tid, 0u);
+  if (ROWPOS)
+    for (int i = tid; i < NBUF * 2 * GCAP; i += THREADS) sh_st32(spos + 4u * i, ((i / GCAP) & 1) ? 0u : 0xFFFFFFFFu);
   if (IDX) {
     for (int i = tid; i < ISLOTS; i += THREADS) sh_st32(sindex + 4u * i, 0u);
     if (tid == 0) sh_st32(sicount, 0u);
@@ -498,6 +510,16 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
       }
 #pragma unroll
       for (int i = 0; i < 2; ++i) rk[i] = (VAR & 2u) ? sh_rank_if(cc + 4u * id[i], take[i]) : sh_rank(take[i] ? cc + 4u * id[i] : dummy);
+      if (ROWPOS) {
+        // position inside the tile (+ 1 for the maximum: 0 = none); rows that take no bucket aim at the lane's dummy cell
+        const uint32_t pb = spos + (uint32_t)b * (2u * GCAP * 4u);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const uint32_t r = (uint32_t)lane_row + (uint32_t)i;
+          if (FIRSTW) asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(take[i] ? pb + 4u * id[i] : dummy), "r"(r) : "memory");
+          if (LASTW) asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(take[i] ? pb + (GCAP + id[i]) * 4u : dummy), "r"(r + 1u) : "memory");
+        }
+      }
       bool late = false;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
@@ -560,7 +582,8 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
       c = c < (uint32_t)J ? c : (uint32_t)J;
       uint32_t q = bb + ((uint32_t)my_sub * GCAP + g) * 8u;
       uint32_t mine = 0;
-      const BucketRegSink<NACC, LEN_ACC, NATIVE, (VAR & 1u) == 0> sink{acc[gi]};
+      constexpr uint32_t SKIPW = (LEN_ACC >= 0 ? (1u << LEN_ACC) : 0u) | (ROWPOS ? (FIRSTW | LASTW) : 0u);
+      const BucketRegSink<NACC, SKIPW, NATIVE, (VAR & 1u) == 0> sink{acc[gi]};
 #pragma unroll 1
       for (uint32_t j = my_sub; j < c; j += SUB, q += (uint32_t)SUB * GCAP * 8u) {
         RowOut<KW, NV> o;
@@ -586,6 +609,31 @@ __device__ __forceinline__ void bucket_body(const ScanPlan& P) {
         o.tval = 0ull;
         accumulate_row<CT, NV, KW>(P, o, grow, sink);
         ++mine;
+      }
+      if (ROWPOS && my_sub == 0 && mine + c > 0u) {
+        // (the list scan above only adds to `mine` for sub-owner 0, and every bucketed or listed row registered itself)
+        const uint32_t pa = spos + (uint32_t)b * (2u * GCAP * 4u) + 4u * (uint32_t)g;
+        const uint64_t row0 = global_row<CT>(P, t * TILE);
+        if (FIRSTW) {
+          const uint32_t fp = sh_ld32(pa);
+          if (fp != 0xFFFFFFFFu) {
+            sh_st32(pa, 0xFFFFFFFFu);
+            const uint64_t row = row0 + fp;
+#pragma unroll
+            for (int a = 0; a < NACC; ++a)
+              if ((FIRSTW >> a) & 1u) { const uint64_t w = ((ROWTAG >> a) & 1u) ? ((row << 1) | 1ull) : row; acc[gi][a] = w < acc[gi][a] ? w : acc[gi][a]; }
+          }
+        }
+        if (LASTW) {
+          const uint32_t lp = sh_ld32(pa + GCAP * 4u);
+          if (lp != 0u) {
+            sh_st32(pa + GCAP * 4u, 0u);
+            const uint64_t row = row0 + (lp - 1u);
+#pragma unroll
+            for (int a = 0; a < NACC; ++a)
+              if ((LASTW >> a) & 1u) { const uint64_t w = ((ROWTAG >> a) & 1u) ? ((row << 1) | 1ull) : row; acc[gi][a] = w > acc[gi][a] ? w : acc[gi][a]; }
+          }
+        }
       }
       if (mine) {
         seen[gi] = true;

@@ -760,13 +760,19 @@ static bool plan_bucket(ScanPlan& P, int64_t groups, int64_t dense_range, bool s
   if ((P.dyn.enabled != 0) != windowed || P.row_group_out || P.rowid_slot_p1 || P.check_sorted || !P.vec_ok || P.row_begin != 0 || P.row_stride != 1) return false;
   if ((!indexed && P.n_kw != (windowed ? 2 : 1)) || P.n_kw > 6 || P.n_vexpr > 8 || P.n_acc < 1 || (P.gflags & GF_TMIN)) return false;
   const int kw_pad = P.n_kw <= 1 ? 1 : (P.n_kw <= 2 ? 2 : (P.n_kw <= 4 ? 4 : 6));   // the kernel's key-word class (launch_scan)
-  bool meta = (P.gflags & GF_ROW) != 0;
+  // the meta plane ((row << 8) | validity bits per bucketed row) is needed when a value can be null; first / last /
+  // first-occurrence words alone are served by two row positions per group and tile (ROWPOS, pw_bucket.cuh)
+  bool needs_valid = false, needs_row = (P.gflags & GF_ROW) != 0;
   for (int e = 0; e < P.n_vexpr; ++e) {
     const VExpr& V = P.vexprs[e];
-    if (V.flags & (VF_FIRST | VF_LAST | VF_FIRST_NN | VF_LAST_NN)) meta = true;
-    if (V.n_factors == 0) meta = meta || P.slots[V.slot].validity != nullptr;
-    else for (int k = 0; k < V.n_factors; ++k) meta = meta || P.slots[V.f[k].slot].validity != nullptr;
+    if (V.flags & (VF_FIRST | VF_LAST | VF_FIRST_NN | VF_LAST_NN)) needs_row = true;
+    if (V.n_factors == 0) needs_valid = needs_valid || P.slots[V.slot].validity != nullptr;
+    else for (int k = 0; k < V.n_factors; ++k) needs_valid = needs_valid || P.slots[V.f[k].slot].validity != nullptr;
   }
+  static const bool no_rowpos = getenv("PW_NO_ROWPOS") != nullptr;
+  const bool meta = needs_valid || (needs_row && no_rowpos);
+  const bool rowpos = needs_row && !meta;
+  g.b_rowpos = rowpos ? 1 : 0;
   const int planes = P.n_vexpr + (meta ? 1 : 0);
   if (planes < 1) return false;   // len-only queries: nothing to bucket, the per-cell counters are already cheap
   int gcap = windowed ? 16 : 64;
@@ -818,7 +824,8 @@ static bool plan_bucket(ScanPlan& P, int64_t groups, int64_t dense_range, bool s
     static const int idx_mul = getenv("PW_BUCKET_IDXMUL") ? atoi(getenv("PW_BUCKET_IDXMUL")) : 8;   // measured on C2 without dense ids: 8 -> 0.73 ms, 4 -> 1.01 ms (old per-cell table 0.91 ms)
     g.b_idx_mul = idx_mul;
     const size_t idx_bytes = indexed ? (size_t)idx_mul * gcap * 4 + (size_t)gcap * kw_pad * 8 + 16 : 0;   // key index (pw_bucket.cuh IDX_BYTES)
-    const size_t fixed = (size_t)ncnt * gcap * 4 + 128 + ovf + idx_bytes;   // counters + one dummy counter per lane + overflow list + index
+    const size_t pos_bytes = rowpos ? (size_t)cd.nbuf * 2 * gcap * 4 : 0;   // ROWPOS: first / last position per id and buffer
+    const size_t fixed = (size_t)ncnt * gcap * 4 + 128 + ovf + idx_bytes + pos_bytes;   // counters + one dummy counter per lane + overflow list + index
     const size_t per_j = (size_t)cd.nbuf * planes * gcap * 8;
     if (tma_ok && cd.cps == 1) {
       // staged: shared memory holds the buckets AND the tiles in flight; L1 is not needed for the stream

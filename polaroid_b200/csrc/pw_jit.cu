@@ -177,6 +177,17 @@ std::string jit_ctl(const ScanPlan& P) {
       << ", kBJ = " << (P.hot.b_j > 0 ? P.hot.b_j : 1) << ", kBNbuf = " << (P.hot.b_nbuf > 0 ? P.hot.b_nbuf : 1)
       << ", kBStages = " << P.hot.b_stages << ";\n";
   g.o << "  static constexpr int kBRange = " << P.hot.b_range << ";\n  static constexpr bool kBSent = " << (P.hot.b_sent ? "true" : "false") << ";\n";
+  {
+    uint32_t firstw = 0, lastw = 0, tagw = 0;
+    for (int a = 0; a < P.n_acc && P.hot.b_rowpos; ++a) {
+      const int src = P.accs[a].src, op = P.accs[a].op;
+      if (src != SRC_ROWIDX && src != SRC_ROWIDX_NN && src != SRC_ROW) continue;
+      if (op == OP_MIN_U64) firstw |= 1u << a; else lastw |= 1u << a;
+      if (src != SRC_ROW) tagw |= 1u << a;
+    }
+    g.o << "  static constexpr bool kBRowPos = " << (P.hot.b_rowpos ? "true" : "false") << ";\n  static constexpr unsigned kBFirstAcc = " << firstw
+        << "u, kBLastAcc = " << lastw << "u, kBRowTagAcc = " << tagw << "u;\n";
+  }
   g.o << "  static constexpr int kBIdxMul = " << (P.hot.b_idx_mul > 0 ? P.hot.b_idx_mul : 8) << ";\n";
   g.o << "  static constexpr bool kBIdx = " << (P.hot.b_idx ? "true" : "false") << ";\n";
   g.o << "  static constexpr bool kBWin = " << (P.hot.b_win ? "true" : "false") << ";\n";

@@ -201,7 +201,7 @@ struct HotGeom {
   int32_t b_sent;      // the range contains the key images -1 / -2 (table sentinels): those rows take the HBM path
   int32_t b_win;       // group_by_dynamic by one dense key: buckets and registers hold one window at a time
   int32_t b_idx_mul;   // index slots per id (power of two)
-  int32_t b_pad2;
+  int32_t b_rowpos;    // first / last / first-occurrence words from two row positions per id and tile (no meta plane)
   int32_t b_idx;       // ids come from a CTA-local key index in shared memory (keys without a small dense range)
   int32_t b_stage_bytes;  // bytes of one staged tile (every slot's TILE rows, 16-byte aligned parts)
   int32_t acc_kind[MAX_ACC];

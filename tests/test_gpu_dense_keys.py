@@ -113,3 +113,18 @@ def test_dense_skewed_keys_fill_the_overflow_list(hot_share):
                                           pw.col("f").sum().alias("fsum"), pw.col("f").min().alias("fmin"), pw.col("f").max().alias("fmax"),
                                           pw.len().alias("n"))
     run(q, ["k"])
+
+
+@pytest.mark.parametrize("maintain_order", [False, True])
+def test_dense_first_last_of_non_nullable_values_use_row_positions(maintain_order):
+    # no value can be null: first / last / first-occurrence words come from two row positions per id and tile instead
+    # of a meta word per row (ROWPOS, pw_bucket.cuh); rows that overflow a bucket or take the HBM path still count
+    rng = np.random.default_rng(27)
+    n = 900_000
+    keys = rng.integers(0, 700, n)
+    keys[rng.random(n) < 0.05] = 13            # a hot id: overflow list and HBM path in every tile
+    t = pa.table({"k": pa.array(keys), "v": pa.array(rng.integers(-10**6, 10**6, n)), "f": pa.array(rng.normal(3.0, 1.0, n))})
+    q = pw.LazyFrame(t).group_by("k", maintain_order=maintain_order).agg(
+        pw.col("v").first().alias("v_first"), pw.col("v").last().alias("v_last"), pw.col("f").first(ignore_nulls=True).alias("f_first"),
+        pw.col("f").last().alias("f_last"), pw.col("v").sum().alias("v_sum"), pw.col("f").max().alias("f_max"), pw.len().alias("n"))
+    run(q, None if maintain_order else ["k"])
