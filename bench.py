@@ -68,7 +68,8 @@ WORKLOADS = {
 STRATEGY = {1: "hot table + spill tier", 2: "HBM table", 3: "segmented sorted windows", 4: "hot table, dense ids + spill tier",
             5: "radix partition + hot table", 6: "sorted windows by key (dense ids per window)",
             7: "dense ids bucketed per tile, accumulators in registers + spill tier",
-            8: "sorted-key runs in registers", 9: "key-index ids bucketed per tile, accumulators in registers + spill tier"}
+            8: "sorted-key runs in registers", 9: "key-index ids bucketed per tile, accumulators in registers + spill tier",
+            10: "two-level radix partition (staged writes) + one shared-memory table per partition"}
 
 
 def measured_peak_gbs():
@@ -559,7 +560,7 @@ def main():
     def roofline(rows, bytes_per_row, out_rows, out_bytes_per_row, k_ms, step_ms, tm):
         algo = rows * bytes_per_row + out_rows * out_bytes_per_row
         ach = algo / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-        return {"kernel": {3: "pw_seg_jit", 6: "pw_bucket_jit", 7: "pw_bucket_jit", 8: "pw_runs_jit", 9: "pw_bucket_jit"}.get(tm["strategy"], "pw_scan_jit") if tm["reserved"] else "ahead-of-time kernel",
+        return {"kernel": {3: "pw_seg_jit", 6: "pw_bucket_jit", 7: "pw_bucket_jit", 8: "pw_runs_jit", 9: "pw_bucket_jit", 10: "pw_radix_jit_m0..m3"}.get(tm["strategy"], "pw_scan_jit") if tm["reserved"] else "ahead-of-time kernel",
                 "kernel_ms": k_ms, "algorithmic_bytes_per_launch": algo, "achieved_gbs": ach,
                 "frac_measured": ach / peak, "frac_nominal_8tbs": ach / NOMINAL_GBS,
                 "whole_step_frac_measured": (algo / (step_ms * 1e-3) / 1e9) / peak}
@@ -733,7 +734,7 @@ def main():
             ms3, k3, out3, tm3 = timed(lambda: f.group_by(plan3), max(cs, 5), 3)   # warm-up 3: the pinned result pool grows by one 0.6 GB block in each of the first two calls
             dev_ms = tm3["scan_ms"]   # partition + scan: the whole device phase of the group-by
             configs["c3"] = entry("c3", n, ms3, dev_ms, tm3, out3.num_rows, 60, check=check_c3(out3, tensors, plan3, n),
-                                  kernel_note="kernel_ms = partition passes + scan over the partitioned copy (whole device phase)")
+                                  kernel_note="kernel_ms = histogram + two scatter passes + per-partition aggregation (whole device phase)")
             f.free()
         guarded("c3", run_c3)
 

@@ -183,14 +183,15 @@ typedef struct PwTimings {
   int32_t strategy;      /* 1 hot table, 2 global table, 3 segmented, 4 hot table with dense ids (small integer key range), 5 partitioned,
                             6 the same per (key, window) for group_by_dynamic by one dense key,
                             7 dense ids bucketed per tile, accumulators in registers (pw_bucket.cuh), 8 sorted-key runs (pw_runs.cuh),
-                            9 the bucket tier with ids from a shared-memory key index (sparse integers, strings, several keys) */
+                            9 the bucket tier with ids from a shared-memory key index (sparse integers, strings, several keys),
+                            10 two-level radix partition + one shared-memory table per partition (pw_radix.cuh; high cardinality) */
   int32_t retries;       /* table growth re-runs */
   int64_t kernel_launches; /* launches of this library's kernels in the last call */
   int64_t spilled_rows;  /* rows that bypassed the hot table (spill tier) */
   float scan_kernel_ms;  /* the dominant kernel alone (events immediately around its launch) */
   float reserved;         /* 1 = the query-shape specialised (NVRTC) kernel ran, 0 = the ahead-of-time kernel */
   float host_ms;          /* wall-clock time spent inside the last pw_b200_frame_groupby call (host + device) */
-  float partition_ms;     /* strategy 5: histogram + scatter passes (part of scan_ms) */
+  float partition_ms;     /* strategies 5 and 10: histogram + scatter passes (part of scan_ms) */
   int32_t jit_compiles;   /* NVRTC compilations during the last call */
   int32_t jit_cache_hits; /* specialised kernels loaded from the on-disk cubin cache during the last call */
 } PwTimings;

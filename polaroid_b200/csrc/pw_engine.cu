@@ -16,6 +16,7 @@
 
 #include "pw_engine.h"
 #include "pw_pilot.cuh"
+#include "pw_radix.cuh"
 
 namespace pw {
 
@@ -878,6 +879,13 @@ extern "C" __attribute__((visibility("default"))) int pw_b200_jit_selftest(char*
     P.accs[3].op = OP_MIN_U64; P.accs[3].src = SRC_ROW; P.accs[4].op = OP_MAX_U64; P.accs[4].src = SRC_ROW;
     P.accs[5].op = OP_ADD_I64; P.accs[5].src = SRC_ONE; P.n_acc = 6; P.acc_gbase = 5;
   }
+  if (getenv("PW_SELFTEST_RADIX")) {   // C3 shape over the radix tier's records: (key, value, row id), null-aware sum/count/min/max/first/last
+    P.n_slots = 3; P.slots[2].dtype = DT_U64; P.rowid_slot_p1 = 3;
+    P.vexprs[0].flags = VF_SUM_F | VF_COUNT | VF_MIN | VF_MAX | VF_FIRST | VF_LAST;
+    P.accs[1].op = OP_ADD_I64; P.accs[1].src = SRC_VALID; P.accs[2].op = OP_MIN_I64; P.accs[2].src = SRC_F64_ORD;
+    P.accs[3].op = OP_MAX_I64; P.accs[3].src = SRC_F64_ORD; P.accs[4].op = OP_MIN_U64; P.accs[4].src = SRC_ROWIDX;
+    P.accs[5].op = OP_MAX_U64; P.accs[5].src = SRC_ROWIDX; P.n_acc = 6; P.gflags = 0; P.acc_gbase = 6;
+  }
   if (!plan_hot(P, 1000, 0, getenv("PW_SELFTEST_DENSE") && !win ? 1000 : 0)) return -1;
   P.hot_slots = P.hot.idx_slots;
   if (win) {
@@ -1173,6 +1181,165 @@ static int partition_input(const ScanPlan& P, double g_hint, ScanPlan* P2out, Pa
   return 0;
 }
 
+// ---- high-cardinality tier, second form (strategy 10): two-level radix partition with staged writes + one CTA per
+// partition aggregating in shared memory (pw_radix.cuh)
+struct RadixTemp {
+  uint4* buf_a = nullptr;
+  uint4* buf_b = nullptr;
+  uint32_t* small = nullptr;   // hist[P] | offs[P + 1] | cursor1[256] | cursor2[P] | tile_first[257] | pad | dense_count (u64)
+  unsigned long long* dense_count = nullptr;
+  size_t smem3 = 0;
+  int kwc = 1;
+};
+static void radix_free(RadixTemp& t) { dev_free(t.buf_a); dev_free(t.buf_b); dev_free(t.small); t = RadixTemp{}; }
+static bool radix_eligible(const PwQuery* q, const ScanPlan& P) {
+  static const bool off = getenv("PW_NO_RADIX") != nullptr;
+  return !off && part_eligible(q, P) && P.n_slots <= 3 && P.n_acc >= 1;
+}
+// exclusive prefix of the partition histogram, the cursors of both levels and the tile list of the level-2 pass
+static __global__ void __launch_bounds__(1024) radix_setup_kernel(const uint32_t* hist, uint32_t* offs, uint32_t* cursor1, uint32_t* cursor2,
+                                                                  uint32_t* tile_first, uint32_t n_parts, uint32_t log2_p2) {
+  __shared__ uint32_t wsum[32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t chunk = (n_parts + 1023u) / 1024u;
+  const uint32_t b = min(tid * chunk, n_parts), e = min(b + chunk, n_parts);
+  uint32_t sum = 0;
+  for (uint32_t i = b; i < e; ++i) sum += hist[i];
+  uint32_t incl = sum;
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += t; }
+  if (lane == 31u) wsum[warp] = incl;
+  __syncthreads();
+  uint32_t off = 0;
+  for (uint32_t w = 0; w < warp; ++w) off += wsum[w];
+  uint32_t run = off + incl - sum;
+  for (uint32_t i = b; i < e; ++i) { offs[i] = run; cursor2[i] = run; run += hist[i]; }
+  if (tid == 1023u) offs[n_parts] = off + incl;
+  __syncthreads();
+  const uint32_t n_l1 = n_parts >> log2_p2;  // <= 256
+  uint32_t t = 0;
+  if (tid < n_l1) {
+    const uint32_t first = offs[tid << log2_p2], last = offs[(tid + 1u) << log2_p2];
+    cursor1[tid] = first;
+    t = (last - first + (uint32_t)RADIX_TILE - 1u) / (uint32_t)RADIX_TILE;
+  }
+  incl = t;
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += u; }
+  if (lane == 31u) wsum[warp] = incl;
+  __syncthreads();
+  off = 0;
+  for (uint32_t w = 0; w < warp; ++w) off += wsum[w];
+  if (tid < n_l1) tile_first[tid] = off + incl - t;
+  if (tid == n_l1 - 1u) tile_first[n_l1] = off + incl;
+}
+// Partitions the rows that pass the predicate into 32-byte records grouped by final partition.  Returns 0 (done: *P2out
+// scans records, *rp carries the partition table and the record buffer as `src`), 1 (not applicable: caller keeps
+// another tier), < 0 error.
+static int radix_prepare(const ScanPlan& P, double g_hint, ScanPlan* P2out, RadixParams* rp, RadixTemp* tmp) {
+  ThreadCtx& c = ctx();
+  const int64_t N = P.n_rows;
+  const int kw = padded_kw(P.n_kw);
+  const int kwc = kw <= 1 ? 1 : (kw <= 2 ? 2 : (kw <= 4 ? 4 : 6));
+  tmp->kwc = kwc;
+  // shared memory of the aggregation pass: the staging area of one round + as many table slots as the rest holds
+  const size_t slot_bytes = (size_t)(kwc + P.n_acc) * 8 + 8 + 2 + (kwc > 1 ? 4 : 0);
+  const size_t stage_bytes = (size_t)(P.n_slots + 1) * 8 * RADIX_ROUND * RADIX_THREADS;
+  const size_t budget = 220 * 1024 - 512;
+  if (stage_bytes + (slot_bytes << 6) > budget) return 1;
+  int log2_slots = 12;
+  while (log2_slots > 6 && stage_bytes + (slot_bytes << log2_slots) > budget) --log2_slots;
+  const double per_part = 0.4 * (double)(1u << log2_slots);   // groups per partition the table is planned for
+  const double want = std::max(g_hint, 1.0) * 1.1 / per_part;
+  int log2_parts = 1;
+  while (log2_parts < 15 && (double)(1u << log2_parts) < want) ++log2_parts;
+  if (const char* e = getenv("PW_RADIX_LOG2_PARTS")) log2_parts = std::max(1, std::min(15, atoi(e)));   // tests: both levels on small inputs
+  else if ((double)(1u << log2_parts) * per_part * 1.75 < std::max(g_hint, 1.0)) return 1;  // more groups than 2^15 tables hold
+  const int log2_p1 = log2_parts <= 8 ? log2_parts : (log2_parts + 1) / 2;
+  const int log2_p2 = log2_parts - log2_p1;
+  const uint32_t n_parts = 1u << log2_parts;
+  if (getenv("PW_DEBUG"))
+    fprintf(stderr, "[pw] radix tier: rows=%lld groups~%.0f parts=2^%d (2^%d x 2^%d) table slots=2^%d (%zu B each) accs=%d\n", (long long)N, g_hint, log2_parts,
+            log2_p1, log2_p2, log2_slots, slot_bytes, P.n_acc);
+  ScanPlan P2 = P;
+  for (int s = 0; s < P.n_slots; ++s) {
+    RawSlot& d = P2.slots[s];
+    d.values = nullptr; d.validity = nullptr; d.bit_offset = 0;
+    const int cls = dtype_class(P.slots[s].dtype);
+    d.dtype = cls == CLS_F64 ? DT_F64 : (cls == CLS_U64 ? DT_U64 : DT_I64);  // canonical 64-bit image of the class
+  }
+  RawSlot& rid = P2.slots[P.n_slots];
+  rid.values = nullptr; rid.validity = nullptr; rid.bit_offset = 0; rid.dtype = DT_U64;
+  P2.n_slots = P.n_slots + 1;
+  P2.rowid_slot_p1 = P.n_slots + 1;
+  for (int k = 0; k < P2.n_keys; ++k) P2.keys[k].dtype = P2.slots[P2.keys[k].slot].dtype;
+  P2.n_preds = 0; P2.check_sorted = 0; P2.vec_ok = 1; P2.row_begin = 0; P2.row_stride = 1;
+  P2.n_kw = kw; P2.hot_slots = 0; memset(&P2.hot, 0, sizeof P2.hot);
+  ScanPlan PA = P;  // the histogram and the first scatter read the original frame
+  PA.n_kw = kw; PA.hot_slots = 0; memset(&PA.hot, 0, sizeof PA.hot);
+
+  const size_t n_small = (size_t)n_parts * 2 + 1 + 256 + n_parts + 257 + 8;
+  { void* p = nullptr; PW_TRY(dev_alloc(&p, n_small * 4)); tmp->small = (uint32_t*)p; }
+  uint32_t* hist = tmp->small;
+  uint32_t* offs = hist + n_parts;
+  uint32_t* cursor1 = offs + n_parts + 1;
+  uint32_t* cursor2 = cursor1 + 256;
+  uint32_t* tile_first = cursor2 + n_parts;
+  tmp->dense_count = (unsigned long long*)(((uintptr_t)(tile_first + 257) + 7) & ~(uintptr_t)7);
+  const size_t rec_bytes = ((size_t)N + 64) * 32;
+  { void* p = nullptr; PW_TRY(dev_alloc(&p, rec_bytes)); tmp->buf_a = (uint4*)p; }
+  if (log2_p2 > 0) { void* p = nullptr; PW_TRY(dev_alloc(&p, rec_bytes)); tmp->buf_b = (uint4*)p; }
+  PW_CUDA(cudaMemsetAsync(hist, 0, (size_t)n_parts * 4, c.stream));
+  RadixParams r{};
+  r.log2_parts = log2_parts; r.log2_p2 = log2_p2; r.log2_slots = log2_slots; r.probe_limit = 32;
+  r.hist = hist; r.offs = offs; r.tile_first = tile_first;
+  const int64_t n_steps = (N + ROWS_PER_STEP - 1) / ROWS_PER_STEP;
+  const int64_t n_tiles = (N + RADIX_TILE - 1) / RADIX_TILE;
+  r.mode = 0;
+  if (int rc = launch_radix_jit(PA, r, 4, kwc, (size_t)n_parts * 4, (n_steps + 7) / 8, c.sm_count, c.stream)) return rc;
+  radix_setup_kernel<<<1, 1024, 0, c.stream>>>(hist, offs, cursor1, cursor2, tile_first, n_parts, (uint32_t)log2_p2);
+  PW_CUDA(cudaGetLastError());
+  c.timings.kernel_launches++;
+  r.mode = 1; r.cursor = cursor1; r.dst = tmp->buf_a;
+  if (int rc = launch_radix_jit(PA, r, 4, kwc, RADIX_SCATTER_SMEM, n_tiles, c.sm_count, c.stream)) return rc;
+  const uint4* records = tmp->buf_a;
+  if (log2_p2 > 0) {
+    r.mode = 2; r.cursor = cursor2; r.src = tmp->buf_a; r.dst = tmp->buf_b;
+    if (int rc = launch_radix_jit(P2, r, 4, kwc, RADIX_SCATTER_SMEM, n_tiles + (1 << log2_p1), c.sm_count, c.stream)) return rc;
+    records = tmp->buf_b;
+  }
+  r.mode = 3; r.src = records; r.dst = nullptr; r.cursor = nullptr;
+  tmp->smem3 = stage_bytes + ((size_t)slot_bytes << log2_slots) + 512;
+  *rp = r;
+  *P2out = P2;
+  return 0;
+}
+// group list of the radix tier: occupied slots of the overflow region and the escape slots, then the dense region
+// (its first *dense_count slots are groups by construction: no occupancy marker to initialise or to read)
+static __global__ void radix_compact_kernel(Table T, int n_kw, uint64_t ovf_cap, const unsigned long long* dense_count, uint64_t dense_cap,
+                                            uint32_t* slot_list, unsigned long long* counter) {
+  const uint64_t nd = min((uint64_t)*dense_count, dense_cap);
+  const uint64_t n = ovf_cap + 2 + nd;
+  const int lane = threadIdx.x & 31;
+  for (uint64_t s0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane; s0 < n; s0 += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = s0 + lane;
+    uint64_t s = 0;
+    bool occ = false;
+    if (i < ovf_cap) { s = i; occ = slot_occupied(T, n_kw, s); }
+    else if (i < ovf_cap + 2) { s = T.cap + (i - ovf_cap); occ = slot_occupied(T, n_kw, s); }
+    else if (i < n) { s = ovf_cap + (i - ovf_cap - 2); occ = true; }
+    const uint32_t m = __ballot_sync(0xffffffffu, occ);
+    if (m == 0u) continue;
+    unsigned long long basei = 0;
+    if (lane == 0) basei = atomicAdd(counter, (unsigned long long)__popc(m));
+    basei = __shfl_sync(0xffffffffu, basei, 0);
+    if (occ) slot_list[basei + __popc(m & ((1u << lane) - 1u))] = (uint32_t)s;
+  }
+}
+// table split of the aggregation pass: [overflow region | dense region]
+static void radix_split(uint64_t cap, RadixParams* rp) {
+  rp->ovf_cap = std::max<uint64_t>(std::min<uint64_t>(8192, cap / 2), cap / 16);
+  rp->dense_cap = cap - rp->ovf_cap;
+}
+
 // ---- result block layout: [header][values 0][validity 0][values 1] ... every piece 256-byte aligned
 struct BlockLayout {
   std::vector<size_t> val_bytes, valid_bytes, val_off, valid_off;
@@ -1407,11 +1574,25 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
   PartTemp ptmp;
   ScanPlan PP{};  // plan over the partitioned copy
   bool partitioned = false;
+  RadixTemp rtmp;
+  RadixParams rprm{};
+  bool radix = false;
   {
     const bool forced = (q->flags & PW_FLAG_FORCE_PARTITION) != 0;
     const bool pays = !use_hot && g_est >= 262144.0 && N >= (4ll << 20) && (double)N >= 3.0 * g_est &&
                       !(q->flags & (PW_FLAG_FORCE_HOT_TABLE | PW_FLAG_FORCE_GLOBAL_TABLE));
-    if ((forced || pays) && N > 0 && !runs && part_eligible(q, P)) {
+    // second form first (pw_radix.cuh); a retry after an overflow seen late (opts->min_cap) keeps the older tiers
+    if ((forced || pays) && N > 0 && !runs && radix_eligible(q, P) && !(opts && opts->min_cap) && !getenv("PW_NO_RADIX_NOW")) {
+      const double g_hint = g_est > 0 ? g_est : (double)N;
+      PW_CUDA(cudaEventRecord(c.ev[10], c.stream));
+      const int prc = radix_prepare(P, g_hint, &PP, &rprm, &rtmp);
+      PW_CUDA(cudaEventRecord(c.ev[11], c.stream));
+      if (prc < 0) { radix_free(rtmp); return prc; }
+      radix = prc == 0;
+      if (!radix) radix_free(rtmp);
+      else cap = std::min<uint64_t>((uint64_t)2 * (uint64_t)N + 64, (uint64_t)(1.4 * g_hint) + 16384);
+    }
+    if (!radix && (forced || pays) && N > 0 && !runs && part_eligible(q, P)) {
       PW_CUDA(cudaEventRecord(c.ev[10], c.stream));
       const int prc = partition_input(P, g_est > 0 ? g_est : std::max<double>((double)N / 4.0, 64.0), &PP, &ptmp);
       PW_CUDA(cudaEventRecord(c.ev[11], c.stream));
@@ -1440,16 +1621,31 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
   Table T{};
   uint32_t* slots = nullptr;
   if (!(opts && opts->min_cap)) tm.retries = 0;
-  auto drop = [&]() { part_free(ptmp); if (T.keys) free_table(T); dev_free(slots); dev_free(deferred ? (void*)block : (void*)dctl); };
+  auto drop = [&]() { part_free(ptmp); radix_free(rtmp); if (T.keys) free_table(T); dev_free(slots); dev_free(deferred ? (void*)block : (void*)dctl); };
   for (;;) {
     int rc = alloc_table(&T, padded_kw(P.n_kw), P.n_acc, cap, dctl);
+    if (!rc && radix) {
+      // only the overflow region and the escape slots are probed: the dense region is written whole by its CTAs
+      radix_split(cap, &rprm);
+      Table V = T; V.cap = rprm.ovf_cap;
+      rc = init_table(V, P, c.stream, dctl);
+      Table E = T; E.keys = T.keys + cap * T.key_ss; E.accs = T.accs + cap * T.acc_ss; E.state = T.state + cap; E.cap = 0;
+      if (!rc) rc = init_table(E, P, c.stream, nullptr);
+    } else
     if (!rc) rc = init_table(T, P, c.stream, dctl);  // also clears the control block
     if (rc) { drop(); return rc; }
     P.table = T;
     P.not_sorted = &dctl->not_sorted;
     P.hot_slots = use_hot ? P.hot.idx_slots : 0;
     cudaEventRecord(c.ev[8], c.stream);
-    if (partitioned) {
+    if (radix) {
+      PP.table = T; PP.not_sorted = &dctl->not_sorted;
+      radix_split(cap, &rprm);
+      rprm.dense_count = rtmp.dense_count;
+      if (cudaMemsetAsync(rtmp.dense_count, 0, 16, c.stream) != cudaSuccess) { drop(); return fail(PW_ERR_CUDA, "radix tier: memset failed"); }
+      rc = launch_radix_jit(PP, rprm, 4, rtmp.kwc, rtmp.smem3, (int64_t)1 << rprm.log2_parts, c.sm_count, c.stream);
+      if (rc > 0) rc = fail(PW_ERR_INTERNAL, "radix tier: the aggregation kernel is not available");
+    } else if (partitioned) {
       PP.table = T; PP.not_sorted = &dctl->not_sorted; PP.hot_slots = PP.hot.idx_slots;
       if (PP.n_rows > 0) rc = launch_scan(PP, c.sm_count, c.stream);
     } else if (N > 0) rc = launch_scan(P, c.sm_count, c.stream);
@@ -1457,7 +1653,12 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     cudaEventRecord(c.ev[9], c.stream);
     // queue the compaction right behind the scan: its result is simply discarded when the scan overflowed
     { void* p = nullptr; rc = dev_alloc(&p, (cap + 2) * 4); if (rc) { drop(); return rc; } slots = (uint32_t*)p; }
-    {
+    if (radix) {
+      int grid = (int)std::min<uint64_t>((cap + 2 + 255) / 256, 148 * 8);
+      radix_compact_kernel<<<grid, 256, 0, c.stream>>>(T, padded_kw(P.n_kw), rprm.ovf_cap, rtmp.dense_count, rprm.dense_cap, slots, &dctl->counter);
+      if (cudaGetLastError() != cudaSuccess) { drop(); return fail(PW_ERR_CUDA, "radix_compact_kernel launch failed"); }
+      tm.kernel_launches++;
+    } else {
       int grid = (int)std::min<uint64_t>((cap + 2 + 255) / 256, 148 * 8);
       compact_kernel<<<grid, 256, 0, c.stream>>>(T, padded_kw(P.n_kw), slots, &dctl->counter);
       if (cudaGetLastError() != cudaSuccess) { drop(); return fail(PW_ERR_CUDA, "compact_kernel launch failed"); }
@@ -1475,16 +1676,18 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
       if (cap >= (uint64_t)2 * (uint64_t)N + 64) { drop(); return fail(PW_ERR_INTERNAL, "hash table overflow at maximum size"); }
       cap = std::min<uint64_t>(cap * 4, (uint64_t)2 * (uint64_t)N + 64);
       tm.retries++;
+      if (radix) { radix = false; radix_free(rtmp); }  // group estimate too low or a skewed partition: the plain HBM table takes over
       continue;
     }
     break;
   }
-  tm.strategy = runs ? 8 : partitioned ? 5 : (use_hot ? (P.hot.bucket ? (P.hot.b_win ? 6 : (P.hot.b_idx ? 9 : 7)) : (P.hot.dense ? 4 : 1)) : 2);
+  tm.strategy = runs ? 8 : radix ? 10 : partitioned ? 5 : (use_hot ? (P.hot.bucket ? (P.hot.b_win ? 6 : (P.hot.b_idx ? 9 : 7)) : (P.hot.dense ? 4 : 1)) : 2);
   tm.table_slots = (int64_t)cap;
   tm.partition_ms = 0.0f;
   if (deferred) {
     // count, overflow and sortedness are looked at by emit_results, after the single synchronisation
     part_free(ptmp);
+    radix_free(rtmp);
     cudaEventRecord(c.ev[3], c.stream);
     const uint64_t bound = cap + 2;
     int rc = order_groups(L, T, padded_kw(P.n_kw), &slots, bound, &dctl->counter);
@@ -1500,7 +1703,9 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     return fail(PW_ERR_NOT_SORTED, "argument in operation 'group_by_dynamic' is not sorted, please sort the 'expr/series/column' first");
   }
   part_free(ptmp);
-  if (partitioned) { float ms = 0; if (cudaEventElapsedTime(&ms, c.ev[10], c.ev[11]) == cudaSuccess) tm.partition_ms = ms; }
+  const bool was_radix = radix || rtmp.small != nullptr;
+  radix_free(rtmp);
+  if (partitioned || was_radix) { float ms = 0; if (cudaEventElapsedTime(&ms, c.ev[10], c.ev[11]) == cudaSuccess) tm.partition_ms = ms; }
   tm.spilled_rows = (int64_t)hctl.spilled;
   PW_CUDA(cudaEventRecord(c.ev[3], c.stream));
   const uint64_t G = hctl.counter;

@@ -22,6 +22,7 @@
 #include "pw_engine.h"
 #include "pw_partition.cuh"
 #include "pw_pilot.cuh"
+#include "pw_radix.cuh"
 #include "pw_scan.cuh"
 
 namespace pw {
@@ -251,6 +252,13 @@ std::string part_entry(int nc, int kw, int threads) {
   return src.str();
 }
 
+std::string radix_entry(int nc, int kw, int mode, int threads) {
+  std::ostringstream src;
+  src << "extern \"C\" __global__ void __launch_bounds__(" << threads << ") pw_radix_jit_m" << mode << "(const __grid_constant__ pw::ScanPlan P, const pw::RadixParams rp) {\n"
+      << "  pw::radix_body<pw::JitCtl, " << nc << ", " << kw << ", " << mode << ">(P, rp);\n}\n";
+  return src.str();
+}
+
 std::string pilot_entry(int nc, int kw, int threads) {
   std::ostringstream src;
   src << "extern \"C\" __global__ void __launch_bounds__(" << threads << ") pw_pilot_jit(const __grid_constant__ pw::ScanPlan P, const pw::PilotParams pp) {\n"
@@ -273,7 +281,7 @@ void sources_hash(uint64_t* h0, uint64_t* h1) {
   static std::once_flag once;
   std::call_once(once, [] {
     a0 = 0xcbf29ce484222325ull; a1 = 0x84222325cbf29ce4ull;
-    for (const char* name : {"pw_plan.h", "pw_ctl.h", "pw_scan.cuh", "pw_segmented.cuh", "pw_partition.cuh", "pw_pilot.cuh", "pw_bucket.cuh", "pw_runs.cuh"}) {
+    for (const char* name : {"pw_plan.h", "pw_ctl.h", "pw_scan.cuh", "pw_segmented.cuh", "pw_partition.cuh", "pw_pilot.cuh", "pw_bucket.cuh", "pw_runs.cuh", "pw_radix.cuh"}) {
       const std::string path = csrc_dir() + "/" + name;
       FILE* f = fopen(path.c_str(), "rb");
       if (!f) continue;
@@ -345,7 +353,7 @@ void cache_write(const std::string& path, const std::vector<char>& cubin) {
 Compiled compile(const std::string& ctl, const std::string& entry, const char* entry_name) {
   Api& a = api();
   Compiled c;
-  const std::string text = "#include \"pw_segmented.cuh\"\n#include \"pw_partition.cuh\"\n#include \"pw_pilot.cuh\"\n#include \"pw_bucket.cuh\"\n#include \"pw_runs.cuh\"\nnamespace pw {\n" + ctl + "}\n" + entry;
+  const std::string text = "#include \"pw_segmented.cuh\"\n#include \"pw_partition.cuh\"\n#include \"pw_pilot.cuh\"\n#include \"pw_bucket.cuh\"\n#include \"pw_runs.cuh\"\n#include \"pw_radix.cuh\"\nnamespace pw {\n" + ctl + "}\n" + entry;
   const std::string cpath = getenv("PW_JIT_DUMP") || getenv("PW_DEBUG") ? std::string() : cache_path(text);
   {
     std::vector<char> cached;
@@ -407,7 +415,8 @@ int jit_selftest_compile(const ScanPlan& P, int nc, int kw, bool hot, int thread
     *(void**)(&a.nvrtcGetCUBIN) = dlsym(rtc, "nvrtcGetCUBIN");
     *(void**)(&a.nvrtcDestroyProgram) = dlsym(rtc, "nvrtcDestroyProgram");
   }
-  const std::string text = "#include \"pw_segmented.cuh\"\n#include \"pw_partition.cuh\"\n#include \"pw_pilot.cuh\"\n#include \"pw_bucket.cuh\"\n#include \"pw_runs.cuh\"\nnamespace pw {\n" + jit_ctl(P) + "}\n" + scan_entry(nc, kw, hot, threads) + seg_entry(nc, 256) + part_entry(nc, kw, 256) + pilot_entry(nc, kw, 256) + runs_entry(nc, kw, 256) +
+  const std::string text = "#include \"pw_segmented.cuh\"\n#include \"pw_partition.cuh\"\n#include \"pw_pilot.cuh\"\n#include \"pw_bucket.cuh\"\n#include \"pw_runs.cuh\"\n#include \"pw_radix.cuh\"\nnamespace pw {\n" + jit_ctl(P) + "}\n" + scan_entry(nc, kw, hot, threads) + seg_entry(nc, 256) + part_entry(nc, kw, 256) + pilot_entry(nc, kw, 256) + runs_entry(nc, kw, 256) +
+                           (nc <= 4 && P.n_slots <= 3 && !P.dyn.enabled ? radix_entry(nc, kw, 0, 256) + radix_entry(nc, kw, 1, RADIX_THREADS) + radix_entry(nc, kw, 2, RADIX_THREADS) + radix_entry(nc, kw, 3, RADIX_THREADS) : std::string()) +
                            (P.hot.bucket ? bucket_entry(nc, kw, P.hot.b_threads, P.hot.b_cps) : std::string());
   nvrtcProgram prog = nullptr;
   if (a.nvrtcCreateProgram(&prog, text.c_str(), "pw_scan_jit.cu", 0, nullptr, nullptr) != 0) { *err = "nvrtcCreateProgram failed"; return 2; }
@@ -610,6 +619,43 @@ int launch_part_jit(const ScanPlan& P, const PartParams& pp, int nc, int kw, int
   const CUresult rc = a.cuLaunchKernel(c.fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, 0, (CUstream)st, params, nullptr);
   if (rc != 0) return fail(PW_ERR_CUDA, "cuLaunchKernel(pw_part_jit) failed with %d", rc);
   ctx().timings.kernel_launches++;
+  return 0;
+}
+// the radix tier's passes (pw_radix.cuh), one specialised kernel per mode; returns 0 launched, 1 unavailable
+int launch_radix_jit(const ScanPlan& P, const RadixParams& rp, int nc, int kw, size_t smem, int64_t work_ctas, int sm_count, cudaStream_t st) {
+  static const bool disabled = getenv("PW_NO_JIT") != nullptr;
+  if (disabled) return 1;
+  Api& a = api();
+  if (!a.ok) return 1;
+  const int threads = rp.mode == 0 ? 256 : RADIX_THREADS;
+  std::string key = plan_key(P);
+  const int32_t tail[5] = {-4 /* radix */, nc, kw, rp.mode, (int32_t)smem};
+  key.append((const char*)tail, sizeof tail);
+  Compiled c;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_cache.find(key);
+    if (it == g_cache.end()) {
+      const std::string name = "pw_radix_jit_m" + std::to_string(rp.mode);
+      c = compile(jit_ctl(P), radix_entry(nc, kw, rp.mode, threads), name.c_str());
+      if (!c.failed && c.fn) {
+        if ((smem > 48 * 1024 && a.cuFuncSetAttribute(c.fn, 8, (int)smem) != 0) ||
+            a.cuOccupancyMaxActiveBlocksPerMultiprocessor(&c.per_sm, c.fn, threads, smem) != 0 || c.per_sm < 1)
+          c.failed = true;
+      }
+      g_cache[key] = c;
+    } else c = it->second;
+  }
+  if (c.failed || !c.fn) return 1;
+  int64_t grid = std::min<int64_t>((int64_t)sm_count * c.per_sm, work_ctas);
+  if (grid < 1) grid = 1;
+  ScanPlan copy = P;
+  RadixParams rpc = rp;
+  void* params[] = {&copy, &rpc};
+  const CUresult rc = a.cuLaunchKernel(c.fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)smem, (CUstream)st, params, nullptr);
+  if (rc != 0) return fail(PW_ERR_CUDA, "cuLaunchKernel(pw_radix_jit mode %d) failed with %d", rp.mode, rc);
+  ctx().timings.kernel_launches++;
+  ctx().timings.reserved = 1.0f;
   return 0;
 }
 // the fused key-sample pilot; returns 0 launched, 1 unavailable

@@ -251,6 +251,28 @@ struct PartParams {
   int32_t mode;
 };
 
+// two-level radix partitioning + per-partition aggregation in shared memory (pw_radix.cuh).  A record is 32 bytes:
+// one 64-bit word per raw slot, then (row << 8 | validity bits).
+constexpr int RADIX_TILE = 4096;     // records a CTA stages per tile
+constexpr int RADIX_THREADS = 1024;
+struct RadixParams {
+  int32_t mode;          // 0 histogram, 1 scatter (frame -> level-1 partitions), 2 scatter (level 1 -> final), 3 aggregate
+  int32_t log2_parts;    // final partitions P = 2^log2_parts; partition = top bits of the key hash
+  int32_t log2_p2;       // level-2 fan-out (0: one level, mode 1 writes the final partitions)
+  int32_t log2_slots;    // mode 3: slots of the shared-memory table
+  int32_t probe_limit;   // mode 3: probes before a key leaves for the overflow region of the HBM table
+  int32_t pad;
+  uint32_t* hist;        // [P]      mode 0 out: records per final partition
+  const uint32_t* offs;  // [P + 1]  first record of every final partition
+  uint32_t* cursor;      // mode 1: [P >> log2_p2], mode 2: [P] next free record
+  const uint32_t* tile_first;  // mode 2: [(P >> log2_p2) + 1] first tile of every level-1 partition
+  const uint4* src;      // modes 2, 3
+  uint4* dst;            // modes 1, 2
+  uint64_t ovf_cap;      // mode 3: slots [0, ovf_cap) of ScanPlan::table = open-addressing overflow region
+  uint64_t dense_cap;    //         slots [ovf_cap, ovf_cap + dense_cap) = groups appended by the CTAs
+  unsigned long long* dense_count;  // [0] groups appended so far, [1] next partition to hand out
+};
+
 constexpr uint64_t KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;  // n_kw == 1 occupancy sentinel
 constexpr uint64_t KEY_NULL = 0xFFFFFFFFFFFFFFFEull;   // n_kw == 1 image of a null key
 

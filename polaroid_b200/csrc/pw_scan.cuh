@@ -165,8 +165,10 @@ __device__ __forceinline__ void minmax_apply_shared(uint64_t* p, int op, uint64_
 //            the slot owner has to leave first).
 // ---------------------------------------------------------------------------------------------------
 template <int KW>
-__device__ __forceinline__ uint64_t table_upsert(const Table& T, const uint64_t (&k)[KW], uint64_t h, bool key0_is_sentinel_free) {
+__device__ __forceinline__ uint64_t table_upsert(const Table& T, const uint64_t (&k)[KW], uint64_t h, bool key0_is_sentinel_free,
+                                                 uint64_t max_probes = ~0ull) {
   const uint64_t cap = T.cap;
+  const uint64_t lim = max_probes < cap ? max_probes : cap;   // pw_radix.cuh bounds the probe sequence of its overflow region
   if (KW == 1) {
     const uint64_t k0 = k[0];
     if (!key0_is_sentinel_free) {
@@ -175,7 +177,7 @@ __device__ __forceinline__ uint64_t table_upsert(const Table& T, const uint64_t 
       if (k0 == KEY_NULL) { st_volatile_u32(&T.state[cap + 1], 2u); tkey(T, 0, cap + 1) = k0; return cap + 1; }
     }
     uint64_t slot = __umul64hi(h, cap);
-    for (uint64_t probes = 0; probes < cap; ++probes) {
+    for (uint64_t probes = 0; probes < lim; ++probes) {
       unsigned long long old = __ldcg((const unsigned long long*)&tkey(T, 0, slot));
       if (old == k0) return slot;
       if (old == KEY_EMPTY) {
@@ -208,7 +210,7 @@ __device__ __forceinline__ uint64_t table_upsert(const Table& T, const uint64_t 
         if (eq) { result = slot; done = true; }
         else {
           slot = (slot + 1 == cap) ? 0 : slot + 1;
-          if (++probes >= cap) { *T.overflow = 1; done = true; }
+          if (++probes >= lim) { *T.overflow = 1; done = true; }
         }
       }
       // s == 1: busy -> look again next iteration
