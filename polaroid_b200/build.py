@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libpolarway_b200.so")
-SOURCES = [*[f"pw_launch_nc{nc}_kw{kw}.cu" for nc in (12, 4) for kw in (6, 4, 2, 1)], "pw_launch_nc4.cu", "pw_launch_nc12.cu", "pw_jit.cu", "pw_dynamic.cu", "pw_partial.cu", "pw_filter.cu", "pw_engine.cu", "pw_capi.cu", "pw_plugin.cu", "pw_arrow.cpp"]
+SOURCES = [*[f"pw_launch_nc{nc}_kw{kw}.cu" for nc in (12, 4) for kw in (6, 4, 2, 1)], "pw_launch_nc4.cu", "pw_launch_nc12.cu", "pw_jit.cu", "pw_dynamic.cu", "pw_partial.cu", "pw_filter.cu", "pw_views.cu", "pw_engine.cu", "pw_capi.cu", "pw_plugin.cu", "pw_arrow.cpp"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
               "-Xptxas", "-v" if os.environ.get("PW_PTXAS_V") else "-O3"]

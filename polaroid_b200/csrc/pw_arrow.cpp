@@ -165,6 +165,33 @@ int make_host_array(int64_t length, int64_t null_count, void* validity, void* va
   return 0;
 }
 
+// View array whose long values live in one variadic data buffer: buffers = [validity, views, data, sizes]
+// (the layout polars-arrow's FFI reads: the variadic buffer sizes travel as the last buffer).
+int make_host_view_array(int64_t length, int64_t null_count, void* validity, void* values, void* data, int64_t data_bytes, struct ArrowArray* out) {
+  ArrayPrivate* p = (ArrayPrivate*)calloc(1, sizeof(ArrayPrivate));
+  if (!p) return fail(PW_ERR_INTERNAL, "out of host memory");
+  p->owned[0] = validity;
+  p->owned[1] = values;
+  p->owned[2] = data;
+  p->owned[3] = calloc(1, 8);
+  if (!p->owned[3]) { free(p); return fail(PW_ERR_INTERNAL, "out of host memory"); }
+  *(int64_t*)p->owned[3] = data_bytes;
+  p->buffers[0] = null_count ? validity : nullptr;
+  p->buffers[1] = values;
+  p->buffers[2] = data;
+  p->buffers[3] = p->owned[3];
+  memset(out, 0, sizeof(*out));
+  out->length = length;
+  out->null_count = null_count;
+  out->offset = 0;
+  out->n_buffers = 4;
+  out->n_children = 0;
+  out->buffers = p->buffers;
+  out->release = release_array;
+  out->private_data = p;
+  return 0;
+}
+
 int make_schema(const char* format, const char* name, bool nullable, struct ArrowSchema* out) {
   SchemaPrivate* p = (SchemaPrivate*)calloc(1, sizeof(SchemaPrivate));
   if (!p) return fail(PW_ERR_INTERNAL, "out of host memory");

@@ -57,11 +57,27 @@ int upload_column(const struct ArrowArray* a, const struct ArrowSchema* s, bool 
   else if (nulls < 0) nulls = 1;  // unknown: treat as nullable
   out->null_count = nulls;
   cudaStream_t st = ctx().stream;
+  // view columns: the variadic data buffers behind values longer than 12 bytes — buffers = [validity, views, data...,
+  // sizes] (polars-arrow/src/ffi: the variadic buffer sizes are the last buffer)
+  if (out->dtype == DT_VIEW && a->n_buffers >= 4) {
+    const int64_t n_var = a->n_buffers - 3;
+    const int64_t* sizes = (const int64_t*)a->buffers[a->n_buffers - 1];
+    for (int64_t v = 0; v < n_var; ++v) {
+      const void* src = a->buffers[2 + v];
+      if (zero_copy) { out->var_bufs.push_back(src); continue; }
+      const size_t bytes = sizes && sizes[v] > 0 ? (size_t)sizes[v] : 0;
+      void* dv = nullptr;
+      PW_TRY(dev_alloc(&dv, bytes + 32));
+      out->owned_var.push_back(dv);
+      out->var_bufs.push_back(dv);
+      if (bytes && src) PW_CUDA(cudaMemcpyAsync(dv, src, bytes, cudaMemcpyHostToDevice, st));
+    }
+  }
   if (zero_copy) {
     out->values = vals;
     out->validity = nulls ? valid + (a->offset >> 3) : nullptr;
     out->bit_offset = (int32_t)(a->offset & 7);
-    return 0;
+    return views_intern(out, n);
   }
   void* d = nullptr;
   PW_TRY(dev_alloc(&d, (size_t)n * w + 32));
@@ -76,7 +92,7 @@ int upload_column(const struct ArrowArray* a, const struct ArrowSchema* s, bool 
     out->validity = (const uint8_t*)dv; out->owned_validity = dv;
     out->bit_offset = (int32_t)(a->offset & 7);
   }
-  return 0;
+  return views_intern(out, n);
 }
 
 int make_frame(const struct ArrowArray* const* cols, const struct ArrowSchema* const* schemas, size_t n_cols,
@@ -141,7 +157,10 @@ int pw_b200_frame_from_device(const struct ArrowArray* const* cols, const struct
 int64_t pw_b200_frame_num_rows(const PwFrame* f) { return f ? f->n_rows : -1; }
 int pw_b200_frame_free(PwFrame* f) {
   if (!f) return 0;
-  for (auto& c : f->cols) { dev_free(c.owned_values); dev_free(c.owned_validity); }
+  for (auto& c : f->cols) {
+    dev_free(c.owned_values); dev_free(c.owned_validity); dev_free((void*)c.d_var_ptrs);
+    for (void* v : c.owned_var) dev_free(v);
+  }
   delete f;
   return 0;
 }

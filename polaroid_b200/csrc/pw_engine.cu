@@ -284,6 +284,8 @@ int lower_query(const PwQuery* q, const PwFrame* f, Lowered* L) {
     if (s < 0) return fail(PW_ERR_UNSUPPORTED, "too many column slots");
     KeyCol& k = P.keys[P.n_keys++];
     k.slot = s; k.dtype = c.dtype; k.n_words = c.dtype == DT_VIEW ? 2 : 1; k.nullable = c.null_count != 0;
+    // windows are emitted key slice by key slice in key order, and the view words only order values of up to 12 bytes
+    if (dyn && c.has_long) return fail(PW_ERR_UNSUPPORTED, "group_by_dynamic by a string key longer than 12 bytes (column '%s')", c.name.c_str());
     any_nullable = any_nullable || k.nullable;
     n_words += k.n_words;
   }
@@ -303,6 +305,7 @@ int lower_query(const PwQuery* q, const PwFrame* f, Lowered* L) {
     OutCol o;
     o.name = c.name; o.format = c.format; o.nullable = c.null_count != 0;
     o.emit.kind = c.dtype == DT_VIEW ? EMIT_KEY_VIEW : EMIT_KEY_INT;
+    if (c.dtype == DT_VIEW) o.src_col = &c;
     o.emit.out_dtype = c.dtype; o.out_dtype = c.dtype;
     o.emit.word = word;
     o.emit.null_word = P.keys[i].nullable ? L->null_word : -1;
@@ -1819,6 +1822,17 @@ int emit_results(const Lowered& L, const Table& T, const uint32_t* slot_list, ui
     const OutCol& o = L.outs[i];
     // a validity bitmap shorter than the bound's may carry bits past the count in its last word: harmless (Arrow readers
     // look at `length` bits)
+    if (o.out_dtype == DT_VIEW && o.src_col && o.src_col->has_long) {
+      // long keys: their bytes leave the device in one data buffer of the result's own
+      void* h_data = nullptr;
+      int64_t data_bytes = 0;
+      PW_TRY(views_gather_long(o.src_col, h_vals[i], h_nulls[i] ? h_valid[i] : nullptr, Gf, &h_data, &data_bytes));
+      if (h_data) {
+        PW_TRY(make_host_view_array((int64_t)Gf, (int64_t)h_nulls[i], h_valid[i], h_vals[i], h_data, data_bytes, &out_cols[i]));
+        PW_TRY(make_schema(o.format.c_str(), o.name.c_str(), true, &out_schemas[i]));
+        continue;
+      }
+    }
     PW_TRY(make_host_array((int64_t)Gf, (int64_t)h_nulls[i], h_valid[i], h_vals[i], o.out_dtype == DT_VIEW ? 1 : 0, &out_cols[i]));
     PW_TRY(make_schema(o.format.c_str(), o.name.c_str(), true, &out_schemas[i]));
   }

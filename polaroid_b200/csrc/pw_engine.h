@@ -51,6 +51,11 @@ struct FrameColumn {
   int32_t bit_offset = 0;
   void* owned_values = nullptr; // freed with the frame
   void* owned_validity = nullptr;
+  // view columns: the variadic data buffers behind views longer than 12 bytes (pw_views.cu)
+  std::vector<const void*> var_bufs;   // device pointers
+  std::vector<void*> owned_var;        // the uploaded ones, freed with the frame
+  const void** d_var_ptrs = nullptr;   // device copy of var_bufs (owned)
+  bool has_long = false;               // long views present: `values` is the canonicalised copy (owned)
   // var/std shift (a sample mean of the column), computed the first time a query needs it (guarded by PwFrame::mu)
   mutable bool shift_known = false;
   mutable double var_shift = 0.0;
@@ -83,6 +88,7 @@ namespace pw {
 // one result column: how to emit it + its Arrow schema
 struct OutCol {
   std::string name, format;
+  const FrameColumn* src_col = nullptr;  // view keys: the frame column whose data buffers long values reference
   EmitDesc emit{};
   int32_t out_dtype = DT_I64;  // buffer dtype (DT_VIEW for string keys)
   bool nullable = false;
@@ -153,5 +159,10 @@ void host_free(void* p);
 int make_host_array(int64_t length, int64_t null_count, void* validity, void* values, size_t n_extra_buffers,
                     struct ArrowArray* out);
 int make_schema(const char* format, const char* name, bool nullable, struct ArrowSchema* out);
+// view array with one variadic data buffer (takes ownership of all four blocks)
+int make_host_view_array(int64_t length, int64_t null_count, void* validity, void* values, void* data, int64_t data_bytes, struct ArrowArray* out);
+// long string keys (pw_views.cu)
+int views_intern(FrameColumn* col, int64_t n);
+int views_gather_long(const FrameColumn* col, void* h_views, const void* h_validity, uint64_t G, void** h_data, int64_t* data_bytes);
 
 }  // namespace pw

@@ -187,6 +187,8 @@ int pw_b200_frame_groupby_partial(const PwQuery* q, const PwFrame* frame, int32_
   PW_CUDA(cudaEventRecord(c.ev[0], c.stream));
   Lowered L;
   PW_TRY(lower_query(q, frame, &L));
+  for (int i = 0; i < q->n_keys; ++i)   // the views of a long value point into THIS rank's data buffers
+    if (frame->cols[q->key_columns[i]].has_long) return fail(PW_ERR_UNSUPPORTED, "partial aggregates by a string key longer than 12 bytes cannot be exchanged between GPUs");
   if (q->dynamic && !L.tumbling) return fail(PW_ERR_UNSUPPORTED, "overlapping windows are not shardable by row range");
   L.sort.clear();  // ordering happens after the merge
   Table T{};
@@ -264,6 +266,8 @@ int64_t pw_b200_partial_row_words(const PwQuery* q, const PwFrame* frame) {
   if (!q || !frame) return fail(PW_ERR_INVALID, "bad argument");
   Lowered L;
   PW_TRY(lower_query(q, frame, &L));
+  for (int i = 0; i < q->n_keys; ++i)   // the views of a long value point into THIS rank's data buffers
+    if (frame->cols[q->key_columns[i]].has_long) return fail(PW_ERR_UNSUPPORTED, "partial aggregates by a string key longer than 12 bytes cannot be exchanged between GPUs");
   return make_layout(L, kw_class(L.plan.n_kw)).row_words;
 }
 
@@ -275,6 +279,8 @@ int pw_b200_frame_groupby_partial_into(const PwQuery* q, const PwFrame* frame, i
   PW_CUDA(cudaEventRecord(c.ev[0], c.stream));
   Lowered L;
   PW_TRY(lower_query(q, frame, &L));
+  for (int i = 0; i < q->n_keys; ++i)   // the views of a long value point into THIS rank's data buffers
+    if (frame->cols[q->key_columns[i]].has_long) return fail(PW_ERR_UNSUPPORTED, "partial aggregates by a string key longer than 12 bytes cannot be exchanged between GPUs");
   if (q->dynamic && !L.tumbling) return fail(PW_ERR_UNSUPPORTED, "overlapping windows are not shardable by row range");
   L.sort.clear();
   Table T{};

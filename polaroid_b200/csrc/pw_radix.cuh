@@ -275,7 +275,7 @@ struct RadixRegSink {
 
 // find-or-insert in the CTA's table; ~0 when no slot within the probe limit
 template <int KW>
-__device__ __forceinline__ uint32_t smem_upsert(const SmemTable& T, const uint64_t (&k)[KW], uint32_t s0, int limit, uint32_t* n_ins) {
+__device__ __forceinline__ uint32_t smem_upsert(const SmemTable& T, const uint64_t (&k)[KW], uint32_t s0, int limit, uint32_t* n_ins, bool& inserted) {
   const uint32_t mask = T.S - 1u;
   uint32_t s = s0 & mask;
   if (KW == 1) {
@@ -285,7 +285,7 @@ __device__ __forceinline__ uint32_t smem_upsert(const SmemTable& T, const uint64
       if (old == k0) return s;
       if (old == KEY_EMPTY) {
         old = atomicCAS((unsigned long long*)&T.keys[s], (unsigned long long)KEY_EMPTY, (unsigned long long)k0);
-        if (old == KEY_EMPTY) { atomicAdd(n_ins, 1u); return s; }
+        if (old == KEY_EMPTY) { atomicAdd(n_ins, 1u); inserted = true; return s; }
         if (old == k0) return s;
       }
       s = (s + 1u) & mask;
@@ -304,6 +304,7 @@ __device__ __forceinline__ uint32_t smem_upsert(const SmemTable& T, const uint64
         __threadfence_block();
         *(volatile uint32_t*)&T.state[s] = 2u;
         atomicAdd(n_ins, 1u);
+        inserted = true;
         result = s; done = true;
       } else if (st == 2u) {
         __threadfence_block();
@@ -378,9 +379,7 @@ __device__ __forceinline__ void radix_aggregate_body(const ScanPlan& P, const Ra
     if (begin == end) continue;
     for (uint32_t s = tid; s < T.S; s += blockDim.x) {
       if (KW == 1) T.keys[s] = KEY_EMPTY; else T.state[s] = 0u;
-      T.cnt[s] = 0u;
-#pragma unroll 1
-      for (int a = 0; a < n_acc; ++a) T.accs[(uint32_t)a * T.S + s] = acc_init(CT::acc_op(P, a));
+      T.cnt[s] = 0u;   // (the accumulators of a slot are initialised by the thread that inserts its key)
     }
     if (tid < 2) ctl[tid] = 0u;
     if (tid == 2) ctl[5] = (uint32_t)*(volatile int32_t*)G.overflow;
@@ -405,7 +404,12 @@ __device__ __forceinline__ void radix_aggregate_body(const ScanPlan& P, const Ra
         radix_record_row<CT, NC>(P, lo[u], hi[u], r, rowid);
         const uint64_t h = radix_record_hash<CT, NC, KW>(P, r, o.k, o.sentinel_free);
         slot[u] = ~0u;
-        if (o.sentinel_free) slot[u] = smem_upsert<KW>(T, o.k, (uint32_t)((h << rp.log2_parts) >> (64 - rp.log2_slots)), rp.probe_limit, &ctl[0]);
+        bool inserted = false;
+        if (o.sentinel_free) slot[u] = smem_upsert<KW>(T, o.k, (uint32_t)((h << rp.log2_parts) >> (64 - rp.log2_slots)), rp.probe_limit, &ctl[0], inserted);
+        if (inserted) {
+#pragma unroll
+          for (int a = 0; a < NACC; ++a) T.accs[(uint32_t)a * T.S + slot[u]] = acc_init(CT::acc_op(P, a));
+        }
         if (slot[u] != ~0u) rank[u] = atomicAdd(&T.cnt[slot[u]], 1u);
         else {
           // a data value equal to a key sentinel lives in the escape slots of the whole table; everything else that found
@@ -538,10 +542,12 @@ __device__ __forceinline__ void radix_aggregate_body(const ScanPlan& P, const Ra
         const bool occ = KW == 1 ? T.keys[s] != KEY_EMPTY : T.state[s] == 2u;
         if (!occ) continue;
         const uint64_t d = dbase + atomicAdd(&ctl[1], 1u);
+        uint64_t* kp = &tkey(G, 0, d);
+        uint64_t* ap = &tacc(G, 0, d);
 #pragma unroll
-        for (int w = 0; w < KW; ++w) tkey(G, w, d) = T.keys[(uint32_t)w * T.S + s];
-#pragma unroll 1
-        for (int a = 0; a < n_acc; ++a) tacc(G, a, d) = T.accs[(uint32_t)a * T.S + s];
+        for (int w = 0; w < KW; ++w) kp[(uint64_t)w * G.key_sw] = T.keys[(uint32_t)w * T.S + s];
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) ap[(uint64_t)a * G.acc_sw] = T.accs[(uint32_t)a * T.S + s];
         if (KW > 1) G.state[d] = 2u;
       }
     }

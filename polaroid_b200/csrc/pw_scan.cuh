@@ -707,7 +707,8 @@ __device__ __forceinline__ bool row_keys(const ScanPlan& P, const Row<NC>& r, co
       w0 = (uint64_t)v.y << 32 | v.x;
       w1 = (uint64_t)v.w << 32 | v.z;
       ok = (pick32<NC>(vbits, kslot) >> j) & 1u;
-      if ((uint32_t)w0 > 12u && alive && ok) *P.table.overflow = 2;  // long string: unsupported here
+      // (values longer than 12 bytes were canonicalised when the frame was created, pw_views.cu: equal strings carry
+      // equal view bytes, so the two words are the key for every length)
     } else {
       w0 = pick<NC>(r.in, kslot);
       ok = (r.in_valid >> kslot) & 1u;

@@ -260,7 +260,8 @@ class _Exported:
 
 
 def _import_view_array(c_array: "ArrowArray", c_schema: "ArrowSchema") -> pa.Array:
-    """Inline-only Utf8View result (library output) -> pyarrow large_string, then release the C structs."""
+    """Utf8View result (library output: inline values, plus one data buffer when keys longer than 12 bytes were
+    gathered) -> pyarrow large_string, then release the C structs."""
     import numpy as np
     n = int(c_array.length)
     binary = c_schema.format == b"vz"
@@ -271,9 +272,22 @@ def _import_view_array(c_array: "ArrowArray", c_schema: "ArrowSchema") -> pa.Arr
         if c_array.null_count and c_array.buffers[0]:
             vb = np.ctypeslib.as_array(C.cast(c_array.buffers[0], C.POINTER(C.c_uint8)), shape=((n + 7) // 8,)).copy()
             valid = np.unpackbits(vb, bitorder="little")[:n].astype(bool)
-        take = np.arange(12)[None, :] < lens[:, None]
-        data = views[:, 4:16][take]
         off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        longm = lens > 12
+        if longm.any():
+            # buffers = [validity, views, data, sizes]: views of long values are (length, prefix, buffer 0, offset)
+            size = int(C.cast(c_array.buffers[3], C.POINTER(C.c_int64))[0])
+            blob = np.ctypeslib.as_array(C.cast(c_array.buffers[2], C.POINTER(C.c_uint8)), shape=(size,))
+            data = np.zeros(int(off[-1]), dtype=np.uint8)
+            take = (np.arange(12)[None, :] < lens[:, None]) & ~longm[:, None]
+            pos = (off[:-1, None] + np.arange(12)[None, :])[take]
+            data[pos] = views[:, 4:16][take]
+            src = views[:, 12:16].copy().view("<u4").reshape(n).astype(np.int64)
+            for i in np.nonzero(longm)[0]:
+                data[off[i]:off[i + 1]] = blob[src[i]:src[i] + lens[i]]
+        else:
+            take = np.arange(12)[None, :] < lens[:, None]
+            data = views[:, 4:16][take]
         arr = pa.Array.from_buffers(pa.large_binary() if binary else pa.large_string(), n,
                                     [None, pa.py_buffer(off.tobytes()), pa.py_buffer(data.tobytes())])
         if valid is not None:
