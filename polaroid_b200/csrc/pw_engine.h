@@ -81,6 +81,7 @@ struct PwFrame {
   std::vector<pw::FrameColumn> cols;
   mutable std::mutex mu;
   mutable std::map<std::string, pw::PilotStats> pilot;
+  mutable std::map<std::string, int> sorted_cache;   // check_sorted_within_keys: 1 ascending, 2 not (per index column / per keys + index)
 };
 
 namespace pw {
@@ -161,6 +162,8 @@ int make_host_array(int64_t length, int64_t null_count, void* validity, void* va
 int make_schema(const char* format, const char* name, bool nullable, struct ArrowSchema* out);
 // view array with one variadic data buffer (takes ownership of all four blocks)
 int make_host_view_array(int64_t length, int64_t null_count, void* validity, void* values, void* data, int64_t data_bytes, struct ArrowArray* out);
+// group_by_dynamic with keys: is the index ascending inside every key? (pw_filter.cu)
+int check_sorted_within_keys(const PwQuery* q, const PwFrame* frame);
 // long string keys (pw_views.cu)
 int views_intern(FrameColumn* col, int64_t n);
 int views_gather_long(const FrameColumn* col, void* h_views, const void* h_validity, uint64_t G, void** h_data, int64_t* data_bytes);

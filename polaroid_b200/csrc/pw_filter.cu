@@ -371,6 +371,154 @@ int pw_b200_frame_group_tuples(const PwFrame* frame, const int32_t* key_columns,
   return rc;
 }
 
+}  // extern "C"  (the sortedness check below is internal)
+
+namespace pw {
+namespace {
+__device__ __forceinline__ int64_t index_at(const void* values, int w, int64_t row) {
+  return w == 4 ? (int64_t)((const int32_t*)values)[row] : ((const int64_t*)values)[row];
+}
+static __global__ void index_sorted_kernel(const void* values, int w, int64_t n, int32_t* flag) {
+  bool bad = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    bad = bad || index_at(values, w, i) < index_at(values, w, i - 1);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *flag = 1;
+}
+static __global__ void gather_u32_kernel(const uint32_t* src, const uint32_t* ids, int64_t n, uint32_t* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[ids[i]];
+}
+// (group, row) pairs in group-major, row-ascending order: a neighbour of the same group with a smaller index value
+static __global__ void sorted_within_groups_kernel(const uint32_t* group, const uint32_t* rows, int64_t n, const void* values, int w, int32_t* flag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (i < n && group[i] == group[i - 1] && index_at(values, w, rows[i]) < index_at(values, w, rows[i - 1])) *flag = 1;
+}
+}  // namespace
+
+// group_by_dynamic with `group_by=` keys: the reference sorts the frame by the keys (stable) and raises when the index
+// is not ascending inside a key slice (polars-time/src/group_by/dynamic.rs:77-80, 327).  Neither the hash path nor the
+// windowed bucket tier needs that order, so the check is its own step:
+//   1. is the index column ascending over ALL rows?  (one pass, remembered on the frame) — then it is inside every key;
+//   2. otherwise the exact check: every row's group (the group-by on the keys alone, as pw_b200_frame_group_tuples
+//      does), stable radix sort of (group, row) over the rows that pass the predicate, neighbours compared.  The verdict
+//      for the unfiltered frame is remembered per (keys, index) — a subsequence of an ascending sequence is ascending.
+// Returns 0 sorted, PW_ERR_NOT_SORTED, or another error.
+int check_sorted_within_keys(const PwQuery* q, const PwFrame* frame) {
+  ThreadCtx& c = ctx();
+  const int64_t n = frame->n_rows;
+  const int icol = q->dynamic->index_column;
+  if (n < 2 || icol < 0 || icol >= (int)frame->cols.size()) return 0;
+  const FrameColumn& ic = frame->cols[icol];
+  if (ic.dtype != DT_I32 && ic.dtype != DT_I64) return 0;   // lower_query refuses the query with the reference's message
+  const int w = ic.dtype == DT_I32 ? 4 : 8;
+  auto not_sorted = [&]() { return fail(PW_ERR_NOT_SORTED, "argument in operation 'group_by_dynamic' is not sorted, please sort the 'expr/series/column' first"); };
+  std::string gkey = "g:" + std::to_string(icol), kkey = "k:" + std::to_string(icol);
+  for (int i = 0; i < q->n_keys; ++i) kkey += ":" + std::to_string(q->key_columns[i]);
+  int global_state = 0, keyed_state = 0;   // 0 unknown, 1 sorted, 2 not sorted
+  {
+    std::lock_guard<std::mutex> lk(frame->mu);
+    auto it = frame->sorted_cache.find(gkey);
+    if (it != frame->sorted_cache.end()) global_state = it->second;
+    it = frame->sorted_cache.find(kkey);
+    if (it != frame->sorted_cache.end()) keyed_state = it->second;
+  }
+  if (global_state == 1 || keyed_state == 1) return 0;
+  if (keyed_state == 2 && q->n_predicates == 0) return not_sorted();
+  void* v = nullptr;
+  int32_t* d_flag = nullptr;
+  PW_TRY(dev_alloc(&v, 64)); d_flag = (int32_t*)v;
+  auto read_flag = [&](int32_t* out) -> int {
+    if (cudaMemcpyAsync(out, d_flag, 4, cudaMemcpyDeviceToHost, c.stream) != cudaSuccess || cudaStreamSynchronize(c.stream) != cudaSuccess)
+      return fail(PW_ERR_CUDA, "sortedness check failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+  };
+  if (global_state == 0) {
+    int32_t h = 0;
+    int rc = cudaMemsetAsync(d_flag, 0, 64, c.stream) == cudaSuccess ? 0 : fail(PW_ERR_CUDA, "memset failed");
+    if (!rc) {
+      index_sorted_kernel<<<148 * 8, 256, 0, c.stream>>>(ic.values, w, n, d_flag);
+      c.timings.kernel_launches++;
+      rc = read_flag(&h);
+    }
+    if (rc) { dev_free(d_flag); return rc; }
+    global_state = h ? 2 : 1;
+    std::lock_guard<std::mutex> lk(frame->mu);
+    if (frame->sorted_cache.size() > 256) frame->sorted_cache.clear();
+    frame->sorted_cache[gkey] = global_state;
+    if (global_state == 1) { dev_free(d_flag); return 0; }
+  }
+  // ---- exact check per key
+  if (n > 0xFFFFFFF0ll) { dev_free(d_flag); return fail(PW_ERR_UNSUPPORTED, "sortedness check inside keys: more than 2^32 rows"); }
+  PwAgg len_agg{};
+  len_agg.kind = PW_LEN; len_agg.column = -1; len_agg.name = "len";
+  PwQuery gq{};
+  gq.abi_version = PW_ABI_VERSION; gq.n_keys = q->n_keys; gq.key_columns = q->key_columns;
+  gq.n_aggs = 1; gq.aggs = &len_agg; gq.flags = PW_FLAG_FORCE_GLOBAL_TABLE;
+  Lowered L;
+  Table T{};
+  uint32_t *slots = nullptr, *slot_rank = nullptr, *row_rank = nullptr, *ids = nullptr, *keys_in = nullptr, *keys_out = nullptr, *ids_out = nullptr;
+  uint64_t* sizes = nullptr;
+  void* tmp = nullptr;
+  uint64_t G = 0;
+  int64_t n_sel = n;
+  int32_t h = 0;
+  auto run = [&]() -> int {
+    PW_TRY(lower_query(&gq, frame, &L));
+    PW_TRY(run_groupby(&gq, frame, L, &T, &slots, &G));
+    const uint64_t nn = T.cap + 2;
+    PW_TRY(dev_alloc(&v, nn * 4)); slot_rank = (uint32_t*)v;
+    PW_TRY(dev_alloc(&v, (G + 1) * 8)); sizes = (uint64_t*)v;
+    int acc_len = -1;
+    for (int a = 0; a < L.plan.n_acc; ++a) if (L.plan.accs[a].src == SRC_ONE) acc_len = a;
+    rank_kernel<<<(unsigned)std::max<uint64_t>(1, (G + 1 + 255) / 256), 256, 0, c.stream>>>(slots, slot_rank, sizes, T, acc_len, G);
+    PW_CUDA(cudaGetLastError());
+    PW_TRY(dev_alloc(&v, (size_t)n * 4)); row_rank = (uint32_t*)v;
+    ScanPlan P = L.plan;
+    P.table = T; P.hot_slots = 0; P.row_group_out = row_rank; P.slot_rank = slot_rank;
+    PW_CUDA(cudaMemsetAsync(d_flag, 0, 64, c.stream));
+    P.not_sorted = d_flag + 4; P.table.overflow = d_flag + 5; P.table.spilled = (unsigned long long*)(d_flag + 6);
+    PW_TRY(launch_scan_aot(P, c.sm_count, c.stream));
+    if (q->n_predicates > 0) {
+      PredPlan pp;
+      PW_TRY(build_pred_plan(q->predicates, q->n_predicates, frame, &pp));
+      PW_TRY(select_rows(pp, n, &ids, &n_sel));
+      if (n_sel < 2) return 0;
+      PW_TRY(dev_alloc(&v, (size_t)n_sel * 4)); keys_in = (uint32_t*)v;
+      gather_u32_kernel<<<(unsigned)((n_sel + 255) / 256), 256, 0, c.stream>>>(row_rank, ids, n_sel, keys_in);
+      PW_CUDA(cudaGetLastError());
+    } else {
+      PW_TRY(dev_alloc(&v, (size_t)n * 4)); ids = (uint32_t*)v;
+      iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(ids, (uint64_t)n);
+      PW_CUDA(cudaGetLastError());
+    }
+    const uint32_t* kin = keys_in ? keys_in : row_rank;
+    PW_TRY(dev_alloc(&v, (size_t)n_sel * 4)); keys_out = (uint32_t*)v;
+    PW_TRY(dev_alloc(&v, (size_t)n_sel * 4)); ids_out = (uint32_t*)v;
+    int bits = 1;
+    while ((1ull << bits) < G + 1 && bits < 32) ++bits;
+    size_t sb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sb, kin, keys_out, ids, ids_out, n_sel, 0, bits, c.stream);
+    PW_TRY(dev_alloc(&tmp, sb));
+    PW_CUDA(cub::DeviceRadixSort::SortPairs(tmp, sb, kin, keys_out, ids, ids_out, n_sel, 0, bits, c.stream));
+    sorted_within_groups_kernel<<<(unsigned)((n_sel + 255) / 256), 256, 0, c.stream>>>(keys_out, ids_out, n_sel, ic.values, w, d_flag);
+    PW_CUDA(cudaGetLastError());
+    c.timings.kernel_launches += 5;
+    return read_flag(&h);
+  };
+  const int rc = run();
+  dev_free(slots); dev_free(slot_rank); dev_free(sizes); dev_free(row_rank); dev_free(ids); dev_free(keys_in); dev_free(keys_out); dev_free(ids_out);
+  dev_free(tmp); dev_free(d_flag);
+  if (T.keys) free_table(T);
+  if (rc) return rc;
+  if (q->n_predicates == 0) {
+    std::lock_guard<std::mutex> lk(frame->mu);
+    frame->sorted_cache[kkey] = h ? 2 : 1;
+  }
+  return h ? not_sorted() : 0;
+}
+}  // namespace pw
+
+extern "C" {
 int pw_b200_frame_group_slices(const PwFrame* frame, const int32_t* key_columns, int32_t n_keys, struct ArrowArray* out_first,
                                struct ArrowArray* out_len, struct ArrowSchema* out_schemas) {
   PW_TRY(ensure_device());

@@ -99,3 +99,53 @@ def test_index_dtypes_the_reference_accepts(typ):
     every = "2i" if typ == pa.int32() else ("2d" if typ == pa.date32() else "2ms")
     q = pw.LazyFrame(t).group_by_dynamic("ts", every=every).agg(pw.col("v").sum(), pw.len().alias("n"))
     G.assert_tables_equal(engine.run_group_by(q.table, q.plan), oracle.collect(q))
+
+
+def _keyed_frame(n=60_000, n_keys=6, seed=41):
+    rng = np.random.default_rng(seed)
+    ts = np.sort(rng.integers(0, 10_000_000, n)).astype(np.int64)
+    return ts, rng.integers(0, n_keys, n).astype(np.int64), rng.integers(1, 100, n).astype(np.int64)
+
+
+def test_index_unsorted_inside_a_key_raises_like_the_reference():
+    """polars-time/src/group_by/dynamic.rs:77-80, 327: with `group_by=` keys the frame is sorted by the keys (stable) and
+    every key slice must be ascending.  One swapped pair inside ONE key — the rows of the other keys between them keep the
+    column far from obviously unsorted."""
+    ts, key, v = _keyed_frame()
+    rows = np.flatnonzero(key == 3)
+    a, b = rows[len(rows) // 2], rows[len(rows) // 2 + 1]
+    assert ts[a] < ts[b]
+    ts[a], ts[b] = ts[b], ts[a]
+    t = pa.table({"ts": pa.array(ts), "k": pa.array(key), "v": pa.array(v)})
+    q = pw.LazyFrame(t).group_by_dynamic("ts", every="1000i", group_by="k").agg(pw.col("v").sum().alias("s"))
+    with pytest.raises(ValueError):
+        oracle.collect(q)
+    for opts in ({}, {"flags": engine.FLAG_FORCE_HOT}, {"flags": engine.FLAG_FORCE_GLOBAL}):
+        with pytest.raises(engine.PolarwayError) as e:
+            engine.run_group_by(q.table, q.plan, **opts)
+        assert e.value.code == -4
+    # a filter that drops one row of the pair leaves every key slice ascending: no error, same answer as the oracle
+    q2 = (pw.LazyFrame(t.append_column("row", pa.array(np.arange(len(ts), dtype=np.int64)))).filter(pw.col("row") != int(a))
+          .group_by_dynamic("ts", every="1000i", group_by="k").agg(pw.col("v").sum().alias("s"), pw.len().alias("n")))
+    G.assert_tables_equal(engine.run_group_by(q2.table, q2.plan), oracle.collect(q2))
+    # ... and one that keeps both still raises
+    q3 = (pw.LazyFrame(t).filter(pw.col("v") > 0).group_by_dynamic("ts", every="1000i", group_by="k").agg(pw.col("v").sum().alias("s")))
+    with pytest.raises(engine.PolarwayError) as e:
+        engine.run_group_by(q3.table, q3.plan)
+    assert e.value.code == -4
+
+
+def test_keys_sorted_first_then_time_is_accepted_on_a_resident_frame():
+    # the layout `sort(["k", "ts"])` leaves: ascending inside every key, not over the whole column; the verdict is
+    # remembered on the frame (second query: no second check)
+    ts, key, v = _keyed_frame(seed=42)
+    order = np.lexsort((ts, key))
+    t = pa.table({"ts": pa.array(ts[order]), "k": pa.array(key[order]), "v": pa.array(v[order])})
+    frame = engine.DeviceFrame(t)
+    q = pw.LazyFrame(t).group_by_dynamic("ts", every="1000i", group_by="k").agg(pw.col("v").sum().alias("s"), pw.len().alias("n"))
+    want = oracle.collect(q)
+    G.assert_tables_equal(frame.group_by(q.plan), want)
+    first = engine.last_timings()["kernel_launches"]
+    G.assert_tables_equal(frame.group_by(q.plan), want)
+    assert engine.last_timings()["kernel_launches"] < first
+    frame.free()
