@@ -254,7 +254,7 @@ std::string part_entry(int nc, int kw, int threads) {
 
 std::string radix_entry(int nc, int kw, int mode, int threads) {
   std::ostringstream src;
-  src << "extern \"C\" __global__ void __launch_bounds__(" << threads << ") pw_radix_jit_m" << mode << "(const __grid_constant__ pw::ScanPlan P, const pw::RadixParams rp) {\n"
+  src << "extern \"C\" __global__ void __launch_bounds__(" << threads << (mode == 1 || mode == 2 ? ", 2" : "") << ") pw_radix_jit_m" << mode << "(const __grid_constant__ pw::ScanPlan P, const pw::RadixParams rp) {\n"
       << "  pw::radix_body<pw::JitCtl, " << nc << ", " << kw << ", " << mode << ">(P, rp);\n}\n";
   return src.str();
 }
@@ -416,7 +416,7 @@ int jit_selftest_compile(const ScanPlan& P, int nc, int kw, bool hot, int thread
     *(void**)(&a.nvrtcDestroyProgram) = dlsym(rtc, "nvrtcDestroyProgram");
   }
   const std::string text = "#include \"pw_segmented.cuh\"\n#include \"pw_partition.cuh\"\n#include \"pw_pilot.cuh\"\n#include \"pw_bucket.cuh\"\n#include \"pw_runs.cuh\"\n#include \"pw_radix.cuh\"\nnamespace pw {\n" + jit_ctl(P) + "}\n" + scan_entry(nc, kw, hot, threads) + seg_entry(nc, 256) + part_entry(nc, kw, 256) + pilot_entry(nc, kw, 256) + runs_entry(nc, kw, 256) +
-                           (nc <= 4 && P.n_slots <= 3 && !P.dyn.enabled ? radix_entry(nc, kw, 0, 256) + radix_entry(nc, kw, 1, RADIX_THREADS) + radix_entry(nc, kw, 2, RADIX_THREADS) + radix_entry(nc, kw, 3, RADIX_THREADS) : std::string()) +
+                           (nc <= 4 && P.n_slots <= 3 && !P.dyn.enabled ? radix_entry(nc, kw, 0, 256) + radix_entry(nc, kw, 1, RADIX_SC_THREADS) + radix_entry(nc, kw, 2, RADIX_SC_THREADS) + radix_entry(nc, kw, 3, RADIX_THREADS) : std::string()) +
                            (P.hot.bucket ? bucket_entry(nc, kw, P.hot.b_threads, P.hot.b_cps) : std::string());
   nvrtcProgram prog = nullptr;
   if (a.nvrtcCreateProgram(&prog, text.c_str(), "pw_scan_jit.cu", 0, nullptr, nullptr) != 0) { *err = "nvrtcCreateProgram failed"; return 2; }
@@ -627,7 +627,7 @@ int launch_radix_jit(const ScanPlan& P, const RadixParams& rp, int nc, int kw, s
   if (disabled) return 1;
   Api& a = api();
   if (!a.ok) return 1;
-  const int threads = rp.mode == 0 ? 256 : RADIX_THREADS;
+  const int threads = rp.mode == 0 ? 256 : (rp.mode == 3 ? RADIX_THREADS : RADIX_SC_THREADS);
   std::string key = plan_key(P);
   const int32_t tail[5] = {-4 /* radix */, nc, kw, rp.mode, (int32_t)smem};
   key.append((const char*)tail, sizeof tail);

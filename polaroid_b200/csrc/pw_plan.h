@@ -253,8 +253,9 @@ struct PartParams {
 
 // two-level radix partitioning + per-partition aggregation in shared memory (pw_radix.cuh).  A record is 32 bytes:
 // one 64-bit word per raw slot, then (row << 8 | validity bits).
-constexpr int RADIX_TILE = 4096;     // records a CTA stages per tile
-constexpr int RADIX_THREADS = 1024;
+constexpr int RADIX_TILE = 2048;        // records a scatter CTA stages per tile (two CTAs per SM: one loads while the other copies out)
+constexpr int RADIX_SC_THREADS = 512;   // scatter passes: 4 rows per thread
+constexpr int RADIX_THREADS = 1024;     // aggregation pass
 struct RadixParams {
   int32_t mode;          // 0 histogram, 1 scatter (frame -> level-1 partitions), 2 scatter (level 1 -> final), 3 aggregate
   int32_t log2_parts;    // final partitions P = 2^log2_parts; partition = top bits of the key hash

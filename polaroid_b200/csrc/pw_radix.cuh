@@ -6,7 +6,7 @@
 // row, then the ordinary scan with its HBM table behind the hot table) ran at the L2's request rate, not at HBM speed:
 // C3 = 8.3 ms partitioning + 6.3 ms scan for 2.0 GB of algorithmic traffic.  Here every pass streams:
 //   mode 0  histogram of the FINAL partition of every surviving row (shared-memory counters, flushed once per CTA)
-//   mode 1  frame -> level-1 partitions (<= 256): a CTA ranks a 4096-row tile with shared-memory atomics, takes one
+//   mode 1  frame -> level-1 partitions (<= 256): a 512-thread CTA ranks a 2048-row tile with shared-memory atomics, takes one
 //           global cursor step per (tile, partition), sorts the tile's records by partition in shared memory and copies
 //           them out as runs of consecutive 32-byte records (two threads per record: 16-byte stores, full sectors)
 //   mode 2  level-1 partition -> final partitions (<= 256 per level-1 partition), same tile machinery
@@ -76,7 +76,7 @@ __device__ __forceinline__ void radix_flush_tile(const RadixSmem& s, uint32_t* c
   }
   __syncthreads();
   const uint32_t total = s.misc[0];
-  for (uint32_t i = tid; i < 2 * total; i += RADIX_THREADS) {
+  for (uint32_t i = tid; i < 2 * total; i += RADIX_SC_THREADS) {
     const uint32_t rec = i >> 1, b = s.binid[rec];
     dst[2 * ((uint64_t)s.gb[b] + (rec - s.pre[b])) + (i & 1u)] = s.stage[i];
   }
@@ -225,7 +225,7 @@ __device__ __forceinline__ void radix_scatter_records_body(const ScanPlan& P, co
     uint32_t bin[4], rank[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const uint32_t idx = begin + (uint32_t)i * RADIX_THREADS + tid;
+      const uint32_t idx = begin + (uint32_t)i * RADIX_SC_THREADS + tid;
       bin[i] = 0xFFFFu; rank[i] = 0u;
       lo[i] = make_uint4(0u, 0u, 0u, 0u); hi[i] = lo[i];
       if (idx < end) { lo[i] = __ldcs(rp.src + 2 * (uint64_t)idx); hi[i] = __ldcs(rp.src + 2 * (uint64_t)idx + 1); bin[i] = 0u; }
