@@ -1243,12 +1243,16 @@ static int radix_prepare(const ScanPlan& P, double g_hint, ScanPlan* P2out, Radi
   const int kw = padded_kw(P.n_kw);
   const int kwc = kw <= 1 ? 1 : (kw <= 2 ? 2 : (kw <= 4 ? 4 : 6));
   tmp->kwc = kwc;
-  // shared memory of the aggregation pass: the staging area of one round + as many table slots as the rest holds
-  const size_t slot_bytes = (size_t)(kwc + P.n_acc) * 8 + 8 + 2 + (kwc > 1 ? 4 : 0);
-  const size_t stage_bytes = (size_t)(P.n_slots + 1) * 8 * RADIX_ROUND * RADIX_THREADS;
-  const size_t budget = 220 * 1024 - 512;
+  // shared memory of the aggregation pass: the staging area of one round + as many table slots as the rest holds.
+  // Two 512-thread CTAs per SM with half-size tables (one CTA's barriers and latencies hide behind the other's work)
+  // or one 1024-thread CTA: PW_RADIX_AGG_THREADS
+  const char* at_env = getenv("PW_RADIX_AGG_THREADS");
+  const int agg_threads = at_env && atoi(at_env) == 1024 ? 1024 : 512;
+  const size_t slot_bytes = (size_t)(kwc + P.n_acc) * 8 + 8 + 2 + 2 + (kwc > 1 ? 4 : 0);
+  const size_t stage_bytes = (size_t)(P.n_slots + 1) * 8 * RADIX_ROUND * agg_threads;
+  const size_t budget = (agg_threads == 1024 ? 220 : 110) * 1024 - 512;
   if (stage_bytes + (slot_bytes << 6) > budget) return 1;
-  int log2_slots = 12;
+  int log2_slots = agg_threads == 1024 ? 12 : 11;   // at most four slots per thread
   while (log2_slots > 6 && stage_bytes + (slot_bytes << log2_slots) > budget) --log2_slots;
   const double per_part = 0.4 * (double)(1u << log2_slots);   // groups per partition the table is planned for
   const double want = std::max(g_hint, 1.0) * 1.1 / per_part;
@@ -1292,7 +1296,7 @@ static int radix_prepare(const ScanPlan& P, double g_hint, ScanPlan* P2out, Radi
   if (log2_p2 > 0) { void* p = nullptr; PW_TRY(dev_alloc(&p, rec_bytes)); tmp->buf_b = (uint4*)p; }
   PW_CUDA(cudaMemsetAsync(hist, 0, (size_t)n_parts * 4, c.stream));
   RadixParams r{};
-  r.log2_parts = log2_parts; r.log2_p2 = log2_p2; r.log2_slots = log2_slots; r.probe_limit = 32;
+  r.log2_parts = log2_parts; r.log2_p2 = log2_p2; r.log2_slots = log2_slots; r.probe_limit = 32; r.agg_threads = agg_threads;
   r.hist = hist; r.offs = offs; r.tile_first = tile_first;
   const int64_t n_steps = (N + ROWS_PER_STEP - 1) / ROWS_PER_STEP;
   const int64_t n_tiles = (N + RADIX_TILE - 1) / RADIX_TILE;

@@ -254,7 +254,7 @@ std::string part_entry(int nc, int kw, int threads) {
 
 std::string radix_entry(int nc, int kw, int mode, int threads) {
   std::ostringstream src;
-  src << "extern \"C\" __global__ void __launch_bounds__(" << threads << (mode == 1 || mode == 2 ? ", 2" : "") << ") pw_radix_jit_m" << mode << "(const __grid_constant__ pw::ScanPlan P, const pw::RadixParams rp) {\n"
+  src << "extern \"C\" __global__ void __launch_bounds__(" << threads << (mode == 1 || mode == 2 || (mode == 3 && threads <= 512) ? ", 2" : "") << ") pw_radix_jit_m" << mode << "(const __grid_constant__ pw::ScanPlan P, const pw::RadixParams rp) {\n"
       << "  pw::radix_body<pw::JitCtl, " << nc << ", " << kw << ", " << mode << ">(P, rp);\n}\n";
   return src.str();
 }
@@ -627,9 +627,9 @@ int launch_radix_jit(const ScanPlan& P, const RadixParams& rp, int nc, int kw, s
   if (disabled) return 1;
   Api& a = api();
   if (!a.ok) return 1;
-  const int threads = rp.mode == 0 ? 256 : (rp.mode == 3 ? RADIX_THREADS : RADIX_SC_THREADS);
+  const int threads = rp.mode == 0 ? (smem > 64 * 1024 ? 1024 : 256) : (rp.mode == 3 ? rp.agg_threads : RADIX_SC_THREADS);
   std::string key = plan_key(P);
-  const int32_t tail[5] = {-4 /* radix */, nc, kw, rp.mode, (int32_t)smem};
+  const int32_t tail[6] = {-4 /* radix */, nc, kw, rp.mode, (int32_t)smem, threads};
   key.append((const char*)tail, sizeof tail);
   Compiled c;
   {

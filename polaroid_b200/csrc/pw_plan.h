@@ -255,14 +255,14 @@ struct PartParams {
 // one 64-bit word per raw slot, then (row << 8 | validity bits).
 constexpr int RADIX_TILE = 2048;        // records a scatter CTA stages per tile (two CTAs per SM: one loads while the other copies out)
 constexpr int RADIX_SC_THREADS = 512;   // scatter passes: 4 rows per thread
-constexpr int RADIX_THREADS = 1024;     // aggregation pass
+constexpr int RADIX_THREADS = 1024;     // aggregation pass: largest CTA
 struct RadixParams {
   int32_t mode;          // 0 histogram, 1 scatter (frame -> level-1 partitions), 2 scatter (level 1 -> final), 3 aggregate
   int32_t log2_parts;    // final partitions P = 2^log2_parts; partition = top bits of the key hash
   int32_t log2_p2;       // level-2 fan-out (0: one level, mode 1 writes the final partitions)
   int32_t log2_slots;    // mode 3: slots of the shared-memory table
   int32_t probe_limit;   // mode 3: probes before a key leaves for the overflow region of the HBM table
-  int32_t pad;
+  int32_t agg_threads;   // mode 3: CTA size (1024: one CTA per SM; 512: two per SM with half-size tables)
   uint32_t* hist;        // [P]      mode 0 out: records per final partition
   const uint32_t* offs;  // [P + 1]  first record of every final partition
   uint32_t* cursor;      // mode 1: [P >> log2_p2], mode 2: [P] next free record

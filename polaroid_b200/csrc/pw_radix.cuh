@@ -252,14 +252,15 @@ __device__ __forceinline__ void radix_scatter_records_body(const ScanPlan& P, co
 // (its rank among the rows of its group in this round); the round's rows are then laid out group by group in a
 // shared-memory staging area (counting sort by table slot) and every slot's OWNER thread folds its rows into registers —
 // plain loads, no atomics — and writes the accumulators back to the table.
-constexpr int RADIX_ROUND = 3;   // rows a thread stages per round (round = RADIX_ROUND * RADIX_THREADS rows)
+constexpr int RADIX_ROUND = 3;   // rows a thread stages per round (round = RADIX_ROUND * blockDim.x rows)
 struct SmemTable {
   uint64_t* keys;    // [KW][S]
   uint64_t* accs;    // [n_acc][S]
   uint32_t* state;   // [S]   (KW > 1)
   uint32_t* cnt;     // [S]   rows of the current round
   uint32_t* start;   // [S]   first staged row of the slot
-  uint64_t* stage;   // [n_slots + 1][RADIX_ROUND * RADIX_THREADS]
+  uint64_t* stage;   // [n_slots + 1][RADIX_ROUND * blockDim.x]
+  uint16_t* occ;     // [S]   occupied slots in insertion order
   uint32_t S;
 };
 template <int NACC>
@@ -285,7 +286,7 @@ __device__ __forceinline__ uint32_t smem_upsert(const SmemTable& T, const uint64
       if (old == k0) return s;
       if (old == KEY_EMPTY) {
         old = atomicCAS((unsigned long long*)&T.keys[s], (unsigned long long)KEY_EMPTY, (unsigned long long)k0);
-        if (old == KEY_EMPTY) { atomicAdd(n_ins, 1u); inserted = true; return s; }
+        if (old == KEY_EMPTY) { T.occ[atomicAdd(n_ins, 1u)] = (uint16_t)s; inserted = true; return s; }
         if (old == k0) return s;
       }
       s = (s + 1u) & mask;
@@ -303,7 +304,7 @@ __device__ __forceinline__ uint32_t smem_upsert(const SmemTable& T, const uint64
         for (int w = 0; w < KW; ++w) *(volatile uint64_t*)&T.keys[(uint32_t)w * T.S + s] = k[w];
         __threadfence_block();
         *(volatile uint32_t*)&T.state[s] = 2u;
-        atomicAdd(n_ins, 1u);
+        T.occ[atomicAdd(n_ins, 1u)] = (uint16_t)s;
         inserted = true;
         result = s; done = true;
       } else if (st == 2u) {
@@ -348,7 +349,8 @@ template <class CT, int NC, int KW>
 __device__ __forceinline__ void radix_aggregate_body(const ScanPlan& P, const RadixParams& rp) {
   constexpr int NV = NVof<NC>::value;
   constexpr int NACC = CT::kNAcc;
-  constexpr uint32_t CAP = RADIX_ROUND * RADIX_THREADS;
+  const uint32_t NT = blockDim.x;                 // 1024 (one CTA per SM) or 512 (two per SM, half-size tables): RadixParams::agg_threads
+  const uint32_t CAP = RADIX_ROUND * NT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n_acc = CT::n_acc(P), n_words = CT::n_slots(P);   // n_slots of the record plan counts the row-id word
   SmemTable T;
@@ -363,6 +365,7 @@ __device__ __forceinline__ void radix_aggregate_body(const ScanPlan& P, const Ra
   uint32_t* wsum = ctl + 8;      // [32] block scan
   uint32_t* chist = ctl + 40;    // [64] slots per row count (descending)
   uint16_t* order = (uint16_t*)(ctl + 104);   // [S] slots that have rows in this round, longest first
+  T.occ = order + T.S;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t n_parts = 1u << rp.log2_parts;
   const Table& G = P.table;          // host view: [overflow region | dense region | two escape slots]
@@ -391,7 +394,7 @@ __device__ __forceinline__ void radix_aggregate_body(const ScanPlan& P, const Ra
       uint32_t slot[RADIX_ROUND], rank[RADIX_ROUND];
 #pragma unroll
       for (int u = 0; u < RADIX_ROUND; ++u) {
-        const uint64_t idx = r0 + (uint64_t)u * RADIX_THREADS + tid;
+        const uint64_t idx = r0 + (uint64_t)u * NT + tid;
         slot[u] = ~0u; rank[u] = 0u;
         if (idx < end) { lo[u] = __ldcs(rp.src + 2 * idx); hi[u] = __ldcs(rp.src + 2 * idx + 1); slot[u] = 0u; }
       }
@@ -433,7 +436,7 @@ __device__ __forceinline__ void radix_aggregate_body(const ScanPlan& P, const Ra
       __syncthreads();
       // ---- phase B: exclusive prefix of the slots' row counts
       {
-        const uint32_t per = T.S / RADIX_THREADS > 0 ? T.S / RADIX_THREADS : 1u;   // consecutive slots per thread
+        const uint32_t per = T.S / NT > 0 ? T.S / NT : 1u;   // consecutive slots per thread
         const uint32_t s_b = (uint32_t)tid * per;
         uint32_t sum = 0;
         if (s_b < T.S)
@@ -443,8 +446,9 @@ __device__ __forceinline__ void radix_aggregate_body(const ScanPlan& P, const Ra
         for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
         if (lane == 31) wsum[warp] = incl;
         __syncthreads();
-        uint32_t off = 0;
-        for (int w = 0; w < warp; ++w) off += wsum[w];
+        uint32_t off = lane < warp ? wsum[lane] : 0u;   // totals of the warps before this one (32 warps: one per lane)
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) off += __shfl_xor_sync(0xffffffffu, off, d);
         uint32_t run = off + incl - sum;
         if (s_b < T.S)
           for (uint32_t i = 0; i < per; ++i) { T.start[s_b + i] = run; run += T.cnt[s_b + i]; }
@@ -470,7 +474,7 @@ __device__ __forceinline__ void radix_aggregate_body(const ScanPlan& P, const Ra
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const uint32_t s = (uint32_t)tid + (uint32_t)i * RADIX_THREADS;
+          const uint32_t s = (uint32_t)tid + (uint32_t)i * NT;
           my_b[i] = ~0u; my_r[i] = 0u;
           if (s < T.S) {
             const uint32_t n = T.cnt[s];
@@ -490,14 +494,14 @@ __device__ __forceinline__ void radix_aggregate_body(const ScanPlan& P, const Ra
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (my_b[i] != ~0u) order[chist[my_b[i]] + my_r[i]] = (uint16_t)((uint32_t)tid + (uint32_t)i * RADIX_THREADS);
+          if (my_b[i] != ~0u) order[chist[my_b[i]] + my_r[i]] = (uint16_t)((uint32_t)tid + (uint32_t)i * NT);
         __syncthreads();
       }
       // ---- phase D: every slot's rows are folded in registers — by its owner thread, or, for a slot with 63 or more
       // rows in the round (heavy hitters: the null-key group of C3 holds 1e5 rows, and one thread folding them alone
       // was two thirds of the kernel's time), by a whole warp whose lanes then combine by shuffles
       const uint32_t n_busy = ctl[6], n_heavy = chist[1];
-      for (uint32_t t = warp; t < n_heavy; t += RADIX_THREADS / 32) {
+      for (uint32_t t = warp; t < n_heavy; t += NT / 32) {
         const uint32_t s = order[t];
         const uint32_t n = T.cnt[s], first = T.start[s];
         uint64_t acc[NACC];
@@ -538,10 +542,9 @@ __device__ __forceinline__ void radix_aggregate_body(const ScanPlan& P, const Ra
     __syncthreads();
     if (n_groups && ctl[4]) {
       const uint64_t dbase = rp.ovf_cap + ((uint64_t)ctl[3] << 32 | ctl[2]);
-      for (uint32_t s = tid; s < T.S; s += blockDim.x) {
-        const bool occ = KW == 1 ? T.keys[s] != KEY_EMPTY : T.state[s] == 2u;
-        if (!occ) continue;
-        const uint64_t d = dbase + atomicAdd(&ctl[1], 1u);
+      for (uint32_t t = tid; t < n_groups; t += blockDim.x) {
+        const uint32_t s = T.occ[t];
+        const uint64_t d = dbase + t;
         uint64_t* kp = &tkey(G, 0, d);
         uint64_t* ap = &tacc(G, 0, d);
 #pragma unroll
