@@ -202,7 +202,8 @@ typedef struct PwFrame PwFrame; /* opaque: columns resident on one device */
 
 /* Copy `n_cols` host Arrow arrays to the device.  Arrays are borrowed for the duration of the call
  * (not released).  All columns must have the same length.  Supported formats: b c C s S i I l L f g,
- * tdD, ts{s,m,u,n}:*, tD{s,m,u,n}, vu, vz (inline views). */
+ * tdD, ts{s,m,u,n}:*, tD{s,m,u,n}, vu, vz (views of any length: buffers = [validity, views, data..., variadic sizes];
+ * values longer than 12 bytes are canonicalised when the frame is created, pw_views.cu). */
 int pw_b200_frame_upload(const struct ArrowArray* const* cols, const struct ArrowSchema* const* schemas,
                          size_t n_cols, PwFrame** out);
 /* Wrap buffers that already live on the current device (zero copy).  `cols[i]->buffers` hold DEVICE

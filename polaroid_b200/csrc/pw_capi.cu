@@ -183,8 +183,6 @@ int pw_b200_frame_groupby(const PwQuery* q, const PwFrame* frame, struct ArrowAr
   }
   Lowered L;
   PW_TRY(lower_query(q, frame, &L));
-  if (q->dynamic && !L.tumbling)
-    return fail(PW_ERR_UNSUPPORTED, "overlapping windows (period > every) together with group_by keys (SURVEY 8f rank 4)");
   if (q->dynamic && q->n_keys > 0) PW_TRY(check_sorted_within_keys(q, frame));   // dynamic.rs:77-80, 327
   RunOpts ro;
   ro.allow_deferred = true;

@@ -285,9 +285,8 @@ int run_dynamic_segmented(const PwQuery* q, const PwFrame* f, struct ArrowArray*
   if (!q->dynamic || q->n_keys != 0) return 0;
   const PwDynamic& d = *q->dynamic;
   const bool overlapping = d.closed == PW_CLOSED_BOTH ? d.period >= d.every : d.period > d.every;
-  if (!overlapping && (q->flags & PW_FLAG_NO_SEGMENTED)) return 0;       // tumbling windows through the hash path (test hook)
-  if (q->n_predicates > 0 && overlapping)
-    return fail(PW_ERR_UNSUPPORTED, "filter + overlapping dynamic windows (needs a compacted index; SURVEY 8f rank 4)");
+  if (q->flags & PW_FLAG_NO_SEGMENTED) return 0;       // windows through the hash path (test hook)
+  if (q->n_predicates > 0 && overlapping) return 0;    // filter + overlapping windows: the hash path (pw_overlap.cuh) applies the predicate in registers
   ThreadCtx& c = ctx();
   Lowered L;
   PW_TRY(lower_query(q, f, &L));

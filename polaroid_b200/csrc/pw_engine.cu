@@ -264,6 +264,7 @@ int lower_query(const PwQuery* q, const PwFrame* f, Lowered* L) {
     if (dyn_slot < 0) return fail(PW_ERR_UNSUPPORTED, "too many column slots");
     const bool overlapping = dyn->closed == PW_CLOSED_BOTH ? dyn->period >= dyn->every : dyn->period > dyn->every;  // dynamic.rs:312-315
     L->tumbling = !overlapping;
+    P.overlap = overlapping ? 1 : 0;   // hash path: every row joins all the windows that contain it (pw_overlap.cuh)
     P.dyn.enabled = 1; P.dyn.slot = dyn_slot; P.dyn.closed = dyn->closed;
     P.dyn.every = dyn->every; P.dyn.period = dyn->period;
     // window starts lie on the grid offset + k*every: truncate(t0, every) + offset (window.rs:115-170)
@@ -608,6 +609,11 @@ static int launch_scan(ScanPlan P, int sm, cudaStream_t st) {
   const bool narrow = narrow_class(P);
   // query-shape specialised kernel (NVRTC); falls back to the ahead-of-time kernel of the same class
   const int kwc = P.n_kw <= 1 ? 1 : (P.n_kw <= 2 ? 2 : (P.n_kw <= 4 ? 4 : 6));
+  if (P.overlap) {
+    const int orc = launch_overlap_jit(P, narrow ? 4 : 12, kwc, sm, st);
+    if (orc > 0) return fail(PW_ERR_UNSUPPORTED, "overlapping windows through the hash path need the run-time compiler (libnvrtc)");
+    return orc;
+  }
   if (P.runs) {
     // sorted keys: run-combining scan (specialised build only; otherwise the regular tiers below)
     const int rrc = launch_runs_jit(P, narrow ? 4 : 12, kwc, sm, st);
@@ -1572,6 +1578,15 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
             P.hot.b_stages, P.hot.b_meta, P.hot.b_bytes, P.hot.b_idx, P.hot.b_win, P.hot.b_range);
   PW_CUDA(cudaEventRecord(c.ev[2], c.stream));
 
+  // ---- overlapping windows: plain HBM table, sized for the windows every row joins
+  uint64_t cap_max = (uint64_t)2 * (uint64_t)N + 64;
+  if (P.overlap) {
+    use_hot = false; memset(&P.hot, 0, sizeof P.hot);
+    const uint64_t m = (uint64_t)((P.dyn.period + P.dyn.every - 1) / P.dyn.every) + 1;
+    cap_max = (uint64_t)2 * (uint64_t)N * m + 64;
+    cap = std::min<uint64_t>(cap * m, cap_max);
+    if (cap > 0xFFFFFFF0ull) return fail(PW_ERR_UNSUPPORTED, "table larger than 2^32 slots");
+  }
   // ---- sorted keys (the caller's flag, as the reference's IsSorted): groups are runs of equal keys
   const bool runs = (q->flags & PW_FLAG_KEYS_SORTED) && !P.dyn.enabled && !P.row_group_out && P.rowid_slot_p1 == 0 && N > 0 && jit_available() &&
                     !getenv("PW_NO_RUNS") && !(q->flags & (PW_FLAG_FORCE_HOT_TABLE | PW_FLAG_FORCE_GLOBAL_TABLE | PW_FLAG_FORCE_PARTITION));
@@ -1626,9 +1641,10 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
 
   // ---- scan (with growth retries) ------------------------------------------------------------------
   Table T{};
+  Table T0{};   // overlapping windows: earliest index value per key slice
   uint32_t* slots = nullptr;
   if (!(opts && opts->min_cap)) tm.retries = 0;
-  auto drop = [&]() { part_free(ptmp); radix_free(rtmp); if (T.keys) free_table(T); dev_free(slots); dev_free(deferred ? (void*)block : (void*)dctl); };
+  auto drop = [&]() { part_free(ptmp); radix_free(rtmp); if (T0.keys) { free_table(T0); T0 = Table{}; } if (T.keys) free_table(T); dev_free(slots); dev_free(deferred ? (void*)block : (void*)dctl); };
   for (;;) {
     int rc = alloc_table(&T, padded_kw(P.n_kw), P.n_acc, cap, dctl);
     if (!rc && radix) {
@@ -1652,6 +1668,21 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
       if (cudaMemsetAsync(rtmp.dense_count, 0, 16, c.stream) != cudaSuccess) { drop(); return fail(PW_ERR_CUDA, "radix tier: memset failed"); }
       rc = launch_radix_jit(PP, rprm, 4, rtmp.kwc, rtmp.smem3, (int64_t)1 << rprm.log2_parts, c.sm_count, c.stream);
       if (rc > 0) rc = fail(PW_ERR_INTERNAL, "radix tier: the aggregation kernel is not available");
+    } else if (P.overlap && N > 0) {
+      // overlapping windows: first the earliest index value of every key slice (its own table, one MIN word), then the
+      // rows join their windows (pw_overlap.cuh)
+      if (T0.keys) free_table(T0);
+      const uint64_t cap0 = std::min<uint64_t>(cap, (uint64_t)2 * (uint64_t)N + 64);
+      rc = alloc_table_raw(&T0, padded_kw(P.n_kw), 1, cap0, &dctl->overflow, &dctl->spilled);
+      if (!rc) {
+        AccOps ops0{}; ops0.n = 1; ops0.op[0] = OP_MIN_I64;
+        const int g0 = (int)std::min<uint64_t>((cap0 + 2 + 255) / 256, 148 * 8);
+        table_init_kernel<<<g0, 256, 0, c.stream>>>(T0, padded_kw(P.n_kw), ops0, nullptr);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(PW_ERR_CUDA, "table_init_kernel launch failed");
+        tm.kernel_launches++;
+      }
+      if (!rc) { P.t0 = T0; P.overlap = 2; rc = launch_scan(P, c.sm_count, c.stream); P.overlap = 1; }
+      if (!rc) rc = launch_scan(P, c.sm_count, c.stream);
     } else if (partitioned) {
       PP.table = T; PP.not_sorted = &dctl->not_sorted; PP.hot_slots = PP.hot.idx_slots;
       if (PP.n_rows > 0) rc = launch_scan(PP, c.sm_count, c.stream);
@@ -1680,8 +1711,8 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     if (hctl.overflow == 2) { drop(); return fail(PW_ERR_UNSUPPORTED, "string key longer than 12 bytes (long views need the data buffers: SURVEY 8f rank 1)"); }
     if (hctl.overflow == 1) {
       free_table(T); dev_free(slots); slots = nullptr;
-      if (cap >= (uint64_t)2 * (uint64_t)N + 64) { drop(); return fail(PW_ERR_INTERNAL, "hash table overflow at maximum size"); }
-      cap = std::min<uint64_t>(cap * 4, (uint64_t)2 * (uint64_t)N + 64);
+      if (cap >= cap_max) { drop(); return fail(PW_ERR_INTERNAL, "hash table overflow at maximum size"); }
+      cap = std::min<uint64_t>(cap * 4, cap_max);
       tm.retries++;
       if (radix) { radix = false; radix_free(rtmp); }  // group estimate too low or a skewed partition: the plain HBM table takes over
       continue;
@@ -1695,6 +1726,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     // count, overflow and sortedness are looked at by emit_results, after the single synchronisation
     part_free(ptmp);
     radix_free(rtmp);
+    if (T0.keys) { free_table(T0); T0 = Table{}; }
     cudaEventRecord(c.ev[3], c.stream);
     const uint64_t bound = cap + 2;
     int rc = order_groups(L, T, padded_kw(P.n_kw), &slots, bound, &dctl->counter);
@@ -1710,6 +1742,7 @@ int run_groupby(const PwQuery* q, const PwFrame* f, Lowered& L, Table* table_out
     return fail(PW_ERR_NOT_SORTED, "argument in operation 'group_by_dynamic' is not sorted, please sort the 'expr/series/column' first");
   }
   part_free(ptmp);
+  if (T0.keys) { free_table(T0); T0 = Table{}; }
   const bool was_radix = radix || rtmp.small != nullptr;
   radix_free(rtmp);
   if (partitioned || was_radix) { float ms = 0; if (cudaEventElapsedTime(&ms, c.ev[10], c.ev[11]) == cudaSuccess) tm.partition_ms = ms; }

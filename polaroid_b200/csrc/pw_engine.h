@@ -112,6 +112,7 @@ int launch_seg_jit(const ScanPlan& P, const SegParams& sp, int nc, int threads, 
 int launch_bucket_jit(const ScanPlan& P, int nc, int kw, int sm_count, cudaStream_t st);
 int launch_runs_jit(const ScanPlan& P, int nc, int kw, int sm_count, cudaStream_t st);
 int launch_part_jit(const ScanPlan& P, const PartParams& pp, int nc, int kw, int sm_count, cudaStream_t st);
+int launch_overlap_jit(const ScanPlan& P, int nc, int kw, int sm_count, cudaStream_t st);
 int launch_radix_jit(const ScanPlan& P, const RadixParams& rp, int nc, int kw, size_t smem, int64_t work_ctas, int sm_count, cudaStream_t st);
 bool jit_available();
 struct PilotParams;

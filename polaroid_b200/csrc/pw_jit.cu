@@ -21,6 +21,7 @@
 
 #include "pw_engine.h"
 #include "pw_partition.cuh"
+#include "pw_overlap.cuh"
 #include "pw_pilot.cuh"
 #include "pw_radix.cuh"
 #include "pw_scan.cuh"
@@ -252,6 +253,12 @@ std::string part_entry(int nc, int kw, int threads) {
   return src.str();
 }
 
+std::string overlap_entry(int nc, int kw, int threads) {
+  std::ostringstream src;
+  src << "extern \"C\" __global__ void __launch_bounds__(" << threads << ") pw_overlap_jit(const __grid_constant__ pw::ScanPlan P) {\n"
+      << "  pw::overlap_body<pw::JitCtl, " << nc << ", " << kw << ">(P);\n}\n";
+  return src.str();
+}
 std::string radix_entry(int nc, int kw, int mode, int threads) {
   std::ostringstream src;
   src << "extern \"C\" __global__ void __launch_bounds__(" << threads << (mode == 1 || mode == 2 || (mode == 3 && threads <= 512) ? ", 2" : "") << ") pw_radix_jit_m" << mode << "(const __grid_constant__ pw::ScanPlan P, const pw::RadixParams rp) {\n"
@@ -281,7 +288,7 @@ void sources_hash(uint64_t* h0, uint64_t* h1) {
   static std::once_flag once;
   std::call_once(once, [] {
     a0 = 0xcbf29ce484222325ull; a1 = 0x84222325cbf29ce4ull;
-    for (const char* name : {"pw_plan.h", "pw_ctl.h", "pw_scan.cuh", "pw_segmented.cuh", "pw_partition.cuh", "pw_pilot.cuh", "pw_bucket.cuh", "pw_runs.cuh", "pw_radix.cuh"}) {
+    for (const char* name : {"pw_plan.h", "pw_ctl.h", "pw_scan.cuh", "pw_segmented.cuh", "pw_partition.cuh", "pw_pilot.cuh", "pw_bucket.cuh", "pw_runs.cuh", "pw_radix.cuh", "pw_overlap.cuh"}) {
       const std::string path = csrc_dir() + "/" + name;
       FILE* f = fopen(path.c_str(), "rb");
       if (!f) continue;
@@ -353,7 +360,7 @@ void cache_write(const std::string& path, const std::vector<char>& cubin) {
 Compiled compile(const std::string& ctl, const std::string& entry, const char* entry_name) {
   Api& a = api();
   Compiled c;
-  const std::string text = "#include \"pw_segmented.cuh\"\n#include \"pw_partition.cuh\"\n#include \"pw_pilot.cuh\"\n#include \"pw_bucket.cuh\"\n#include \"pw_runs.cuh\"\n#include \"pw_radix.cuh\"\nnamespace pw {\n" + ctl + "}\n" + entry;
+  const std::string text = "#include \"pw_segmented.cuh\"\n#include \"pw_partition.cuh\"\n#include \"pw_pilot.cuh\"\n#include \"pw_bucket.cuh\"\n#include \"pw_runs.cuh\"\n#include \"pw_radix.cuh\"\n#include \"pw_overlap.cuh\"\nnamespace pw {\n" + ctl + "}\n" + entry;
   const std::string cpath = getenv("PW_JIT_DUMP") || getenv("PW_DEBUG") ? std::string() : cache_path(text);
   {
     std::vector<char> cached;
@@ -415,8 +422,9 @@ int jit_selftest_compile(const ScanPlan& P, int nc, int kw, bool hot, int thread
     *(void**)(&a.nvrtcGetCUBIN) = dlsym(rtc, "nvrtcGetCUBIN");
     *(void**)(&a.nvrtcDestroyProgram) = dlsym(rtc, "nvrtcDestroyProgram");
   }
-  const std::string text = "#include \"pw_segmented.cuh\"\n#include \"pw_partition.cuh\"\n#include \"pw_pilot.cuh\"\n#include \"pw_bucket.cuh\"\n#include \"pw_runs.cuh\"\n#include \"pw_radix.cuh\"\nnamespace pw {\n" + jit_ctl(P) + "}\n" + scan_entry(nc, kw, hot, threads) + seg_entry(nc, 256) + part_entry(nc, kw, 256) + pilot_entry(nc, kw, 256) + runs_entry(nc, kw, 256) +
+  const std::string text = "#include \"pw_segmented.cuh\"\n#include \"pw_partition.cuh\"\n#include \"pw_pilot.cuh\"\n#include \"pw_bucket.cuh\"\n#include \"pw_runs.cuh\"\n#include \"pw_radix.cuh\"\n#include \"pw_overlap.cuh\"\nnamespace pw {\n" + jit_ctl(P) + "}\n" + scan_entry(nc, kw, hot, threads) + seg_entry(nc, 256) + part_entry(nc, kw, 256) + pilot_entry(nc, kw, 256) + runs_entry(nc, kw, 256) +
                            (nc <= 4 && P.n_slots <= 3 && !P.dyn.enabled ? radix_entry(nc, kw, 0, 256) + radix_entry(nc, kw, 1, RADIX_SC_THREADS) + radix_entry(nc, kw, 2, RADIX_SC_THREADS) + radix_entry(nc, kw, 3, RADIX_THREADS) : std::string()) +
+                           (P.dyn.enabled ? overlap_entry(nc, kw, 256) : std::string()) +
                            (P.hot.bucket ? bucket_entry(nc, kw, P.hot.b_threads, P.hot.b_cps) : std::string());
   nvrtcProgram prog = nullptr;
   if (a.nvrtcCreateProgram(&prog, text.c_str(), "pw_scan_jit.cu", 0, nullptr, nullptr) != 0) { *err = "nvrtcCreateProgram failed"; return 2; }
@@ -619,6 +627,40 @@ int launch_part_jit(const ScanPlan& P, const PartParams& pp, int nc, int kw, int
   const CUresult rc = a.cuLaunchKernel(c.fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, 0, (CUstream)st, params, nullptr);
   if (rc != 0) return fail(PW_ERR_CUDA, "cuLaunchKernel(pw_part_jit) failed with %d", rc);
   ctx().timings.kernel_launches++;
+  return 0;
+}
+// overlapping dynamic windows through the HBM table (pw_overlap.cuh); returns 0 launched, 1 unavailable
+int launch_overlap_jit(const ScanPlan& P, int nc, int kw, int sm_count, cudaStream_t st) {
+  static const bool disabled = getenv("PW_NO_JIT") != nullptr;
+  if (disabled) return 1;
+  Api& a = api();
+  if (!a.ok) return 1;
+  const int threads = 256;
+  std::string key = plan_key(P);
+  const int32_t tail[3] = {-5 /* overlap */, nc, kw};
+  key.append((const char*)tail, sizeof tail);
+  Compiled c;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_cache.find(key);
+    if (it == g_cache.end()) {
+      c = compile(jit_ctl(P), overlap_entry(nc, kw, threads), "pw_overlap_jit");
+      if (!c.failed && c.fn) {
+        if (a.cuOccupancyMaxActiveBlocksPerMultiprocessor(&c.per_sm, c.fn, threads, 0) != 0 || c.per_sm < 1) c.failed = true;
+      }
+      g_cache[key] = c;
+    } else c = it->second;
+  }
+  if (c.failed || !c.fn) return 1;
+  const int64_t n_steps = (P.n_rows + ROWS_PER_STEP - 1) / ROWS_PER_STEP;
+  int64_t grid = std::min<int64_t>((int64_t)sm_count * c.per_sm, (n_steps + (threads / 32) - 1) / (threads / 32));
+  if (grid < 1) grid = 1;
+  ScanPlan copy = P;
+  void* params[] = {&copy};
+  const CUresult rc = a.cuLaunchKernel(c.fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, 0, (CUstream)st, params, nullptr);
+  if (rc != 0) return fail(PW_ERR_CUDA, "cuLaunchKernel(pw_overlap_jit) failed with %d", rc);
+  ctx().timings.kernel_launches++;
+  ctx().timings.reserved = 1.0f;
   return 0;
 }
 // the radix tier's passes (pw_radix.cuh), one specialised kernel per mode; returns 0 launched, 1 unavailable

@@ -238,6 +238,10 @@ struct ScanPlan {
   // `rowid_slot_p1 - 1` holds (original row << 8) | validity bit of every slot.  0 = plain input.
   int32_t rowid_slot_p1;
   int32_t runs;            // != 0: sorted keys — the run-combining scan (pw_runs.cuh) instead of the hot table
+  int32_t overlap;         // overlapping dynamic windows (pw_overlap.cuh): 2 = first pass (earliest index value per key slice
+                           // into `t0`), 1 = main pass (every row joins all its windows from the slice's first window on)
+  int32_t pad5;
+  Table t0;                // overlap: (key words, window word = 0) -> MIN_I64 of the index value
   HotGeom hot;
 };
 

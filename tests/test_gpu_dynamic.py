@@ -149,3 +149,50 @@ def test_keys_sorted_first_then_time_is_accepted_on_a_resident_frame():
     G.assert_tables_equal(frame.group_by(q.plan), want)
     assert engine.last_timings()["kernel_launches"] < first
     frame.free()
+
+
+@pytest.mark.parametrize("closed", ["left", "right", "both", "none"])
+@pytest.mark.parametrize("every,period,offset", [("1m", "3m", None), ("1m", "150s", "20s"), ("2m", "2m", "-30s"), ("30s", "5m", None)])
+def test_overlapping_windows_with_group_by_keys(closed, every, period, offset):
+    """period > every together with `group_by=` keys.  Every row joins all the windows that contain it
+    (pw_overlap.cuh); the non-empty (key, window) groups are the reference's windows, key slice by key slice
+    (windows/group_by.rs:79-246 per slice, dynamic.rs:317-362)."""
+    t = synth.ohlcv(40_000, n_symbols=7, seed=51, mean_gap_us=400_000)
+    c = pw.col
+    q = (pw.LazyFrame(t).group_by_dynamic("ts", every=every, period=period, offset=offset, closed=closed, group_by="symbol", include_boundaries=True)
+         .agg(c("price").first().alias("open"), c("price").max().alias("high"), c("price").min().alias("low"),
+              c("price").last().alias("close"), c("volume").sum().alias("volume"), c("price").mean().alias("mean"), pw.len().alias("n")))
+    got = engine.run_group_by(q.table, q.plan)
+    G.assert_tables_equal(got, oracle.collect(q), rtol=1e-12)   # row order included: key slices ascending, windows ascending
+
+
+@pytest.mark.parametrize("keys", [None, "symbol"])
+def test_overlapping_windows_with_a_filter(keys):
+    t = synth.ohlcv(50_000, n_symbols=5, seed=52, mean_gap_us=300_000)
+    c = pw.col
+    q = (pw.LazyFrame(t).filter(c("volume") > 300).group_by_dynamic("ts", every="1m", period="4m", closed="right", group_by=keys)
+         .agg(c("price").first().alias("open"), c("price").last().alias("close"), c("volume").sum().alias("v"), pw.len().alias("n")))
+    got = engine.run_group_by(q.table, q.plan)
+    G.assert_tables_equal(got, oracle.collect(q), rtol=1e-12)
+
+
+def test_overlapping_windows_hash_path_equals_slice_path_without_keys():
+    # keys empty, no filter: the closed-form slice path (pw_dynamic.cu) is the default; the hash path must agree
+    t = synth.ohlcv(30_000, n_symbols=3, seed=53, mean_gap_us=500_000)
+    c = pw.col
+    q = (pw.LazyFrame(t).group_by_dynamic("ts", every="1m", period="3m", offset="-45s", closed="left", include_boundaries=True)
+         .agg(c("price").sum().alias("s"), c("price").first().alias("open"), pw.len().alias("n")))
+    want = oracle.collect(q)
+    G.assert_tables_equal(engine.run_group_by(q.table, q.plan), want, rtol=1e-12)
+    G.assert_tables_equal(engine.run_group_by(q.table, q.plan, flags=engine.FLAG_NO_SEGMENTED), want, rtol=1e-12)
+
+
+def test_overlapping_windows_two_keys_one_nullable_and_integer_index():
+    rng = np.random.default_rng(54)
+    n = 20_000
+    ts = np.sort(rng.integers(-5_000, 200_000, n)).astype(np.int64)      # negative index values: windows of negative number
+    t = pa.table({"ts": pa.array(ts), "a": pa.array(rng.integers(0, 4, n).astype("int8"), mask=rng.random(n) < 0.05),
+                  "b": pa.array(rng.integers(0, 3, n).astype(str)), "v": pa.array(rng.integers(-9, 9, n))})
+    q = (pw.LazyFrame(t).group_by_dynamic("ts", every="1000i", period="2500i", group_by=["a", "b"])
+         .agg(pw.col("v").sum().alias("s"), pw.col("v").min().alias("lo"), pw.len().alias("n")))
+    G.assert_tables_equal(engine.run_group_by(q.table, q.plan), oracle.collect(q))
