@@ -1298,6 +1298,11 @@ static int radix_prepare(const ScanPlan& P, double g_hint, ScanPlan* P2out, Radi
   uint32_t* tile_first = cursor2 + n_parts;
   tmp->dense_count = (unsigned long long*)(((uintptr_t)(tile_first + 257) + 7) & ~(uintptr_t)7);
   const size_t rec_bytes = ((size_t)N + 64) * 32;
+  {
+    // the record copies (one per level) must fit next to the frame and the result table: otherwise another tier
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && rec_bytes * (log2_p2 > 0 ? 2 : 1) > free_b / 10 * 7) return 1;
+  }
   { void* p = nullptr; PW_TRY(dev_alloc(&p, rec_bytes)); tmp->buf_a = (uint4*)p; }
   if (log2_p2 > 0) { void* p = nullptr; PW_TRY(dev_alloc(&p, rec_bytes)); tmp->buf_b = (uint4*)p; }
   PW_CUDA(cudaMemsetAsync(hist, 0, (size_t)n_parts * 4, c.stream));
