@@ -426,6 +426,10 @@ int jit_selftest_compile(const ScanPlan& P, int nc, int kw, bool hot, int thread
                            (nc <= 4 && P.n_slots <= 3 && !P.dyn.enabled ? radix_entry(nc, kw, 0, 256) + radix_entry(nc, kw, 1, RADIX_SC_THREADS) + radix_entry(nc, kw, 2, RADIX_SC_THREADS) + radix_entry(nc, kw, 3, RADIX_THREADS) : std::string()) +
                            (P.dyn.enabled ? overlap_entry(nc, kw, 256) : std::string()) +
                            (P.hot.bucket ? bucket_entry(nc, kw, P.hot.b_threads, P.hot.b_cps) : std::string());
+  if (const char* dump_src = getenv("PW_JIT_DUMP_SRC")) {   // the generated translation unit, for offline experiments
+    FILE* f = fopen(dump_src, "wb");
+    if (f) { fwrite(text.data(), 1, text.size(), f); fclose(f); }
+  }
   nvrtcProgram prog = nullptr;
   if (a.nvrtcCreateProgram(&prog, text.c_str(), "pw_scan_jit.cu", 0, nullptr, nullptr) != 0) { *err = "nvrtcCreateProgram failed"; return 2; }
   const std::string inc = "--include-path=" + csrc_dir();
