@@ -87,3 +87,29 @@ def test_host_side_arithmetic_and_result_pool_without_a_gpu():
     L = engine.lib()
     L.pw_b200_host_selftest.restype = C.c_int64
     assert L.pw_b200_host_selftest() == 0
+
+
+def test_view_columns_cross_the_boundary_with_their_data_buffers():
+    """Host side of SURVEY 8-f1 (no device work): a string column is exported as Utf8View buffers
+    [validity, views, data, variadic sizes] (polars-arrow/src/array/binview/view.rs:19-55) — values of up to 12 bytes inline,
+    longer ones as (length, 4-byte prefix, buffer 0, offset) — and a view array of that layout (what the library returns
+    when a result carries long keys) is read back value for value."""
+    import numpy as np
+    vals = ["", "a", "exactly12byt", "thirteen byte", "a string of more than twelve bytes", None, "x" * 300, "a string of more than twelve bytez"]
+    arr = pa.array(vals, type=pa.large_string())
+    vc = engine._ViewColumn(arr)
+    lens = vc.views[:, 0:4].copy().view("<u4").reshape(-1)
+    assert lens.tolist() == [0, 1, 12, 13, 34, 0, 300, 34]
+    assert bytes(vc.views[2, 4:16]) == b"exactly12byt"                      # inline: the bytes live in the view
+    long_rows = [3, 4, 6, 7]
+    for i in long_rows:                                                     # long: prefix + (buffer 0, offset) into the data buffer
+        off = int(vc.views[i, 12:16].copy().view("<u4")[0])
+        assert int(vc.views[i, 8:12].copy().view("<u4")[0]) == 0
+        assert bytes(vc.views[i, 4:8]) == vals[i].encode()[:4]
+        assert bytes(vc.data[off:off + lens[i]]) == vals[i].encode()
+    assert int(vc.sizes[0]) == len(vc.data)
+    c_array, c_schema = engine.ArrowArray(), engine.ArrowSchema()
+    vc.fill(c_array, c_schema)
+    assert c_array.n_buffers == 4 and c_schema.format == b"vu"
+    back = engine._import_view_array(c_array, c_schema)
+    assert back.to_pylist() == vals
