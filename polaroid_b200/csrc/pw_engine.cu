@@ -1800,7 +1800,7 @@ int emit_results(const Lowered& L, const Table& T, const uint32_t* slot_list, ui
       d.null_count = d_nulls + i0 + j;
       batch.d[j] = d;
     }
-    emit_kernel<<<dim3((unsigned)grid, (unsigned)nb), 256, 0, c.stream>>>(T, kw, batch, slot_list, G, deferred ? state->dctl : nullptr);
+    emit_kernel<<<(unsigned)((uint64_t)grid * nb), 256, 0, c.stream>>>(T, kw, batch, (int)nb, slot_list, G, deferred ? state->dctl : nullptr);
     if (cudaGetLastError() != cudaSuccess) { dev_free(d_block); if (deferred) state->block = nullptr; return fail(PW_ERR_CUDA, "emit_kernel launch failed"); }
     c.timings.kernel_launches++;
   }

@@ -161,16 +161,19 @@ __device__ __forceinline__ void store_typed(void* base, uint64_t i, int dt, uint
   }
 }
 
-// One launch emits up to EMIT_BATCH result columns: blockIdx.y selects the column.
+// One launch emits up to EMIT_BATCH result columns.  Blocks are numbered column-fastest (block b: column b % n_cols, rows
+// of block b / n_cols), so the blocks that read the same table rows — one per column — run next to each other and the
+// rows come from L2 after the first touch (a (rows, columns) grid walked a 1e7-group table once per column from HBM:
+// C3's emit 1.7 ms).
 constexpr int EMIT_BATCH = 16;
 struct EmitBatch { EmitDesc d[EMIT_BATCH]; };
 // ctl (optional, "count on the device" mode): n is an upper bound, the real count is ctl->counter.  In that mode the
 // control block is the header of the result block itself, so the null counts this kernel accumulates, the group count
 // and the overflow / not-sorted flags reach the host with the same copy as the columns.
-static __global__ void emit_kernel(Table T, int n_kw, const __grid_constant__ EmitBatch batch, const uint32_t* slot_list, uint64_t n,
+static __global__ void emit_kernel(Table T, int n_kw, const __grid_constant__ EmitBatch batch, int n_cols, const uint32_t* slot_list, uint64_t n,
                                    const Control* ctl = nullptr) {
-  const EmitDesc& d = batch.d[blockIdx.y];
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const EmitDesc& d = batch.d[blockIdx.x % (unsigned)n_cols];
+  const uint64_t i = (uint64_t)(blockIdx.x / (unsigned)n_cols) * blockDim.x + threadIdx.x;
   if (ctl) {
     const uint64_t cnt = ctl->counter;
     n = cnt < n ? cnt : n;
