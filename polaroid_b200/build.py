@@ -20,7 +20,16 @@ def _stale() -> bool:
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "polarway_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    if any(os.path.getmtime(d) > t for d in deps):
+        return True
+    # a header edited WHILE a build was running leaves objects older than the header behind a library that is newer
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f not in SOURCES] + [os.path.join(HERE, "..", "include", "polarway_b200.h")]
+    t_hdr = max(os.path.getmtime(h) for h in headers)
+    for src in SOURCES:
+        obj = os.path.join(LIB_DIR, src.rsplit(".", 1)[0] + ".o")
+        if os.path.exists(obj) and os.path.getmtime(obj) < max(t_hdr, os.path.getmtime(os.path.join(CSRC, src))):
+            return True
+    return False
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
