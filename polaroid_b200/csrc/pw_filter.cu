@@ -271,6 +271,7 @@ int pw_b200_filter(const PwPredicate* predicates, int32_t n_predicates, const st
     rc = dev_alloc(&dv, vb);
     if (!rc) rc = dev_alloc(&db, bb);
     if (!rc && n_sel) {
+      cudaMemsetAsync(d_long, 0, 4, c.stream);   // per column
       gather_kernel<<<(unsigned)((n_sel + 255) / 256), 256, 0, c.stream>>>(s, w, ids, (uint64_t)n_sel, (unsigned char*)dv, (uint32_t*)db, d_nulls + i, d_long);
       if (cudaGetLastError() != cudaSuccess) rc = fail(PW_ERR_CUDA, "gather launch failed");
       c.timings.kernel_launches++;
@@ -281,8 +282,25 @@ int pw_b200_filter(const PwPredicate* predicates, int32_t n_predicates, const st
       cudaMemcpyAsync(&nulls, d_nulls + i, 8, cudaMemcpyDeviceToHost, c.stream);
       cudaMemcpyAsync(&is_long, d_long, 4, cudaMemcpyDeviceToHost, c.stream);
       cudaStreamSynchronize(c.stream);
-      if (is_long) rc = fail(PW_ERR_UNSUPPORTED, "string longer than 12 bytes in column '%s' (long views need the data buffers: SURVEY 8f rank 1)", col.name.c_str());
+      if (is_long && col.dtype == DT_VIEW && !col.has_long) rc = fail(PW_ERR_INVALID, "column '%s' holds values longer than 12 bytes but no data buffer", col.name.c_str());
     }
+    if (!rc && col.dtype == DT_VIEW && col.has_long) {
+      // values longer than 12 bytes: the selected views still point into the frame's data buffers — gather their
+      // bytes into a data buffer of the result's own (pw_views.cu), as the group-by does for its keys
+      void* hv = host_alloc(vb);
+      void* hb = host_alloc(bb);
+      void* h_data = nullptr;
+      int64_t data_bytes = 0;
+      if (!hv || !hb) rc = fail(PW_ERR_INTERNAL, "out of host memory");
+      if (!rc && vb && cudaMemcpyAsync(hv, dv, vb, cudaMemcpyDeviceToHost, c.stream) != cudaSuccess) rc = fail(PW_ERR_CUDA, "copy failed");
+      if (!rc && bb && cudaMemcpyAsync(hb, db, bb, cudaMemcpyDeviceToHost, c.stream) != cudaSuccess) rc = fail(PW_ERR_CUDA, "copy failed");
+      if (!rc && cudaStreamSynchronize(c.stream) != cudaSuccess) rc = fail(PW_ERR_CUDA, "copy failed");
+      if (!rc) rc = views_gather_long(&col, hv, nulls ? hb : nullptr, (uint64_t)n_sel, &h_data, &data_bytes);
+      if (!rc) rc = h_data ? make_host_view_array(n_sel, (int64_t)nulls, hb, hv, h_data, data_bytes, &out_cols[i])
+                           : make_host_array(n_sel, (int64_t)nulls, hb, hv, 1, &out_cols[i]);
+      if (rc) { host_free(hv); host_free(hb); host_free(h_data); }
+      else rc = make_schema(col.format.c_str(), col.name.c_str(), true, &out_schemas[i]);
+    } else
     if (!rc) rc = device_to_arrow(dv, vb, db, bb, n_sel, (int64_t)nulls, col.dtype == DT_VIEW, col.format.c_str(), col.name.c_str(), &out_cols[i], &out_schemas[i]);
     dev_free(dv); dev_free(db);
     if (rc) for (size_t k = 0; k < i; ++k) { if (out_cols[k].release) out_cols[k].release(&out_cols[k]); if (out_schemas[k].release) out_schemas[k].release(&out_schemas[k]); }

@@ -62,3 +62,22 @@ def test_sorted_key_fast_path_equivalence():
     assert first.to_numpy().tolist() == starts.tolist()
     assert np.diff(offsets.to_numpy().astype(np.int64)).tolist() == lens.tolist()
     assert row_ids.to_numpy().tolist() == list(range(len(keys)))
+
+
+def test_filter_carries_strings_longer_than_twelve_bytes():
+    # the selected views of long values point into the frame's data buffers; the result gathers their
+    # bytes into a data buffer of its own (binview/view.rs:19-55)
+    rng = np.random.default_rng(6)
+    n = 30_000
+    names = ["short", "exactly12byt", "a value of more than twelve bytes", "a value of more than twelve bytez", "y" * 200, ""]
+    t = pa.table({"i": pa.array(rng.integers(-100, 100, n)),
+                  "s": pa.array([names[k] for k in rng.integers(0, len(names), n)], mask=rng.random(n) < 0.05),
+                  "f": pa.array(rng.random(n))})
+    lf = pw.LazyFrame(t).filter((pw.col("i") > 10) & (pw.col("f") <= 0.7))
+    got = lf.collect()
+    want = oracle.filter_table(t, lf._preds)
+    G.assert_tables_equal(got, want)
+    # group tuples over the same column: equal long strings are one group
+    first, offsets, row_ids = engine.group_tuples(t, ["s"], maintain_order=True)
+    ofirst, ooff, oids, _ = oracle.group_tuples(t, ["s"])
+    assert first.to_numpy().tolist() == ofirst.tolist() and offsets.to_numpy().tolist() == list(ooff)
